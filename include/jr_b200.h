@@ -1,0 +1,197 @@
+/*
+ * jr_b200.h -- C ABI of the B200-native rasterisation path of jaxrenderer.
+ *
+ * Drop-in boundary: `renderer.pipeline.render(camera, shader, buffers,
+ * face_indices, extra, loop_unroll)` (reference renderer/pipeline.py:470-537)
+ * for the seven built-in shaders, and its reverse-mode derivative (the
+ * reference obtains it from jax.grad, tests/smoke_test_grad.py:92-128).
+ * A host binding (ctypes here; XLA-FFI handler for a JAX host, see
+ * INTEGRATION.md) fills one JrRenderArgs and calls one entry point per render.
+ *
+ * Rules
+ *  - every pointer is DEVICE memory owned by the caller; dense, row-major,
+ *    fp32 / int32 (the reference's dtypes without x64);
+ *  - every array argument is a JrF32/JrI32 {ptr, batch_stride}: element b of
+ *    the batch starts at ptr + b * batch_stride ELEMENTS; batch_stride == 0
+ *    broadcasts one array to the whole batch (jax.vmap in_axes=None);
+ *  - buffers are x-major: zbuffer[b][x][y], canvas[b][x][y][c]
+ *    (renderer/types.py:148-155), updated IN PLACE (the reference donates
+ *    them, pipeline.py:466);
+ *  - calls are asynchronous on `stream`, never allocate, never synchronise,
+ *    never throw; they return 0 or a negative JrStatus;
+ *  - re-entrant: no global state.
+ */
+#ifndef JR_B200_H_
+#define JR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JR_ABI_VERSION 1
+
+typedef void* jr_stream_t; /* cudaStream_t */
+
+typedef enum JrShader {
+  JR_DEPTH = 0,                   /* shaders/depth.py:38-61 */
+  JR_GOURAUD = 1,                 /* shaders/gouraud.py:49-124 */
+  JR_GOURAUD_TEXTURE = 2,         /* shaders/gouraud_texture.py:55-167 */
+  JR_PHONG = 3,                   /* shaders/phong.py:65-187 */
+  JR_PHONG_DARBOUX = 4,           /* shaders/phong_darboux.py:106-316 */
+  JR_PHONG_REFLECTION = 5,        /* shaders/phong_reflection.py:91-258 */
+  JR_PHONG_REFLECTION_SHADOW = 6, /* shaders/phong_reflection_shadow.py:99-295 */
+  JR_NUM_SHADERS = 7
+} JrShader;
+
+typedef enum JrStatus {
+  JR_OK = 0,
+  JR_ERR_NULL = -1,        /* a required pointer is NULL */
+  JR_ERR_DIMS = -2,        /* non-positive / inconsistent dimensions */
+  JR_ERR_SHADER = -3,      /* unknown shader id */
+  JR_ERR_WORKSPACE = -4,   /* workspace too small (see jr_workspace_bytes) */
+  JR_ERR_UNSUPPORTED = -5, /* combination not supported */
+  JR_ERR_CUDA = -6         /* a launch failed (cudaGetLastError) */
+} JrStatus;
+
+typedef struct JrF32 { const float* ptr; long long batch_stride; } JrF32;
+typedef struct JrI32 { const int32_t* ptr; long long batch_stride; } JrI32;
+typedef struct JrF32Out { float* ptr; long long batch_stride; } JrF32Out;
+
+/*
+ * One render call == reference `pipeline.render` vmapped over B images.
+ * Fields a shader does not read may be left zero.
+ */
+typedef struct JrRenderArgs {
+  int32_t shader;          /* JrShader */
+  int32_t B, W, H;         /* batch, canvas width (axis 0), height (axis 1) */
+  int32_t T;               /* triangles: face_indices (T,3) */
+  int32_t n_pos;           /* rows of `position` (= extra[0].shape[0], pipeline.py:488-491) */
+  int32_t n_nrm, n_uv;     /* rows of `normal`, `uv` */
+
+  /* Camera (geometry.py:205-225): only the three matrices the path reads. */
+  JrF32 world_to_clip;     /* (4,4) */
+  JrF32 viewport;          /* (4,4) */
+  JrF32 world_to_eye_norm; /* (4,4)  S4-S7 */
+
+  /* Geometry.  `faces` indexes `position` (and `colour`).  faces_norm /
+   * faces_uv / faces_tex index normal / uv / texture_index; NULL ptr means
+   * "same as faces" (the generic pipeline.render call).  Renderer.render
+   * (renderer.py:277-296) passes the model's three index buffers instead of
+   * materialising the corner-expanded copies. */
+  JrF32 position;          /* (n_pos,3) world space */
+  JrI32 faces;             /* (T,3) */
+  JrF32 normal;            /* (n_nrm,3) */
+  JrI32 faces_norm;        /* (T,3) or NULL */
+  JrF32 uv;                /* (n_uv,2) */
+  JrI32 faces_uv;          /* (T,3) or NULL */
+  JrF32 colour;            /* (n_pos,3)  S2 */
+
+  /* Light (types.py:134-141; renderer.py:298-327). */
+  JrF32 light_direction;   /* (3)  S2-S5 */
+  JrF32 light_colour;      /* (3) */
+  JrF32 light_dir_eye;     /* (3)  S6-S7 */
+  JrF32 ambient, diffuse, specular; /* (3) each, S6-S7 */
+
+  /* Maps. */
+  JrF32 texture;           /* (tex_w, tex_h, 3) */
+  int32_t tex_w, tex_h;
+  JrF32 specular_map;      /* (spec_w, spec_h)  S6-S7 */
+  int32_t spec_w, spec_h;
+  JrF32 normal_map;        /* (tex_w, tex_h, 3)  S5 */
+  JrI32 texture_shape;     /* (n_objects,2)  S6-S7 */
+  int32_t n_objects;
+  JrI32 texture_index;     /* (n_texidx)  S6-S7, read at faces_tex[t][0] */
+  JrI32 faces_tex;         /* (T,3) or NULL */
+  int32_t n_texidx;
+  int32_t texture_offset;  /* model.py:552 */
+  JrI32 id_to_face;        /* (n_pos)  S5 */
+  JrI32 faces_indices;     /* (n_faces_indices,3)  S5 */
+  int32_t n_faces_indices;
+
+  /* Shadow (shadow.py:27-38)  S7. */
+  JrF32 shadow_map;        /* (shadow_w, shadow_h) */
+  int32_t shadow_w, shadow_h;
+  JrF32 shadow_strength;   /* (3) */
+  JrF32 shadow_world_to_clip; /* (4,4) light camera */
+  JrF32 shadow_viewport;      /* (4,4) */
+
+  /* Buffers, in/out (B,W,H) and (B,W,H,3).  canvas may be NULL for JR_DEPTH. */
+  float* zbuffer;
+  float* canvas;
+  /* G-buffer out (B,W,H) int32: triangle written at each pixel, -1 if the
+   * pixel kept its old value.  Required (it is what backward consumes). */
+  int32_t* tri_id;
+
+  void* workspace;         /* >= jr_workspace_bytes(args) bytes, or NULL if that is 0 */
+  size_t workspace_bytes;
+} JrRenderArgs;
+
+/*
+ * Cotangents.  Inputs: d_zbuffer (B,W,H), d_canvas (B,W,H,3) (either may be
+ * NULL == zero).  Outputs are ACCUMULATED INTO (caller zero-fills) and may
+ * be NULL when not wanted.  Batch strides follow the forward argument of the
+ * same name: a broadcast input (stride 0) receives the batch-summed gradient.
+ * d_zbuffer / d_canvas are overwritten in place with the cotangent w.r.t. the
+ * INCOMING buffers (d_old = d_new * (1 - keep), pipeline.py:420-437).
+ */
+typedef struct JrGradArgs {
+  float* d_zbuffer;            /* in: d/d z_out; out: d/d z_in   (B,W,H) */
+  float* d_canvas;             /* in: d/d canvas_out; out: d/d canvas_in */
+  JrF32Out d_position;         /* (n_pos,3) */
+  JrF32Out d_normal;           /* (n_nrm,3) */
+  JrF32Out d_colour;           /* (n_pos,3) */
+  JrF32Out d_world_to_clip;    /* (4,4) */
+  JrF32Out d_viewport;         /* (4,4) */
+  JrF32Out d_world_to_eye_norm;/* (4,4) */
+  JrF32Out d_light_direction, d_light_colour, d_light_dir_eye;
+  JrF32Out d_ambient, d_diffuse, d_specular;
+  JrF32Out d_texture;          /* (tex_w,tex_h,3) deterministic scatter */
+  JrF32Out d_specular_map;     /* (spec_w,spec_h) */
+  JrF32Out d_shadow_strength;  /* (3) */
+  void* workspace;
+  size_t workspace_bytes;
+} JrGradArgs;
+
+int jr_abi_version(void);
+const char* jr_strerror(int status);
+
+/* Bytes of scratch `jr_render_forward` needs for these dimensions. */
+size_t jr_workspace_bytes(const JrRenderArgs* args);
+/* Bytes of scratch `jr_render_backward` needs. */
+size_t jr_backward_workspace_bytes(const JrRenderArgs* args, const JrGradArgs* grads);
+
+/* pipeline.render, forward (pipeline.py:470-537), any built-in shader. */
+int jr_render_forward(const JrRenderArgs* args, jr_stream_t stream);
+/* Reverse mode through fixed visibility (SURVEY 8a row BWD / Q9). */
+int jr_render_backward(const JrRenderArgs* args, const JrGradArgs* grads, jr_stream_t stream);
+
+/* Per-shader entry points (what an XLA-FFI target per shader binds to);
+ * each checks args->shader and forwards to jr_render_forward/backward. */
+int jr_depth_forward(const JrRenderArgs*, jr_stream_t);
+int jr_gouraud_forward(const JrRenderArgs*, jr_stream_t);
+int jr_gouraud_texture_forward(const JrRenderArgs*, jr_stream_t);
+int jr_phong_forward(const JrRenderArgs*, jr_stream_t);
+int jr_phong_darboux_forward(const JrRenderArgs*, jr_stream_t);
+int jr_phong_reflection_forward(const JrRenderArgs*, jr_stream_t);
+int jr_phong_reflection_shadow_forward(const JrRenderArgs*, jr_stream_t);
+
+/* Shadow-map epilogue of Shadow.render_shadow_map (shadow.py:116):
+ * shadow_map[i] += offset over n floats. */
+int jr_add_scalar(float* data, long long n, float value, jr_stream_t stream);
+
+/* Output epilogue: canvas (B,W,H,3) fp32 -> (B,H,W,3) uint8,
+ * clamp(0,1)*255, transposed and vertically flipped (utils.py:79-98). */
+int jr_canvas_to_uint8_display(const float* canvas, uint8_t* out, int B, int W, int H,
+                               jr_stream_t stream);
+
+/* Introspection for benchmarks: number of kernel launches issued by this
+ * library since load (monotonic). */
+long long jr_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JR_B200_H_ */

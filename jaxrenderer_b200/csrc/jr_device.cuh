@@ -1,0 +1,145 @@
+// jr_device.cuh -- exact-order fp32 device math shared by the visibility,
+// shading and backward kernels.
+//
+// This translation unit is compiled with -fmad=false: every `*`, `+`, `-` below
+// is ONE rounded fp32 operation and `/`, sqrtf are IEEE round-to-nearest, so the
+// discrete outcomes (edge inclusion, depth order, texel choice) are bit-equal
+// to the oracle's scalar-order restatement of the reference
+// (renderer/pipeline.py:76-113, :163-279; geometry.py:71-110, :284-315).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace jr {
+
+struct Vec3 { float x, y, z; };
+
+__device__ __forceinline__ float dot3(float a0, float a1, float a2, float b0, float b1, float b2) {
+  return (a0 * b0 + a1 * b1) + a2 * b2;
+}
+__device__ __forceinline__ Vec3 normalise3(Vec3 v) {
+  float n = sqrtf(dot3(v.x, v.y, v.z, v.x, v.y, v.z));
+  return Vec3{v.x / n, v.y / n, v.z / n};
+}
+
+// to_homogeneous(p) @ M.T  (Camera.to_clip, geometry.py:420-438)
+__device__ __forceinline__ void to_clip(const float* __restrict__ M, float x, float y, float z,
+                                        float out[4]) {
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+    out[r] = ((x * M[4 * r + 0] + y * M[4 * r + 1]) + z * M[4 * r + 2]) + M[4 * r + 3];
+}
+
+// Camera.apply_vec (geometry.py:352-389): normalise, rotate (w = 0), normalise.
+__device__ __forceinline__ Vec3 apply_vec(const float* __restrict__ M, Vec3 v) {
+  Vec3 n = normalise3(v);
+  Vec3 t;
+  t.x = (n.x * M[0] + n.y * M[1]) + n.z * M[2];
+  t.y = (n.x * M[4] + n.y * M[5]) + n.z * M[6];
+  t.z = (n.x * M[8] + n.y * M[9]) + n.z * M[10];
+  return normalise3(t);
+}
+
+// jnp.linalg.det closed form, jax `_det_3x3` term order (pipeline.py:91-94).
+__device__ __forceinline__ float det3(const float a[9]) {
+  return a[0] * a[4] * a[8] + a[1] * a[5] * a[6] + a[2] * a[3] * a[7] - a[2] * a[4] * a[6] -
+         a[0] * a[5] * a[7] - a[1] * a[3] * a[8];
+}
+
+__device__ __forceinline__ void swapf(float& a, float& b) { float t = a; a = b; b = t; }
+
+// jnp.linalg.inv of a 3x3 (pipeline.py:105): LU with partial pivoting in LAPACK
+// sgetrf2 order (column scaled by the reciprocal pivot) and strsm-ordered
+// substitutions against the permuted identity.  Mirrors oracle.lu_inverse3.
+__device__ __forceinline__ void lu_inverse3(const float A[9], float inv[9]) {
+  float r0[6] = {A[0], A[1], A[2], 1.f, 0.f, 0.f};
+  float r1[6] = {A[3], A[4], A[5], 0.f, 1.f, 0.f};
+  float r2[6] = {A[6], A[7], A[8], 0.f, 0.f, 1.f};
+  float a0 = fabsf(r0[0]), a1 = fabsf(r1[0]), a2 = fabsf(r2[0]);
+  bool p1 = a1 > a0;
+  float best = p1 ? a1 : a0;
+  bool p2 = a2 > best;
+  p1 = p1 && !p2;
+  if (p1) {
+#pragma unroll
+    for (int c = 0; c < 6; ++c) swapf(r0[c], r1[c]);
+  }
+  if (p2) {
+#pragma unroll
+    for (int c = 0; c < 6; ++c) swapf(r0[c], r2[c]);
+  }
+  float r00 = 1.0f / r0[0];
+  float l10 = r1[0] * r00, l20 = r2[0] * r00;
+  float u00 = r0[0], u01 = r0[1], u02 = r0[2];
+  float a11 = r1[1] - l10 * u01, a12 = r1[2] - l10 * u02;
+  float a21 = r2[1] - l20 * u01, a22 = r2[2] - l20 * u02;
+  if (fabsf(a21) > fabsf(a11)) {
+    swapf(l10, l20); swapf(a11, a21); swapf(a12, a22);
+#pragma unroll
+    for (int c = 3; c < 6; ++c) swapf(r1[c], r2[c]);
+  }
+  float u11 = a11, u12 = a12;
+  float l21 = a21 * (1.0f / u11);
+  float u22 = a22 - l21 * u12;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    float y0 = r0[3 + j];
+    float y1 = r1[3 + j] - y0 * l10;
+    float y2 = (r2[3 + j] - y0 * l20) - y1 * l21;
+    float x2 = y2 / u22;
+    float t1 = y1 - x2 * u12;
+    float t0 = y0 - x2 * u02;
+    float x1 = t1 / u11;
+    t0 = t0 - x1 * u01;
+    float x0 = t0 / u00;
+    inv[0 + j] = x0; inv[3 + j] = x1; inv[6 + j] = x2;
+  }
+}
+
+// Monotone map float -> uint32 (-0 canonicalised to +0 first).
+__device__ __forceinline__ uint32_t orderable(float z) {
+  uint32_t f = __float_as_uint(z + 0.0f);
+  return f ^ ((f >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
+__device__ __forceinline__ float from_orderable(uint32_t u) {
+  uint32_t f = u ^ ((u >> 31) ? 0x80000000u : 0xFFFFFFFFu);
+  return __uint_as_float(f);
+}
+
+// Per-triangle raster record (PerPrimitive, pipeline.py:49-113).
+struct TriSetup {
+  float inv[9];  // matrix_inv, row-major [row][col]
+  float zc[3];   // clip-space z of the three vertices
+  float det;
+};
+
+// Build PerPrimitive from three clip-space vertices.  Returns det.
+__device__ __forceinline__ float tri_matrix(const float c0[4], const float c1[4], const float c2[4],
+                                            float M[9]) {
+  M[0] = c0[0]; M[1] = c0[1]; M[2] = c0[3];
+  M[3] = c1[0]; M[4] = c1[1]; M[5] = c1[3];
+  M[6] = c2[0]; M[7] = c2[1]; M[8] = c2[3];
+  return det3(M);
+}
+
+// Edge functions / clip_coef at NDC pixel (xn, yn) (pipeline.py:190).
+__device__ __forceinline__ void clip_coef(const float inv[9], float xn, float yn, float c[3]) {
+#pragma unroll
+  for (int k = 0; k < 3; ++k) c[k] = (xn * inv[k] + yn * inv[3 + k]) + inv[6 + k];
+}
+
+__device__ __forceinline__ float interp3(const float tc[3], float v0, float v1, float v2) {
+  return (tc[0] * v0 + tc[1] * v1) + tc[2] * v2;
+}
+
+__device__ __forceinline__ int pymod(int a, int n) {
+  int m = a % n;
+  return m < 0 ? m + n : m;
+}
+// jnp arr[i]: negative wraps once, then clamp.
+__device__ __forceinline__ int wrap_clamp(int i, int n) {
+  if (i < 0) i += n;
+  return i < 0 ? 0 : (i > n - 1 ? n - 1 : i);
+}
+
+}  // namespace jr

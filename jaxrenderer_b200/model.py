@@ -1,0 +1,213 @@
+"""Mesh containers and object merging (host side), mirroring ``renderer/model.py``.
+
+``Model`` (:37-143), ``MergedModel`` (:155-339), ``ModelObject`` (:342-421),
+``batch_models`` (:425-442), ``merge_objects`` (:447-555).  ``uv_repeat``
+(:306-339) additionally lives inside the phong_reflection* fragment kernels.
+
+Batch convention: any tensor leaf may carry one extra leading batch axis (the
+reference gets this from ``jax.vmap``); ``merge_objects`` broadcasts them.
+"""
+from __future__ import annotations
+
+from typing import Any, List, NamedTuple, Optional, Sequence, Tuple
+
+import torch
+
+from .geometry import to_cartesian, to_homogeneous, transform_matrix_from_rotation
+from .types import Tensor, _f32, _i32
+
+
+class Model(NamedTuple):
+    """``model.py:37-53``."""
+
+    verts: Tensor
+    norms: Tensor
+    uvs: Tensor
+    faces: Tensor
+    faces_norm: Tensor
+    faces_uv: Tensor
+    diffuse_map: Tensor
+    specular_map: Tensor
+
+    @classmethod
+    def create(cls, verts: Tensor, norms: Tensor, uvs: Tensor, faces: Tensor,
+               diffuse_map: Tensor, specular_map: Optional[Tensor] = None) -> "Model":
+        """``model.py:55-90``: same index buffer for all attributes; default
+        specular map is a constant 2.0."""
+        diffuse_map = _f32(diffuse_map)
+        if specular_map is None:
+            specular_map = torch.full(diffuse_map.shape[:2], 2.0, dtype=torch.float32,
+                                      device=diffuse_map.device)
+        faces = _i32(faces)
+        return cls(verts=_f32(verts), norms=_f32(norms), uvs=_f32(uvs), faces=faces,
+                   faces_norm=faces, faces_uv=faces, diffuse_map=diffuse_map,
+                   specular_map=_f32(specular_map))
+
+    def value_checks(self) -> None:
+        """Index-range validation (``model.py:105-143``); raises ``ValueError``."""
+        for name, idx, n in (("faces", self.faces, self.verts.shape[-2]),
+                             ("faces_norm", self.faces_norm, self.norms.shape[-2]),
+                             ("faces_uv", self.faces_uv, self.uvs.shape[-2])):
+            lo, hi = int(idx.min()), int(idx.max())
+            if lo < 0 or hi >= n:
+                raise ValueError(f"{name} out of bound, expected [0, {n}), got [{lo}, {hi}].")
+
+
+class MergedModel(NamedTuple):
+    """``model.py:155-178``."""
+
+    verts: Tensor
+    norms: Tensor
+    uvs: Tensor
+    faces: Tensor
+    faces_norm: Tensor
+    faces_uv: Tensor
+    texture_index: Tensor
+    double_sided: Tensor
+    texture_shape: Tensor
+    offset: int
+    diffuse_map: Tensor
+    specular_map: Tensor
+
+    @staticmethod
+    def generate_object_vert_info(counts: Sequence[int], values: Sequence[Any]) -> Tensor:
+        """``model.py:180-213``: repeat one value per object over its vertices."""
+        parts = []
+        for count, value in zip(counts, values):
+            v = torch.as_tensor(value)
+            parts.append(v.expand(count, *v.shape).clone() if v.ndim else v.repeat(count))
+        return torch.cat(parts, dim=0)
+
+    @staticmethod
+    def merge_verts(vs: Sequence[Tensor], fs: Sequence[Tensor]) -> Tuple[Tensor, Tensor]:
+        """``model.py:215-247``: concatenate attribute arrays, offset indices."""
+        cumsum = [0]
+        for v in vs[:-1]:
+            cumsum.append(cumsum[-1] + v.shape[-2])
+        nb = max(v.ndim for v in vs)
+        batch = torch.broadcast_shapes(*[v.shape[:-2] for v in vs])
+        verts = torch.cat([v.expand(*batch, *v.shape[-2:]) if nb > 2 else v for v in vs], dim=-2)
+        fb = torch.broadcast_shapes(*[f.shape[:-2] for f in fs])
+        faces = torch.cat([(f + cumsum[i]).expand(*fb, *f.shape[-2:]) for i, f in enumerate(fs)],
+                          dim=-2)
+        return verts, faces.to(torch.int32)
+
+    @staticmethod
+    def merge_maps(maps: Sequence[Tensor], rank: Optional[int] = None) -> Tuple[Tensor, Tuple[int, int]]:
+        """``model.py:249-301``: zero-pad every map to the max shape and
+        concatenate along the first (width) axis.  ``base`` rank = rank of an
+        un-batched map (2 for specular, 3 for diffuse)."""
+        if rank is None:
+            rank = min(m.ndim for m in maps)
+        # a map is batched iff it has rank+1 dims; all maps share `rank`
+        single = tuple(max(m.shape[m.ndim - rank + i] for m in maps) for i in range(rank))
+        batch = torch.broadcast_shapes(*[m.shape[: m.ndim - rank] for m in maps])
+        padded = []
+        for m in maps:
+            pad: List[int] = []
+            for i in reversed(range(rank)):
+                pad += [0, single[i] - m.shape[m.ndim - rank + i]]
+            p = torch.nn.functional.pad(_f32(m), pad)
+            padded.append(p.expand(*batch, *p.shape[p.ndim - rank:]))
+        return torch.cat(padded, dim=len(batch)), (single[0], single[1])
+
+    @staticmethod
+    def uv_repeat(uv: Tensor, shape: Tensor, map_index: Tensor, offset: Any) -> Tensor:
+        """``model.py:306-339`` (host twin of the in-kernel version)."""
+        frac = uv - torch.trunc(uv)
+        frac = torch.where(frac < 0, frac + 1, frac)
+        out = frac * shape
+        out[..., 0] = out[..., 0] + map_index * offset
+        return out
+
+
+class ModelObject(NamedTuple):
+    """``model.py:342-421``."""
+
+    model: Model
+    local_scaling: Any = (1.0, 1.0, 1.0)
+    transform: Any = ((1.0, 0.0, 0.0, 0.0), (0.0, 1.0, 0.0, 0.0), (0.0, 0.0, 1.0, 0.0), (0.0, 0.0, 0.0, 1.0))
+    double_sided: Any = False
+
+    def replace_with_position(self, position: Tensor) -> "ModelObject":
+        t = _f32(self.transform).clone()
+        t[..., :3, 3] = _f32(position)
+        return self._replace(transform=t)
+
+    def replace_with_orientation(self, orientation: Optional[Tensor] = None,
+                                 rotation_matrix: Optional[Tensor] = None) -> "ModelObject":
+        if rotation_matrix is None:
+            if orientation is None:
+                orientation = torch.tensor((0.0, 0.0, 0.0, 1.0))
+            rotation_matrix = transform_matrix_from_rotation(_f32(orientation))
+        t = _f32(self.transform).clone()
+        t[..., :3, :3] = rotation_matrix
+        return self._replace(transform=t)
+
+    def replace_with_local_scaling(self, local_scaling: Tensor) -> "ModelObject":
+        return self._replace(local_scaling=local_scaling)
+
+    def replace_with_double_sided(self, double_sided: Any) -> "ModelObject":
+        return self._replace(double_sided=double_sided)
+
+
+def batch_models(models: Sequence[MergedModel]) -> MergedModel:
+    """Stack several ``MergedModel`` along a new leading axis (``model.py:425-442``).
+    ``offset`` (a Python int) must agree and stays un-batched."""
+    fields = []
+    for i, name in enumerate(MergedModel._fields):
+        if name == "offset":
+            assert all(m.offset == models[0].offset for m in models)
+            fields.append(models[0].offset)
+        else:
+            fields.append(torch.stack([torch.as_tensor(m[i]) for m in models], dim=0))
+    return MergedModel._make(fields)
+
+
+def _frob_normalise(x: Tensor) -> Tensor:
+    """``normalise`` applied by the reference to a whole ``(N, 3)`` array."""
+    return x / torch.linalg.norm(x, dim=(-2, -1), keepdim=True)
+
+
+def merge_objects(objects: Sequence[ModelObject]) -> MergedModel:
+    """World-space merge of all objects into one mesh + texture atlas
+    (``model.py:447-555``)."""
+    models = [obj.model for obj in objects]
+    dev = models[0].verts.device
+    counts = [m.verts.shape[-2] for m in models]
+    map_indices = MergedModel.generate_object_vert_info(counts, list(range(len(models)))).to(
+        torch.int32).to(dev)
+    map_wh = torch.tensor([tuple(m.diffuse_map.shape[-3:-1]) for m in models], dtype=torch.int32,
+                          device=dev)
+    double_sided = MergedModel.generate_object_vert_info(
+        counts, [bool(torch.as_tensor(o.double_sided).reshape(-1)[0]) for o in objects]).to(dev)
+
+    diffuse_map, single = MergedModel.merge_maps([m.diffuse_map for m in models], rank=3)
+    specular_map = MergedModel.merge_maps([m.specular_map for m in models], rank=2)[0]
+
+    def transform_vert(verts: Tensor, local_scaling: Any, transform: Any) -> Tensor:
+        ls = _f32(local_scaling, dev)
+        tf = _f32(transform, dev)
+        scaled = _f32(verts) * ls[..., None, :]
+        return to_cartesian(to_homogeneous(scaled) @ tf.transpose(-1, -2))
+
+    def transform_normals(normals: Tensor, transform: Any) -> Tensor:
+        tf = _f32(transform, dev)
+        m = torch.linalg.inv(tf).transpose(-1, -2)
+        n = _frob_normalise(_f32(normals))
+        t = (to_homogeneous(n, 0.0) @ m.transpose(-1, -2))[..., :3]
+        return _frob_normalise(t)
+
+    verts, faces = MergedModel.merge_verts(
+        [transform_vert(o.model.verts, o.local_scaling, o.transform) for o in objects],
+        [m.faces for m in models])
+    norms, faces_norm = MergedModel.merge_verts(
+        [transform_normals(o.model.norms, o.transform) for o in objects],
+        [m.faces_norm for m in models])
+    uvs, faces_uv = MergedModel.merge_verts([_f32(m.uvs) for m in models],
+                                            [m.faces_uv for m in models])
+    return MergedModel(
+        verts=verts, norms=norms, uvs=uvs, faces=faces, faces_norm=faces_norm,
+        faces_uv=faces_uv, texture_shape=map_wh, texture_index=map_indices,
+        double_sided=double_sided, offset=int(single[0]), diffuse_map=diffuse_map,
+        specular_map=specular_map)

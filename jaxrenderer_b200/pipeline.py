@@ -1,0 +1,368 @@
+"""``pipeline.render`` -- the drop-in boundary (``renderer/pipeline.py:470-537``).
+
+Same call as the reference::
+
+    render(camera, shader, buffers, face_indices, extra, loop_unroll=1) -> Buffers
+
+but the body is one call into ``libjr_b200.so`` (``jr_render_forward`` /
+``jr_render_backward``, ``include/jr_b200.h``): a tiled visibility kernel and a
+fused interpolate + fragment + mix kernel per built-in shader.  Differences a
+caller can observe:
+
+* batching is native -- any leaf of ``camera`` / ``buffers`` / ``extra`` /
+  ``face_indices`` may carry one extra leading axis (what ``jax.vmap`` would
+  add, ``examples/batch_rendering.py:87-95``); un-batched leaves broadcast;
+* ``shader`` must be one of the seven built-in classes, anything else raises
+  ``UnsupportedShaderError`` (no fallback);
+* ``loop_unroll`` is accepted and ignored (it never changed results,
+  ``changelog.md:57``);
+* gradients flow through ``torch.autograd`` (custom backward kernel through
+  fixed visibility), the reference's ``jax.grad``;
+* host (CPU) tensors are copied to the current CUDA device and the result is
+  copied back, like JAX's implicit ``device_put``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _native
+from ._native import JrF32, JrGradArgs, JrI32, JrRenderArgs
+from .geometry import Camera
+from .shader import Shader, UnsupportedShaderError
+from .shaders import BUILTIN_SHADERS
+from .types import Buffers, Tensor
+
+# name -> (un-batched rank, is_float)
+_SPEC: Dict[str, Tuple[int, bool]] = {
+    "world_to_clip": (2, True), "viewport": (2, True), "world_to_eye_norm": (2, True),
+    "position": (2, True), "faces": (2, False), "normal": (2, True), "faces_norm": (2, False),
+    "uv": (2, True), "faces_uv": (2, False), "colour": (2, True),
+    "light_direction": (1, True), "light_colour": (1, True), "light_dir_eye": (1, True),
+    "ambient": (1, True), "diffuse": (1, True), "specular": (1, True),
+    "texture": (3, True), "specular_map": (2, True), "normal_map": (3, True),
+    "texture_shape": (2, False), "texture_index": (1, False), "faces_tex": (2, False),
+    "id_to_face": (1, False), "faces_indices": (2, False),
+    "shadow_map": (2, True), "shadow_strength": (1, True),
+    "shadow_world_to_clip": (2, True), "shadow_viewport": (2, True),
+    "zbuffer": (2, True), "canvas": (3, True),
+}
+
+# differentiable inputs, in the positional order of _RenderFn
+_DIFF = (
+    "zbuffer", "canvas", "position", "normal", "colour", "world_to_clip", "viewport",
+    "world_to_eye_norm", "light_direction", "light_colour", "light_dir_eye", "ambient",
+    "diffuse", "specular", "texture", "specular_map", "shadow_strength",
+)
+_GRAD_FIELD = {n: "d_" + n for n in _DIFF if n not in ("zbuffer", "canvas")}
+
+
+def _as(t: Any, is_float: bool, device: torch.device) -> Tensor:
+    dt = torch.float32 if is_float else torch.int32
+    if not isinstance(t, torch.Tensor):
+        t = torch.as_tensor(t, dtype=dt)
+    if t.dtype != dt:
+        t = t.to(dt)
+    if t.device != device:
+        t = t.to(device, non_blocking=True)
+    return t.contiguous()
+
+
+def _collect(shader: type, camera: Any, face_indices: Any, extra: Any) -> Dict[str, Any]:
+    """Map the reference's ``extra`` NamedTuple of a built-in shader onto the
+    flat array names of ``JrRenderArgs``."""
+    sid = shader._jr_shader
+    arr: Dict[str, Any] = {
+        "world_to_clip": camera.world_to_clip, "viewport": camera.viewport,
+        "position": extra.position, "faces": face_indices,
+    }
+    if sid == _native.JR_DEPTH:
+        return arr
+    arr["normal"] = extra.normal
+    arr["light_colour"] = extra.light.colour
+    if sid == _native.JR_GOURAUD:
+        arr["colour"] = extra.colour
+        arr["light_direction"] = extra.light.direction
+        return arr
+    arr["uv"] = extra.uv
+    arr["texture"] = extra.texture
+    if sid >= _native.JR_PHONG:
+        arr["world_to_eye_norm"] = camera.world_to_eye_norm
+    if sid in (_native.JR_GOURAUD_TEXTURE, _native.JR_PHONG, _native.JR_PHONG_DARBOUX):
+        arr["light_direction"] = extra.light.direction
+    if sid == _native.JR_PHONG_DARBOUX:
+        arr["normal_map"] = extra.normal_map
+        arr["id_to_face"] = extra.id_to_face
+        arr["faces_indices"] = extra.faces_indices
+    if sid >= _native.JR_PHONG_REFLECTION:
+        arr["light_dir_eye"] = extra.light_dir_eye
+        arr["ambient"], arr["diffuse"], arr["specular"] = extra.ambient, extra.diffuse, extra.specular
+        arr["specular_map"] = extra.specular_map
+        arr["texture_shape"] = extra.texture_shape
+        arr["texture_index"] = extra.texture_index
+        arr["texture_offset"] = int(extra.texture_offset)
+    if sid == _native.JR_PHONG_REFLECTION_SHADOW:
+        sh = extra.shadow
+        arr["shadow_map"] = sh.shadow_map
+        arr["shadow_strength"] = sh.strength
+        arr["shadow_world_to_clip"] = sh.camera.world_to_clip
+        arr["shadow_viewport"] = sh.camera.viewport
+    return arr
+
+
+class _Call:
+    """Everything about one render call that is not a differentiable tensor."""
+
+    def __init__(self, sid: int, arrays: Dict[str, Tensor], B: int, W: int, H: int,
+                 texture_offset: int, batched: Dict[str, bool]):
+        self.sid, self.arrays, self.B, self.W, self.H = sid, arrays, B, W, H
+        self.texture_offset = texture_offset
+        self.batched = batched
+        self.tri_id: Optional[Tensor] = None
+
+    def stride(self, name: str) -> int:
+        t = self.arrays[name]
+        return int(t[0].numel()) if self.batched[name] else 0
+
+    def fill(self, zbuffer: Tensor, canvas: Optional[Tensor], tri_id: Tensor) -> JrRenderArgs:
+        a = JrRenderArgs()
+        a.shader, a.B, a.W, a.H = self.sid, self.B, self.W, self.H
+        A = self.arrays
+        faces = A["faces"]
+        a.T = faces.shape[-2]
+        a.n_pos = A["position"].shape[-2]
+        a.n_nrm = A["normal"].shape[-2] if "normal" in A else 0
+        a.n_uv = A["uv"].shape[-2] if "uv" in A else 0
+        for name, t in A.items():
+            if name in ("zbuffer", "canvas"):
+                continue
+            is_float = _SPEC[name][1]
+            setattr(a, name, (JrF32 if is_float else JrI32)(t.data_ptr(), self.stride(name)))
+        if "texture" in A:
+            a.tex_w, a.tex_h = A["texture"].shape[-3], A["texture"].shape[-2]
+        if "specular_map" in A:
+            a.spec_w, a.spec_h = A["specular_map"].shape[-2], A["specular_map"].shape[-1]
+        if "texture_shape" in A:
+            a.n_objects = A["texture_shape"].shape[-2]
+            a.n_texidx = A["texture_index"].shape[-1]
+            a.texture_offset = self.texture_offset
+        if "faces_indices" in A:
+            a.n_faces_indices = A["faces_indices"].shape[-2]
+        if "shadow_map" in A:
+            a.shadow_w, a.shadow_h = A["shadow_map"].shape[-2], A["shadow_map"].shape[-1]
+        a.zbuffer = zbuffer.data_ptr()
+        a.canvas = canvas.data_ptr() if canvas is not None else None
+        a.tri_id = tri_id.data_ptr()
+        a.workspace, a.workspace_bytes = None, 0
+        return a
+
+
+def _forward_native(call: _Call, zbuffer: Tensor, canvas: Optional[Tensor]) -> Tensor:
+    lib = _native.load()
+    dev = zbuffer.device
+    tri_id = torch.empty((call.B, call.W, call.H), dtype=torch.int32, device=dev)
+    args = call.fill(zbuffer, canvas, tri_id)
+    need = lib.jr_workspace_bytes(C.byref(args))
+    ws = None
+    if need:
+        ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        args.workspace, args.workspace_bytes = ws.data_ptr(), need
+    with torch.cuda.device(dev):
+        _native.check(lib.jr_render_forward(C.byref(args), _native.stream_ptr(dev)))
+    call.tri_id = tri_id
+    return tri_id
+
+
+class _RenderFn(torch.autograd.Function):
+    """custom_vjp: forward = visibility + shading kernels, backward = the
+    gradient kernels through the saved triangle-id G-buffer."""
+
+    @staticmethod
+    def forward(ctx: Any, call: _Call, *diff: Optional[Tensor]):  # type: ignore[override]
+        named = dict(zip(_DIFF, diff))
+        zbuffer = named["zbuffer"].clone()
+        canvas = named["canvas"].clone() if named["canvas"] is not None else None
+        tri_id = _forward_native(call, zbuffer, canvas)
+        ctx.call = call
+        ctx.present = [t is not None for t in diff]
+        ctx.save_for_backward(*[t for t in diff if t is not None and t is not named["zbuffer"]
+                                and t is not named["canvas"]])
+        ctx.mark_non_differentiable(tri_id)
+        if canvas is None:
+            return zbuffer, tri_id
+        return zbuffer, canvas, tri_id
+
+    @staticmethod
+    def backward(ctx: Any, *grads: Optional[Tensor]):  # type: ignore[override]
+        call: _Call = ctx.call
+        lib = _native.load()
+        has_canvas = call.sid != _native.JR_DEPTH
+        d_z = grads[0]
+        d_c = grads[1] if has_canvas else None
+        dev = call.tri_id.device
+        zshape = (call.B, call.W, call.H)
+        d_z = torch.zeros(zshape, device=dev) if d_z is None else d_z.reshape(zshape).contiguous().clone()
+        if has_canvas:
+            d_c = torch.zeros(zshape + (3,), device=dev) if d_c is None else d_c.reshape(zshape + (3,)).contiguous().clone()
+        g = JrGradArgs()
+        g.d_zbuffer = d_z.data_ptr()
+        g.d_canvas = d_c.data_ptr() if has_canvas else None
+        outs: Dict[str, Tensor] = {}
+        for i, name in enumerate(_DIFF):
+            if name in ("zbuffer", "canvas") or not ctx.present[i] or not ctx.needs_input_grad[i + 1]:
+                continue
+            t = call.arrays[name]
+            buf = torch.zeros_like(t)
+            outs[name] = buf
+            setattr(g, _GRAD_FIELD[name], JrF32(buf.data_ptr(), call.stride(name)))
+        # dummy buffers for the forward arrays are not needed by backward
+        dummy_z = torch.empty(0, device=dev)
+        args = call.fill(d_z, d_c, call.tri_id)  # zbuffer/canvas slots unused by backward
+        _ = dummy_z
+        need = lib.jr_backward_workspace_bytes(C.byref(args), C.byref(g))
+        ws = None
+        if need:
+            ws = torch.empty(need, dtype=torch.uint8, device=dev)
+            g.workspace, g.workspace_bytes = ws.data_ptr(), need
+        with torch.cuda.device(dev):
+            _native.check(lib.jr_render_backward(C.byref(args), C.byref(g), _native.stream_ptr(dev)))
+        result: List[Optional[Tensor]] = [None]
+        for i, name in enumerate(_DIFF):
+            if not ctx.present[i] or not ctx.needs_input_grad[i + 1]:
+                result.append(None)
+            elif name == "zbuffer":
+                result.append(d_z)
+            elif name == "canvas":
+                result.append(d_c)
+            else:
+                result.append(outs[name])
+        return tuple(result)
+
+
+def _render_arrays(sid: int, arrays: Dict[str, Any], zbuffer: Any, canvas: Optional[Any],
+                   inplace: bool = False, return_tri_id: bool = False):
+    """Internal entry: flat C-ABI array names -> (zbuffer, canvas, tri_id)."""
+    _native.load()  # fail loudly before anything else when the extension is missing
+    texture_offset = int(arrays.pop("texture_offset", 0))
+    host_in = not (isinstance(zbuffer, torch.Tensor) and zbuffer.is_cuda)
+    if host_in:
+        if not torch.cuda.is_available():
+            raise RuntimeError("jaxrenderer_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        dev = torch.device("cuda", torch.cuda.current_device())
+    else:
+        dev = zbuffer.device
+    tens: Dict[str, Tensor] = {}
+    for name, v in arrays.items():
+        if v is None:
+            continue
+        tens[name] = _as(v, _SPEC[name][1], dev)
+    z = _as(zbuffer, True, dev)
+    c = _as(canvas, True, dev) if canvas is not None else None
+    # batch size: every leaf is un-batched (rank r) or batched (rank r + 1)
+    B = None
+    batched: Dict[str, bool] = {}
+    items = dict(tens)
+    items["zbuffer"] = z
+    if c is not None:
+        items["canvas"] = c
+    for name, t in items.items():
+        r = _SPEC[name][0]
+        if t.ndim == r:
+            batched[name] = False
+        elif t.ndim == r + 1:
+            batched[name] = True
+            if B is None:
+                B = t.shape[0]
+            elif B != t.shape[0]:
+                raise ValueError(f"inconsistent batch size for `{name}`: {t.shape[0]} vs {B}")
+        else:
+            raise ValueError(f"`{name}` has rank {t.ndim}, expected {r} or {r + 1}")
+    squeeze = B is None
+    B = 1 if B is None else B
+    W, H = z.shape[-2], z.shape[-1]
+    if c is not None and tuple(c.shape[-3:]) != (W, H, 3):
+        raise ValueError(f"canvas must be (..., {W}, {H}, 3), got {tuple(c.shape)}")
+    if tens["faces"].shape[-1] != 3:
+        raise ValueError("face_indices must be (T, 3)")
+    # buffers always get a batch axis (vmap would broadcast them on output)
+    if not batched["zbuffer"]:
+        z = z.unsqueeze(0).expand(B, W, H)
+    if c is not None and not batched["canvas"]:
+        c = c.unsqueeze(0).expand(B, W, H, 3)
+    call = _Call(sid, tens, B, W, H, texture_offset, batched)
+    needs_grad = torch.is_grad_enabled() and any(
+        t.requires_grad for t in list(tens.values()) + [z] + ([c] if c is not None else []))
+    if needs_grad:
+        diff = []
+        for name in _DIFF:
+            if name == "zbuffer":
+                diff.append(z.contiguous())
+            elif name == "canvas":
+                diff.append(c.contiguous() if c is not None else None)
+            else:
+                diff.append(tens.get(name))
+        out = _RenderFn.apply(call, *diff)
+        if c is None:
+            z_out, tri = out
+            c_out = None
+        else:
+            z_out, c_out, tri = out
+    else:
+        def _own(t: Tensor, src: Any) -> Tensor:
+            tc = t.contiguous()
+            fresh = tc.data_ptr() != t.data_ptr() or host_in or not (
+                isinstance(src, torch.Tensor) and src.data_ptr() == tc.data_ptr())
+            return tc if (fresh or inplace) else tc.clone()
+
+        z_out = _own(z, zbuffer)
+        c_out = _own(c, canvas) if c is not None else None
+        tri = _forward_native(call, z_out, c_out)
+    if squeeze:
+        z_out = z_out[0]
+        c_out = c_out[0] if c_out is not None else None
+        tri = tri[0]
+    if host_in:
+        z_out = z_out.cpu()
+        c_out = c_out.cpu() if c_out is not None else None
+        tri = tri.cpu() if return_tri_id else tri
+    return z_out, c_out, tri
+
+
+def render(camera: Camera, shader: type, buffers: Buffers, face_indices: Any, extra: Any,
+           loop_unroll: int = 1, *, inplace: bool = False, return_tri_id: bool = False):
+    """Render a scene with a built-in shader (reference ``pipeline.py:470-537``).
+
+    ``inplace=True`` is the reference's buffer donation (``pipeline.py:466``):
+    the given CUDA buffers are updated in place and returned.
+    ``return_tri_id=True`` additionally returns the triangle-id G-buffer.
+    """
+    del loop_unroll
+    if not (isinstance(shader, type) and shader in BUILTIN_SHADERS):
+        name = getattr(shader, "__name__", repr(shader))
+        raise UnsupportedShaderError(
+            f"shader `{name}` is not one of the built-in shaders "
+            f"({', '.join(s.__name__ for s in BUILTIN_SHADERS)}). Custom `Shader` subclasses are "
+            "not supported by jaxrenderer_b200: the five stages are fused into CUDA kernels and "
+            "there is no Python fallback.")
+    if len(extra) == 0:
+        raise ValueError("`extra` must have the per-vertex array as its first field (pipeline.py:488-491)")
+    sid = shader._jr_shader
+    targets = tuple(buffers.targets)
+    if sid == _native.JR_DEPTH:
+        if len(targets) != 0:
+            raise ValueError("DepthShader renders to the z-buffer only: buffers.targets must be ()")
+        canvas = None
+    else:
+        if len(targets) != 1:
+            raise ValueError(f"{shader.__name__} renders to exactly one target (canvas)")
+        canvas = targets[0]
+    arrays = _collect(shader, camera, face_indices, extra)
+    z, c, tri = _render_arrays(sid, arrays, buffers.zbuffer, canvas, inplace=inplace,
+                               return_tri_id=return_tri_id)
+    out = Buffers(zbuffer=z, targets=() if c is None else (c,))
+    return (out, tri) if return_tri_id else out
+
+
+__all__ = ["render", "Shader"]

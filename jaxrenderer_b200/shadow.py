@@ -1,0 +1,66 @@
+"""Shadow-map pass (``renderer/shadow.py:27-153``).
+
+``render_shadow_map`` is pass 1 of ``phong_reflection_shadow``: an orthographic
+light camera + the depth kernel + ``+ offset``.  The lookup ``Shadow.get``
+(:129-153) is fused into the S7 shading kernel (``k_shade<6>``); the method
+here is the host twin kept for API parity.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any, NamedTuple
+
+import torch
+
+from . import _native
+from .geometry import Camera
+from .types import Tensor, _f32
+
+
+class Shadow(NamedTuple):
+    """``shadow.py:27-38``."""
+
+    shadow_map: Tensor
+    strength: Any
+    camera: Camera
+
+    @staticmethod
+    def render_shadow_map(shadow_map: Tensor, verts: Tensor, faces: Tensor, light_direction: Any,
+                          viewport_matrix: Tensor, centre: Any, up: Any, strength: Any,
+                          offset: float = 0.001, distance: float = 10.0,
+                          loop_unroll: int = 1) -> "Shadow":
+        """``shadow.py:49-125``.  NB the light direction is used as given
+        (un-normalised), exactly like the reference (``renderer.py:357``)."""
+        from .pipeline import _render_arrays  # local: pipeline imports this module's users
+
+        dev = shadow_map.device if isinstance(shadow_map, torch.Tensor) else None
+        centre = _f32(centre, dev)
+        ld = _f32(light_direction, dev)
+        up = _f32(up, dev)
+        view = Camera.view_matrix(eye=centre + ld * distance, centre=centre, up=up)
+        proj = Camera.orthographic_projection_matrix(-1.0, 1.0, -1.0, 1.0, -1.0, 1.0).to(view.device)
+        cam = Camera.create(view=view, projection=proj, viewport=_f32(viewport_matrix, dev))
+        arrays = {"world_to_clip": cam.world_to_clip, "viewport": cam.viewport,
+                  "position": verts, "faces": faces}
+        z, _, _ = _render_arrays(_native.JR_DEPTH, arrays, shadow_map, None, inplace=False)
+        if z.is_cuda:
+            lib = _native.load()
+            with torch.cuda.device(z.device):
+                _native.check(lib.jr_add_scalar(z.data_ptr(), z.numel(), C.c_float(float(offset)),
+                                                _native.stream_ptr(z.device)))
+        else:  # host buffers came back from the device already; tiny epilogue
+            z = z + float(offset)
+        return Shadow(shadow_map=z, strength=strength, camera=cam)
+
+    def get(self, position: Tensor) -> Tensor:
+        """Host twin of the in-kernel lookup (``shadow.py:129-153``): round half
+        away from zero, one negative wrap, out of bounds -> +inf."""
+        r = torch.trunc(position)
+        pos = (r + torch.where((position - r).abs() >= 0.5, torch.sign(position),
+                               torch.zeros_like(position))).to(torch.int64)
+        n0, n1 = self.shadow_map.shape[-2:]
+        u = torch.where(pos[..., 0] < 0, pos[..., 0] + n0, pos[..., 0])
+        v = torch.where(pos[..., 1] < 0, pos[..., 1] + n1, pos[..., 1])
+        ok = (u >= 0) & (u < n0) & (v >= 0) & (v < n1)
+        val = self.shadow_map[u.clamp(0, n0 - 1), v.clamp(0, n1 - 1)]
+        return torch.where(ok, val, torch.full_like(val, float("inf")))

@@ -1,0 +1,578 @@
+"""CPU ORACLE -- test infrastructure, NOT product code.
+
+A restatement, in fp32 torch-CPU tensor ops, of the reference's brute-force
+rasterisation path (jaxrenderer v0.3.2).  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs may import it;
+the product (``jaxrenderer_b200``) never does.
+
+What it follows (file:line into the reference checkout):
+
+* ``renderer/pipeline.py:470-537``  ``render``: vertex stage, per-primitive
+  setup, per-pixel brute force over ALL triangles, chooser, interpolate,
+  fragment, mix, ``merge_buffers`` (:401-440, no test against the old z).
+* ``renderer/pipeline.py:76-113``   ``PerPrimitive.create``: ``M = clip[:, (x,y,w)]``,
+  closed-form 3x3 ``det``, ``keep = |det| > 1e-6``, ``inv(M)`` by LU.
+* ``renderer/pipeline.py:163-279``  ``_per_primitive_preprocess`` (edge functions
+  ``clip_coef = (x_ndc, y_ndc, 1) @ inv``, ``in_triangle``, ``z``, ``1/w``).
+* ``renderer/shader.py:159-251``    default ``primitive_chooser`` (first-index
+  argmin over ``keep & inside & front`` depths; index 0 when none).
+* ``renderer/shader.py:257-290``, ``geometry.py:71-110`` ``interpolate`` (SMOOTH).
+* ``renderer/shader.py:339-396``    default ``mix``.
+* ``renderer/shaders/*.py``         the seven built-in shaders.
+* ``renderer/shadow.py:49-153``     shadow-map pass and ``Shadow.get``.
+* ``renderer/model.py:306-339``     ``uv_repeat``.
+* ``renderer/renderer.py:254-385``  ``Renderer.render`` glue (corner expansion,
+  ``light_dir_eye``, ``extra`` assembly, optional shadow pass).
+
+PINNING.  jax/jaxlib are not installable in the build image, so the oracle
+cannot be diffed against the reference's own outputs; it IS checked against
+every assertion of the reference's own tests for this path
+(``tests/smoke_test.py:104-132``, ``:312-329``; see ``tests/test_oracle_pins.py``)
+and against the analytic answer for ``examples/simple_cube.py``.  Arithmetic
+whose rounding decides discrete outcomes (edge inclusion, depth order, texel
+choice) is written as explicit scalar fp32 operations in a fixed order with no
+fused multiply-add, which is (a) what XLA:CPU computes without contraction and
+(b) reproducible bit-for-bit by the CUDA kernels (compiled with -fmad=false).
+The 3x3 inverse follows LAPACK ``sgetrf2`` (partial pivoting, reciprocal
+scaling) + reference-BLAS ``strsm`` operation order, the algorithm family
+``jnp.linalg.inv`` dispatches to on CPU.
+
+Differentiability.  Visibility (argmin) is evaluated without autograd; the
+per-pixel shading of the CHOSEN triangle is recomputed with autograd enabled,
+which is exactly the part of the reference's graph that carries gradient
+(``argmin``/``floor``/``round``/comparisons cut everything else).
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+from typing import Any, Dict, NamedTuple, Optional, Sequence, Tuple
+
+import torch
+
+F32 = torch.float32
+INF = float("inf")
+
+SHADERS = (
+    "depth", "gouraud", "gouraud_texture", "phong", "phong_darboux",
+    "phong_reflection", "phong_reflection_shadow",
+)
+
+_CLASS_TO_NAME = {
+    "DepthShader": "depth",
+    "GouraudShader": "gouraud",
+    "GouraudTextureShader": "gouraud_texture",
+    "PhongTextureShader": "phong",
+    "PhongTextureDarbouxShader": "phong_darboux",
+    "PhongReflectionTextureShader": "phong_reflection",
+    "PhongReflectionShadowTextureShader": "phong_reflection_shadow",
+}
+
+
+def shader_name(shader: Any) -> str:
+    if isinstance(shader, str):
+        assert shader in SHADERS, shader
+        return shader
+    return _CLASS_TO_NAME[shader.__name__]
+
+
+def _t(x: Any, dtype=F32) -> torch.Tensor:
+    if isinstance(x, torch.Tensor):
+        return x.detach().cpu().to(dtype) if not x.requires_grad else x.cpu().to(dtype)
+    return torch.as_tensor(x, dtype=dtype)
+
+
+# --------------------------------------------------------------------------
+# scalar-order helpers (no FMA: every * and + is one rounded fp32 op)
+# --------------------------------------------------------------------------
+def dot3(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """((a0*b0 + a1*b1) + a2*b2) over the last axis."""
+    return (a[..., 0] * b[..., 0] + a[..., 1] * b[..., 1]) + a[..., 2] * b[..., 2]
+
+
+def norm3(v: torch.Tensor) -> torch.Tensor:
+    return torch.sqrt(dot3(v, v))
+
+
+def normalise(v: torch.Tensor) -> torch.Tensor:
+    """Per-vector ``v / ||v||`` (``geometry.py:39-47`` under ``vmap``)."""
+    return v / norm3(v)[..., None]
+
+
+def mat4_apply(p: torch.Tensor, m: torch.Tensor, w_one: bool) -> torch.Tensor:
+    """``to_homogeneous(p, 1 or 0) @ m.T`` (``geometry.py:284-315``), rows
+    accumulated k = 0..3 in order.  ``p (..., 3)``, ``m (4, 4)`` -> ``(..., 4)``."""
+    x, y, z = p[..., 0], p[..., 1], p[..., 2]
+    rows = []
+    for r in range(4):
+        acc = (x * m[r, 0] + y * m[r, 1]) + z * m[r, 2]
+        if w_one:
+            acc = acc + m[r, 3]
+        rows.append(acc)
+    return torch.stack(rows, dim=-1)
+
+
+def mat4_vec4(m: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
+    """``m @ v`` for ``v (..., 4)``."""
+    rows = []
+    for r in range(4):
+        rows.append(((m[r, 0] * v[..., 0] + m[r, 1] * v[..., 1]) + m[r, 2] * v[..., 2])
+                    + m[r, 3] * v[..., 3])
+    return torch.stack(rows, dim=-1)
+
+
+def apply_vec(v: torch.Tensor, m: torch.Tensor) -> torch.Tensor:
+    """``Camera.apply_vec`` (``geometry.py:352-389``) per vector: normalise,
+    rotate by the upper 3x3 (w = 0), normalise."""
+    n = normalise(v)
+    t = mat4_apply(n, m, w_one=False)[..., :3]
+    return normalise(t)
+
+
+def det3(a: torch.Tensor) -> torch.Tensor:
+    """Closed-form 3x3 determinant in jax's ``_det_3x3`` term order
+    (``pipeline.py:91-94``)."""
+    return (a[..., 0, 0] * a[..., 1, 1] * a[..., 2, 2]
+            + a[..., 0, 1] * a[..., 1, 2] * a[..., 2, 0]
+            + a[..., 0, 2] * a[..., 1, 0] * a[..., 2, 1]
+            - a[..., 0, 2] * a[..., 1, 1] * a[..., 2, 0]
+            - a[..., 0, 0] * a[..., 1, 2] * a[..., 2, 1]
+            - a[..., 0, 1] * a[..., 1, 0] * a[..., 2, 2])
+
+
+def _swap_rows(rows, i, j_is):
+    """Swap row ``i`` with the row selected per element by masks ``j_is``
+    (dict row-index -> bool mask).  rows: list of lists of tensors."""
+    new = [list(r) for r in rows]
+    ncol = len(rows[0])
+    for j, mask in j_is.items():
+        if j == i:
+            continue
+        for c in range(ncol):
+            a, b = new[i][c], new[j][c]
+            new[i][c] = torch.where(mask, b, a)
+            new[j][c] = torch.where(mask, a, b)
+    return new
+
+
+def lu_inverse3(A: torch.Tensor) -> torch.Tensor:
+    """``jnp.linalg.inv`` of a batch of 3x3 (``pipeline.py:105``): LU with
+    partial pivoting (LAPACK sgetrf2 order, column scaled by the reciprocal of
+    the pivot), then ``L y = P I`` and ``U x = y`` in reference ``strsm`` order.
+    Garbage in (singular) -> inf/NaN out, as in the reference."""
+    # augmented rows: 3 matrix columns + 3 identity columns
+    one = torch.ones_like(A[..., 0, 0])
+    zero = torch.zeros_like(one)
+    rows = [[A[..., i, 0], A[..., i, 1], A[..., i, 2]] + [one if i == j else zero for j in range(3)]
+            for i in range(3)]
+    # --- column 0 pivot (isamax: first index of max |.|)
+    a0, a1, a2 = rows[0][0].abs(), rows[1][0].abs(), rows[2][0].abs()
+    p1 = a1 > a0
+    best = torch.where(p1, a1, a0)
+    p2 = a2 > best
+    p1 = p1 & ~p2
+    rows = _swap_rows(rows, 0, {1: p1, 2: p2})
+    r00 = 1.0 / rows[0][0]
+    l10 = rows[1][0] * r00
+    l20 = rows[2][0] * r00
+    u00, u01, u02 = rows[0][0], rows[0][1], rows[0][2]
+    a11 = rows[1][1] - l10 * u01
+    a12 = rows[1][2] - l10 * u02
+    a21 = rows[2][1] - l20 * u01
+    a22 = rows[2][2] - l20 * u02
+    # --- column 1 pivot among rows 1, 2 (swap carries the L part and the rhs)
+    p = a21.abs() > a11.abs()
+    sub = [[l10, a11, a12] + rows[1][3:], [l20, a21, a22] + rows[2][3:]]
+    sub = _swap_rows(sub, 0, {1: p})
+    l10, u11, u12 = sub[0][0], sub[0][1], sub[0][2]
+    l20, a21, a22 = sub[1][0], sub[1][1], sub[1][2]
+    b0, b1, b2 = rows[0][3:], sub[0][3:], sub[1][3:]
+    l21 = a21 * (1.0 / u11)
+    u22 = a22 - l21 * u12
+    cols = []
+    for j in range(3):
+        y0 = b0[j]
+        y1 = b1[j] - y0 * l10
+        y2 = (b2[j] - y0 * l20) - y1 * l21
+        x2 = y2 / u22
+        t1 = y1 - x2 * u12
+        t0 = y0 - x2 * u02
+        x1 = t1 / u11
+        t0 = t0 - x1 * u01
+        x0 = t0 / u00
+        cols.append(torch.stack((x0, x1, x2), dim=-1))
+    return torch.stack(cols, dim=-1)  # [..., row, col]
+
+
+def interp(tc: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
+    """``Interpolation.SMOOTH`` (``geometry.py:71-110``): ``sum_k tc[k] * v[k]``
+    accumulated k = 0, 1, 2.  ``tc (..., 3)``, ``v (..., 3, D)`` -> ``(..., D)``."""
+    return (tc[..., 0, None] * v[..., 0, :] + tc[..., 1, None] * v[..., 1, :]) + tc[..., 2, None] * v[..., 2, :]
+
+
+def lax_round(x: torch.Tensor) -> torch.Tensor:
+    """``lax.round`` default (ROUND_AWAY_FROM_ZERO), exact: ``x - trunc(x)``
+    is exact in fp32, so no double rounding at 0.49999997."""
+    r = torch.trunc(x)
+    return r + torch.where(torch.abs(x - r) >= 0.5, torch.sign(x), torch.zeros_like(x))
+
+
+# --------------------------------------------------------------------------
+# shared per-triangle / per-pixel pieces
+# --------------------------------------------------------------------------
+class Setup(NamedTuple):
+    clip: torch.Tensor      # (T, 3, 4)
+    det: torch.Tensor       # (T,)
+    keep: torch.Tensor      # (T,) bool
+    inv: torch.Tensor       # (T, 3, 3)
+
+
+def primitive_setup(clip_v: torch.Tensor, faces: torch.Tensor) -> Setup:
+    """``PerPrimitive.create`` (``pipeline.py:76-113``) for all triangles."""
+    clip = clip_v[faces.long()]                         # (T, 3, 4)
+    M = clip[..., [0, 1, 3]]                            # rows = vertices
+    det = det3(M)
+    keep = det.abs() > 1e-6
+    inv = lu_inverse3(M)
+    return Setup(clip=clip, det=det, keep=keep, inv=inv)
+
+
+def pixel_ndc(viewport: torch.Tensor, W: int, H: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """``(coord - viewport[:2, 3]) / viewport[diag]`` (``pipeline.py:177``)."""
+    xs = (torch.arange(W, dtype=F32) - viewport[0, 3]) / viewport[0, 0]
+    ys = (torch.arange(H, dtype=F32) - viewport[1, 3]) / viewport[1, 1]
+    return xs, ys
+
+
+@torch.no_grad()
+def visibility(setup: Setup, viewport: torch.Tensor, W: int, H: int,
+               max_elems: int = 6_000_000):
+    """Brute force over every pixel x every triangle (``pipeline.py:332-336``).
+
+    Returns ``idx (W,H) int64`` (argmin, 0 when no candidate), ``has (W,H)``
+    (some candidate exists), ``keeps_chosen (W,H)`` = ``(keep & inside)[idx]``
+    and ``gap (W,H)`` = second-smallest minus smallest candidate depth."""
+    T = setup.det.shape[0]
+    inv, keep, det = setup.inv.detach(), setup.keep, setup.det.detach()
+    zc = setup.clip.detach()[:, :, 2]                    # (T, 3)
+    front = det >= 0
+    xs, ys = pixel_ndc(viewport.detach(), W, H)
+    vp22, vp23 = viewport[2, 2].detach(), viewport[2, 3].detach()
+    idx = torch.zeros((W, H), dtype=torch.int64)
+    has = torch.zeros((W, H), dtype=torch.bool)
+    kc = torch.zeros((W, H), dtype=torch.bool)
+    gap = torch.full((W, H), INF)
+    rows = max(1, max_elems // max(1, H * T))
+    for x0 in range(0, W, rows):
+        x1 = min(W, x0 + rows)
+        xn = xs[x0:x1, None, None]                       # (X,1,1)
+        yn = ys[None, :, None]                           # (1,H,1)
+        c = [(xn * inv[None, None, :, 0, k] + yn * inv[None, None, :, 1, k]) + inv[None, None, :, 2, k]
+             for k in range(3)]                          # 3 x (X,H,T)
+        inside = (c[0] >= 0) & (c[1] >= 0) & (c[2] >= 0)
+        z = (c[0] * zc[:, 0] + c[1] * zc[:, 1]) + c[2] * zc[:, 2]
+        zw = z * vp22 + vp23
+        keeps = keep[None, None, :] & inside
+        depth = torch.where(keeps & front[None, None, :], zw, torch.full_like(zw, INF))
+        if T >= 2:
+            two = torch.topk(depth, 2, dim=-1, largest=False).values
+            g = two[..., 1] - two[..., 0]
+            gap[x0:x1] = torch.where(torch.isfinite(two[..., 1]), g, torch.full_like(g, INF))
+        i = torch.argmin(depth, dim=-1)
+        # torch.argmin does not promise the first index among ties: enforce it
+        dmin = depth.gather(-1, i[..., None])
+        first = torch.argmax((depth == dmin).to(torch.int8), dim=-1)
+        idx[x0:x1] = first
+        has[x0:x1] = torch.isfinite(dmin[..., 0])
+        kc[x0:x1] = keeps.gather(-1, first[..., None])[..., 0]
+    return idx, has, kc, gap
+
+
+class Fragments(NamedTuple):
+    """Per-pixel values of the chosen triangle (``pipeline.py:163-279``)."""
+
+    tc: torch.Tensor         # (W,H,3) true_clip_coef
+    zw: torch.Tensor         # (W,H) gl_FragCoord.z
+    w_rec: torch.Tensor      # (W,H) gl_FragCoord.w  (= 1/w)
+    front: torch.Tensor      # (W,H) gl_FrontFacing
+
+
+def chosen_fragments(setup: Setup, viewport: torch.Tensor, idx: torch.Tensor) -> Fragments:
+    W, H = idx.shape
+    xs, ys = pixel_ndc(viewport, W, H)
+    inv = setup.inv[idx]                                 # (W,H,3,3)
+    zc = setup.clip[idx][..., 2]                         # (W,H,3)
+    xn, yn = xs[:, None], ys[None, :]
+    c = torch.stack([(xn * inv[..., 0, k] + yn * inv[..., 1, k]) + inv[..., 2, k] for k in range(3)], -1)
+    w_rec = (c[..., 0] + c[..., 1]) + c[..., 2]
+    z = (c[..., 0] * zc[..., 0] + c[..., 1] * zc[..., 1]) + c[..., 2] * zc[..., 2]
+    zw = z * viewport[2, 2] + viewport[2, 3]
+    tc = c / w_rec[..., None]
+    front = (setup.det >= 0)[idx]
+    return Fragments(tc=tc, zw=zw, w_rec=w_rec, front=front)
+
+
+# --------------------------------------------------------------------------
+# texture helpers
+# --------------------------------------------------------------------------
+def _texel_mod(uv: torch.Tensor, tex: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """``floor(uv).astype(int) % texture.shape[:2]`` (``gouraud_texture.py:124-125``)."""
+    u = torch.floor(uv[..., 0]).to(torch.int64) % tex.shape[0]
+    v = torch.floor(uv[..., 1]).to(torch.int64) % tex.shape[1]
+    return u, v
+
+
+def _gather_clamped(arr: torch.Tensor, u: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
+    """jnp ``arr[u, v]``: negative indices wrap once, then clamp into range."""
+    n0, n1 = arr.shape[0], arr.shape[1]
+    u = torch.where(u < 0, u + n0, u).clamp(0, n0 - 1)
+    v = torch.where(v < 0, v + n1, v).clamp(0, n1 - 1)
+    return arr[u, v]
+
+
+def uv_repeat(uv: torch.Tensor, shape: torch.Tensor, map_index: torch.Tensor, offset: int) -> torch.Tensor:
+    """``MergedModel.uv_repeat`` (``model.py:306-339``)."""
+    frac = uv - torch.trunc(uv)                          # jnp.modf(uv)[0]
+    frac = torch.where(frac < 0, frac + 1, frac)
+    out0 = frac[..., 0] * shape[..., 0].to(F32) + (map_index * offset).to(F32)
+    out1 = frac[..., 1] * shape[..., 1].to(F32)
+    return torch.stack((out0, out1), dim=-1)
+
+
+def shadow_get(shadow_map: torch.Tensor, pos: torch.Tensor) -> torch.Tensor:
+    """``Shadow.get`` (``shadow.py:129-153``): round half away, negative index
+    wraps once, out of bounds -> +inf."""
+    n0, n1 = shadow_map.shape
+    p = lax_round(pos).to(torch.int64)
+    u, v = p[..., 0], p[..., 1]
+    u = torch.where(u < 0, u + n0, u)
+    v = torch.where(v < 0, v + n1, v)
+    ok = (u >= 0) & (u < n0) & (v >= 0) & (v < n1)
+    val = shadow_map[u.clamp(0, n0 - 1), v.clamp(0, n1 - 1)]
+    return torch.where(ok, val, torch.full_like(val, INF))
+
+
+# --------------------------------------------------------------------------
+# the pipeline
+# --------------------------------------------------------------------------
+class RenderOut(NamedTuple):
+    zbuffer: torch.Tensor
+    targets: Tuple[torch.Tensor, ...]
+    tri_id: torch.Tensor      # (W,H) int64: written triangle, -1 where the pixel was not written
+    chosen: torch.Tensor      # (W,H) int64: argmin index (0 when no candidate)
+    has: torch.Tensor         # (W,H) bool: a front-facing candidate exists
+    gap: torch.Tensor         # (W,H) second-best minus best depth
+
+
+def _light(extra: Any) -> Tuple[torch.Tensor, torch.Tensor]:
+    l = extra.light
+    return _t(l.direction), _t(l.colour)
+
+
+def render(camera: Any, shader: Any, zbuffer: Any, targets: Sequence[Any], face_indices: Any,
+           extra: Any) -> RenderOut:
+    """``pipeline.render`` for ONE image (no batch axes)."""
+    name = shader_name(shader)
+    w2c, vp = _t(camera.world_to_clip), _t(camera.viewport)
+    zbuffer = _t(zbuffer)
+    targets = tuple(_t(t) for t in targets)
+    faces = _t(face_indices, torch.int64)
+    W, H = zbuffer.shape
+    pos = _t(extra.position)
+
+    # ---- vertex stage (pipeline.py:500-518; each shader's `vertex`)
+    clip_v = mat4_apply(pos, w2c, w_one=True)
+    setup = primitive_setup(clip_v, faces)
+    idx, has, kc, gap = visibility(setup, vp, W, H)
+    fr = chosen_fragments(setup, vp, idx)
+    f_idx = faces[idx]                                   # (W,H,3) vertex ids of the chosen triangle
+
+    keep = kc.clone()
+    colour: Optional[torch.Tensor] = None
+
+    if name == "depth":
+        pass                                             # depth.py: default fragment, keeps only
+    elif name == "gouraud":
+        ldir, lcol = _light(extra)
+        n = normalise(_t(extra.normal))
+        intensity = dot3(n, normalise(ldir).expand_as(n))
+        col_v = _t(extra.colour) * lcol * intensity[:, None]          # gouraud.py:72-83
+        col = interp(fr.tc, col_v[f_idx])
+        keep = keep & fr.front & (col >= 0).all(-1)                   # gouraud.py:110-121
+        colour = col
+    elif name == "gouraud_texture":
+        ldir, lcol = _light(extra)
+        tex = _t(extra.texture)
+        n = normalise(_t(extra.normal))
+        intensity = dot3(n, normalise(ldir).expand_as(n))
+        lc_v = lcol * intensity[:, None]                              # gouraud_texture.py:82-100
+        lc = interp(fr.tc, lc_v[f_idx])
+        uv = interp(fr.tc, _t(extra.uv)[f_idx])
+        u, v = _texel_mod(uv, tex)
+        colour = tex[u, v] * lc                                       # :124-142
+        keep = keep & fr.front & (lc >= 0).all(-1)
+    elif name in ("phong", "phong_darboux"):
+        ldir, lcol = _light(extra)
+        tex = _t(extra.texture)
+        wen = _t(camera.world_to_eye_norm)
+        n_v = apply_vec(normalise(_t(extra.normal)), wen)             # phong.py:92-103
+        normal = interp(fr.tc, n_v[f_idx])
+        uv = interp(fr.tc, _t(extra.uv)[f_idx])
+        u, v = _texel_mod(uv, tex)
+        nn = normalise(normal)
+        if name == "phong_darboux":
+            # phong_darboux.py:144-151: per-vertex copy of ITS triangle
+            # (faces_indices[id_to_face[v]]) in NDC and uv space; the chosen
+            # triangle's first vertex's copy is used (:194-202).
+            fi = _t(extra.faces_indices, torch.int64)
+            i2f = _t(extra.id_to_face, torch.int64)
+            v0 = f_idx[..., 0]
+            tri_vs = fi[i2f[v0]]                                       # (W,H,3)
+            tclip = clip_v[tri_vs]                                     # (W,H,3,4)
+            wq = tclip[..., 3:4]
+            tri = torch.where(wq == 0.0, tclip[..., :3], (tclip / wq)[..., :3])   # to_cartesian
+            tuv = _t(extra.uv)[tri_vs]                                 # (W,H,3,2)
+            A = torch.stack((tri[..., 1, :] - tri[..., 0, :], tri[..., 2, :] - tri[..., 0, :], nn), dim=-2)
+            AI = lu_inverse3(A)
+            du = torch.stack((tuv[..., 1, 0] - tuv[..., 0, 0], tuv[..., 2, 0] - tuv[..., 0, 0]), -1)
+            dv = torch.stack((tuv[..., 1, 1] - tuv[..., 0, 1], tuv[..., 2, 1] - tuv[..., 0, 1]), -1)
+            # AI @ (a, b, 0): accumulate k = 0, 1, 2 (third term is *0)
+            ivec = torch.stack([AI[..., r, 0] * du[..., 0] + AI[..., r, 1] * du[..., 1] for r in range(3)], -1)
+            jvec = torch.stack([AI[..., r, 0] * dv[..., 0] + AI[..., r, 1] * dv[..., 1] for r in range(3)], -1)
+            ni, nj = normalise(ivec), normalise(jvec)
+            nm = _t(extra.normal_map)[u, v]                            # (W,H,3)
+            bn = torch.stack([(ni[..., r] * nm[..., 0] + nj[..., r] * nm[..., 1]) + nn[..., r] * nm[..., 2]
+                              for r in range(3)], -1)                  # B @ nm
+            nn = normalise(bn)
+        lc = lcol * dot3(nn, normalise(ldir).expand_as(nn))[..., None]  # phong.py:127-135
+        ok = (lc >= 0).all(-1, keepdim=True)
+        colour = torch.where(ok, tex[u, v] * lc, torch.zeros_like(lc))  # :147-159
+        keep = keep & fr.front
+    elif name in ("phong_reflection", "phong_reflection_shadow"):
+        _, lcol = _light(extra)
+        tex = _t(extra.texture)
+        spec_map = _t(extra.specular_map)
+        wen = _t(camera.world_to_eye_norm)
+        n_v = apply_vec(normalise(_t(extra.normal)), wen)             # phong_reflection.py:118-131
+        normal = interp(fr.tc, n_v[f_idx])
+        uv = interp(fr.tc, _t(extra.uv)[f_idx])
+        ti = _t(extra.texture_index, torch.int64)[f_idx[..., 0]]      # first vertex (:149)
+        tshape = _t(extra.texture_shape, torch.int64)[ti]
+        offset = int(_t(extra.texture_offset, torch.int64))
+        uvr = torch.floor(uv_repeat(uv, tshape, ti, offset)).to(torch.int64)   # :175-184
+        tcol = _gather_clamped(tex, uvr[..., 0], uvr[..., 1])
+        nn = normalise(normal)
+        ld = normalise(_t(extra.light_dir_eye))
+        ndl = dot3(nn, ld.expand_as(nn))
+        diffuse = torch.clamp_min(ndl, 0.0)                           # jnp.maximum(., 0)
+        refl = normalise(2 * ndl[..., None] * nn - ld)                # :197-203
+        spec_exp = _gather_clamped(spec_map, uvr[..., 0], uvr[..., 1])
+        specular = torch.pow(torch.clamp_min(refl[..., 2], 0.0), spec_exp)     # :207-212
+        amb, dif, spe = _t(extra.ambient), _t(extra.diffuse), _t(extra.specular)
+        if name == "phong_reflection":
+            colour = amb * tcol + (dif * diffuse[..., None] + spe * specular[..., None]) * lcol * tcol
+        else:
+            sh = extra.shadow
+            s_w2c, s_vp = _t(sh.camera.world_to_clip), _t(sh.camera.viewport)
+            sclip = mat4_apply(pos, s_w2c, w_one=True)
+            sc_v = sclip / sclip[..., 3:4]                            # normalise_homogeneous (:137-139)
+            sc = interp(fr.tc, sc_v[f_idx])                           # (W,H,4)
+            ss = mat4_vec4(s_vp, sc)
+            ss = ss / ss[..., 3:4]                                    # :196-199
+            smap = _t(sh.shadow_map)
+            lit = ss[..., 2] <= shadow_get(smap, ss[..., :2].detach())
+            strength = _t(sh.strength)
+            shadow = torch.where(lit[..., None], torch.ones_like(strength), 1.0 - strength)
+            colour = (amb * tcol
+                      + shadow * (dif * diffuse[..., None] + spe * specular[..., None]) * tcol * lcol)
+        keep = keep & fr.front
+    else:  # pragma: no cover
+        raise ValueError(name)
+
+    # ---- mix + merge_buffers (shader.py:339-396, pipeline.py:401-440)
+    z_out = torch.where(keep, fr.zw, zbuffer)
+    outs = []
+    if colour is not None:
+        assert len(targets) == 1
+        outs.append(torch.where(keep[..., None], colour, targets[0]))
+    tri = torch.where(keep, idx, torch.full_like(idx, -1))
+    return RenderOut(zbuffer=z_out, targets=tuple(outs), tri_id=tri, chosen=idx, has=has, gap=gap)
+
+
+# --------------------------------------------------------------------------
+# geometry restatement needed by the shadow pass (geometry.py:536-575, :720-763)
+# --------------------------------------------------------------------------
+def view_matrix(eye: torch.Tensor, centre: torch.Tensor, up: torch.Tensor) -> torch.Tensor:
+    forward = normalise(centre - eye)
+    up = normalise(up)
+    side = normalise(torch.linalg.cross(forward, up))
+    up = torch.linalg.cross(side, forward)
+    m = torch.eye(4)
+    m[0, :3], m[1, :3], m[2, :3] = side, up, -forward
+    t = torch.eye(4)
+    t[:3, 3] = -eye
+    return m @ t
+
+
+def orthographic(left, right, bottom, top, z_near, z_far) -> torch.Tensor:
+    p = torch.zeros(4, 4)
+    p[0, 0], p[1, 1], p[2, 2], p[3, 3] = 2 / (right - left), 2 / (top - bottom), -2 / (z_far - z_near), 1
+    l_op = torch.tensor([right, top, z_far]); r_op = torch.tensor([left, bottom, z_near])
+    p[:3, 3] = -(l_op + r_op) / (l_op - r_op)
+    return p
+
+
+def shadow_camera(light_direction: Any, viewport: Any, centre: Any, up: Any,
+                  distance: float = 10.0) -> SimpleNamespace:
+    """Light camera of ``Shadow.render_shadow_map`` (``shadow.py:84-103``)."""
+    centre, up, ld = _t(centre), _t(up), _t(light_direction)
+    view = view_matrix(centre + ld * distance, centre, up)
+    proj = orthographic(-1.0, 1.0, -1.0, 1.0, -1.0, 1.0)
+    return SimpleNamespace(view=view, projection=proj, viewport=_t(viewport),
+                           world_to_clip=proj @ view,
+                           world_to_eye_norm=torch.linalg.inv(view).T)
+
+
+def render_shadow_map(shadow_map: Any, verts: Any, faces: Any, camera: Any, offset: float) -> torch.Tensor:
+    """Pass 1 of ``Shadow.render_shadow_map`` (``shadow.py:106-116``) given the
+    light camera."""
+    out = render(camera, "depth", shadow_map, (), faces, SimpleNamespace(position=verts))
+    return out.zbuffer + offset
+
+
+def renderer_render(model: Any, light: Any, camera: Any, zbuffer: Any, canvas: Any,
+                    shadow_param: Any = None, shadow_cam: Any = None) -> Dict[str, Any]:
+    """``Renderer.render`` (``renderer.py:254-385``) for one image.  ``model``
+    has the ``MergedModel`` fields, ``light`` the ``LightParameters`` fields.
+    ``shadow_cam`` overrides the light camera (tests pass the product's own so
+    that host-side matrix rounding is excluded from the comparison)."""
+    faces = _t(model.faces, torch.int64)
+    position = _t(model.verts)[faces.reshape(-1)]
+    normal = _t(model.norms)[_t(model.faces_norm, torch.int64).reshape(-1)]
+    fuv = _t(model.faces_uv, torch.int64).reshape(-1)
+    uv = _t(model.uvs)[fuv]
+    texture_index = _t(model.texture_index, torch.int64)[fuv]
+    face_indices = torch.arange(faces.numel()).reshape(faces.shape)
+    light_dir = normalise(_t(light.direction))
+    light_dir_eye = apply_vec(light_dir, _t(camera.view))
+    extra = SimpleNamespace(
+        position=position, normal=normal, uv=uv,
+        light=SimpleNamespace(direction=light_dir, colour=_t(light.colour)),
+        light_dir_eye=light_dir_eye, texture_shape=model.texture_shape,
+        texture_index=texture_index, texture_offset=int(model.offset),
+        texture=model.diffuse_map, specular_map=model.specular_map,
+        ambient=light.ambient, diffuse=light.diffuse, specular=light.specular)
+    res: Dict[str, Any] = {}
+    if shadow_param is None:
+        out = render(camera, "phong_reflection", zbuffer, (canvas,), face_indices, extra)
+    else:
+        if shadow_cam is None:
+            shadow_cam = shadow_camera(light.direction, camera.viewport, shadow_param.centre,
+                                       shadow_param.up)
+        sm0 = torch.full_like(_t(zbuffer), torch.finfo(F32).max)
+        smap = render_shadow_map(sm0, model.verts, faces, shadow_cam, float(shadow_param.offset))
+        extra.shadow = SimpleNamespace(shadow_map=smap, strength=shadow_param.strength, camera=shadow_cam)
+        extra.camera = camera
+        out = render(camera, "phong_reflection_shadow", zbuffer, (canvas,), face_indices, extra)
+        res["shadow_map"] = smap
+    res["out"] = out
+    return res

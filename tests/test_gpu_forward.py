@@ -1,0 +1,271 @@
+"""GPU parity tests (forward): CUDA path through the C ABI vs the CPU oracle.
+
+Tolerances are BASELINE.json's: triangle-id buffer bit-exact except pixels
+whose competing depths differ by < 1e-6 (counted in the report), z bit-exact
+on agreeing pixels, colours within 1e-5 relative.
+"""
+from types import SimpleNamespace as NS
+
+import pytest
+import torch
+
+import jaxrenderer_b200 as jr
+from jaxrenderer_b200 import synthetic
+from jaxrenderer_b200.shaders import (
+    DepthExtraInput, DepthShader, GouraudExtraInput, GouraudShader, GouraudTextureExtraInput,
+    GouraudTextureShader, PhongReflectionShadowTextureExtraInput, PhongReflectionShadowTextureShader,
+    PhongReflectionTextureExtraInput, PhongReflectionTextureShader, PhongTextureDarbouxExtraInput,
+    PhongTextureDarbouxShader, PhongTextureExtraInput, PhongTextureShader,
+)
+from oracle import jr_oracle as O
+from tests.helpers import assert_parity, compare, load_brax_fixture, random_mesh_scene, smoke_scene
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _cuda(x):
+    if isinstance(x, torch.Tensor):
+        return x.to(DEV)
+    if isinstance(x, tuple) and hasattr(x, "_fields"):
+        return type(x)(*[_cuda(v) for v in x])
+    return x
+
+
+def _run(cam, shader, z0, c0, faces, extra):
+    bufs = jr.Buffers(zbuffer=z0.to(DEV), targets=() if c0 is None else (c0.to(DEV),))
+    out, tri = jr.render(_cuda(cam), shader, bufs, faces.to(DEV), _cuda(extra), return_tri_id=True)
+    torch.cuda.synchronize()
+    return out.zbuffer, (out.targets[0] if out.targets else None), tri
+
+
+def test_reference_smoke_scene_1920x1080():
+    """reference tests/smoke_test.py:27-132, every assertion + oracle parity (tiled path)."""
+    W, H = 1920, 1080
+    cam, faces, extra = smoke_scene(W, H)
+    z0, c0 = torch.full((W, H), 1.0), torch.zeros(W, H, 3)
+    z, c, tri = _run(cam, GouraudShader, z0, c0, faces, extra)
+    zd, cd = jr.transpose_for_display(z.cpu()), jr.transpose_for_display(c.cpu())
+    assert zd.shape == (H, W) and cd.shape == (H, W, 3)
+    assert torch.unique(zd[293:528, 964:1423].to(torch.uint8)).shape == (1,)
+    assert bool((zd[590:1049, 964:1423] == 1.0).all())
+    assert zd[551, 914] < zd[1026, 92]
+    empty = int((cd == 0).all(dim=2).sum())
+    assert W * H // 2 < empty < W * H
+    ref = O.render(cam, "gouraud", z0, (c0,), faces, extra)
+    rep = compare("smoke1920", z, c, tri, ref)
+    print(rep)
+    assert_parity(rep)
+
+
+@pytest.mark.parametrize("wh", [(84, 84), (32, 32), (200, 120)])
+def test_depth_brax_like(wh):
+    """BASELINE config 2 shape (depth shader, ant-like scenes), small batch vs oracle."""
+    W, H = wh
+    B = 3
+    sc = synthetic.brax_like_batch(B, n_capsules=10)
+    cam = synthetic.brax_cameras(sc["eye"], sc["target"], W, H)
+    z0 = torch.full((B, W, H), 1.0)
+    bufs = jr.Buffers(zbuffer=z0.to(DEV), targets=())
+    out, tri = jr.render(_cuda(cam), DepthShader, bufs, sc["faces"].to(DEV),
+                         DepthExtraInput(position=sc["position"].to(DEV)), return_tri_id=True)
+    for b in range(B):
+        camb = NS(world_to_clip=cam.world_to_clip[b], viewport=cam.viewport[b])
+        ref = O.render(camb, "depth", z0[b], (), sc["faces"][b], NS(position=sc["position"][b]))
+        rep = compare(f"depth{W}x{H}[{b}]", out.zbuffer[b], None, tri[b], ref)
+        print(rep)
+        assert_parity(rep)
+        assert int((ref.tri_id >= 0).sum()) > W * H // 2  # ground plane covers most of the view
+
+
+def test_depth_triangle0_backfacing_leak():
+    """a kept back-facing triangle 0 leaks into the depth buffer where
+    no candidate exists (DepthShader has no front-face term)."""
+    W, H = 40, 36
+    cam, faces, extra = smoke_scene(W, H, depth=1.0)
+    faces = faces.clone()
+    faces[0] = faces[0][[0, 2, 1]]  # flip winding of triangle 0
+    z0 = torch.full((W, H), 7.0)
+    z, _, tri = _run(cam, DepthShader, z0, None, faces, DepthExtraInput(position=extra.position))
+    ref = O.render(cam, "depth", z0, (), faces, NS(position=extra.position))
+    assert int(((ref.tri_id == 0) & ~ref.has).sum()) > 0, "scene must exercise the leak"
+    rep = compare("tri0leak", z, None, tri, ref)
+    print(rep)
+    assert_parity(rep)
+
+
+def _shader_cases(s):
+    light = s.light
+    yield "gouraud", GouraudShader, GouraudExtraInput(s.pos, s.col, s.nrm, light)
+    yield "gouraud_texture", GouraudTextureShader, GouraudTextureExtraInput(s.pos, s.nrm, s.uv_texel, light, s.texture)
+    yield "phong", PhongTextureShader, PhongTextureExtraInput(s.pos, s.nrm, s.uv_texel, light, s.texture)
+    n_tri = s.faces.shape[0]
+    id_to_face = torch.arange(n_tri, dtype=torch.int32).repeat_interleave(3)
+    yield "phong_darboux", PhongTextureDarbouxShader, PhongTextureDarbouxExtraInput(
+        s.pos, s.nrm, s.uv_texel, light, s.texture, s.normal_map, id_to_face, s.faces)
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_simple_shaders_random_soup(seed):
+    s = random_mesh_scene(seed)
+    z0, c0 = torch.full((s.W, s.H), 1.0), torch.full((s.W, s.H, 3), 0.25)
+    for name, shader, extra in _shader_cases(s):
+        z, c, tri = _run(s.cam, shader, z0, c0, s.faces, extra)
+        ref = O.render(s.cam, name, z0, (c0,), s.faces, extra)
+        rep = compare(name, z, c, tri, ref)
+        print(rep)
+        assert_parity(rep)
+        assert rep["pixels"] - int((ref.tri_id < 0).sum()) > 50
+
+
+def _atlas_inputs(s, n_obj=3):
+    g = s.gen
+    tw, th = 8, 6
+    shapes = torch.tensor([[8, 6], [5, 4], [8, 3]], dtype=torch.int32)
+    atlas = torch.rand(n_obj * tw, th, 3, generator=g)
+    spec = torch.rand(n_obj * 2, 2, generator=g) * 6 + 0.5
+    tix = torch.randint(0, n_obj, (s.pos.shape[0] // 3,), generator=g).repeat_interleave(3).to(torch.int32)
+    return shapes, atlas, spec, tix, tw
+
+
+@pytest.mark.parametrize("seed", [0, 3])
+def test_phong_reflection_and_shadow_random_soup(seed):
+    s = random_mesh_scene(seed, n_tri=80)
+    shapes, atlas, spec, tix, off = _atlas_inputs(s)
+    lde = torch.tensor((0.2, 0.3, 0.9))
+    base = dict(position=s.pos, normal=s.nrm, uv=s.uv01, light=s.light, light_dir_eye=lde,
+                texture_shape=shapes, texture_index=tix, texture_offset=off, texture=atlas,
+                specular_map=spec, ambient=torch.tensor((0.3, 0.2, 0.1)),
+                diffuse=torch.tensor((0.5, 0.6, 0.7)), specular=torch.tensor((0.2, 0.3, 0.4)))
+    z0, c0 = torch.full((s.W, s.H), 1.0), torch.full((s.W, s.H, 3), 0.25)
+    extra = PhongReflectionTextureExtraInput(**base)
+    z, c, tri = _run(s.cam, PhongReflectionTextureShader, z0, c0, s.faces, extra)
+    ref = O.render(s.cam, "phong_reflection", z0, (c0,), s.faces, extra)
+    rep = compare("phong_reflection", z, c, tri, ref)
+    print(rep)
+    assert_parity(rep)
+    # shadow pass through the product API, then S7
+    sm0 = torch.full((s.W, s.H), torch.finfo(torch.float32).max)
+    shadow = jr.Shadow.render_shadow_map(sm0.to(DEV), s.pos.to(DEV), s.faces.to(DEV),
+                                         torch.tensor((0.4, 0.3, 0.9)), s.cam.viewport.to(DEV),
+                                         torch.zeros(3), torch.tensor((0.0, 0.0, 1.0)),
+                                         torch.tensor((0.6, 0.5, 0.4)), offset=0.05)
+    scam = NS(world_to_clip=shadow.camera.world_to_clip.cpu(), viewport=shadow.camera.viewport.cpu())
+    ref_sm = O.render_shadow_map(sm0, s.pos, s.faces, scam, 0.05)
+    assert torch.equal(shadow.shadow_map.cpu(), ref_sm), "shadow map must be bit-equal"
+    assert int((ref_sm < 1e30).sum()) > 20
+    extra7 = PhongReflectionShadowTextureExtraInput(**base, shadow=shadow, camera=s.cam)
+    z, c, tri = _run(s.cam, PhongReflectionShadowTextureShader, z0, c0, s.faces, extra7)
+    oshadow = NS(shadow_map=ref_sm, strength=shadow.strength, camera=scam)
+    ref = O.render(s.cam, "phong_reflection_shadow", z0, (c0,), s.faces,
+                   NS(**base, shadow=oshadow, camera=s.cam))
+    rep = compare("phong_reflection_shadow", z, c, tri, ref)
+    print(rep)
+    assert_parity(rep)
+
+
+def _cube_objects():
+    cube = jr.create_cube(torch.ones(3), torch.ones(2),
+                          torch.zeros(2, 2, 3).index_fill_(2, torch.tensor([2]), 1.0), torch.ones(2, 2) * 2.0)
+    return [jr.ModelObject(model=cube)]
+
+
+@pytest.mark.parametrize("shadow", [False, True])
+def test_simple_cube_example(shadow):
+    """BASELINE config 1: examples/simple_cube.py (640x480), default and shadow modes,
+    plus the analytic check of SURVEY 8c(3)."""
+    W, H = 640, 480
+    objs = _cube_objects()
+    camp = jr.CameraParameters(viewWidth=W, viewHeight=H, position=torch.tensor([2.0, 4.0, 1.0]))
+    light = jr.LightParameters()
+    sp = jr.ShadowParameters() if shadow else None
+    objs_d = [o._replace(model=_cuda(o.model)) for o in objs]
+    # host-side matrices are computed once on the CPU and shared with the oracle
+    model = jr.merge_objects(objs)
+    cam = jr.Renderer.create_camera_from_parameters(camp)
+    img = jr.Renderer.get_camera_image(objs_d, light, _cuda(cam), W, H, shadow_param=sp)
+    assert img.shape == (W, H, 3) and img.is_cuda
+    img_p = jr.Renderer.get_camera_image(objs_d, light, camp, W, H, shadow_param=sp)
+    assert float((img_p - img).abs().max()) < 1e-3      # CameraParameters route, device-built camera
+    scam = None
+    if shadow:
+        sh = jr.Shadow.render_shadow_map(
+            torch.full((W, H), torch.finfo(torch.float32).max, device=DEV), model.verts.to(DEV),
+            model.faces.to(DEV), torch.tensor(light.direction), cam.viewport.to(DEV), sp.centre, sp.up,
+            sp.strength, offset=sp.offset)
+        scam = NS(world_to_clip=sh.camera.world_to_clip.cpu(), viewport=sh.camera.viewport.cpu())
+    lightp = NS(**{k: torch.tensor(v) for k, v in light._asdict().items()})
+    spo = NS(centre=torch.tensor(sp.centre), up=torch.tensor(sp.up), strength=torch.tensor(sp.strength),
+             offset=sp.offset) if shadow else None
+    res = O.renderer_render(model, lightp, cam, torch.ones(W, H), torch.ones(W, H, 3), spo, scam)
+    ref = res["out"]
+    ok = torch.ones(W, H, dtype=torch.bool)
+    err = ((img.cpu() - ref.targets[0]).abs() / ref.targets[0].abs().clamp_min(1e-3))
+    print("simple_cube shadow=%s max rel err %.3g, covered %d" % (shadow, float(err.max()), int((ref.tri_id >= 0).sum())))
+    assert float(err.max()) <= 1e-5
+    covered = ref.tri_id >= 0
+    assert 10000 < int(covered.sum()) < W * H // 2
+    px = img.cpu()[covered]
+    assert float(px[:, :2].abs().max()) == 0.0          # pure-blue texture: R = G = 0
+    assert bool((img.cpu()[~covered] == 1.0).all())      # background
+
+
+def test_brax_fixture_frame_with_shadow_84():
+    """Real Brax ant fixture (3276 triangles), full view 84x84, shadow pass on."""
+    W, H = 84, 84
+    objs, camp = load_brax_fixture()
+    f = 1
+    objs1 = [o._replace(local_scaling=o.local_scaling[f], transform=o.transform[f]) for o in objs]
+    camp1 = jr.CameraParameters(**{k: v[f] for k, v in camp._asdict().items()})._replace(
+        viewWidth=W, viewHeight=H, vfov=58.0 * H / W)
+    light = jr.LightParameters(direction=(0.57735, -0.57735, 0.57735), ambient=(0.8,) * 3,
+                               diffuse=(0.8,) * 3, specular=(0.6,) * 3)
+    sp = jr.ShadowParameters(centre=camp1.target)
+    model = jr.merge_objects(objs1)
+    assert model.faces.shape[0] == 3276
+    cam = jr.Renderer.create_camera_from_parameters(camp1)
+    bufs = jr.Renderer.create_buffers(W, H, device=DEV)
+    img = jr.Renderer.render(_cuda(model), light, _cuda(cam), bufs, shadow_param=sp).targets[0]
+    sh = jr.Shadow.render_shadow_map(
+        torch.full((W, H), torch.finfo(torch.float32).max, device=DEV), model.verts.to(DEV),
+        model.faces.to(DEV), torch.tensor(light.direction), cam.viewport.to(DEV), sp.centre, sp.up,
+        sp.strength, offset=sp.offset)
+    scam = NS(world_to_clip=sh.camera.world_to_clip.cpu(), viewport=sh.camera.viewport.cpu())
+    lightp = NS(**{k: torch.tensor(v) for k, v in light._asdict().items()})
+    spo = NS(centre=sp.centre, up=torch.tensor(sp.up), strength=torch.tensor(sp.strength), offset=sp.offset)
+    res = O.renderer_render(model, lightp, cam, torch.ones(W, H), torch.ones(W, H, 3), spo, scam)
+    assert torch.equal(sh.shadow_map.cpu(), res["shadow_map"])
+    ref = res["out"]
+    err = ((img.cpu() - ref.targets[0]).abs() / ref.targets[0].abs().clamp_min(1e-3))
+    bad = int((err > 1e-5).sum())
+    print("brax frame: max rel err %.3g, pixels over tol %d, shadowed texels %d"
+          % (float(err.max()), bad, int((res["shadow_map"] < 1e30).sum())))
+    assert bad == 0
+
+
+def test_batch_broadcast_and_inplace():
+    """vmap semantics: batched positions, shared camera/faces; donated buffers."""
+    W, H, B = 32, 24, 5
+    sc = synthetic.brax_like_batch(B, n_capsules=2)
+    cam = synthetic.brax_cameras(sc["eye"][0], sc["target"][0], W, H)          # un-batched camera
+    z0 = torch.full((B, W, H), 1.0, device=DEV)
+    out = jr.render(_cuda(cam), DepthShader, jr.Buffers(z0, ()), sc["faces"][0].to(DEV),
+                    DepthExtraInput(position=sc["position"].to(DEV)), inplace=True)
+    assert out.zbuffer.data_ptr() == z0.data_ptr()
+    for b in (0, B - 1):
+        one = jr.render(_cuda(cam), DepthShader, jr.Buffers(torch.full((W, H), 1.0, device=DEV), ()),
+                        sc["faces"][0].to(DEV), DepthExtraInput(position=sc["position"][b].to(DEV)))
+        assert one.zbuffer.shape == (W, H)
+        assert torch.equal(one.zbuffer, out.zbuffer[b])
+    # host tensors in -> host tensors out (implicit device_put)
+    host = jr.render(cam, DepthShader, jr.Buffers(torch.full((W, H), 1.0), ()), sc["faces"][0],
+                     DepthExtraInput(position=sc["position"][0]))
+    assert not host.zbuffer.is_cuda and torch.equal(host.zbuffer, out.zbuffer[0].cpu())
+
+
+def test_uint8_display_epilogue():
+    W, H, B = 37, 21, 3
+    c = torch.rand(B, W, H, 3, device=DEV) * 1.4 - 0.2
+    got = jr.canvas_to_uint8_display(c)
+    want = (c.clamp(0, 1) * 255).to(torch.uint8).transpose(1, 2).flip(1)
+    assert torch.equal(got, want)
