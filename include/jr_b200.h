@@ -122,7 +122,8 @@ typedef struct JrRenderArgs {
   float* zbuffer;
   float* canvas;
   /* G-buffer out (B,W,H) int32: triangle written at each pixel, -1 if the
-   * pixel kept its old value.  Required (it is what backward consumes). */
+   * pixel kept its old value.  Required (it is what shading and backward
+   * consume); may be NULL for JR_DEPTH when no gradient is wanted. */
   int32_t* tri_id;
 
   void* workspace;         /* >= jr_workspace_bytes(args) bytes, or NULL if that is 0 */

@@ -198,7 +198,7 @@ k_visibility(const __grid_constant__ JrRenderArgs a, int tile_w, int tile_h, int
   }
   __syncthreads();
   // resolve
-  int32_t* __restrict__ tri_out = a.tri_id + (long long)b * a.W * a.H;
+  int32_t* __restrict__ tri_out = a.tri_id ? a.tri_id + (long long)b * a.W * a.H : nullptr;
   float* __restrict__ z_out = DEPTH ? a.zbuffer + (long long)b * a.W * a.H : nullptr;
   const bool use0 = DEPTH && tri0_flag;
   for (int i = tid; i < tw * th; i += VIS_THREADS) {
@@ -218,7 +218,7 @@ k_visibility(const __grid_constant__ JrRenderArgs a, int tile_w, int tile_h, int
         tri = 0;
       }
     }
-    tri_out[pix] = tri;
+    if (tri_out) tri_out[pix] = tri;
   }
 }
 
@@ -514,7 +514,8 @@ static int check_common(const JrRenderArgs* a) {
   if (a->shader < 0 || a->shader >= JR_NUM_SHADERS) return JR_ERR_SHADER;
   if (a->B <= 0 || a->W <= 0 || a->H <= 0 || a->T < 0 || a->n_pos < 0) return JR_ERR_DIMS;
   if (a->W > 32767 || a->H > 32767) return JR_ERR_DIMS;
-  if (!a->world_to_clip.ptr || !a->viewport.ptr || !a->zbuffer || !a->tri_id) return JR_ERR_NULL;
+  if (!a->world_to_clip.ptr || !a->viewport.ptr || !a->zbuffer) return JR_ERR_NULL;
+  if (!a->tri_id && a->shader != JR_DEPTH) return JR_ERR_NULL;
   if (a->T > 0 && (!a->position.ptr || !a->faces.ptr)) return JR_ERR_NULL;
   const int s = a->shader;
   if (s != JR_DEPTH) {

@@ -154,15 +154,18 @@ class _Call:
             a.shadow_w, a.shadow_h = A["shadow_map"].shape[-2], A["shadow_map"].shape[-1]
         a.zbuffer = zbuffer.data_ptr()
         a.canvas = canvas.data_ptr() if canvas is not None else None
-        a.tri_id = tri_id.data_ptr()
+        a.tri_id = tri_id.data_ptr() if tri_id is not None else None
         a.workspace, a.workspace_bytes = None, 0
         return a
 
 
-def _forward_native(call: _Call, zbuffer: Tensor, canvas: Optional[Tensor]) -> Tensor:
+def _forward_native(call: _Call, zbuffer: Tensor, canvas: Optional[Tensor],
+                    need_tri: bool = True) -> Optional[Tensor]:
     lib = _native.load()
     dev = zbuffer.device
-    tri_id = torch.empty((call.B, call.W, call.H), dtype=torch.int32, device=dev)
+    tri_id = None
+    if need_tri or call.sid != _native.JR_DEPTH:
+        tri_id = torch.empty((call.B, call.W, call.H), dtype=torch.int32, device=dev)
     args = call.fill(zbuffer, canvas, tri_id)
     need = lib.jr_workspace_bytes(C.byref(args))
     ws = None
@@ -318,15 +321,15 @@ def _render_arrays(sid: int, arrays: Dict[str, Any], zbuffer: Any, canvas: Optio
 
         z_out = _own(z, zbuffer)
         c_out = _own(c, canvas) if c is not None else None
-        tri = _forward_native(call, z_out, c_out)
+        tri = _forward_native(call, z_out, c_out, need_tri=return_tri_id)
     if squeeze:
         z_out = z_out[0]
         c_out = c_out[0] if c_out is not None else None
-        tri = tri[0]
+        tri = tri[0] if tri is not None else None
     if host_in:
         z_out = z_out.cpu()
         c_out = c_out.cpu() if c_out is not None else None
-        tri = tri.cpu() if return_tri_id else tri
+        tri = tri.cpu() if (return_tri_id and tri is not None) else tri
     return z_out, c_out, tri
 
 

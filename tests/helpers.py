@@ -99,3 +99,8 @@ def random_mesh_scene(seed: int, n_tri: int = 60, W: int = 48, H: int = 40, tex:
     return NS(W=W, H=H, pos=pos, nrm=nrm, uv_texel=uv_texel, uv01=uv01, col=col, faces=faces, cam=cam,
               light=light, texture=texture, normal_map=torch.randn(tex, tex + 3, 3, generator=g),
               gen=g)
+
+
+def cam_at(cam, b: int):
+    """Un-batch element ``b`` of a (partly) batched Camera."""
+    return NS(**{k: (v[b] if v.ndim == 3 else v) for k, v in cam._asdict().items()})

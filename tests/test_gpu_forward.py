@@ -18,7 +18,7 @@ from jaxrenderer_b200.shaders import (
     PhongTextureDarbouxShader, PhongTextureExtraInput, PhongTextureShader,
 )
 from oracle import jr_oracle as O
-from tests.helpers import assert_parity, compare, load_brax_fixture, random_mesh_scene, smoke_scene
+from tests.helpers import cam_at, assert_parity, compare, load_brax_fixture, random_mesh_scene, smoke_scene
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -70,7 +70,7 @@ def test_depth_brax_like(wh):
     out, tri = jr.render(_cuda(cam), DepthShader, bufs, sc["faces"].to(DEV),
                          DepthExtraInput(position=sc["position"].to(DEV)), return_tri_id=True)
     for b in range(B):
-        camb = NS(world_to_clip=cam.world_to_clip[b], viewport=cam.viewport[b])
+        camb = cam_at(cam, b)
         ref = O.render(camb, "depth", z0[b], (), sc["faces"][b], NS(position=sc["position"][b]))
         rep = compare(f"depth{W}x{H}[{b}]", out.zbuffer[b], None, tri[b], ref)
         print(rep)
@@ -82,12 +82,13 @@ def test_depth_triangle0_backfacing_leak():
     """a kept back-facing triangle 0 leaks into the depth buffer where
     no candidate exists (DepthShader has no front-face term)."""
     W, H = 40, 36
-    cam, faces, extra = smoke_scene(W, H, depth=1.0)
-    faces = faces.clone()
-    faces[0] = faces[0][[0, 2, 1]]  # flip winding of triangle 0
+    cam, _, extra = smoke_scene(W, H, depth=1.0)
+    pos = torch.cat((extra.position, torch.tensor(((-2.0, -1.0, 0.0), (-1.0, -1.0, 0.0), (-1.5, -0.2, 0.3)))))
+    faces = torch.tensor(((0, 2, 1), (6, 7, 8)), dtype=torch.int32)  # tri 0 = flipped (0,1,2)
     z0 = torch.full((W, H), 7.0)
-    z, _, tri = _run(cam, DepthShader, z0, None, faces, DepthExtraInput(position=extra.position))
-    ref = O.render(cam, "depth", z0, (), faces, NS(position=extra.position))
+    z, _, tri = _run(cam, DepthShader, z0, None, faces, DepthExtraInput(position=pos))
+    ref = O.render(cam, "depth", z0, (), faces, NS(position=pos))
+    assert int(ref.has.sum()) > 0, "scene must also contain a regular front-facing triangle"
     assert int(((ref.tri_id == 0) & ~ref.has).sum()) > 0, "scene must exercise the leak"
     rep = compare("tri0leak", z, None, tri, ref)
     print(rep)
