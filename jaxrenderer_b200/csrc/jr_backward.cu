@@ -1,0 +1,727 @@
+// jr_backward.cu -- reverse mode of pipeline.render through FIXED visibility
+// (the reference gets it from jax.grad over renderer/pipeline.py:470-537; the
+// integer argmin / floor / round / comparisons cut the graph).
+//
+// Inputs: the saved triangle-id G-buffer + output cotangents.  Every pixel's
+// fragment is recomputed with the forward's own code (jr_shade.cuh) and
+// back-propagated analytically.  Accumulation is DETERMINISTIC, no float
+// atomics anywhere:
+//   * scene-global parameters (camera matrices, light, shadow strength):
+//     per-thread fixed-order partial sums -> fixed-shape block tree reduction
+//     -> per-block partials -> fixed-order final reduction;
+//   * keyed targets (diffuse texture, specular map, vertex positions /
+//     colours / normals): (key, pixel) pairs -> CUB radix sort (stable) ->
+//     fused "recompute + segmented reduction" kernel over the sorted order
+//     (fixed 256-entry chunks, Hillis-Steele segmented scan, fixed-order carry
+//     resolution across chunks).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include "../../include/jr_b200.h"
+#include "jr_common.cuh"
+#include "jr_device.cuh"
+#include "jr_shade.cuh"
+
+namespace jr {
+
+// ---- packed layout of the scene-global gradient vector
+enum : int {
+  G_W2C = 0,    // 16
+  G_VP00 = 16, G_VP03 = 17, G_VP11 = 18, G_VP13 = 19, G_VP22 = 20, G_VP23 = 21,
+  G_WEN = 22,   // 9: upper-left 3x3, row-major
+  G_LDIR = 31, G_LCOL = 34, G_LDE = 37, G_AMB = 40, G_DIF = 43, G_SPE = 46, G_STR = 49,
+  NG = 52
+};
+
+enum : int { MODE_TEXEL = 0, MODE_SPEC = 1, MODE_POS = 2, MODE_NRM = 3 };
+
+struct PixGrad {
+  float g[NG];
+  float d_tex[3];
+  float d_sexp;
+  float d_pos[3][3];
+  float d_col[3][3];
+  float d_nrm[3][3];
+};
+
+__device__ __forceinline__ Vec3 normalise_bwd(Vec3 v, Vec3 dy) {
+  const float n = sqrtf(v.x * v.x + v.y * v.y + v.z * v.z);
+  const float inv_n = 1.0f / n;
+  const Vec3 y = {v.x * inv_n, v.y * inv_n, v.z * inv_n};
+  const float d = y.x * dy.x + y.y * dy.y + y.z * dy.z;
+  return Vec3{(dy.x - y.x * d) * inv_n, (dy.y - y.y * d) * inv_n, (dy.z - y.z * d) * inv_n};
+}
+
+// Back-propagate one pixel.  WG/WT/WV select which outputs are produced.
+template <int S, bool WG, bool WT, bool WV>
+__device__ __forceinline__ void backprop_pixel(const JrRenderArgs& a, int b, const Frag& f, float d_zw,
+                                               const float d_col[3], PixGrad& o) {
+  float d_tc[3] = {0.f, 0.f, 0.f};
+  const float* tc = f.tc;
+  if (WT) { o.d_tex[0] = o.d_tex[1] = o.d_tex[2] = 0.f; o.d_sexp = 0.f; }
+  if (WV) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { o.d_pos[k][c] = 0.f; o.d_col[k][c] = 0.f; o.d_nrm[k][c] = 0.f; }
+  }
+
+  if (S == JR_GOURAUD || S == JR_GOURAUD_TEXTURE) {
+    float d_I[3] = {0.f, 0.f, 0.f};
+    if (S == JR_GOURAUD) {
+      const float* __restrict__ cv = a.colour.ptr + (long long)b * a.colour.batch_stride;
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const float ck = cv[3 * f.fi[k] + c];
+          const float d_colv = tc[k] * d_col[c];
+          d_tc[k] += d_col[c] * ((ck * f.lcol[c]) * f.inten[k]);
+          if (WG) o.g[G_LCOL + c] += d_colv * ck * f.inten[k];
+          d_I[k] += d_colv * ck * f.lcol[c];
+          if (WV) o.d_col[k][c] = d_colv * f.lcol[c] * f.inten[k];
+        }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        if (WT) o.d_tex[c] = d_col[c] * f.lc[c];
+        const float d_lc = d_col[c] * f.tex[c];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          d_tc[k] += d_lc * (f.lcol[c] * f.inten[k]);
+          if (WG) o.g[G_LCOL + c] += tc[k] * d_lc * f.inten[k];
+          d_I[k] += tc[k] * d_lc * f.lcol[c];
+        }
+      }
+    }
+    Vec3 d_nl = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      d_nl.x += d_I[k] * f.nvert[k].x; d_nl.y += d_I[k] * f.nvert[k].y; d_nl.z += d_I[k] * f.nvert[k].z;
+      if (WV) {
+        const Vec3 dn = normalise_bwd(f.nraw[k], Vec3{d_I[k] * f.nl.x, d_I[k] * f.nl.y, d_I[k] * f.nl.z});
+        o.d_nrm[k][0] = dn.x; o.d_nrm[k][1] = dn.y; o.d_nrm[k][2] = dn.z;
+      }
+    }
+    if (WG) {
+      const Vec3 dl = normalise_bwd(Vec3{f.lraw[0], f.lraw[1], f.lraw[2]}, d_nl);
+      o.g[G_LDIR] += dl.x; o.g[G_LDIR + 1] += dl.y; o.g[G_LDIR + 2] += dl.z;
+    }
+  } else if (S >= JR_PHONG) {
+    Vec3 d_nn = {0.f, 0.f, 0.f};
+    bool active = true;
+    if (S == JR_PHONG) {
+      active = f.ok;
+      if (active) {
+        float d_ndl = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          if (WT) o.d_tex[c] = d_col[c] * f.lc[c];
+          const float d_lc = d_col[c] * f.tex[c];
+          if (WG) o.g[G_LCOL + c] += d_lc * f.ndl;
+          d_ndl += d_lc * f.lcol[c];
+        }
+        d_nn = Vec3{d_ndl * f.nl.x, d_ndl * f.nl.y, d_ndl * f.nl.z};
+        if (WG) {
+          const Vec3 dl = normalise_bwd(Vec3{f.lraw[0], f.lraw[1], f.lraw[2]},
+                                        Vec3{d_ndl * f.nn.x, d_ndl * f.nn.y, d_ndl * f.nn.z});
+          o.g[G_LDIR] += dl.x; o.g[G_LDIR + 1] += dl.y; o.g[G_LDIR + 2] += dl.z;
+        }
+      }
+    } else {  // S6 / S7
+      float d_diffuse = 0.f, d_s = 0.f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float sh = (S == JR_PHONG_REFLECTION_SHADOW) ? f.shadow[c] : 1.f;
+        const float tl = f.tex[c] * f.lcol[c];
+        if (WG) {
+          o.g[G_AMB + c] += d_col[c] * f.tex[c];
+          o.g[G_LCOL + c] += d_col[c] * sh * f.ds[c] * f.tex[c];
+          if (S == JR_PHONG_REFLECTION_SHADOW && !f.lit) o.g[G_STR + c] += -d_col[c] * f.ds[c] * tl;
+        }
+        if (WT) o.d_tex[c] = d_col[c] * (f.amb[c] + sh * f.ds[c] * f.lcol[c]);
+        const float d_ds = d_col[c] * sh * tl;
+        if (WG) { o.g[G_DIF + c] += d_ds * f.diffuse; o.g[G_SPE + c] += d_ds * f.specular; }
+        d_diffuse += d_ds * f.dif[c];
+        d_s += d_ds * f.spe[c];
+      }
+      // s = pow(base, e)
+      float d_base = 0.f;
+      if (f.sexp != 0.f) d_base = d_s * f.sexp * powf(f.base, f.sexp - 1.f);
+      if (WT) o.d_sexp = (f.base > 0.f) ? d_s * f.specular * logf(f.base) : 0.f;
+      const Vec3 rv = f.rv;
+      const float rn = sqrtf(rv.x * rv.x + rv.y * rv.y + rv.z * rv.z);
+      const float refl_z = rv.z / rn;
+      const float d_refl_z = (refl_z > 0.f) ? d_base : 0.f;
+      const Vec3 d_rv = normalise_bwd(rv, Vec3{0.f, 0.f, d_refl_z});
+      const Vec3 nn = f.nn, ld = f.nl;
+      const float d_ndl = ((f.ndl > 0.f) ? d_diffuse : 0.f) + 2.f * (d_rv.x * nn.x + d_rv.y * nn.y + d_rv.z * nn.z);
+      const float t2 = 2.f * f.ndl;
+      d_nn = Vec3{t2 * d_rv.x + d_ndl * ld.x, t2 * d_rv.y + d_ndl * ld.y, t2 * d_rv.z + d_ndl * ld.z};
+      if (WG) {
+        const Vec3 d_ld = {-d_rv.x + d_ndl * nn.x, -d_rv.y + d_ndl * nn.y, -d_rv.z + d_ndl * nn.z};
+        const Vec3 dl = normalise_bwd(Vec3{f.lraw[0], f.lraw[1], f.lraw[2]}, d_ld);
+        o.g[G_LDE] += dl.x; o.g[G_LDE + 1] += dl.y; o.g[G_LDE + 2] += dl.z;
+      }
+    }
+    if (active) {
+      const Vec3 d_normal = normalise_bwd(f.normal, d_nn);
+      const float* __restrict__ wen = a.world_to_eye_norm.ptr + (long long)b * a.world_to_eye_norm.batch_stride;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        d_tc[k] += d_normal.x * f.nvert[k].x + d_normal.y * f.nvert[k].y + d_normal.z * f.nvert[k].z;
+        if (WG || WV) {
+          const Vec3 d_nv = {tc[k] * d_normal.x, tc[k] * d_normal.y, tc[k] * d_normal.z};
+          const Vec3 d_t = normalise_bwd(f.tvert[k], d_nv);
+          const Vec3 m = f.mvert[k];
+          if (WG) {
+            o.g[G_WEN + 0] += d_t.x * m.x; o.g[G_WEN + 1] += d_t.x * m.y; o.g[G_WEN + 2] += d_t.x * m.z;
+            o.g[G_WEN + 3] += d_t.y * m.x; o.g[G_WEN + 4] += d_t.y * m.y; o.g[G_WEN + 5] += d_t.y * m.z;
+            o.g[G_WEN + 6] += d_t.z * m.x; o.g[G_WEN + 7] += d_t.z * m.y; o.g[G_WEN + 8] += d_t.z * m.z;
+          }
+          if (WV) {
+            const Vec3 d_m = {wen[0] * d_t.x + wen[4] * d_t.y + wen[8] * d_t.z,
+                              wen[1] * d_t.x + wen[5] * d_t.y + wen[9] * d_t.z,
+                              wen[2] * d_t.x + wen[6] * d_t.y + wen[10] * d_t.z};
+            const Vec3 q = normalise3(f.nraw[k]);
+            const Vec3 d_q = normalise_bwd(q, d_m);
+            const Vec3 dn = normalise_bwd(f.nraw[k], d_q);
+            o.d_nrm[k][0] = dn.x; o.d_nrm[k][1] = dn.y; o.d_nrm[k][2] = dn.z;
+          }
+        }
+      }
+    }
+  }
+
+  // ---- common: weights, depth, triangle setup, camera
+  if (WG || WV) {
+    const float* __restrict__ vp = a.viewport.ptr + (long long)b * a.viewport.batch_stride;
+    const float* __restrict__ w2c = a.world_to_clip.ptr + (long long)b * a.world_to_clip.batch_stride;
+    const float d_z = d_zw * vp[10];
+    if (WG) { o.g[G_VP22] += d_zw * f.z; o.g[G_VP23] += d_zw; }
+    const float s = d_tc[0] * tc[0] + d_tc[1] * tc[1] + d_tc[2] * tc[2];
+    float d_cc[3], d_zc[3], gv[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      d_cc[j] = (d_tc[j] - s) / f.w_rec + d_z * f.cl[j][2];
+      d_zc[j] = d_z * f.cc[j];
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+      gv[r] = f.inv[3 * r] * d_cc[0] + f.inv[3 * r + 1] * d_cc[1] + f.inv[3 * r + 2] * d_cc[2];
+    if (WG) {
+      o.g[G_VP03] += -gv[0] / vp[0];
+      o.g[G_VP00] += -gv[0] * f.xn / vp[0];
+      o.g[G_VP13] += -gv[1] / vp[5];
+      o.g[G_VP11] += -gv[1] * f.yn / vp[5];
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      // d gl_Position of vertex k: (x, y, z, w)
+      const float dc[4] = {-f.cc[k] * gv[0], -f.cc[k] * gv[1], d_zc[k], -f.cc[k] * gv[2]};
+      const float ph[4] = {f.P[k].x, f.P[k].y, f.P[k].z, 1.f};
+      if (WG) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) o.g[G_W2C + 4 * r + c] += dc[r] * ph[c];
+      }
+      if (WV) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          o.d_pos[k][c] = w2c[c] * dc[0] + w2c[4 + c] * dc[1] + w2c[8 + c] * dc[2] + w2c[12 + c] * dc[3];
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void load_cotangent(const JrGradArgs& g, long long gi, bool has_canvas, float& d_zw,
+                                               float d_col[3]) {
+  d_zw = g.d_zbuffer ? g.d_zbuffer[gi] : 0.f;
+  if (has_canvas && g.d_canvas) {
+    d_col[0] = g.d_canvas[gi * 3]; d_col[1] = g.d_canvas[gi * 3 + 1]; d_col[2] = g.d_canvas[gi * 3 + 2];
+  } else {
+    d_col[0] = d_col[1] = d_col[2] = 0.f;
+  }
+}
+
+// ------------------------------------------------------------ global parameters
+constexpr int BWD_THREADS = 256;
+
+template <int S>
+__global__ void __launch_bounds__(BWD_THREADS)
+k_bwd_global(const __grid_constant__ JrRenderArgs a, const __grid_constant__ JrGradArgs g, float* __restrict__ partials) {
+  const int b = blockIdx.y;
+  const int npix = a.W * a.H;
+  PixGrad o;
+#pragma unroll
+  for (int j = 0; j < NG; ++j) o.g[j] = 0.f;
+  for (int pix = blockIdx.x * BWD_THREADS + threadIdx.x; pix < npix; pix += gridDim.x * BWD_THREADS) {
+    const long long gi = (long long)b * npix + pix;
+    const int tri = a.tri_id[gi];
+    if (tri < 0) continue;
+    const int x = pix / a.H, y = pix - x * a.H;
+    Frag f;
+    shade_pixel<S>(a, b, x, y, tri, f);
+    float d_zw, d_col[3];
+    load_cotangent(g, gi, S != JR_DEPTH, d_zw, d_col);
+    backprop_pixel<S, true, false, false>(a, b, f, d_zw, d_col, o);
+  }
+  // fixed-shape block reduction: xor-butterfly inside each warp, then warps in order
+  __shared__ float red[BWD_THREADS / 32][NG];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < NG; ++j) {
+    float v = o.g[j];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if (lane == 0) red[warp][j] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < NG) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < BWD_THREADS / 32; ++w) v += red[w][threadIdx.x];
+    partials[((long long)b * gridDim.x + blockIdx.x) * NG + threadIdx.x] = v;
+  }
+}
+
+struct GlobalOut {
+  float* ptr[NG];
+  long long stride[NG];
+};
+
+// one thread per slot: sums the per-block partials in fixed (b, block) order
+__global__ void k_bwd_global_final(const float* __restrict__ partials, int B, int nblk, GlobalOut out) {
+  const int j = threadIdx.x;
+  if (j >= NG || out.ptr[j] == nullptr) return;
+  if (out.stride[j] == 0) {
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b)
+      for (int k = 0; k < nblk; ++k) acc += partials[((long long)b * nblk + k) * NG + j];
+    *out.ptr[j] += acc;
+  } else {
+    for (int b = 0; b < B; ++b) {
+      float acc = 0.f;
+      for (int k = 0; k < nblk; ++k) acc += partials[((long long)b * nblk + k) * NG + j];
+      out.ptr[j][(long long)b * out.stride[j]] += acc;
+    }
+  }
+}
+
+// --------------------------------------------------------------- keyed targets
+struct KeyedPlan {
+  int mode;
+  int per_pixel;        // entries per pixel (1 or 3)
+  long long n_entries;  // B*W*H*per_pixel
+  long long keys_per_image;
+  bool batched;         // target has a batch axis
+  unsigned invalid_key;
+  int C;                // channels reduced
+  float* out;           // target base
+  float* out2;          // MODE_POS: d_colour (may be null)
+};
+
+template <int S, int MODE>
+__global__ void __launch_bounds__(256)
+k_bwd_keys(const __grid_constant__ JrRenderArgs a, KeyedPlan plan, unsigned* __restrict__ keys,
+           unsigned* __restrict__ vals) {
+  const long long npix = (long long)a.W * a.H;
+  const long long total = npix * a.B;
+  for (long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x; gi < total;
+       gi += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(gi / npix);
+    const int pix = (int)(gi - (long long)b * npix);
+    const int tri = a.tri_id[gi];
+    const unsigned boff = plan.batched ? (unsigned)((long long)b * plan.keys_per_image) : 0u;
+    if (MODE == MODE_TEXEL || MODE == MODE_SPEC) {
+      unsigned key = plan.invalid_key;
+      if (tri >= 0) {
+        const int x = pix / a.H, y = pix - x * a.H;
+        Frag f;
+        shade_pixel<S>(a, b, x, y, tri, f);
+        const long long k = (MODE == MODE_TEXEL) ? f.texel : f.spec_idx;
+        bool contributes = true;
+        if (S == JR_PHONG || S == JR_PHONG_DARBOUX) contributes = f.ok;
+        if (k >= 0 && contributes) key = boff + (unsigned)k;
+      }
+      keys[gi] = key;
+      vals[gi] = (unsigned)gi;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        unsigned key = plan.invalid_key;
+        if (tri >= 0) {
+          const int32_t* fp = a.faces.ptr + (long long)b * a.faces.batch_stride + 3 * tri;
+          if (MODE == MODE_NRM && a.faces_norm.ptr)
+            fp = a.faces_norm.ptr + (long long)b * a.faces_norm.batch_stride + 3 * tri;
+          key = boff + (unsigned)fp[k];
+        }
+        keys[gi * 3 + k] = key;
+        vals[gi * 3 + k] = (unsigned)(gi * 4 + k);
+      }
+    }
+  }
+}
+
+template <int C>
+struct Carry {
+  unsigned first_key, last_key;
+  int first_open, last_open, whole, pad;
+  float first_val[C], last_val[C];
+};
+
+// One thread per sorted entry, fixed chunks of 256 entries per CTA.
+template <int S, int MODE, int C>
+__global__ void __launch_bounds__(256)
+k_bwd_segreduce(const __grid_constant__ JrRenderArgs a, const __grid_constant__ JrGradArgs g, KeyedPlan plan,
+                const unsigned* __restrict__ keys, const unsigned* __restrict__ vals, Carry<C>* __restrict__ carry) {
+  __shared__ unsigned s_key[256];
+  __shared__ int s_head[256];
+  __shared__ float s_val[C][256];
+  const int tid = threadIdx.x;
+  const long long i = (long long)blockIdx.x * 256 + tid;
+  const long long npix = (long long)a.W * a.H;
+  unsigned key = plan.invalid_key;
+  float v[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) v[c] = 0.f;
+  if (i < plan.n_entries) {
+    key = keys[i];
+    if (key != plan.invalid_key) {
+      const unsigned payload = vals[i];
+      long long gi;
+      int corner = 0;
+      if (MODE == MODE_TEXEL || MODE == MODE_SPEC) gi = payload;
+      else { gi = payload >> 2; corner = payload & 3; }
+      const int b = (int)(gi / npix);
+      const int pix = (int)(gi - (long long)b * npix);
+      const int x = pix / a.H, y = pix - x * a.H;
+      Frag f;
+      shade_pixel<S>(a, b, x, y, a.tri_id[gi], f);
+      float d_zw, d_col[3];
+      load_cotangent(g, gi, S != JR_DEPTH, d_zw, d_col);
+      PixGrad o;
+      backprop_pixel<S, false, (MODE == MODE_TEXEL || MODE == MODE_SPEC), (MODE == MODE_POS || MODE == MODE_NRM)>(
+          a, b, f, d_zw, d_col, o);
+      if (MODE == MODE_TEXEL) { v[0] = o.d_tex[0]; v[1] = o.d_tex[1]; v[2] = o.d_tex[2]; }
+      if (MODE == MODE_SPEC) v[0] = o.d_sexp;
+      if (MODE == MODE_POS) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+          if (k == corner) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { v[c] = o.d_pos[k][c]; if (C > 3) v[3 + c] = o.d_col[k][c]; }
+          }
+      }
+      if (MODE == MODE_NRM) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+          if (k == corner) { v[0] = o.d_nrm[k][0]; v[1] = o.d_nrm[k][1]; v[2] = o.d_nrm[k][2]; }
+      }
+    }
+  }
+  s_key[tid] = key;
+#pragma unroll
+  for (int c = 0; c < C; ++c) s_val[c][tid] = v[c];
+  __syncthreads();
+  // head index of my segment: max-scan of head positions
+  const bool head = (tid == 0) || (s_key[tid - 1] != key);
+  s_head[tid] = head ? tid : 0;
+  __syncthreads();
+  for (int off = 1; off < 256; off <<= 1) {
+    int t = (tid >= off) ? s_head[tid - off] : 0;
+    __syncthreads();
+    s_head[tid] = max(s_head[tid], t);
+    __syncthreads();
+  }
+  const int my_head = s_head[tid];
+  // segmented inclusive scan (Hillis-Steele: fixed association -> deterministic)
+  for (int off = 1; off < 256; off <<= 1) {
+    float t[C];
+    const bool take = (tid >= off) && (tid - off >= my_head);
+#pragma unroll
+    for (int c = 0; c < C; ++c) t[c] = take ? s_val[c][tid - off] : 0.f;
+    __syncthreads();
+    if (take) {
+#pragma unroll
+      for (int c = 0; c < C; ++c) s_val[c][tid] += t[c];
+    }
+    __syncthreads();
+  }
+  const bool tail = (tid == 255) || (s_key[tid + 1] != key);
+  if (!tail) return;
+  // neighbours across the chunk boundary
+  const long long c0 = (long long)blockIdx.x * 256;
+  const bool open_left = (my_head == 0) && (c0 > 0) && (keys[c0 - 1] == key);
+  const bool open_right = (tid == 255) && (c0 + 256 < plan.n_entries) && (keys[c0 + 256] == key);
+  Carry<C>& cr = carry[blockIdx.x];
+  if (my_head == 0) {
+    cr.first_key = key; cr.first_open = open_left ? 1 : 0;
+    cr.whole = (tid == 255) ? 1 : 0;
+#pragma unroll
+    for (int c = 0; c < C; ++c) cr.first_val[c] = s_val[c][tid];
+  }
+  if (tid == 255) {
+    cr.last_key = key; cr.last_open = open_right ? 1 : 0;
+#pragma unroll
+    for (int c = 0; c < C; ++c) cr.last_val[c] = s_val[c][tid];
+  }
+  if (key == plan.invalid_key) return;
+  if (!open_left && !open_right) {
+    // complete segment: single writer of this key in the whole launch
+    if (MODE == MODE_POS && C > 3) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        plan.out[(long long)key * 3 + c] += s_val[c][tid];
+        if (plan.out2) plan.out2[(long long)key * 3 + c] += s_val[3 + c][tid];
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < C; ++c) plan.out[(long long)key * C + c] += s_val[c][tid];
+    }
+  }
+}
+
+// Resolve segments that straddle chunks: one thread per chunk that STARTS a run.
+template <int MODE, int C>
+__global__ void k_bwd_segfix(KeyedPlan plan, const Carry<C>* __restrict__ carry, int nchunks) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nchunks) return;
+  const Carry<C>& me = carry[c];
+  if (!me.last_open) return;
+  if (me.whole && me.first_open) return;  // continues a run started further left
+  const unsigned key = me.last_key;
+  if (key == plan.invalid_key) return;
+  float acc[C];
+#pragma unroll
+  for (int k = 0; k < C; ++k) acc[k] = me.last_val[k];
+  int j = c + 1;
+  while (j < nchunks) {
+    const Carry<C>& nx = carry[j];
+#pragma unroll
+    for (int k = 0; k < C; ++k) acc[k] += nx.first_val[k];
+    if (!(nx.whole && nx.last_open)) break;
+    ++j;
+  }
+  if (MODE == MODE_POS && C > 3) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      plan.out[(long long)key * 3 + k] += acc[k];
+      if (plan.out2) plan.out2[(long long)key * 3 + k] += acc[3 + k];
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < C; ++k) plan.out[(long long)key * C + k] += acc[k];
+  }
+}
+
+// d(out)/d(old buffer) = 1 - keep (pipeline.py:420-437)
+__global__ void k_bwd_mask(const int32_t* __restrict__ tri_id, float* d_z, float* d_c, long long total) {
+  for (long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x; gi < total;
+       gi += (long long)gridDim.x * blockDim.x) {
+    if (tri_id[gi] >= 0) {
+      if (d_z) d_z[gi] = 0.f;
+      if (d_c) { d_c[gi * 3] = 0.f; d_c[gi * 3 + 1] = 0.f; d_c[gi * 3 + 2] = 0.f; }
+    }
+  }
+}
+
+// ----------------------------------------------------------------- host side
+static int bit_length(unsigned long long v) { int n = 0; while (v) { ++n; v >>= 1; } return n; }
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+struct BwdLayout {
+  int nblk;             // global pass blocks per image
+  size_t partials, keys_a, keys_b, vals_a, vals_b, cub_temp, carry, total;
+  size_t cub_bytes;
+  long long max_entries;
+};
+
+static bool wants_global(const JrGradArgs* g) {
+  return g->d_world_to_clip.ptr || g->d_viewport.ptr || g->d_world_to_eye_norm.ptr || g->d_light_direction.ptr ||
+         g->d_light_colour.ptr || g->d_light_dir_eye.ptr || g->d_ambient.ptr || g->d_diffuse.ptr ||
+         g->d_specular.ptr || g->d_shadow_strength.ptr;
+}
+
+static BwdLayout bwd_layout(const JrRenderArgs* a, const JrGradArgs* g) {
+  BwdLayout L{};
+  const long long npix = (long long)a->W * a->H;
+  L.nblk = (int)((npix + BWD_THREADS * 8 - 1) / (BWD_THREADS * 8));
+  if (L.nblk < 1) L.nblk = 1;
+  if (L.nblk > 64) L.nblk = 64;
+  const bool keyed1 = g->d_texture.ptr || g->d_specular_map.ptr;
+  const bool keyed3 = g->d_position.ptr || g->d_colour.ptr || g->d_normal.ptr;
+  L.max_entries = keyed3 ? npix * a->B * 3 : (keyed1 ? npix * a->B : 0);
+  size_t off = 0;
+  L.partials = off; off += align256(sizeof(float) * NG * (size_t)L.nblk * a->B);
+  if (L.max_entries > 0) {
+    const size_t n = (size_t)L.max_entries;
+    L.keys_a = off; off += align256(n * 4);
+    L.keys_b = off; off += align256(n * 4);
+    L.vals_a = off; off += align256(n * 4);
+    L.vals_b = off; off += align256(n * 4);
+    size_t tmp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp, (const unsigned*)nullptr, (unsigned*)nullptr,
+                                    (const unsigned*)nullptr, (unsigned*)nullptr, (int)n, 0, 32);
+    L.cub_bytes = tmp;
+    L.cub_temp = off; off += align256(tmp);
+    const size_t nchunks = (n + 255) / 256;
+    L.carry = off; off += align256(nchunks * sizeof(Carry<6>));
+  }
+  L.total = off;
+  return L;
+}
+
+template <int S, int MODE, int C>
+static int run_keyed(const JrRenderArgs* a, const JrGradArgs* g, const BwdLayout& L, KeyedPlan plan,
+                     cudaStream_t stream) {
+  char* ws = (char*)g->workspace;
+  unsigned* keys_a = (unsigned*)(ws + L.keys_a);
+  unsigned* keys_b = (unsigned*)(ws + L.keys_b);
+  unsigned* vals_a = (unsigned*)(ws + L.vals_a);
+  unsigned* vals_b = (unsigned*)(ws + L.vals_b);
+  Carry<C>* carry = (Carry<C>*)(ws + L.carry);
+  const long long total = (long long)a->B * a->W * a->H;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148LL * 32) blocks = 148LL * 32;
+  k_bwd_keys<S, MODE><<<(unsigned)blocks, 256, 0, stream>>>(*a, plan, keys_a, vals_a);
+  g_launches++;
+  size_t tmp = L.cub_bytes;
+  const int end_bit = bit_length((unsigned long long)plan.invalid_key);
+  cub::DeviceRadixSort::SortPairs(ws + L.cub_temp, tmp, keys_a, keys_b, vals_a, vals_b, (int)plan.n_entries, 0,
+                                  end_bit, stream);
+  const long long nchunks = (plan.n_entries + 255) / 256;
+  k_bwd_segreduce<S, MODE, C><<<(unsigned)nchunks, 256, 0, stream>>>(*a, *g, plan, keys_b, vals_b, carry);
+  g_launches++;
+  k_bwd_segfix<MODE, C><<<(unsigned)((nchunks + 127) / 128), 128, 0, stream>>>(plan, carry, (int)nchunks);
+  g_launches++;
+  return cudaGetLastError() == cudaSuccess ? JR_OK : JR_ERR_CUDA;
+}
+
+template <int S>
+static int backward_impl(const JrRenderArgs* a, const JrGradArgs* g, cudaStream_t stream) {
+  const BwdLayout L = bwd_layout(a, g);
+  if (L.total > 0 && (!g->workspace || g->workspace_bytes < L.total)) return JR_ERR_WORKSPACE;
+  char* ws = (char*)g->workspace;
+  const long long npix = (long long)a->W * a->H;
+  const long long total = npix * a->B;
+  if (total * 4 > 0xFFFFFFFFLL) return JR_ERR_DIMS;  // payload packing (gi * 4 + corner) is 32-bit
+  int rc = JR_OK;
+  if (wants_global(g)) {
+    float* partials = (float*)(ws + L.partials);
+    dim3 grid(L.nblk, a->B);
+    k_bwd_global<S><<<grid, BWD_THREADS, 0, stream>>>(*a, *g, partials);
+    g_launches++;
+    GlobalOut out{};
+    auto set = [&](int base, int n, const JrF32Out& t, const int* offs) {
+      for (int j = 0; j < n; ++j) {
+        out.ptr[base + j] = t.ptr ? t.ptr + (offs ? offs[j] : j) : nullptr;
+        out.stride[base + j] = t.batch_stride;
+      }
+    };
+    set(G_W2C, 16, g->d_world_to_clip, nullptr);
+    const int vp_offs[6] = {0, 3, 5, 7, 10, 11};
+    set(G_VP00, 6, g->d_viewport, vp_offs);
+    const int wen_offs[9] = {0, 1, 2, 4, 5, 6, 8, 9, 10};
+    set(G_WEN, 9, g->d_world_to_eye_norm, wen_offs);
+    set(G_LDIR, 3, g->d_light_direction, nullptr);
+    set(G_LCOL, 3, g->d_light_colour, nullptr);
+    set(G_LDE, 3, g->d_light_dir_eye, nullptr);
+    set(G_AMB, 3, g->d_ambient, nullptr);
+    set(G_DIF, 3, g->d_diffuse, nullptr);
+    set(G_SPE, 3, g->d_specular, nullptr);
+    set(G_STR, 3, g->d_shadow_strength, nullptr);
+    k_bwd_global_final<<<1, 64, 0, stream>>>(partials, a->B, L.nblk, out);
+    g_launches++;
+  }
+  if (S >= JR_GOURAUD_TEXTURE && g->d_texture.ptr) {
+    KeyedPlan p{};
+    p.mode = MODE_TEXEL; p.per_pixel = 1; p.n_entries = total;
+    p.keys_per_image = (long long)a->tex_w * a->tex_h;
+    p.batched = g->d_texture.batch_stride != 0;
+    const long long nk = p.keys_per_image * (p.batched ? a->B : 1);
+    if (nk >= 0x7FFFFFFFLL) return JR_ERR_DIMS;
+    p.invalid_key = (unsigned)nk; p.C = 3; p.out = g->d_texture.ptr; p.out2 = nullptr;
+    rc = run_keyed<S, MODE_TEXEL, 3>(a, g, L, p, stream);
+    if (rc != JR_OK) return rc;
+  }
+  if (S >= JR_PHONG_REFLECTION && g->d_specular_map.ptr) {
+    KeyedPlan p{};
+    p.mode = MODE_SPEC; p.per_pixel = 1; p.n_entries = total;
+    p.keys_per_image = (long long)a->spec_w * a->spec_h;
+    p.batched = g->d_specular_map.batch_stride != 0;
+    const long long nk = p.keys_per_image * (p.batched ? a->B : 1);
+    if (nk >= 0x7FFFFFFFLL) return JR_ERR_DIMS;
+    p.invalid_key = (unsigned)nk; p.C = 1; p.out = g->d_specular_map.ptr; p.out2 = nullptr;
+    rc = run_keyed<S, MODE_SPEC, 1>(a, g, L, p, stream);
+    if (rc != JR_OK) return rc;
+  }
+  if (g->d_position.ptr || (S == JR_GOURAUD && g->d_colour.ptr)) {
+    KeyedPlan p{};
+    p.mode = MODE_POS; p.per_pixel = 3; p.n_entries = total * 3;
+    p.keys_per_image = a->n_pos;
+    const long long bs = g->d_position.ptr ? g->d_position.batch_stride : g->d_colour.batch_stride;
+    p.batched = bs != 0;
+    const long long nk = p.keys_per_image * (p.batched ? a->B : 1);
+    if (nk >= 0x7FFFFFFFLL || p.n_entries >= 0x7FFFFFFFLL) return JR_ERR_DIMS;
+    p.invalid_key = (unsigned)nk; p.C = 6;
+    p.out = g->d_position.ptr; p.out2 = (S == JR_GOURAUD) ? g->d_colour.ptr : nullptr;
+    if (!p.out) return JR_ERR_UNSUPPORTED;  // d_colour alone: ask for d_position too
+    rc = run_keyed<S, MODE_POS, 6>(a, g, L, p, stream);
+    if (rc != JR_OK) return rc;
+  }
+  if (S != JR_DEPTH && g->d_normal.ptr) {
+    KeyedPlan p{};
+    p.mode = MODE_NRM; p.per_pixel = 3; p.n_entries = total * 3;
+    p.keys_per_image = a->n_nrm;
+    p.batched = g->d_normal.batch_stride != 0;
+    const long long nk = p.keys_per_image * (p.batched ? a->B : 1);
+    if (nk >= 0x7FFFFFFFLL || p.n_entries >= 0x7FFFFFFFLL) return JR_ERR_DIMS;
+    p.invalid_key = (unsigned)nk; p.C = 3; p.out = g->d_normal.ptr; p.out2 = nullptr;
+    rc = run_keyed<S, MODE_NRM, 3>(a, g, L, p, stream);
+    if (rc != JR_OK) return rc;
+  }
+  // cotangent of the incoming buffers
+  if (g->d_zbuffer || g->d_canvas) {
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148LL * 16) blocks = 148LL * 16;
+    k_bwd_mask<<<(unsigned)blocks, 256, 0, stream>>>(a->tri_id, g->d_zbuffer, S != JR_DEPTH ? g->d_canvas : nullptr,
+                                                     total);
+    g_launches++;
+  }
+  return cudaGetLastError() == cudaSuccess ? JR_OK : JR_ERR_CUDA;
+}
+
+}  // namespace jr
+
+using namespace jr;
+
+extern "C" {
+
+size_t jr_backward_workspace_bytes(const JrRenderArgs* a, const JrGradArgs* g) {
+  if (!a || !g || a->B <= 0 || a->W <= 0 || a->H <= 0) return 0;
+  return bwd_layout(a, g).total;
+}
+
+int jr_render_backward(const JrRenderArgs* a, const JrGradArgs* g, jr_stream_t stream_) {
+  if (!a || !g) return JR_ERR_NULL;
+  if (a->shader < 0 || a->shader >= JR_NUM_SHADERS) return JR_ERR_SHADER;
+  if (a->B <= 0 || a->W <= 0 || a->H <= 0) return JR_ERR_DIMS;
+  if (!a->tri_id || !a->world_to_clip.ptr || !a->viewport.ptr) return JR_ERR_NULL;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  switch (a->shader) {
+    case JR_DEPTH: return backward_impl<JR_DEPTH>(a, g, stream);
+    case JR_GOURAUD: return backward_impl<JR_GOURAUD>(a, g, stream);
+    case JR_GOURAUD_TEXTURE: return backward_impl<JR_GOURAUD_TEXTURE>(a, g, stream);
+    case JR_PHONG: return backward_impl<JR_PHONG>(a, g, stream);
+    case JR_PHONG_REFLECTION: return backward_impl<JR_PHONG_REFLECTION>(a, g, stream);
+    case JR_PHONG_REFLECTION_SHADOW: return backward_impl<JR_PHONG_REFLECTION_SHADOW>(a, g, stream);
+    case JR_PHONG_DARBOUX: return JR_ERR_UNSUPPORTED;  // gradients of the Darboux shader: not yet
+    default: return JR_ERR_SHADER;
+  }
+}
+
+}  // extern "C"

@@ -22,6 +22,7 @@
 #include "../../include/jr_b200.h"
 #include "jr_device.cuh"
 #include "jr_common.cuh"
+#include "jr_shade.cuh"
 
 namespace jr {
 
@@ -182,56 +183,100 @@ k_visibility(const __grid_constant__ JrRenderArgs a, int tile_w, int tile_h, int
     }
   }
   __syncthreads();
-  // large triangles: whole CTA, lanes over pixels (y fastest)
-  const int nbig = min(bigq_n, BIGQ_CAP);
-  for (int e = 0; e < nbig; ++e) {
-    const BigTri& q = bigq[e];
-    const int bh = q.y1 - q.y0 + 1;
-    const int n = (q.x1 - q.x0 + 1) * bh;
-    for (int i = tid; i < n; i += VIS_THREADS) {
-      const int lx = i / bh;
-      const int x = q.x0 + lx, y = q.y0 + (i - lx * bh);
-      const float xn = xs[x];
-      raster_pixel(q.inv, q.zc, xn * q.inv[0], xn * q.inv[1], xn * q.inv[2], ys[y], vp22, vp23, q.tri,
-                   &keys[x * tile_h + y]);
+  // Large triangles: hierarchical, exact.  fl(fl(xn*i0 + yn*i1) + i2) is monotone in
+  // xn and in yn (every rounded op is monotone), so over a block of pixels each
+  // fp32 edge value attains its max / min at one of the 4 block corners: a block
+  // whose corner max is < 0 for some edge contains no inside pixel (skipped), one
+  // whose corner min is >= 0 for all edges is fully inside (edge tests skipped).
+  // One lane classifies one 4x8 block; surviving blocks are rasterised with one
+  // lane per pixel.
+  {
+    const int lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = VIS_THREADS / 32;
+    const int nbig = min(bigq_n, BIGQ_CAP);
+    int unit = 0;  // (entry, round of 32 blocks) work units, dealt round-robin to the warps
+    for (int e = 0; e < nbig; ++e) {
+      const BigTri& q = bigq[e];
+      const int bw = q.x1 - q.x0 + 1, bh = q.y1 - q.y0 + 1;
+      const int nby = (bh + 7) >> 3;
+      const int nblk = ((bw + 3) >> 2) * nby;
+      for (int base = 0; base < nblk; base += 32, ++unit) {
+        if (unit % NW != warp) continue;
+        const int blk = base + lane;
+        bool live = false, full = false;
+        int xa = 0, ya = 0;
+        if (blk < nblk) {
+          const int bx = blk / nby, by = blk - bx * nby;
+          xa = q.x0 + 4 * bx; ya = q.y0 + 8 * by;
+          const int xb = min(xa + 3, (int)q.x1), yb = min(ya + 7, (int)q.y1);
+          const float xna = xs[xa], xnb = xs[xb], yna = ys[ya], ynb = ys[yb];
+          live = true; full = true;
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const float pa = xna * q.inv[k], pb = xnb * q.inv[k];
+            const float qa = yna * q.inv[3 + k], qb = ynb * q.inv[3 + k];
+            const float v0 = (pa + qa) + q.inv[6 + k], v1 = (pa + qb) + q.inv[6 + k];
+            const float v2 = (pb + qa) + q.inv[6 + k], v3 = (pb + qb) + q.inv[6 + k];
+            live = live && (fmaxf(fmaxf(v0, v1), fmaxf(v2, v3)) >= 0.f);
+            full = full && (v0 >= 0.f) && (v1 >= 0.f) && (v2 >= 0.f) && (v3 >= 0.f);
+          }
+        }
+        unsigned m_live = __ballot_sync(0xffffffffu, live);
+        const unsigned m_full = __ballot_sync(0xffffffffu, full);
+        const int xy = (xa << 16) | ya;
+        while (m_live) {
+          const int j = __ffs(m_live) - 1;
+          m_live &= m_live - 1;
+          const int xyj = __shfl_sync(0xffffffffu, xy, j);
+          const int x = (xyj >> 16) + (lane >> 3), y = (xyj & 0xffff) + (lane & 7);
+          if (x <= q.x1 && y <= q.y1) {
+            const float xn = xs[x], yn = ys[y];
+            const float c0 = (xn * q.inv[0] + yn * q.inv[3]) + q.inv[6];
+            const float c1 = (xn * q.inv[1] + yn * q.inv[4]) + q.inv[7];
+            const float c2 = (xn * q.inv[2] + yn * q.inv[5]) + q.inv[8];
+            if (((m_full >> j) & 1u) || (c0 >= 0.f && c1 >= 0.f && c2 >= 0.f)) {
+              const float z = (c0 * q.zc[0] + c1 * q.zc[1]) + c2 * q.zc[2];
+              const float zw = z * vp22 + vp23;
+              const unsigned long long key = ((unsigned long long)orderable(zw) << 32) | (unsigned)q.tri;
+              unsigned long long* slot = &keys[x * tile_h + y];
+              if (key < *slot) atomicMin(slot, key);
+            }
+          }
+        }
+      }
     }
   }
   __syncthreads();
-  // resolve
+  // resolve (flat index walked without integer division: VIS_THREADS = dq*th + dr)
   int32_t* __restrict__ tri_out = a.tri_id ? a.tri_id + (long long)b * a.W * a.H : nullptr;
   float* __restrict__ z_out = DEPTH ? a.zbuffer + (long long)b * a.W * a.H : nullptr;
   const bool use0 = DEPTH && tri0_flag;
-  for (int i = tid; i < tw * th; i += VIS_THREADS) {
-    const int lx = i / th, ly = i - lx * th;
-    const unsigned long long key = keys[lx * tile_h + ly];
-    const long long pix = (long long)(tx0 + lx) * a.H + (ty0 + ly);
-    int tri = -1;
-    if (key != EMPTY_KEY) {
-      tri = (int)(unsigned)(key & 0xFFFFFFFFull);
-      if (DEPTH) z_out[pix] = from_orderable((uint32_t)(key >> 32));
-    } else if (use0) {
-      float c[3];
-      clip_coef(tri0.inv, xs[lx], ys[ly], c);
-      if (c[0] >= 0.f && c[1] >= 0.f && c[2] >= 0.f) {
-        const float z = (c[0] * tri0.zc[0] + c[1] * tri0.zc[1]) + c[2] * tri0.zc[2];
-        z_out[pix] = z * vp22 + vp23;
-        tri = 0;
+  {
+    const int dq = VIS_THREADS / th, dr = VIS_THREADS - dq * th;
+    int lx = tid / th, ly = tid - lx * th;
+    for (; lx < tw; lx += dq, ly += dr) {
+      if (ly >= th) { ly -= th; ++lx; if (lx >= tw) break; }
+      const unsigned long long key = keys[lx * tile_h + ly];
+      const long long pix = (long long)(tx0 + lx) * a.H + (ty0 + ly);
+      int tri = -1;
+      if (key != EMPTY_KEY) {
+        tri = (int)(unsigned)(key & 0xFFFFFFFFull);
+        if (DEPTH) z_out[pix] = from_orderable((uint32_t)(key >> 32));
+      } else if (use0) {
+        float c[3];
+        clip_coef(tri0.inv, xs[lx], ys[ly], c);
+        if (c[0] >= 0.f && c[1] >= 0.f && c[2] >= 0.f) {
+          const float z = (c[0] * tri0.zc[0] + c[1] * tri0.zc[1]) + c[2] * tri0.zc[2];
+          z_out[pix] = z * vp22 + vp23;
+          tri = 0;
+        }
       }
+      if (tri_out) tri_out[pix] = tri;
     }
-    if (tri_out) tri_out[pix] = tri;
   }
 }
 
 // --------------------------------------------------------------------- shading
-struct Light3 { float v[3]; };
-__device__ __forceinline__ void load3(const JrF32& arr, int b, float out[3]) {
-  const float* p = arr.ptr + (long long)b * arr.batch_stride;
-  out[0] = p[0]; out[1] = p[1]; out[2] = p[2];
-}
-__device__ __forceinline__ Vec3 loadv3(const float* p, int i) {
-  return Vec3{p[3 * i], p[3 * i + 1], p[3 * i + 2]};
-}
-
 template <int SHADER>
 __global__ void __launch_bounds__(256) k_shade(const __grid_constant__ JrRenderArgs a) {
   const long long npix = (long long)a.W * a.H;
@@ -243,224 +288,12 @@ __global__ void __launch_bounds__(256) k_shade(const __grid_constant__ JrRenderA
     const int tri = a.tri_id[gi];
     if (tri < 0) continue;
     const int x = pix / a.H, y = pix - x * a.H;
-
-    const float* __restrict__ w2c = a.world_to_clip.ptr + (long long)b * a.world_to_clip.batch_stride;
-    const float* __restrict__ vp = a.viewport.ptr + (long long)b * a.viewport.batch_stride;
-    const float* __restrict__ pos = a.position.ptr + (long long)b * a.position.batch_stride;
-    const int32_t* __restrict__ faces = a.faces.ptr + (long long)b * a.faces.batch_stride;
-    const int fi[3] = {faces[3 * tri], faces[3 * tri + 1], faces[3 * tri + 2]};
-    float cl[3][4];
-    Vec3 P[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      P[k] = loadv3(pos, fi[k]);
-      to_clip(w2c, P[k].x, P[k].y, P[k].z, cl[k]);
-    }
-    float M[9], inv[9];
-    tri_matrix(cl[0], cl[1], cl[2], M);
-    lu_inverse3(M, inv);
-    const float xn = ((float)x - vp[3]) / vp[0];
-    const float yn = ((float)y - vp[7]) / vp[5];
-    float cc[3];
-    clip_coef(inv, xn, yn, cc);
-    const float w_rec = (cc[0] + cc[1]) + cc[2];
-    const float z = (cc[0] * cl[0][2] + cc[1] * cl[1][2]) + cc[2] * cl[2][2];
-    const float zw = z * vp[10] + vp[11];
-    const float tc[3] = {cc[0] / w_rec, cc[1] / w_rec, cc[2] / w_rec};
-
-    float col[3] = {0.f, 0.f, 0.f};
-    bool keep = true;
-
-    // index rows for the other attributes (NULL -> faces)
-    int fn[3] = {fi[0], fi[1], fi[2]}, fu[3] = {fi[0], fi[1], fi[2]};
-    if (SHADER != JR_DEPTH) {
-      if (a.faces_norm.ptr) {
-        const int32_t* f = a.faces_norm.ptr + (long long)b * a.faces_norm.batch_stride + 3 * tri;
-        fn[0] = f[0]; fn[1] = f[1]; fn[2] = f[2];
-      }
-      if (a.faces_uv.ptr) {
-        const int32_t* f = a.faces_uv.ptr + (long long)b * a.faces_uv.batch_stride + 3 * tri;
-        fu[0] = f[0]; fu[1] = f[1]; fu[2] = f[2];
-      }
-    }
-
-    if (SHADER == JR_GOURAUD || SHADER == JR_GOURAUD_TEXTURE) {
-      float ld[3], lcol[3];
-      load3(a.light_direction, b, ld);
-      load3(a.light_colour, b, lcol);
-      const Vec3 nl = normalise3(Vec3{ld[0], ld[1], ld[2]});
-      const float* __restrict__ nrm = a.normal.ptr + (long long)b * a.normal.batch_stride;
-      float inten[3];
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const Vec3 n = normalise3(loadv3(nrm, fn[k]));
-        inten[k] = dot3(n.x, n.y, n.z, nl.x, nl.y, nl.z);
-      }
-      if (SHADER == JR_GOURAUD) {
-        const float* __restrict__ cv = a.colour.ptr + (long long)b * a.colour.batch_stride;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const float v0 = (cv[3 * fi[0] + c] * lcol[c]) * inten[0];
-          const float v1 = (cv[3 * fi[1] + c] * lcol[c]) * inten[1];
-          const float v2 = (cv[3 * fi[2] + c] * lcol[c]) * inten[2];
-          col[c] = interp3(tc, v0, v1, v2);
-          keep = keep && (col[c] >= 0.f);
-        }
-      } else {
-        const float* __restrict__ uvp = a.uv.ptr + (long long)b * a.uv.batch_stride;
-        const float* __restrict__ tex = a.texture.ptr + (long long)b * a.texture.batch_stride;
-        const float u = interp3(tc, uvp[2 * fu[0]], uvp[2 * fu[1]], uvp[2 * fu[2]]);
-        const float v = interp3(tc, uvp[2 * fu[0] + 1], uvp[2 * fu[1] + 1], uvp[2 * fu[2] + 1]);
-        const int ui = pymod((int)floorf(u), a.tex_w), vi = pymod((int)floorf(v), a.tex_h);
-        const float* texel = tex + ((long long)ui * a.tex_h + vi) * 3;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const float lc = interp3(tc, lcol[c] * inten[0], lcol[c] * inten[1], lcol[c] * inten[2]);
-          keep = keep && (lc >= 0.f);
-          col[c] = texel[c] * lc;
-        }
-      }
-    } else if (SHADER >= JR_PHONG) {
-      const float* __restrict__ wen = a.world_to_eye_norm.ptr + (long long)b * a.world_to_eye_norm.batch_stride;
-      const float* __restrict__ nrm = a.normal.ptr + (long long)b * a.normal.batch_stride;
-      const float* __restrict__ uvp = a.uv.ptr + (long long)b * a.uv.batch_stride;
-      const float* __restrict__ tex = a.texture.ptr + (long long)b * a.texture.batch_stride;
-      Vec3 nv[3];
-#pragma unroll
-      for (int k = 0; k < 3; ++k) nv[k] = apply_vec(wen, normalise3(loadv3(nrm, fn[k])));
-      const Vec3 normal = {interp3(tc, nv[0].x, nv[1].x, nv[2].x), interp3(tc, nv[0].y, nv[1].y, nv[2].y),
-                           interp3(tc, nv[0].z, nv[1].z, nv[2].z)};
-      const float u = interp3(tc, uvp[2 * fu[0]], uvp[2 * fu[1]], uvp[2 * fu[2]]);
-      const float v = interp3(tc, uvp[2 * fu[0] + 1], uvp[2 * fu[1] + 1], uvp[2 * fu[2] + 1]);
-      Vec3 nn = normalise3(normal);
-      float lcol[3];
-      load3(a.light_colour, b, lcol);
-
-      if (SHADER == JR_PHONG || SHADER == JR_PHONG_DARBOUX) {
-        float ld[3];
-        load3(a.light_direction, b, ld);
-        const Vec3 nl = normalise3(Vec3{ld[0], ld[1], ld[2]});
-        const int ui = pymod((int)floorf(u), a.tex_w), vi = pymod((int)floorf(v), a.tex_h);
-        if (SHADER == JR_PHONG_DARBOUX) {
-          // phong_darboux.py:144-151, :231-262
-          const int32_t* __restrict__ i2f = a.id_to_face.ptr + (long long)b * a.id_to_face.batch_stride;
-          const int32_t* __restrict__ fidx = a.faces_indices.ptr + (long long)b * a.faces_indices.batch_stride;
-          const int face = i2f[fi[0]];
-          float tr[3][3], tuv[3][2];
-#pragma unroll
-          for (int k = 0; k < 3; ++k) {
-            const int vtx = fidx[3 * face + k];
-            float tcq[4];
-            to_clip(w2c, pos[3 * vtx], pos[3 * vtx + 1], pos[3 * vtx + 2], tcq);
-            const bool w0 = tcq[3] == 0.0f;
-            tr[k][0] = w0 ? tcq[0] : tcq[0] / tcq[3];
-            tr[k][1] = w0 ? tcq[1] : tcq[1] / tcq[3];
-            tr[k][2] = w0 ? tcq[2] : tcq[2] / tcq[3];
-            tuv[k][0] = uvp[2 * vtx]; tuv[k][1] = uvp[2 * vtx + 1];
-          }
-          const float A[9] = {tr[1][0] - tr[0][0], tr[1][1] - tr[0][1], tr[1][2] - tr[0][2],
-                              tr[2][0] - tr[0][0], tr[2][1] - tr[0][1], tr[2][2] - tr[0][2],
-                              nn.x, nn.y, nn.z};
-          float AI[9];
-          lu_inverse3(A, AI);
-          const float du0 = tuv[1][0] - tuv[0][0], du1 = tuv[2][0] - tuv[0][0];
-          const float dv0 = tuv[1][1] - tuv[0][1], dv1 = tuv[2][1] - tuv[0][1];
-          const Vec3 iv = normalise3(Vec3{AI[0] * du0 + AI[1] * du1, AI[3] * du0 + AI[4] * du1,
-                                          AI[6] * du0 + AI[7] * du1});
-          const Vec3 jv = normalise3(Vec3{AI[0] * dv0 + AI[1] * dv1, AI[3] * dv0 + AI[4] * dv1,
-                                          AI[6] * dv0 + AI[7] * dv1});
-          const float* nm = a.normal_map.ptr + (long long)b * a.normal_map.batch_stride +
-                            ((long long)ui * a.tex_h + vi) * 3;
-          const Vec3 bn = {(iv.x * nm[0] + jv.x * nm[1]) + nn.x * nm[2],
-                           (iv.y * nm[0] + jv.y * nm[1]) + nn.y * nm[2],
-                           (iv.z * nm[0] + jv.z * nm[1]) + nn.z * nm[2]};
-          nn = normalise3(bn);
-        }
-        const float ndl = dot3(nn.x, nn.y, nn.z, nl.x, nl.y, nl.z);
-        const float* texel = tex + ((long long)ui * a.tex_h + vi) * 3;
-        float lc[3];
-        bool ok = true;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) { lc[c] = lcol[c] * ndl; ok = ok && (lc[c] >= 0.f); }
-#pragma unroll
-        for (int c = 0; c < 3; ++c) col[c] = ok ? texel[c] * lc[c] : 0.f;
-      } else {
-        // phong_reflection.py:175-220, phong_reflection_shadow.py:196-257
-        const int32_t* __restrict__ ftp =
-            a.faces_tex.ptr ? a.faces_tex.ptr + (long long)b * a.faces_tex.batch_stride + 3 * tri : nullptr;
-        const int tv = ftp ? ftp[0] : fi[0];
-        const int ti = (a.texture_index.ptr + (long long)b * a.texture_index.batch_stride)[tv];
-        const int32_t* tsh = a.texture_shape.ptr + (long long)b * a.texture_shape.batch_stride + 2 * ti;
-        float fu0 = u - truncf(u), fv0 = v - truncf(v);
-        if (fu0 < 0.f) fu0 = fu0 + 1.f;
-        if (fv0 < 0.f) fv0 = fv0 + 1.f;
-        const float ur = fu0 * (float)tsh[0] + (float)(ti * a.texture_offset);
-        const float vr = fv0 * (float)tsh[1];
-        const int U = (int)floorf(ur), V = (int)floorf(vr);
-        const float* texel = tex + ((long long)wrap_clamp(U, a.tex_w) * a.tex_h + wrap_clamp(V, a.tex_h)) * 3;
-        float lde[3], amb[3], dif[3], spe[3];
-        load3(a.light_dir_eye, b, lde);
-        load3(a.ambient, b, amb);
-        load3(a.diffuse, b, dif);
-        load3(a.specular, b, spe);
-        const Vec3 ld = normalise3(Vec3{lde[0], lde[1], lde[2]});
-        const float ndl = dot3(nn.x, nn.y, nn.z, ld.x, ld.y, ld.z);
-        const float diffuse = fmaxf(ndl, 0.f);
-        const float two_ndl = 2.f * ndl;
-        const Vec3 refl = normalise3(Vec3{two_ndl * nn.x - ld.x, two_ndl * nn.y - ld.y, two_ndl * nn.z - ld.z});
-        const float sexp = (a.specular_map.ptr + (long long)b * a.specular_map.batch_stride)
-            [(long long)wrap_clamp(U, a.spec_w) * a.spec_h + wrap_clamp(V, a.spec_h)];
-        const float specular = powf(fmaxf(refl.z, 0.f), sexp);
-        float shadow[3] = {1.f, 1.f, 1.f};
-        if (SHADER == JR_PHONG_REFLECTION_SHADOW) {
-          const float* __restrict__ sw2c = a.shadow_world_to_clip.ptr + (long long)b * a.shadow_world_to_clip.batch_stride;
-          const float* __restrict__ svp = a.shadow_viewport.ptr + (long long)b * a.shadow_viewport.batch_stride;
-          float scv[3][4];
-#pragma unroll
-          for (int k = 0; k < 3; ++k) {
-            float s[4];
-            to_clip(sw2c, P[k].x, P[k].y, P[k].z, s);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) scv[k][j] = s[j] / s[3];
-          }
-          float sc[4], ss[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) sc[j] = interp3(tc, scv[0][j], scv[1][j], scv[2][j]);
-#pragma unroll
-          for (int r = 0; r < 4; ++r)
-            ss[r] = ((svp[4 * r] * sc[0] + svp[4 * r + 1] * sc[1]) + svp[4 * r + 2] * sc[2]) + svp[4 * r + 3] * sc[3];
-          const float sx = ss[0] / ss[3], sy = ss[1] / ss[3], sz = ss[2] / ss[3];
-          // Shadow.get (shadow.py:129-153)
-          float rx = roundf(sx), ry = roundf(sy);
-          rx = fminf(fmaxf(rx, -1e9f), 1e9f);
-          ry = fminf(fmaxf(ry, -1e9f), 1e9f);
-          int px = (int)rx, py = (int)ry;
-          if (px < 0) px += a.shadow_w;
-          if (py < 0) py += a.shadow_h;
-          float sval = __int_as_float(0x7f800000);
-          if (px >= 0 && px < a.shadow_w && py >= 0 && py < a.shadow_h && rx == rx && ry == ry)
-            sval = (a.shadow_map.ptr + (long long)b * a.shadow_map.batch_stride)[(long long)px * a.shadow_h + py];
-          const bool lit = sz <= sval;
-          float str[3];
-          load3(a.shadow_strength, b, str);
-#pragma unroll
-          for (int c = 0; c < 3; ++c) shadow[c] = lit ? 1.f : 1.f - str[c];
-        }
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const float ds = dif[c] * diffuse + spe[c] * specular;
-          if (SHADER == JR_PHONG_REFLECTION)
-            col[c] = amb[c] * texel[c] + (ds * lcol[c]) * texel[c];
-          else
-            col[c] = amb[c] * texel[c] + ((shadow[c] * ds) * texel[c]) * lcol[c];
-        }
-      }
-    }
-
-    if (keep) {
-      a.zbuffer[gi] = zw;
+    Frag f;
+    shade_pixel<SHADER>(a, b, x, y, tri, f);
+    if (f.keep) {
+      a.zbuffer[gi] = f.zw;
       float* o = a.canvas + gi * 3;
-      o[0] = col[0]; o[1] = col[1]; o[2] = col[2];
+      o[0] = f.col[0]; o[1] = f.col[1]; o[2] = f.col[2];
     } else {
       a.tri_id[gi] = -1;
     }

@@ -1,0 +1,289 @@
+// jr_shade.cuh -- per-pixel interpolate + fragment + mix of the seven built-in
+// shaders (reference renderer/shaders/*.py), shared by the forward shading kernel
+// and the backward kernels so that both see bit-identical discrete decisions
+// (texel choice, shadow test, keep).  Operation order mirrors oracle/jr_oracle.py.
+#pragma once
+#include "../../include/jr_b200.h"
+#include "jr_device.cuh"
+
+namespace jr {
+
+__device__ __forceinline__ void load3(const JrF32& arr, int b, float out[3]) {
+  const float* p = arr.ptr + (long long)b * arr.batch_stride;
+  out[0] = p[0]; out[1] = p[1]; out[2] = p[2];
+}
+__device__ __forceinline__ Vec3 loadv3(const float* p, int i) {
+  return Vec3{p[3 * i], p[3 * i + 1], p[3 * i + 2]};
+}
+
+// Everything the fragment stage computed for one pixel (kept for backward).
+struct Frag {
+  int fi[3], fn[3], fu[3];     // vertex ids of the chosen triangle: position / normal / uv rows
+  Vec3 P[3];                   // world positions
+  float cl[3][4];              // clip positions (gl_Position)
+  float inv[9];                // PerPrimitive.matrix_inv
+  float xn, yn;                // pixel in NDC
+  float cc[3], w_rec, z, zw;   // clip_coef, 1/w, z_ndc, gl_FragCoord.z
+  float tc[3];                 // true_clip_coef (perspective-correct weights)
+  float col[3];
+  bool keep;
+  // shader intermediates
+  float lcol[3];
+  float inten[3];              // S2,S3: n_k . nl
+  Vec3 nraw[3];                // raw per-vertex normals
+  Vec3 nvert[3];               // S2,S3: normalise(n_k);  S4-S7: eye-space vertex normals
+  Vec3 mvert[3], tvert[3];     // S4-S7: m = normalise(normalise(n_k)), t = R m (before the last normalise)
+  Vec3 nl;                     // normalised light direction (S2-S5) / light_dir_eye (S6,S7)
+  float lraw[3];               // raw light vector that was normalised into nl
+  float lc[3];                 // S3: interpolated light colour; S4,S5: lcol * ndl
+  long long texel;             // linear texel index (u * tex_h + v), -1 if none
+  long long spec_idx;          // linear index into specular_map (S6,S7)
+  float tex[3];
+  Vec3 normal, nn;             // interpolated normal and its normalisation
+  float ndl;
+  bool ok;                     // S4,S5: all(lc >= 0)
+  float diffuse, specular, sexp, base;
+  Vec3 rv;                     // 2 ndl nn - ld (before normalise)
+  float ds[3], shadow[3], amb[3], dif[3], spe[3], str[3];
+  bool lit;
+};
+
+// Common part: setup of triangle `tri` of image b and the pixel's weights.
+__device__ __forceinline__ void frag_setup(const JrRenderArgs& a, int b, int x, int y, int tri, Frag& f) {
+  const float* __restrict__ w2c = a.world_to_clip.ptr + (long long)b * a.world_to_clip.batch_stride;
+  const float* __restrict__ vp = a.viewport.ptr + (long long)b * a.viewport.batch_stride;
+  const float* __restrict__ pos = a.position.ptr + (long long)b * a.position.batch_stride;
+  const int32_t* __restrict__ faces = a.faces.ptr + (long long)b * a.faces.batch_stride;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    f.fi[k] = faces[3 * tri + k];
+    f.P[k] = loadv3(pos, f.fi[k]);
+    to_clip(w2c, f.P[k].x, f.P[k].y, f.P[k].z, f.cl[k]);
+  }
+  float M[9];
+  tri_matrix(f.cl[0], f.cl[1], f.cl[2], M);
+  lu_inverse3(M, f.inv);
+  f.xn = ((float)x - vp[3]) / vp[0];
+  f.yn = ((float)y - vp[7]) / vp[5];
+  clip_coef(f.inv, f.xn, f.yn, f.cc);
+  f.w_rec = (f.cc[0] + f.cc[1]) + f.cc[2];
+  f.z = (f.cc[0] * f.cl[0][2] + f.cc[1] * f.cl[1][2]) + f.cc[2] * f.cl[2][2];
+  f.zw = f.z * vp[10] + vp[11];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) f.tc[k] = f.cc[k] / f.w_rec;
+}
+
+template <int SHADER>
+__device__ __forceinline__ void shade_pixel(const JrRenderArgs& a, int b, int x, int y, int tri, Frag& f) {
+  frag_setup(a, b, x, y, tri, f);
+  const float* tc = f.tc;
+  f.col[0] = f.col[1] = f.col[2] = 0.f;
+  f.keep = true;
+  f.texel = -1;
+  f.spec_idx = -1;
+  if (SHADER == JR_DEPTH) return;
+
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { f.fn[k] = f.fi[k]; f.fu[k] = f.fi[k]; }
+  if (a.faces_norm.ptr) {
+    const int32_t* q = a.faces_norm.ptr + (long long)b * a.faces_norm.batch_stride + 3 * tri;
+    f.fn[0] = q[0]; f.fn[1] = q[1]; f.fn[2] = q[2];
+  }
+  if (a.faces_uv.ptr) {
+    const int32_t* q = a.faces_uv.ptr + (long long)b * a.faces_uv.batch_stride + 3 * tri;
+    f.fu[0] = q[0]; f.fu[1] = q[1]; f.fu[2] = q[2];
+  }
+  const float* __restrict__ nrm = a.normal.ptr + (long long)b * a.normal.batch_stride;
+  load3(a.light_colour, b, f.lcol);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) f.nraw[k] = loadv3(nrm, f.fn[k]);
+
+  if (SHADER == JR_GOURAUD || SHADER == JR_GOURAUD_TEXTURE) {
+    load3(a.light_direction, b, f.lraw);
+    f.nl = normalise3(Vec3{f.lraw[0], f.lraw[1], f.lraw[2]});
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      f.nvert[k] = normalise3(f.nraw[k]);
+      f.inten[k] = dot3(f.nvert[k].x, f.nvert[k].y, f.nvert[k].z, f.nl.x, f.nl.y, f.nl.z);
+    }
+    if (SHADER == JR_GOURAUD) {
+      const float* __restrict__ cv = a.colour.ptr + (long long)b * a.colour.batch_stride;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float v0 = (cv[3 * f.fi[0] + c] * f.lcol[c]) * f.inten[0];
+        const float v1 = (cv[3 * f.fi[1] + c] * f.lcol[c]) * f.inten[1];
+        const float v2 = (cv[3 * f.fi[2] + c] * f.lcol[c]) * f.inten[2];
+        f.col[c] = interp3(tc, v0, v1, v2);
+        f.keep = f.keep && (f.col[c] >= 0.f);
+      }
+    } else {
+      const float* __restrict__ uvp = a.uv.ptr + (long long)b * a.uv.batch_stride;
+      const float* __restrict__ tex = a.texture.ptr + (long long)b * a.texture.batch_stride;
+      const float u = interp3(tc, uvp[2 * f.fu[0]], uvp[2 * f.fu[1]], uvp[2 * f.fu[2]]);
+      const float v = interp3(tc, uvp[2 * f.fu[0] + 1], uvp[2 * f.fu[1] + 1], uvp[2 * f.fu[2] + 1]);
+      const int ui = pymod((int)floorf(u), a.tex_w), vi = pymod((int)floorf(v), a.tex_h);
+      f.texel = (long long)ui * a.tex_h + vi;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        f.tex[c] = tex[f.texel * 3 + c];
+        f.lc[c] = interp3(tc, f.lcol[c] * f.inten[0], f.lcol[c] * f.inten[1], f.lcol[c] * f.inten[2]);
+        f.keep = f.keep && (f.lc[c] >= 0.f);
+        f.col[c] = f.tex[c] * f.lc[c];
+      }
+    }
+    return;
+  }
+
+  // ---- S4-S7: eye-space normals (phong.py:92-103)
+  const float* __restrict__ wen = a.world_to_eye_norm.ptr + (long long)b * a.world_to_eye_norm.batch_stride;
+  const float* __restrict__ uvp = a.uv.ptr + (long long)b * a.uv.batch_stride;
+  const float* __restrict__ tex = a.texture.ptr + (long long)b * a.texture.batch_stride;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    // Camera.apply_vec(normalise(n), wen): normalise twice, rotate, normalise
+    const Vec3 m = normalise3(normalise3(f.nraw[k]));
+    Vec3 t;
+    t.x = (m.x * wen[0] + m.y * wen[1]) + m.z * wen[2];
+    t.y = (m.x * wen[4] + m.y * wen[5]) + m.z * wen[6];
+    t.z = (m.x * wen[8] + m.y * wen[9]) + m.z * wen[10];
+    f.mvert[k] = m; f.tvert[k] = t;
+    f.nvert[k] = normalise3(t);
+  }
+  f.normal = Vec3{interp3(tc, f.nvert[0].x, f.nvert[1].x, f.nvert[2].x),
+                  interp3(tc, f.nvert[0].y, f.nvert[1].y, f.nvert[2].y),
+                  interp3(tc, f.nvert[0].z, f.nvert[1].z, f.nvert[2].z)};
+  const float u = interp3(tc, uvp[2 * f.fu[0]], uvp[2 * f.fu[1]], uvp[2 * f.fu[2]]);
+  const float v = interp3(tc, uvp[2 * f.fu[0] + 1], uvp[2 * f.fu[1] + 1], uvp[2 * f.fu[2] + 1]);
+  f.nn = normalise3(f.normal);
+
+  if (SHADER == JR_PHONG || SHADER == JR_PHONG_DARBOUX) {
+    load3(a.light_direction, b, f.lraw);
+    f.nl = normalise3(Vec3{f.lraw[0], f.lraw[1], f.lraw[2]});
+    const int ui = pymod((int)floorf(u), a.tex_w), vi = pymod((int)floorf(v), a.tex_h);
+    f.texel = (long long)ui * a.tex_h + vi;
+    Vec3 nn = f.nn;
+    if (SHADER == JR_PHONG_DARBOUX) {
+      // phong_darboux.py:144-151, :231-262
+      const float* __restrict__ w2c = a.world_to_clip.ptr + (long long)b * a.world_to_clip.batch_stride;
+      const float* __restrict__ pos = a.position.ptr + (long long)b * a.position.batch_stride;
+      const int32_t* __restrict__ i2f = a.id_to_face.ptr + (long long)b * a.id_to_face.batch_stride;
+      const int32_t* __restrict__ fidx = a.faces_indices.ptr + (long long)b * a.faces_indices.batch_stride;
+      const int face = i2f[f.fi[0]];
+      float tr[3][3], tuv[3][2];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int vtx = fidx[3 * face + k];
+        float tcq[4];
+        to_clip(w2c, pos[3 * vtx], pos[3 * vtx + 1], pos[3 * vtx + 2], tcq);
+        const bool w0 = tcq[3] == 0.0f;
+        tr[k][0] = w0 ? tcq[0] : tcq[0] / tcq[3];
+        tr[k][1] = w0 ? tcq[1] : tcq[1] / tcq[3];
+        tr[k][2] = w0 ? tcq[2] : tcq[2] / tcq[3];
+        tuv[k][0] = uvp[2 * vtx]; tuv[k][1] = uvp[2 * vtx + 1];
+      }
+      const float A[9] = {tr[1][0] - tr[0][0], tr[1][1] - tr[0][1], tr[1][2] - tr[0][2],
+                          tr[2][0] - tr[0][0], tr[2][1] - tr[0][1], tr[2][2] - tr[0][2],
+                          nn.x, nn.y, nn.z};
+      float AI[9];
+      lu_inverse3(A, AI);
+      const float du0 = tuv[1][0] - tuv[0][0], du1 = tuv[2][0] - tuv[0][0];
+      const float dv0 = tuv[1][1] - tuv[0][1], dv1 = tuv[2][1] - tuv[0][1];
+      const Vec3 iv = normalise3(Vec3{AI[0] * du0 + AI[1] * du1, AI[3] * du0 + AI[4] * du1,
+                                      AI[6] * du0 + AI[7] * du1});
+      const Vec3 jv = normalise3(Vec3{AI[0] * dv0 + AI[1] * dv1, AI[3] * dv0 + AI[4] * dv1,
+                                      AI[6] * dv0 + AI[7] * dv1});
+      const float* nm = a.normal_map.ptr + (long long)b * a.normal_map.batch_stride + f.texel * 3;
+      const Vec3 bn = {(iv.x * nm[0] + jv.x * nm[1]) + nn.x * nm[2],
+                       (iv.y * nm[0] + jv.y * nm[1]) + nn.y * nm[2],
+                       (iv.z * nm[0] + jv.z * nm[1]) + nn.z * nm[2]};
+      nn = normalise3(bn);
+    }
+    f.ndl = dot3(nn.x, nn.y, nn.z, f.nl.x, f.nl.y, f.nl.z);
+    f.ok = true;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      f.tex[c] = tex[f.texel * 3 + c];
+      f.lc[c] = f.lcol[c] * f.ndl;
+      f.ok = f.ok && (f.lc[c] >= 0.f);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) f.col[c] = f.ok ? f.tex[c] * f.lc[c] : 0.f;
+    return;
+  }
+
+  // ---- S6 / S7 (phong_reflection.py:175-220, phong_reflection_shadow.py:196-257)
+  const int32_t* __restrict__ ftp =
+      a.faces_tex.ptr ? a.faces_tex.ptr + (long long)b * a.faces_tex.batch_stride + 3 * tri : nullptr;
+  const int tv = ftp ? ftp[0] : f.fi[0];
+  const int ti = (a.texture_index.ptr + (long long)b * a.texture_index.batch_stride)[tv];
+  const int32_t* tsh = a.texture_shape.ptr + (long long)b * a.texture_shape.batch_stride + 2 * ti;
+  float fu0 = u - truncf(u), fv0 = v - truncf(v);  // jnp.modf(uv)[0]
+  if (fu0 < 0.f) fu0 = fu0 + 1.f;
+  if (fv0 < 0.f) fv0 = fv0 + 1.f;
+  const float ur = fu0 * (float)tsh[0] + (float)(ti * a.texture_offset);
+  const float vr = fv0 * (float)tsh[1];
+  const int U = (int)floorf(ur), V = (int)floorf(vr);
+  f.texel = (long long)wrap_clamp(U, a.tex_w) * a.tex_h + wrap_clamp(V, a.tex_h);
+  f.spec_idx = (long long)wrap_clamp(U, a.spec_w) * a.spec_h + wrap_clamp(V, a.spec_h);
+  load3(a.light_dir_eye, b, f.lraw);
+  load3(a.ambient, b, f.amb);
+  load3(a.diffuse, b, f.dif);
+  load3(a.specular, b, f.spe);
+  f.nl = normalise3(Vec3{f.lraw[0], f.lraw[1], f.lraw[2]});
+  const Vec3 nn = f.nn, ld = f.nl;
+  f.ndl = dot3(nn.x, nn.y, nn.z, ld.x, ld.y, ld.z);
+  f.diffuse = fmaxf(f.ndl, 0.f);
+  const float two_ndl = 2.f * f.ndl;
+  f.rv = Vec3{two_ndl * nn.x - ld.x, two_ndl * nn.y - ld.y, two_ndl * nn.z - ld.z};
+  const Vec3 refl = normalise3(f.rv);
+  f.sexp = (a.specular_map.ptr + (long long)b * a.specular_map.batch_stride)[f.spec_idx];
+  f.base = fmaxf(refl.z, 0.f);
+  f.specular = powf(f.base, f.sexp);
+  f.shadow[0] = f.shadow[1] = f.shadow[2] = 1.f;
+  f.lit = true;
+  if (SHADER == JR_PHONG_REFLECTION_SHADOW) {
+    const float* __restrict__ sw2c = a.shadow_world_to_clip.ptr + (long long)b * a.shadow_world_to_clip.batch_stride;
+    const float* __restrict__ svp = a.shadow_viewport.ptr + (long long)b * a.shadow_viewport.batch_stride;
+    float scv[3][4];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      float s[4];
+      to_clip(sw2c, f.P[k].x, f.P[k].y, f.P[k].z, s);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) scv[k][j] = s[j] / s[3];
+    }
+    float sc[4], ss[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sc[j] = interp3(tc, scv[0][j], scv[1][j], scv[2][j]);
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      ss[r] = ((svp[4 * r] * sc[0] + svp[4 * r + 1] * sc[1]) + svp[4 * r + 2] * sc[2]) + svp[4 * r + 3] * sc[3];
+    const float sx = ss[0] / ss[3], sy = ss[1] / ss[3], sz = ss[2] / ss[3];
+    // Shadow.get (shadow.py:129-153): round half away, one negative wrap, OOB -> +inf
+    float rx = roundf(sx), ry = roundf(sy);
+    const bool finite = (rx == rx) && (ry == ry);
+    rx = fminf(fmaxf(rx, -1e9f), 1e9f);
+    ry = fminf(fmaxf(ry, -1e9f), 1e9f);
+    int px = (int)rx, py = (int)ry;
+    if (px < 0) px += a.shadow_w;
+    if (py < 0) py += a.shadow_h;
+    float sval = __int_as_float(0x7f800000);
+    if (finite && px >= 0 && px < a.shadow_w && py >= 0 && py < a.shadow_h)
+      sval = (a.shadow_map.ptr + (long long)b * a.shadow_map.batch_stride)[(long long)px * a.shadow_h + py];
+    f.lit = sz <= sval;
+    load3(a.shadow_strength, b, f.str);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) f.shadow[c] = f.lit ? 1.f : 1.f - f.str[c];
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    f.tex[c] = tex[f.texel * 3 + c];
+    f.ds[c] = f.dif[c] * f.diffuse + f.spe[c] * f.specular;
+    if (SHADER == JR_PHONG_REFLECTION)
+      f.col[c] = f.amb[c] * f.tex[c] + (f.ds[c] * f.lcol[c]) * f.tex[c];
+    else
+      f.col[c] = f.amb[c] * f.tex[c] + ((f.shadow[c] * f.ds[c]) * f.tex[c]) * f.lcol[c];
+  }
+}
+
+}  // namespace jr

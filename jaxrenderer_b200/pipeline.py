@@ -212,18 +212,24 @@ class _RenderFn(torch.autograd.Function):
         g = JrGradArgs()
         g.d_zbuffer = d_z.data_ptr()
         g.d_canvas = d_c.data_ptr() if has_canvas else None
+        if call.sid == _native.JR_PHONG_DARBOUX:
+            raise UnsupportedShaderError(
+                "gradients through PhongTextureDarbouxShader are not implemented in jaxrenderer_b200")
         outs: Dict[str, Tensor] = {}
+        wanted = []
         for i, name in enumerate(_DIFF):
-            if name in ("zbuffer", "canvas") or not ctx.present[i] or not ctx.needs_input_grad[i + 1]:
+            if name in ("zbuffer", "canvas") or not ctx.present[i]:
                 continue
+            if ctx.needs_input_grad[i + 1]:
+                wanted.append(name)
+        if "colour" in wanted and "position" not in wanted:
+            wanted.append("position")  # the kernel reduces both in one keyed pass
+        for name in wanted:
             t = call.arrays[name]
             buf = torch.zeros_like(t)
             outs[name] = buf
             setattr(g, _GRAD_FIELD[name], JrF32(buf.data_ptr(), call.stride(name)))
-        # dummy buffers for the forward arrays are not needed by backward
-        dummy_z = torch.empty(0, device=dev)
-        args = call.fill(d_z, d_c, call.tri_id)  # zbuffer/canvas slots unused by backward
-        _ = dummy_z
+        args = call.fill(d_z, d_c, call.tri_id)  # zbuffer/canvas slots are unused by backward
         need = lib.jr_backward_workspace_bytes(C.byref(args), C.byref(g))
         ws = None
         if need:

@@ -296,18 +296,28 @@ class Fragments(NamedTuple):
     front: torch.Tensor      # (W,H) gl_FrontFacing
 
 
-def chosen_fragments(setup: Setup, viewport: torch.Tensor, idx: torch.Tensor) -> Fragments:
-    W, H = idx.shape
+def chosen_fragments(clip_v: torch.Tensor, f_idx: torch.Tensor, viewport: torch.Tensor) -> Fragments:
+    """Per-pixel values of the chosen triangle, recomputed WITH autograd from the
+    chosen triangle's own vertices only (same operations, hence the same bits,
+    as ``primitive_setup`` + ``visibility``).  Restricting the differentiable
+    graph to the chosen triangle is what keeps gradients finite when some OTHER
+    triangle of the mesh is degenerate: the reference's ``jax.grad`` would return
+    NaN there (0 * inf through the discarded branches, SURVEY 7 "where-NaN");
+    parity of gradients is defined on the finite, intended value."""
+    W, H = f_idx.shape[:2]
     xs, ys = pixel_ndc(viewport, W, H)
-    inv = setup.inv[idx]                                 # (W,H,3,3)
-    zc = setup.clip[idx][..., 2]                         # (W,H,3)
+    clip = clip_v[f_idx]                                 # (W,H,3,4)
+    M = clip[..., [0, 1, 3]]
+    det = det3(M)
+    inv = lu_inverse3(M)                                 # (W,H,3,3)
+    zc = clip[..., 2]                                    # (W,H,3)
     xn, yn = xs[:, None], ys[None, :]
     c = torch.stack([(xn * inv[..., 0, k] + yn * inv[..., 1, k]) + inv[..., 2, k] for k in range(3)], -1)
     w_rec = (c[..., 0] + c[..., 1]) + c[..., 2]
     z = (c[..., 0] * zc[..., 0] + c[..., 1] * zc[..., 1]) + c[..., 2] * zc[..., 2]
     zw = z * viewport[2, 2] + viewport[2, 3]
     tc = c / w_rec[..., None]
-    front = (setup.det >= 0)[idx]
+    front = det >= 0
     return Fragments(tc=tc, zw=zw, w_rec=w_rec, front=front)
 
 
@@ -381,10 +391,11 @@ def render(camera: Any, shader: Any, zbuffer: Any, targets: Sequence[Any], face_
 
     # ---- vertex stage (pipeline.py:500-518; each shader's `vertex`)
     clip_v = mat4_apply(pos, w2c, w_one=True)
-    setup = primitive_setup(clip_v, faces)
+    with torch.no_grad():
+        setup = primitive_setup(clip_v.detach(), faces)
     idx, has, kc, gap = visibility(setup, vp, W, H)
-    fr = chosen_fragments(setup, vp, idx)
     f_idx = faces[idx]                                   # (W,H,3) vertex ids of the chosen triangle
+    fr = chosen_fragments(clip_v, f_idx, vp)
 
     keep = kc.clone()
     colour: Optional[torch.Tensor] = None
