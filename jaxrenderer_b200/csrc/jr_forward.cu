@@ -23,6 +23,8 @@
 #include "jr_device.cuh"
 #include "jr_common.cuh"
 #include "jr_shade.cuh"
+#include "jr_visibility.cuh"
+#include <stdlib.h>
 
 namespace jr {
 
@@ -381,7 +383,8 @@ static int check_common(const JrRenderArgs* a) {
 // Tile choice: whole canvas in one CTA when the key tile fits comfortably in
 // shared memory (<= 96 KB -> e.g. 84x84, 110x110), else 64x64 tiles.
 static void choose_tiles(int W, int H, int* tw, int* th, int* nx, int* ny) {
-  if ((size_t)W * H * 8 <= 96 * 1024) { *tw = W; *th = H; *nx = 1; *ny = 1; return; }
+  // (tile-local coordinates are packed into 8 bits by k_vis2)
+  if ((size_t)W * H * 8 <= 96 * 1024 && W <= 255 && H <= 255) { *tw = W; *th = H; *nx = 1; *ny = 1; return; }
   *tw = 64; *th = 64;
   if (W < 64) *tw = W;
   if (H < 64) *th = H;
@@ -416,27 +419,29 @@ int jr_render_forward(const JrRenderArgs* a, jr_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   int tw, th, nx, ny;
   choose_tiles(a->W, a->H, &tw, &th, &nx, &ny);
-  const VisSmemLayout L = vis_layout(tw, th);
   const long long ctas = (long long)a->B * nx * ny;
   if (ctas > 2147483647LL) return JR_ERR_DIMS;
-  if (a->shader == JR_DEPTH) {
-    static bool attr_done = false;
-    if (!attr_done) {
-      cudaFuncSetAttribute(k_visibility<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      cudaFuncSetAttribute(k_visibility<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      attr_done = true;
-    }
-    k_visibility<true><<<(unsigned)ctas, VIS_THREADS, L.total, stream>>>(*a, tw, th, nx, ny);
-    jr::g_launches++;
+  static const bool use_v1 = getenv("JR_VIS_V1") != nullptr;  // A/B switch: first kernel version
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(k_visibility<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_visibility<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_vis2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_vis2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_done = true;
+  }
+  const bool depth = a->shader == JR_DEPTH;
+  if (use_v1) {
+    const VisSmemLayout L = vis_layout(tw, th);
+    if (depth) k_visibility<true><<<(unsigned)ctas, VIS_THREADS, L.total, stream>>>(*a, tw, th, nx, ny);
+    else k_visibility<false><<<(unsigned)ctas, VIS_THREADS, L.total, stream>>>(*a, tw, th, nx, ny);
   } else {
-    static bool attr_done2 = false;
-    if (!attr_done2) {
-      cudaFuncSetAttribute(k_visibility<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      cudaFuncSetAttribute(k_visibility<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      attr_done2 = true;
-    }
-    k_visibility<false><<<(unsigned)ctas, VIS_THREADS, L.total, stream>>>(*a, tw, th, nx, ny);
-    jr::g_launches++;
+    const V2Layout L = v2_layout(tw, th);
+    if (depth) k_vis2<true><<<(unsigned)ctas, V2_THREADS, L.total, stream>>>(*a, tw, th, nx, ny);
+    else k_vis2<false><<<(unsigned)ctas, V2_THREADS, L.total, stream>>>(*a, tw, th, nx, ny);
+  }
+  jr::g_launches++;
+  if (!depth) {
     const long long total = (long long)a->B * a->W * a->H;
     const int threads = 256;
     long long blocks = (total + threads - 1) / threads;

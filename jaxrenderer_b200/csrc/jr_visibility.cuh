@@ -1,0 +1,282 @@
+// jr_visibility.cuh -- k_vis2: the tuned visibility kernel.
+//
+// One CTA (256 threads) per (image, screen tile); the tile's packed 64-bit
+// (orderable z | triangle id) keys live in shared memory.  There is NO block
+// barrier inside the triangle loop (ncu showed barrier stalls dominating a
+// queue-per-round variant); work is balanced at warp granularity instead:
+//
+//   lane = triangle   gather vertices, clip x/y/w (z only for survivors), det,
+//                     back-face / degenerate / behind-camera cull, approximate
+//                     bbox (+-0.5 px), exact LU inverse for survivors.
+//   small  (<= 32 px) rasterised by the owning lane.
+//   medium (<= 1024)  rasterised by the whole warp right away: the owner's
+//                     record is broadcast with shuffles, lanes cover the bbox
+//                     pixels flat (no integer division).
+//   large  (> 1024)   queued in shared memory, rasterised by the whole CTA after
+//                     the loop (flat; the ground plane of Brax scenes).
+//   resolve           keys -> tri_id (+ z for the depth shader).
+//
+// The 64-bit shared atomicMin is an explicit ld.shared / atom.shared.cas.b64 loop on
+// a 32-bit shared-window address (the compiler's generic-pointer emulation costs ~3x).
+#pragma once
+#include "jr_device.cuh"
+
+namespace jr {
+
+constexpr int V2_THREADS = 256;
+constexpr int V2_BIGCAP = 32;
+constexpr int V2_SMALL_AREA = 32;
+constexpr int V2_MEDIUM_AREA = 1024;
+
+struct V2Layout { size_t keys, xs, ys, bigq, total; };
+__host__ __device__ inline V2Layout v2_layout(int tile_w, int tile_h) {
+  V2Layout L;
+  L.keys = 0;
+  L.xs = (size_t)tile_w * tile_h * 8;
+  L.ys = L.xs + (size_t)tile_w * 4;
+  size_t e = L.ys + (size_t)tile_h * 4;
+  L.bigq = (e + 15) & ~(size_t)15;
+  L.total = L.bigq + (size_t)V2_BIGCAP * 64;
+  return L;
+}
+
+__device__ __forceinline__ void key_min(uint32_t saddr, unsigned long long key) {
+  unsigned long long old;
+  asm volatile("ld.shared.u64 %0, [%1];" : "=l"(old) : "r"(saddr));
+  while (key < old) {
+    unsigned long long prev;
+    asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(prev) : "r"(saddr), "l"(old), "l"(key) : "memory");
+    if (prev == old) break;
+    old = prev;
+  }
+}
+
+struct V2Big {  // 64 bytes
+  float inv[9];
+  float zc[3];
+  int tri;
+  short x0, x1, y0, y1;
+  int pad;
+};
+
+template <bool DEPTH>
+__global__ void __launch_bounds__(V2_THREADS)
+k_vis2(const __grid_constant__ JrRenderArgs a, int tile_w, int tile_h, int tiles_x, int tiles_y) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const V2Layout L = v2_layout(tile_w, tile_h);
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem + L.keys);
+  float* xs = reinterpret_cast<float*>(smem + L.xs);
+  float* ys = reinterpret_cast<float*>(smem + L.ys);
+  V2Big* bigq = reinterpret_cast<V2Big*>(smem + L.bigq);
+  __shared__ int bigq_n;
+  __shared__ int tri0_flag;
+  __shared__ TriSetup tri0;
+  __shared__ float s_w2c[16];
+  __shared__ float s_vp[16];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = V2_THREADS / 32;
+  const int tiles = tiles_x * tiles_y;
+  const int b = blockIdx.x / tiles;
+  const int tile = blockIdx.x - b * tiles;
+  const int tx0 = (tile / tiles_y) * tile_w;
+  const int ty0 = (tile % tiles_y) * tile_h;
+  const int tw = min(tile_w, a.W - tx0);
+  const int th = min(tile_h, a.H - ty0);
+  const uint32_t keys_saddr = (uint32_t)__cvta_generic_to_shared(keys);
+
+  if (tid < 16) {
+    s_w2c[tid] = a.world_to_clip.ptr[(long long)b * a.world_to_clip.batch_stride + tid];
+    s_vp[tid] = a.viewport.ptr[(long long)b * a.viewport.batch_stride + tid];
+  }
+  if (tid == 0) { bigq_n = 0; tri0_flag = 0; }
+  for (int i = tid; i < tile_w * tile_h; i += V2_THREADS) keys[i] = 0xFFFFFFFFFFFFFFFFull;
+  __syncthreads();
+  for (int i = tid; i < tw; i += V2_THREADS) xs[i] = ((float)(tx0 + i) - s_vp[3]) / s_vp[0];
+  for (int i = tid; i < th; i += V2_THREADS) ys[i] = ((float)(ty0 + i) - s_vp[7]) / s_vp[5];
+  __syncthreads();
+
+  const float vp00 = s_vp[0], vp03 = s_vp[3], vp11 = s_vp[5], vp13 = s_vp[7];
+  const float vp22 = s_vp[10], vp23 = s_vp[11];
+  const float* __restrict__ pos = a.position.ptr + (long long)b * a.position.batch_stride;
+  const int32_t* __restrict__ faces = a.faces.ptr + (long long)b * a.faces.batch_stride;
+  const float fx_lo = (float)tx0, fx_hi = (float)(tx0 + tw - 1);
+  const float fy_lo = (float)ty0, fy_hi = (float)(ty0 + th - 1);
+
+  // rasterise one small triangle with this lane
+  auto raster_small = [&](const float* inv, const float* zc, int tri, int x0, int x1, int y0, int y1) {
+    for (int x = x0; x <= x1; ++x) {
+      const float xn = xs[x];
+      const float pk0 = xn * inv[0], pk1 = xn * inv[1], pk2 = xn * inv[2];
+      for (int y = y0; y <= y1; ++y) {
+        const float yn = ys[y];
+        const float c0 = (pk0 + yn * inv[3]) + inv[6];
+        const float c1 = (pk1 + yn * inv[4]) + inv[7];
+        const float c2 = (pk2 + yn * inv[5]) + inv[8];
+        if (c0 >= 0.f && c1 >= 0.f && c2 >= 0.f) {
+          const float z = (c0 * zc[0] + c1 * zc[1]) + c2 * zc[2];
+          const float zw = z * vp22 + vp23;
+          key_min(keys_saddr + (uint32_t)(x * tile_h + y) * 8u,
+                  ((unsigned long long)orderable(zw) << 32) | (unsigned)tri);
+        }
+      }
+    }
+  };
+  // flat raster of one bbox by a group of `nlanes` lanes (lane index `li`): pixel i -> (i / bh, i % bh)
+  // with the quotient taken in fp32 ((i + 0.5) / bh is never within rounding distance of an integer
+  // for i < 2^16, bh <= 255)
+  auto raster_flat = [&](const float* inv, const float* zc, int tri, int x0, int y0, int bw, int bh, int li,
+                         int nlanes) {
+    const int n = bw * bh;
+    const float rbh = 1.0f / (float)bh;
+    for (int i = li; i < n; i += nlanes) {
+      const int dx = (int)(((float)i + 0.5f) * rbh);
+      const int x = x0 + dx, y = y0 + (i - dx * bh);
+      const float xn = xs[x], yn = ys[y];
+      const float c0 = (xn * inv[0] + yn * inv[3]) + inv[6];
+      const float c1 = (xn * inv[1] + yn * inv[4]) + inv[7];
+      const float c2 = (xn * inv[2] + yn * inv[5]) + inv[8];
+      if (c0 >= 0.f && c1 >= 0.f && c2 >= 0.f) {
+        const float z = (c0 * zc[0] + c1 * zc[1]) + c2 * zc[2];
+        const float zw = z * vp22 + vp23;
+        key_min(keys_saddr + (uint32_t)(x * tile_h + y) * 8u,
+                ((unsigned long long)orderable(zw) << 32) | (unsigned)tri);
+      }
+    }
+  };
+
+  const int t_end = ((a.T + 31) / 32) * 32;  // whole warps stay in the loop (shuffles below)
+  for (int t = tid; t < t_end; t += V2_THREADS) {
+    bool surv = false;
+    float M[9], zc[3], inv[9];
+    int x0 = 0, x1 = tw - 1, y0 = 0, y1 = th - 1;
+    if (t < a.T) {
+      const int i0 = faces[3 * t + 0], i1 = faces[3 * t + 1], i2 = faces[3 * t + 2];
+      const float p0x = pos[3 * i0], p0y = pos[3 * i0 + 1], p0z = pos[3 * i0 + 2];
+      const float p1x = pos[3 * i1], p1y = pos[3 * i1 + 1], p1z = pos[3 * i1 + 2];
+      const float p2x = pos[3 * i2], p2y = pos[3 * i2 + 1], p2z = pos[3 * i2 + 2];
+      // rows 0, 1, 3 of to_clip (x, y, w); row 2 (z) only for survivors
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const int rr = (r == 2) ? 3 : r;
+        const float m0 = s_w2c[4 * rr], m1 = s_w2c[4 * rr + 1], m2 = s_w2c[4 * rr + 2], m3 = s_w2c[4 * rr + 3];
+        M[0 + r] = ((p0x * m0 + p0y * m1) + p0z * m2) + m3;
+        M[3 + r] = ((p1x * m0 + p1y * m1) + p1z * m2) + m3;
+        M[6 + r] = ((p2x * m0 + p2y * m1) + p2z * m2) + m3;
+      }
+      const float det = det3(M);
+      const bool cand = det > 1e-6f;  // keep & front (pipeline.py:98-100, :232)
+      const bool fallback0 = DEPTH && (t == 0) && (det < -1e-6f);
+      const float w0 = M[2], w1 = M[5], w2 = M[8];
+      const bool behind = (w0 <= 0.f && w1 <= 0.f && w2 <= 0.f);
+      if ((cand || fallback0) && !behind) {
+        surv = true;
+        if (w0 > 0.f && w1 > 0.f && w2 > 0.f && !fallback0) {
+          const float r0 = __fdividef(1.f, w0), r1 = __fdividef(1.f, w1), r2 = __fdividef(1.f, w2);
+          const float sx0 = (M[0] * r0) * vp00 + vp03, sx1 = (M[3] * r1) * vp00 + vp03, sx2 = (M[6] * r2) * vp00 + vp03;
+          const float sy0 = (M[1] * r0) * vp11 + vp13, sy1 = (M[4] * r1) * vp11 + vp13, sy2 = (M[7] * r2) * vp11 + vp13;
+          // conservative +-0.5 px margin; fmaxf/fminf drop NaN towards "whole tile"
+          const float mnx = fmaxf(fminf(fminf(sx0, sx1), sx2) - 0.5f, fx_lo);
+          const float mxx = fminf(fmaxf(fmaxf(sx0, sx1), sx2) + 0.5f, fx_hi);
+          const float mny = fmaxf(fminf(fminf(sy0, sy1), sy2) - 0.5f, fy_lo);
+          const float mxy = fminf(fmaxf(fmaxf(sy0, sy1), sy2) + 0.5f, fy_hi);
+          if (!(mnx <= mxx) || !(mny <= mxy)) surv = false;
+          x0 = (int)ceilf(mnx) - tx0; x1 = (int)floorf(mxx) - tx0;
+          y0 = (int)ceilf(mny) - ty0; y1 = (int)floorf(mxy) - ty0;
+          if (x0 > x1 || y0 > y1) surv = false;
+        }
+        if (surv) {
+          const float m0 = s_w2c[8], m1 = s_w2c[9], m2 = s_w2c[10], m3 = s_w2c[11];
+          zc[0] = ((p0x * m0 + p0y * m1) + p0z * m2) + m3;
+          zc[1] = ((p1x * m0 + p1y * m1) + p1z * m2) + m3;
+          zc[2] = ((p2x * m0 + p2y * m1) + p2z * m2) + m3;
+          lu_inverse3(M, inv);
+          if (fallback0) {
+            // DepthShader quirk: kept back-facing triangle 0 fills pixels no candidate covers
+#pragma unroll
+            for (int k = 0; k < 9; ++k) tri0.inv[k] = inv[k];
+            tri0.zc[0] = zc[0]; tri0.zc[1] = zc[1]; tri0.zc[2] = zc[2];
+            tri0.det = det;
+            tri0_flag = 1;
+            surv = false;
+          }
+        }
+      }
+    }
+    const int bw = x1 - x0 + 1, bh = y1 - y0 + 1;
+    const int area = surv ? bw * bh : 0;
+    bool is_medium = area > V2_SMALL_AREA && area <= V2_MEDIUM_AREA;
+    if (area > V2_MEDIUM_AREA) {
+      const int slot = atomicAdd(&bigq_n, 1);
+      if (slot < V2_BIGCAP) {
+        V2Big& q = bigq[slot];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) q.inv[k] = inv[k];
+        q.zc[0] = zc[0]; q.zc[1] = zc[1]; q.zc[2] = zc[2];
+        q.tri = t;
+        q.x0 = (short)x0; q.x1 = (short)x1; q.y0 = (short)y0; q.y1 = (short)y1;
+      } else {
+        is_medium = true;  // queue full: the warp takes it
+      }
+    }
+    if (area > 0 && area <= V2_SMALL_AREA) raster_small(inv, zc, t, x0, x1, y0, y1);
+    // medium triangles: one at a time, the whole warp on each
+    unsigned mm = __ballot_sync(0xffffffffu, is_medium);
+    while (mm) {
+      const int src = __ffs(mm) - 1;
+      mm &= mm - 1;
+      float binv[9], bzc[3];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) binv[k] = __shfl_sync(0xffffffffu, inv[k], src);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) bzc[k] = __shfl_sync(0xffffffffu, zc[k], src);
+      const int btri = __shfl_sync(0xffffffffu, t, src);
+      const int bx0 = __shfl_sync(0xffffffffu, x0, src), by0 = __shfl_sync(0xffffffffu, y0, src);
+      const int bbw = __shfl_sync(0xffffffffu, bw, src), bbh = __shfl_sync(0xffffffffu, bh, src);
+      raster_flat(binv, bzc, btri, bx0, by0, bbw, bbh, lane, 32);
+    }
+  }
+  __syncthreads();
+  // ---------------- large triangles: whole CTA, flat
+  {
+    const int nbig = min(bigq_n, V2_BIGCAP);
+    for (int e = 0; e < nbig; ++e) {
+      const V2Big& q = bigq[e];
+      float binv[9], bzc[3];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) binv[k] = q.inv[k];
+      bzc[0] = q.zc[0]; bzc[1] = q.zc[1]; bzc[2] = q.zc[2];
+      raster_flat(binv, bzc, q.tri, q.x0, q.y0, q.x1 - q.x0 + 1, q.y1 - q.y0 + 1, tid, V2_THREADS);
+    }
+  }
+  __syncthreads();
+  // ---------------- resolve (flat index walked without integer division)
+  int32_t* __restrict__ tri_out = a.tri_id ? a.tri_id + (long long)b * a.W * a.H : nullptr;
+  float* __restrict__ z_out = DEPTH ? a.zbuffer + (long long)b * a.W * a.H : nullptr;
+  const bool use0 = DEPTH && tri0_flag;
+  {
+    const int dq = V2_THREADS / th, dr = V2_THREADS - dq * th;
+    int lx = tid / th, ly = tid - lx * th;
+    for (; lx < tw; lx += dq, ly += dr) {
+      if (ly >= th) { ly -= th; ++lx; if (lx >= tw) break; }
+      const unsigned long long key = keys[lx * tile_h + ly];
+      const long long pix = (long long)(tx0 + lx) * a.H + (ty0 + ly);
+      int tri = -1;
+      if (key != 0xFFFFFFFFFFFFFFFFull) {
+        tri = (int)(unsigned)(key & 0xFFFFFFFFull);
+        if (DEPTH) z_out[pix] = from_orderable((uint32_t)(key >> 32));
+      } else if (use0) {
+        float c[3];
+        clip_coef(tri0.inv, xs[lx], ys[ly], c);
+        if (c[0] >= 0.f && c[1] >= 0.f && c[2] >= 0.f) {
+          const float z = (c[0] * tri0.zc[0] + c[1] * tri0.zc[1]) + c[2] * tri0.zc[2];
+          z_out[pix] = z * vp22 + vp23;
+          tri = 0;
+        }
+      }
+      if (tri_out) tri_out[pix] = tri;
+    }
+  }
+}
+
+}  // namespace jr
