@@ -60,7 +60,7 @@ struct V2Big {  // 64 bytes
 };
 
 template <bool DEPTH>
-__global__ void __launch_bounds__(V2_THREADS)
+__global__ void __launch_bounds__(V2_THREADS, 3)
 k_vis2(const __grid_constant__ JrRenderArgs a, int tile_w, int tile_h, int tiles_x, int tiles_y) {
   extern __shared__ __align__(16) unsigned char smem[];
   const V2Layout L = v2_layout(tile_w, tile_h);
@@ -90,7 +90,12 @@ k_vis2(const __grid_constant__ JrRenderArgs a, int tile_w, int tile_h, int tiles
     s_vp[tid] = a.viewport.ptr[(long long)b * a.viewport.batch_stride + tid];
   }
   if (tid == 0) { bigq_n = 0; tri0_flag = 0; }
-  for (int i = tid; i < tile_w * tile_h; i += V2_THREADS) keys[i] = 0xFFFFFFFFFFFFFFFFull;
+  {
+    const int nk = tile_w * tile_h;
+    ulonglong2* k2 = reinterpret_cast<ulonglong2*>(keys);
+    for (int i = tid; i < (nk >> 1); i += V2_THREADS) k2[i] = make_ulonglong2(~0ull, ~0ull);
+    if ((nk & 1) && tid == 0) keys[nk - 1] = ~0ull;
+  }
   __syncthreads();
   for (int i = tid; i < tw; i += V2_THREADS) xs[i] = ((float)(tx0 + i) - s_vp[3]) / s_vp[0];
   for (int i = tid; i < th; i += V2_THREADS) ys[i] = ((float)(ty0 + i) - s_vp[7]) / s_vp[5];
@@ -145,11 +150,51 @@ k_vis2(const __grid_constant__ JrRenderArgs a, int tile_w, int tile_h, int tiles
     }
   };
 
-  const int t_end = ((a.T + 31) / 32) * 32;  // whole warps stay in the loop (shuffles below)
+  // exact setup of one surviving triangle + dispatch by bbox size; called with warp-uniform control
+  // flow (`valid` masks lanes without a record)
+  auto fire = [&](bool valid, const float* M, const float* zc, int tri, unsigned bb) {
+    float inv[9];
+    const int x0 = bb & 0xff, x1 = (bb >> 8) & 0xff, y0 = (bb >> 16) & 0xff, y1 = bb >> 24;
+    const int bw = x1 - x0 + 1, bh = y1 - y0 + 1;
+    const int area = valid ? bw * bh : 0;
+    if (valid) lu_inverse3(M, inv);
+    bool is_medium = area > V2_SMALL_AREA && area <= V2_MEDIUM_AREA;
+    if (area > V2_MEDIUM_AREA) {
+      const int slot = atomicAdd(&bigq_n, 1);
+      if (slot < V2_BIGCAP) {
+        V2Big& q = bigq[slot];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) q.inv[k] = inv[k];
+        q.zc[0] = zc[0]; q.zc[1] = zc[1]; q.zc[2] = zc[2];
+        q.tri = tri;
+        q.x0 = (short)x0; q.x1 = (short)x1; q.y0 = (short)y0; q.y1 = (short)y1;
+      } else {
+        is_medium = true;  // queue full: the warp takes it
+      }
+    }
+    if (area > 0 && area <= V2_SMALL_AREA) raster_small(inv, zc, tri, x0, x1, y0, y1);
+    // medium triangles: one at a time, the whole warp on each
+    unsigned mm = __ballot_sync(0xffffffffu, is_medium);
+    while (mm) {
+      const int src = __ffs(mm) - 1;
+      mm &= mm - 1;
+      float binv[9], bzc[3];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) binv[k] = __shfl_sync(0xffffffffu, inv[k], src);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) bzc[k] = __shfl_sync(0xffffffffu, zc[k], src);
+      const int btri = __shfl_sync(0xffffffffu, tri, src);
+      const unsigned bbb = __shfl_sync(0xffffffffu, bb, src);
+      const int sx0 = bbb & 0xff, sx1 = (bbb >> 8) & 0xff, sy0 = (bbb >> 16) & 0xff, sy1 = bbb >> 24;
+      raster_flat(binv, bzc, btri, sx0, sy0, sx1 - sx0 + 1, sy1 - sy0 + 1, lane, 32);
+    }
+  };
+
+  const int t_end = ((a.T + 31) / 32) * 32;  // whole warps stay in the loop
   for (int t = tid; t < t_end; t += V2_THREADS) {
     bool surv = false;
-    float M[9], zc[3], inv[9];
-    int x0 = 0, x1 = tw - 1, y0 = 0, y1 = th - 1;
+    float M[9], zc[3];
+    unsigned bb = 0;
     if (t < a.T) {
       const int i0 = faces[3 * t + 0], i1 = faces[3 * t + 1], i2 = faces[3 * t + 2];
       const float p0x = pos[3 * i0], p0y = pos[3 * i0 + 1], p0z = pos[3 * i0 + 2];
@@ -171,6 +216,7 @@ k_vis2(const __grid_constant__ JrRenderArgs a, int tile_w, int tile_h, int tiles
       const bool behind = (w0 <= 0.f && w1 <= 0.f && w2 <= 0.f);
       if ((cand || fallback0) && !behind) {
         surv = true;
+        int x0 = 0, x1 = tw - 1, y0 = 0, y1 = th - 1;
         if (w0 > 0.f && w1 > 0.f && w2 > 0.f && !fallback0) {
           const float r0 = __fdividef(1.f, w0), r1 = __fdividef(1.f, w1), r2 = __fdividef(1.f, w2);
           const float sx0 = (M[0] * r0) * vp00 + vp03, sx1 = (M[3] * r1) * vp00 + vp03, sx2 = (M[6] * r2) * vp00 + vp03;
@@ -190,9 +236,11 @@ k_vis2(const __grid_constant__ JrRenderArgs a, int tile_w, int tile_h, int tiles
           zc[0] = ((p0x * m0 + p0y * m1) + p0z * m2) + m3;
           zc[1] = ((p1x * m0 + p1y * m1) + p1z * m2) + m3;
           zc[2] = ((p2x * m0 + p2y * m1) + p2z * m2) + m3;
-          lu_inverse3(M, inv);
+          bb = (unsigned)x0 | ((unsigned)x1 << 8) | ((unsigned)y0 << 16) | ((unsigned)y1 << 24);
           if (fallback0) {
             // DepthShader quirk: kept back-facing triangle 0 fills pixels no candidate covers
+            float inv[9];
+            lu_inverse3(M, inv);
 #pragma unroll
             for (int k = 0; k < 9; ++k) tri0.inv[k] = inv[k];
             tri0.zc[0] = zc[0]; tri0.zc[1] = zc[1]; tri0.zc[2] = zc[2];
@@ -203,58 +251,67 @@ k_vis2(const __grid_constant__ JrRenderArgs a, int tile_w, int tile_h, int tiles
         }
       }
     }
-    const int bw = x1 - x0 + 1, bh = y1 - y0 + 1;
-    const int area = surv ? bw * bh : 0;
-    bool is_medium = area > V2_SMALL_AREA && area <= V2_MEDIUM_AREA;
-    if (area > V2_MEDIUM_AREA) {
-      const int slot = atomicAdd(&bigq_n, 1);
-      if (slot < V2_BIGCAP) {
-        V2Big& q = bigq[slot];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) q.inv[k] = inv[k];
-        q.zc[0] = zc[0]; q.zc[1] = zc[1]; q.zc[2] = zc[2];
-        q.tri = t;
-        q.x0 = (short)x0; q.x1 = (short)x1; q.y0 = (short)y0; q.y1 = (short)y1;
-      } else {
-        is_medium = true;  // queue full: the warp takes it
-      }
-    }
-    if (area > 0 && area <= V2_SMALL_AREA) raster_small(inv, zc, t, x0, x1, y0, y1);
-    // medium triangles: one at a time, the whole warp on each
-    unsigned mm = __ballot_sync(0xffffffffu, is_medium);
-    while (mm) {
-      const int src = __ffs(mm) - 1;
-      mm &= mm - 1;
-      float binv[9], bzc[3];
-#pragma unroll
-      for (int k = 0; k < 9; ++k) binv[k] = __shfl_sync(0xffffffffu, inv[k], src);
-#pragma unroll
-      for (int k = 0; k < 3; ++k) bzc[k] = __shfl_sync(0xffffffffu, zc[k], src);
-      const int btri = __shfl_sync(0xffffffffu, t, src);
-      const int bx0 = __shfl_sync(0xffffffffu, x0, src), by0 = __shfl_sync(0xffffffffu, y0, src);
-      const int bbw = __shfl_sync(0xffffffffu, bw, src), bbh = __shfl_sync(0xffffffffu, bh, src);
-      raster_flat(binv, bzc, btri, bx0, by0, bbw, bbh, lane, 32);
-    }
+    // (Compacting survivors into full warps before `fire` was tried and measured SLOWER: +14 KB
+    // shared memory per CTA shrinks L1 for the vertex gather and the per-lane raster loop still
+    // runs to the longest box; see profiles/README.md.)
+    if (__ballot_sync(0xffffffffu, surv)) fire(surv, M, zc, t, bb);
   }
   __syncthreads();
-  // ---------------- large triangles: whole CTA, flat
+  // ---------------- large triangles: whole CTA, one at a time (a barrier between two entries makes
+  // every pixel single-writer, so plain read-modify-write instead of a CAS loop)
   {
     const int nbig = min(bigq_n, V2_BIGCAP);
     for (int e = 0; e < nbig; ++e) {
       const V2Big& q = bigq[e];
-      float binv[9], bzc[3];
-#pragma unroll
-      for (int k = 0; k < 9; ++k) binv[k] = q.inv[k];
-      bzc[0] = q.zc[0]; bzc[1] = q.zc[1]; bzc[2] = q.zc[2];
-      raster_flat(binv, bzc, q.tri, q.x0, q.y0, q.x1 - q.x0 + 1, q.y1 - q.y0 + 1, tid, V2_THREADS);
+      const float i0 = q.inv[0], i1 = q.inv[1], i2 = q.inv[2], i3 = q.inv[3], i4 = q.inv[4], i5 = q.inv[5],
+                  i6 = q.inv[6], i7 = q.inv[7], i8 = q.inv[8];
+      const float z0 = q.zc[0], z1 = q.zc[1], z2 = q.zc[2];
+      const unsigned tri = (unsigned)q.tri;
+      const int qx0 = q.x0, qy0 = q.y0, bh = q.y1 - q.y0 + 1;
+      const int n = (q.x1 - q.x0 + 1) * bh;
+      const float rbh = 1.0f / (float)bh;
+      for (int i = tid; i < n; i += V2_THREADS) {
+        const int dx = (int)(((float)i + 0.5f) * rbh);
+        const int x = qx0 + dx, y = qy0 + (i - dx * bh);
+        const float xn = xs[x], yn = ys[y];
+        const float c0 = (xn * i0 + yn * i3) + i6;
+        const float c1 = (xn * i1 + yn * i4) + i7;
+        const float c2 = (xn * i2 + yn * i5) + i8;
+        if (c0 >= 0.f && c1 >= 0.f && c2 >= 0.f) {
+          const float z = (c0 * z0 + c1 * z1) + c2 * z2;
+          const float zw = z * vp22 + vp23;
+          const unsigned long long key = ((unsigned long long)orderable(zw) << 32) | tri;
+          unsigned long long* slot = &keys[x * tile_h + y];
+          if (key < *slot) *slot = key;
+        }
+      }
+      __syncthreads();
     }
   }
-  __syncthreads();
-  // ---------------- resolve (flat index walked without integer division)
+  // ---------------- resolve
   int32_t* __restrict__ tri_out = a.tri_id ? a.tri_id + (long long)b * a.W * a.H : nullptr;
   float* __restrict__ z_out = DEPTH ? a.zbuffer + (long long)b * a.W * a.H : nullptr;
   const bool use0 = DEPTH && tri0_flag;
-  {
+  const int npix_img = a.W * a.H;
+  if (tiles == 1 && !use0 && !(npix_img & 1)) {
+    // single tile: tile-local index == pixel index; two pixels per thread, 128-bit LDS / 64-bit STG
+    const ulonglong2* k2 = reinterpret_cast<const ulonglong2*>(keys);
+    for (int i = tid; i < (npix_img >> 1); i += V2_THREADS) {
+      const ulonglong2 kk = k2[i];
+      const bool e0 = kk.x == ~0ull, e1 = kk.y == ~0ull;
+      if (DEPTH) {
+        if (!e0 && !e1) {
+          reinterpret_cast<float2*>(z_out)[i] =
+              make_float2(from_orderable((uint32_t)(kk.x >> 32)), from_orderable((uint32_t)(kk.y >> 32)));
+        } else {
+          if (!e0) z_out[2 * i] = from_orderable((uint32_t)(kk.x >> 32));
+          if (!e1) z_out[2 * i + 1] = from_orderable((uint32_t)(kk.y >> 32));
+        }
+      }
+      if (tri_out)
+        reinterpret_cast<int2*>(tri_out)[i] = make_int2(e0 ? -1 : (int)(unsigned)kk.x, e1 ? -1 : (int)(unsigned)kk.y);
+    }
+  } else {
     const int dq = V2_THREADS / th, dr = V2_THREADS - dq * th;
     int lx = tid / th, ly = tid - lx * th;
     for (; lx < tw; lx += dq, ly += dr) {
@@ -262,7 +319,7 @@ k_vis2(const __grid_constant__ JrRenderArgs a, int tile_w, int tile_h, int tiles
       const unsigned long long key = keys[lx * tile_h + ly];
       const long long pix = (long long)(tx0 + lx) * a.H + (ty0 + ly);
       int tri = -1;
-      if (key != 0xFFFFFFFFFFFFFFFFull) {
+      if (key != ~0ull) {
         tri = (int)(unsigned)(key & 0xFFFFFFFFull);
         if (DEPTH) z_out[pix] = from_orderable((uint32_t)(key >> 32));
       } else if (use0) {
