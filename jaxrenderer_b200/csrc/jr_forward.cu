@@ -24,6 +24,7 @@
 #include "jr_common.cuh"
 #include "jr_shade.cuh"
 #include "jr_visibility.cuh"
+#include "jr_tiled.cuh"
 #include <stdlib.h>
 
 namespace jr {
@@ -409,7 +410,13 @@ const char* jr_strerror(int s) {
   }
 }
 
-size_t jr_workspace_bytes(const JrRenderArgs* a) { (void)a; return 0; }
+size_t jr_workspace_bytes(const JrRenderArgs* a) {
+  if (!a || a->B <= 0 || a->W <= 0 || a->H <= 0) return 0;
+  int tw, th, nx, ny;
+  choose_tiles(a->W, a->H, &tw, &th, &nx, &ny);
+  if (nx * ny == 1) return 0;                       // single shared-memory tile: no scratch
+  return tiled_layout(a->B, a->W, a->H, a->T).total;  // triangle records + per-tile bitmasks
+}
 
 long long jr_launch_count(void) { return jr::g_launches.load(); }
 
@@ -431,7 +438,34 @@ int jr_render_forward(const JrRenderArgs* a, jr_stream_t stream_) {
     attr_done = true;
   }
   const bool depth = a->shader == JR_DEPTH;
-  if (use_v1) {
+  static const bool no_bins = getenv("JR_NO_BINS") != nullptr;  // A/B switch: every tile CTA scans all triangles
+  if (nx * ny > 1 && !use_v1 && !no_bins) {
+    // two-level path: per-triangle records + per-tile bitmasks, then one CTA per (image, tile)
+    const TiledLayout TLy = tiled_layout(a->B, a->W, a->H, a->T);
+    if (!a->workspace || a->workspace_bytes < TLy.total) return JR_ERR_WORKSPACE;
+    if (a->B > 65535) return JR_ERR_DIMS;
+    char* ws = (char*)a->workspace;
+    TriRecord* recs = (TriRecord*)(ws + TLy.rec);
+    unsigned* masks = (unsigned*)(ws + TLy.mask);
+    cudaMemsetAsync(masks, 0, (size_t)a->B * TLy.tiles * TLy.words * 4, stream);
+    static bool attr2 = false;
+    if (!attr2) {
+      cudaFuncSetAttribute(k_raster_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+      cudaFuncSetAttribute(k_raster_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+      attr2 = true;
+    }
+    if (a->T > 0) {
+      dim3 g1((a->T + 255) / 256, a->B);
+      if (depth) k_setup_bin<true><<<g1, 256, 0, stream>>>(*a, recs, masks, TLy);
+      else k_setup_bin<false><<<g1, 256, 0, stream>>>(*a, recs, masks, TLy);
+      jr::g_launches++;
+    }
+    const long long ctas2 = (long long)a->B * TLy.tiles;
+    if (ctas2 > 2147483647LL) return JR_ERR_DIMS;
+    const size_t sm = tl_smem().total;
+    if (depth) k_raster_tile<true><<<(unsigned)ctas2, TL_THREADS, sm, stream>>>(*a, recs, masks, TLy);
+    else k_raster_tile<false><<<(unsigned)ctas2, TL_THREADS, sm, stream>>>(*a, recs, masks, TLy);
+  } else if (use_v1) {
     const VisSmemLayout L = vis_layout(tw, th);
     if (depth) k_visibility<true><<<(unsigned)ctas, VIS_THREADS, L.total, stream>>>(*a, tw, th, nx, ny);
     else k_visibility<false><<<(unsigned)ctas, VIS_THREADS, L.total, stream>>>(*a, tw, th, nx, ny);

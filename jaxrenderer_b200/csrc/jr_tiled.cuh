@@ -1,0 +1,360 @@
+// jr_tiled.cuh -- two-level visibility for canvases that do not fit one shared-memory tile.
+//
+//   k_setup_bin      one thread per triangle (all images): vertex transform, cull, approximate
+//                    bbox, exact LU inverse -> 64-byte record in the workspace; each warp then
+//                    publishes, for every 64x64 screen tile its triangles touch, ONE 32-bit word
+//                    (ballot of "lane's triangle overlaps the tile") into the tile's bitmask.
+//                    Each (tile, word) has exactly one writer: no atomics, deterministic.
+//   k_raster_tile    one CTA per (image, tile): keys of the tile in shared memory; warps scan the
+//                    tile's bitmask words, compact the set bits into full warps of triangle ids,
+//                    fetch the records and rasterise (small: lane; medium: warp; large: CTA),
+//                    then resolve to tri_id (+ z for the depth shader).
+//
+// Triangle setup therefore runs once per triangle instead of once per (triangle, tile).
+#pragma once
+#include "jr_device.cuh"
+#include "jr_visibility.cuh"
+
+namespace jr {
+
+constexpr int TL_TILE = 64;
+constexpr int TL_THREADS = 256;
+constexpr int TL_BIGCAP = 32;
+constexpr int TL_MASKCAP = 2048;  // bitmask words staged in shared memory per chunk (65536 triangles)
+
+struct __align__(16) TriRecord {  // 64 bytes
+  float inv[9];
+  float zc[3];
+  unsigned short x0, x1, y0, y1;  // absolute pixel bbox, inclusive
+  int flags;                      // 1 = DepthShader triangle-0 fallback record
+  int pad;
+};
+static_assert(sizeof(TriRecord) == 64, "TriRecord must be 64 bytes");
+
+struct TiledLayout {
+  int tiles_x, tiles_y, tiles, words;
+  size_t rec, mask, total;
+};
+__host__ __device__ inline TiledLayout tiled_layout(int B, int W, int H, int T) {
+  TiledLayout L;
+  L.tiles_x = (W + TL_TILE - 1) / TL_TILE;
+  L.tiles_y = (H + TL_TILE - 1) / TL_TILE;
+  L.tiles = L.tiles_x * L.tiles_y;
+  L.words = (T + 31) / 32;
+  L.rec = 0;
+  size_t r = (size_t)B * (size_t)(T > 0 ? T : 1) * sizeof(TriRecord);
+  L.mask = (r + 255) & ~(size_t)255;
+  L.total = L.mask + (size_t)B * L.tiles * (L.words > 0 ? L.words : 1) * 4;
+  return L;
+}
+
+template <bool DEPTH>
+__global__ void __launch_bounds__(256)
+k_setup_bin(const __grid_constant__ JrRenderArgs a, TriRecord* __restrict__ recs, unsigned* __restrict__ masks,
+            TiledLayout L) {
+  __shared__ float s_w2c[16];
+  __shared__ float s_vp[16];
+  const int b = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31;
+  if (tid < 16) {
+    s_w2c[tid] = a.world_to_clip.ptr[(long long)b * a.world_to_clip.batch_stride + tid];
+    s_vp[tid] = a.viewport.ptr[(long long)b * a.viewport.batch_stride + tid];
+  }
+  __syncthreads();
+  const float vp00 = s_vp[0], vp03 = s_vp[3], vp11 = s_vp[5], vp13 = s_vp[7];
+  const float* __restrict__ pos = a.position.ptr + (long long)b * a.position.batch_stride;
+  const int32_t* __restrict__ faces = a.faces.ptr + (long long)b * a.faces.batch_stride;
+  const int t = blockIdx.x * 256 + tid;
+  bool surv = false;
+  int x0 = 0, x1 = a.W - 1, y0 = 0, y1 = a.H - 1;
+  if (t < a.T) {
+    const int i0 = faces[3 * t + 0], i1 = faces[3 * t + 1], i2 = faces[3 * t + 2];
+    const float p0x = pos[3 * i0], p0y = pos[3 * i0 + 1], p0z = pos[3 * i0 + 2];
+    const float p1x = pos[3 * i1], p1y = pos[3 * i1 + 1], p1z = pos[3 * i1 + 2];
+    const float p2x = pos[3 * i2], p2y = pos[3 * i2 + 1], p2z = pos[3 * i2 + 2];
+    float M[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int rr = (r == 2) ? 3 : r;
+      const float m0 = s_w2c[4 * rr], m1 = s_w2c[4 * rr + 1], m2 = s_w2c[4 * rr + 2], m3 = s_w2c[4 * rr + 3];
+      M[0 + r] = ((p0x * m0 + p0y * m1) + p0z * m2) + m3;
+      M[3 + r] = ((p1x * m0 + p1y * m1) + p1z * m2) + m3;
+      M[6 + r] = ((p2x * m0 + p2y * m1) + p2z * m2) + m3;
+    }
+    const float det = det3(M);
+    const bool cand = det > 1e-6f;
+    const bool fallback0 = DEPTH && (t == 0) && (det < -1e-6f);
+    const float w0 = M[2], w1 = M[5], w2 = M[8];
+    const bool behind = (w0 <= 0.f && w1 <= 0.f && w2 <= 0.f);
+    if ((cand || fallback0) && !behind) {
+      surv = true;
+      if (w0 > 0.f && w1 > 0.f && w2 > 0.f && !fallback0) {
+        const float r0 = __fdividef(1.f, w0), r1 = __fdividef(1.f, w1), r2 = __fdividef(1.f, w2);
+        const float sx0 = (M[0] * r0) * vp00 + vp03, sx1 = (M[3] * r1) * vp00 + vp03, sx2 = (M[6] * r2) * vp00 + vp03;
+        const float sy0 = (M[1] * r0) * vp11 + vp13, sy1 = (M[4] * r1) * vp11 + vp13, sy2 = (M[7] * r2) * vp11 + vp13;
+        const float mnx = fmaxf(fminf(fminf(sx0, sx1), sx2) - 0.5f, 0.f);
+        const float mxx = fminf(fmaxf(fmaxf(sx0, sx1), sx2) + 0.5f, (float)(a.W - 1));
+        const float mny = fmaxf(fminf(fminf(sy0, sy1), sy2) - 0.5f, 0.f);
+        const float mxy = fminf(fmaxf(fmaxf(sy0, sy1), sy2) + 0.5f, (float)(a.H - 1));
+        if (!(mnx <= mxx) || !(mny <= mxy)) surv = false;
+        x0 = (int)ceilf(mnx); x1 = (int)floorf(mxx);
+        y0 = (int)ceilf(mny); y1 = (int)floorf(mxy);
+        if (x0 > x1 || y0 > y1) surv = false;
+      }
+      if (surv) {
+        TriRecord r;
+        lu_inverse3(M, r.inv);
+        const float m0 = s_w2c[8], m1 = s_w2c[9], m2 = s_w2c[10], m3 = s_w2c[11];
+        r.zc[0] = ((p0x * m0 + p0y * m1) + p0z * m2) + m3;
+        r.zc[1] = ((p1x * m0 + p1y * m1) + p1z * m2) + m3;
+        r.zc[2] = ((p2x * m0 + p2y * m1) + p2z * m2) + m3;
+        r.x0 = (unsigned short)x0; r.x1 = (unsigned short)x1; r.y0 = (unsigned short)y0; r.y1 = (unsigned short)y1;
+        r.flags = fallback0 ? 1 : 0;
+        r.pad = 0;
+        float4* dst = reinterpret_cast<float4*>(recs + (size_t)b * a.T + t);
+        const float4* src = reinterpret_cast<const float4*>(&r);
+        dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+        if (fallback0) surv = false;  // not a candidate: never enters a bin
+      }
+    }
+    // record 0's flag is always defined (the raster kernel looks at it for the DepthShader quirk)
+    if (DEPTH && t == 0 && !(cand && !behind) && !(fallback0 && !behind)) recs[(size_t)b * a.T].flags = 0;
+  }
+  // ---- publish tile bitmask words (one writer per (tile, word))
+  int tx0 = x0 / TL_TILE, tx1 = x1 / TL_TILE, ty0 = y0 / TL_TILE, ty1 = y1 / TL_TILE;
+  if (!surv) { tx0 = 1 << 20; tx1 = -1; ty0 = 1 << 20; ty1 = -1; }
+  int ux0 = tx0, ux1 = tx1, uy0 = ty0, uy1 = ty1;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    ux0 = min(ux0, __shfl_xor_sync(0xffffffffu, ux0, off));
+    ux1 = max(ux1, __shfl_xor_sync(0xffffffffu, ux1, off));
+    uy0 = min(uy0, __shfl_xor_sync(0xffffffffu, uy0, off));
+    uy1 = max(uy1, __shfl_xor_sync(0xffffffffu, uy1, off));
+  }
+  if (ux1 < ux0) return;  // no survivor in this warp
+  const int word = t >> 5;
+  unsigned* mrow = masks + (size_t)b * L.tiles * L.words;
+  for (int tx = ux0; tx <= ux1; ++tx)
+    for (int ty = uy0; ty <= uy1; ++ty) {
+      const bool hit = surv && tx >= tx0 && tx <= tx1 && ty >= ty0 && ty <= ty1;
+      const unsigned w = __ballot_sync(0xffffffffu, hit);
+      if (w && lane == 0) mrow[(size_t)(tx * L.tiles_y + ty) * L.words + word] = w;
+    }
+}
+
+struct TLSmem { size_t keys, xs, ys, ring, bigq, mask, total; };
+__host__ __device__ inline TLSmem tl_smem() {
+  TLSmem S;
+  S.keys = 0;
+  S.xs = (size_t)TL_TILE * TL_TILE * 8;
+  S.ys = S.xs + TL_TILE * 4;
+  S.ring = S.ys + TL_TILE * 4;
+  S.bigq = S.ring + (TL_THREADS / 32) * 64 * 4;
+  S.mask = S.bigq + (size_t)TL_BIGCAP * 64;
+  S.total = S.mask + (size_t)TL_MASKCAP * 4;
+  return S;
+}
+
+template <bool DEPTH>
+__global__ void __launch_bounds__(TL_THREADS)
+k_raster_tile(const __grid_constant__ JrRenderArgs a, const TriRecord* __restrict__ recs,
+              const unsigned* __restrict__ masks, TiledLayout L) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const TLSmem S = tl_smem();
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem + S.keys);
+  float* xs = reinterpret_cast<float*>(smem + S.xs);
+  float* ys = reinterpret_cast<float*>(smem + S.ys);
+  V2Big* bigq = reinterpret_cast<V2Big*>(smem + S.bigq);
+  unsigned* s_mask = reinterpret_cast<unsigned*>(smem + S.mask);
+  __shared__ int bigq_n;
+  __shared__ int tri0_flag;
+  __shared__ TriSetup tri0;
+  __shared__ float s_vp[16];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = TL_THREADS / 32;
+  int* ring = reinterpret_cast<int*>(smem + S.ring) + warp * 64;
+  const int b = blockIdx.x / L.tiles;
+  const int tile = blockIdx.x - b * L.tiles;
+  const int tx0 = (tile / L.tiles_y) * TL_TILE;
+  const int ty0 = (tile % L.tiles_y) * TL_TILE;
+  const int tw = min(TL_TILE, a.W - tx0);
+  const int th = min(TL_TILE, a.H - ty0);
+  const uint32_t keys_saddr = (uint32_t)__cvta_generic_to_shared(keys);
+  const TriRecord* __restrict__ rec_b = recs + (size_t)b * a.T;
+
+  if (tid < 16) s_vp[tid] = a.viewport.ptr[(long long)b * a.viewport.batch_stride + tid];
+  if (tid == 0) {
+    bigq_n = 0;
+    tri0_flag = 0;
+  }
+  {
+    ulonglong2* k2 = reinterpret_cast<ulonglong2*>(keys);
+    for (int i = tid; i < TL_TILE * TL_TILE / 2; i += TL_THREADS) k2[i] = make_ulonglong2(~0ull, ~0ull);
+  }
+  __syncthreads();
+  for (int i = tid; i < tw; i += TL_THREADS) xs[i] = ((float)(tx0 + i) - s_vp[3]) / s_vp[0];
+  for (int i = tid; i < th; i += TL_THREADS) ys[i] = ((float)(ty0 + i) - s_vp[7]) / s_vp[5];
+  __syncthreads();
+  const float vp22 = s_vp[10], vp23 = s_vp[11];
+
+  auto put = [&](int x, int y, const float* inv, const float* zc, unsigned tri) {
+    const float xn = xs[x], yn = ys[y];
+    const float c0 = (xn * inv[0] + yn * inv[3]) + inv[6];
+    const float c1 = (xn * inv[1] + yn * inv[4]) + inv[7];
+    const float c2 = (xn * inv[2] + yn * inv[5]) + inv[8];
+    if (c0 >= 0.f && c1 >= 0.f && c2 >= 0.f) {
+      const float z = (c0 * zc[0] + c1 * zc[1]) + c2 * zc[2];
+      const float zw = z * vp22 + vp23;
+      key_min(keys_saddr + (uint32_t)(x * TL_TILE + y) * 8u, ((unsigned long long)orderable(zw) << 32) | tri);
+    }
+  };
+
+  // fetch the record of triangle `t`, clip its bbox to the tile, dispatch by size (warp-uniform call)
+  auto fire = [&](bool valid, int t) {
+    float inv[9], zc[3];
+    int x0 = 0, x1 = -1, y0 = 0, y1 = -1;
+    if (valid) {
+      const float4* src = reinterpret_cast<const float4*>(rec_b + t);
+      const float4 q0 = src[0], q1 = src[1], q2 = src[2], q3 = src[3];
+      inv[0] = q0.x; inv[1] = q0.y; inv[2] = q0.z; inv[3] = q0.w;
+      inv[4] = q1.x; inv[5] = q1.y; inv[6] = q1.z; inv[7] = q1.w;
+      inv[8] = q2.x; zc[0] = q2.y; zc[1] = q2.z; zc[2] = q2.w;
+      const unsigned bx = __float_as_uint(q3.x), by = __float_as_uint(q3.y);
+      x0 = max((int)(bx & 0xffff) - tx0, 0); x1 = min((int)(bx >> 16) - tx0, tw - 1);
+      y0 = max((int)(by & 0xffff) - ty0, 0); y1 = min((int)(by >> 16) - ty0, th - 1);
+    }
+    const int bw = x1 - x0 + 1, bh = y1 - y0 + 1;
+    const int area = (valid && bw > 0 && bh > 0) ? bw * bh : 0;
+    // everything above the per-lane size is rasterised by the whole warp (hierarchically from
+    // V2_HIER_AREA pixels); with hundreds of triangles per tile the warps stay balanced
+    const bool is_medium = area > V2_SMALL_AREA;
+    if (area > 0 && area <= V2_SMALL_AREA) {
+      for (int x = x0; x <= x1; ++x)
+        for (int y = y0; y <= y1; ++y) put(x, y, inv, zc, (unsigned)t);
+    }
+    unsigned mm = __ballot_sync(0xffffffffu, is_medium);
+    while (mm) {
+      const int src = __ffs(mm) - 1;
+      mm &= mm - 1;
+      float binv[9], bzc[3];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) binv[k] = __shfl_sync(0xffffffffu, inv[k], src);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) bzc[k] = __shfl_sync(0xffffffffu, zc[k], src);
+      const unsigned btri = (unsigned)__shfl_sync(0xffffffffu, t, src);
+      const int sx0 = __shfl_sync(0xffffffffu, x0, src), sy0 = __shfl_sync(0xffffffffu, y0, src);
+      const int sbh = __shfl_sync(0xffffffffu, bh, src);
+      const int n = __shfl_sync(0xffffffffu, area, src);
+      if (n >= V2_HIER_AREA) {
+        const int sx1 = __shfl_sync(0xffffffffu, x1, src), sy1 = __shfl_sync(0xffffffffu, y1, src);
+        raster_hier_warp(binv, bzc, btri, sx0, sy0, sx1, sy1, lane, xs, ys, keys_saddr, TL_TILE, vp22, vp23);
+      } else {
+        const float rbh = 1.0f / (float)sbh;
+        for (int i = lane; i < n; i += 32) {
+          const int dx = (int)(((float)i + 0.5f) * rbh);
+          put(sx0 + dx, sy0 + (i - dx * sbh), binv, bzc, btri);
+        }
+      }
+    }
+  };
+
+  // DepthShader triangle-0 fallback record
+  if (DEPTH && tid == 0 && a.T > 0) {
+    const TriRecord& r0 = rec_b[0];
+    if (r0.flags == 1) {  // k_setup_bin always defines record 0's flag
+#pragma unroll
+      for (int k = 0; k < 9; ++k) tri0.inv[k] = r0.inv[k];
+      tri0.zc[0] = r0.zc[0]; tri0.zc[1] = r0.zc[1]; tri0.zc[2] = r0.zc[2];
+      tri0_flag = 1;
+    }
+  }
+
+  // ---- scan the tile's bitmask; compact set bits into full warps of triangle ids
+  const unsigned* __restrict__ mrow = masks + ((size_t)b * L.tiles + tile) * L.words;
+  int head = 0, pc = 0;  // warp-uniform ring state
+  const unsigned lt_mask = (1u << lane) - 1u;
+  for (int chunk0 = 0; chunk0 < L.words; chunk0 += TL_MASKCAP) {
+    // stage the tile's bitmask words in shared memory (coalesced; a per-word global load in the
+    // scan loop below serialised ~80 dependent DRAM round trips per warp)
+    const int n = min(TL_MASKCAP, L.words - chunk0);
+    for (int i = tid; i < n; i += TL_THREADS) s_mask[i] = mrow[chunk0 + i];
+    __syncthreads();
+    for (int i = warp; i < n; i += NW) {
+      const unsigned w = s_mask[i];
+      if (w == 0u) continue;
+      if ((w >> lane) & 1u) ring[(head + pc + __popc(w & lt_mask)) & 63] = (chunk0 + i) * 32 + lane;
+      pc += __popc(w);
+      __syncwarp();
+      if (pc >= 32) {
+        const int t = ring[(head + lane) & 63];
+        head = (head + 32) & 63;
+        pc -= 32;
+        __syncwarp();
+        fire(true, t);
+      }
+    }
+    __syncthreads();
+  }
+  if (pc > 0) {
+    const int t = (lane < pc) ? ring[(head + lane) & 63] : 0;
+    fire(lane < pc, t);
+  }
+  __syncthreads();
+  // ---- large triangles: whole CTA, one at a time, single writer per pixel
+  {
+    const int nbig = min(bigq_n, TL_BIGCAP);
+    for (int e = 0; e < nbig; ++e) {
+      const V2Big& q = bigq[e];
+      const float i0 = q.inv[0], i1 = q.inv[1], i2 = q.inv[2], i3 = q.inv[3], i4 = q.inv[4], i5 = q.inv[5],
+                  i6 = q.inv[6], i7 = q.inv[7], i8 = q.inv[8];
+      const float z0 = q.zc[0], z1 = q.zc[1], z2 = q.zc[2];
+      const unsigned tri = (unsigned)q.tri;
+      const int qx0 = q.x0, qy0 = q.y0, bh = q.y1 - q.y0 + 1;
+      const int n = (q.x1 - q.x0 + 1) * bh;
+      const float rbh = 1.0f / (float)bh;
+      for (int i = tid; i < n; i += TL_THREADS) {
+        const int dx = (int)(((float)i + 0.5f) * rbh);
+        const int x = qx0 + dx, y = qy0 + (i - dx * bh);
+        const float xn = xs[x], yn = ys[y];
+        const float c0 = (xn * i0 + yn * i3) + i6;
+        const float c1 = (xn * i1 + yn * i4) + i7;
+        const float c2 = (xn * i2 + yn * i5) + i8;
+        if (c0 >= 0.f && c1 >= 0.f && c2 >= 0.f) {
+          const float z = (c0 * z0 + c1 * z1) + c2 * z2;
+          const float zw = z * vp22 + vp23;
+          const unsigned long long key = ((unsigned long long)orderable(zw) << 32) | tri;
+          unsigned long long* slot = &keys[x * TL_TILE + y];
+          if (key < *slot) *slot = key;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // ---- resolve
+  int32_t* __restrict__ tri_out = a.tri_id ? a.tri_id + (long long)b * a.W * a.H : nullptr;
+  float* __restrict__ z_out = DEPTH ? a.zbuffer + (long long)b * a.W * a.H : nullptr;
+  const bool use0 = DEPTH && tri0_flag;
+  for (int i = tid; i < tw * TL_TILE; i += TL_THREADS) {
+    const int lx = i >> 6, ly = i & 63;
+    if (ly >= th) continue;
+    const unsigned long long key = keys[i];
+    const long long pix = (long long)(tx0 + lx) * a.H + (ty0 + ly);
+    int tri = -1;
+    if (key != ~0ull) {
+      tri = (int)(unsigned)(key & 0xFFFFFFFFull);
+      if (DEPTH) z_out[pix] = from_orderable((uint32_t)(key >> 32));
+    } else if (use0) {
+      float c[3];
+      clip_coef(tri0.inv, xs[lx], ys[ly], c);
+      if (c[0] >= 0.f && c[1] >= 0.f && c[2] >= 0.f) {
+        const float z = (c[0] * tri0.zc[0] + c[1] * tri0.zc[1]) + c[2] * tri0.zc[2];
+        z_out[pix] = z * vp22 + vp23;
+        tri = 0;
+      }
+    }
+    if (tri_out) tri_out[pix] = tri;
+  }
+}
+
+}  // namespace jr

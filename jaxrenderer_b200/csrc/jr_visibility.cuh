@@ -27,6 +27,7 @@ constexpr int V2_THREADS = 256;
 constexpr int V2_BIGCAP = 32;
 constexpr int V2_SMALL_AREA = 32;
 constexpr int V2_MEDIUM_AREA = 1024;
+constexpr int V2_HIER_AREA = 256;   // warp-cooperative boxes from this size use the hierarchical raster
 
 struct V2Layout { size_t keys, xs, ys, bigq, total; };
 __host__ __device__ inline V2Layout v2_layout(int tile_w, int tile_h) {
@@ -48,6 +49,62 @@ __device__ __forceinline__ void key_min(uint32_t saddr, unsigned long long key) 
     asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(prev) : "r"(saddr), "l"(old), "l"(key) : "memory");
     if (prev == old) break;
     old = prev;
+  }
+}
+
+// Warp-cooperative, EXACT hierarchical rasterisation of one triangle's bbox (tile-local, inclusive).
+// Every rounded fp32 op is monotone, so fl(fl(xn*i0 + yn*i1) + i2) is monotone in xn and in yn and,
+// over a block of pixels, attains its max / min at one of the 4 block corners: a 4x8 block whose
+// corner max is < 0 for some edge has no inside pixel (skipped); one whose corner min is >= 0 for
+// all edges is fully inside (edge tests skipped).  One lane classifies one block (32 blocks per
+// round); surviving blocks get one lane per pixel.  Pays off from ~8 blocks (256 px) upwards.
+__device__ __forceinline__ void raster_hier_warp(const float* inv, const float* zc, unsigned tri, int x0, int y0,
+                                                 int x1, int y1, int lane, const float* xs, const float* ys,
+                                                 uint32_t keys_saddr, int key_stride, float vp22, float vp23) {
+  const int bw = x1 - x0 + 1, bh = y1 - y0 + 1;
+  const int nby = (bh + 7) >> 3;
+  const int nblk = ((bw + 3) >> 2) * nby;
+  const float rnby = 1.0f / (float)nby;
+  for (int base = 0; base < nblk; base += 32) {
+    const int blk = base + lane;
+    bool live = false, full = false;
+    int xa = 0, ya = 0;
+    if (blk < nblk) {
+      const int bx = (int)(((float)blk + 0.5f) * rnby), by = blk - bx * nby;
+      xa = x0 + 4 * bx; ya = y0 + 8 * by;
+      const int xb = min(xa + 3, x1), yb = min(ya + 7, y1);
+      const float xna = xs[xa], xnb = xs[xb], yna = ys[ya], ynb = ys[yb];
+      live = true; full = true;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const float pa = xna * inv[k], pb = xnb * inv[k];
+        const float qa = yna * inv[3 + k], qb = ynb * inv[3 + k];
+        const float v0 = (pa + qa) + inv[6 + k], v1 = (pa + qb) + inv[6 + k];
+        const float v2 = (pb + qa) + inv[6 + k], v3 = (pb + qb) + inv[6 + k];
+        live = live && (fmaxf(fmaxf(v0, v1), fmaxf(v2, v3)) >= 0.f);
+        full = full && (v0 >= 0.f) && (v1 >= 0.f) && (v2 >= 0.f) && (v3 >= 0.f);
+      }
+    }
+    unsigned m_live = __ballot_sync(0xffffffffu, live);
+    const unsigned m_full = __ballot_sync(0xffffffffu, full);
+    const int xy = (xa << 16) | ya;
+    while (m_live) {
+      const int j = __ffs(m_live) - 1;
+      m_live &= m_live - 1;
+      const int xyj = __shfl_sync(0xffffffffu, xy, j);
+      const int x = (xyj >> 16) + (lane >> 3), y = (xyj & 0xffff) + (lane & 7);
+      if (x <= x1 && y <= y1) {
+        const float xn = xs[x], yn = ys[y];
+        const float c0 = (xn * inv[0] + yn * inv[3]) + inv[6];
+        const float c1 = (xn * inv[1] + yn * inv[4]) + inv[7];
+        const float c2 = (xn * inv[2] + yn * inv[5]) + inv[8];
+        if (((m_full >> j) & 1u) || (c0 >= 0.f && c1 >= 0.f && c2 >= 0.f)) {
+          const float z = (c0 * zc[0] + c1 * zc[1]) + c2 * zc[2];
+          const float zw = z * vp22 + vp23;
+          key_min(keys_saddr + (uint32_t)(x * key_stride + y) * 8u, ((unsigned long long)orderable(zw) << 32) | tri);
+        }
+      }
+    }
   }
 }
 
@@ -186,7 +243,10 @@ k_vis2(const __grid_constant__ JrRenderArgs a, int tile_w, int tile_h, int tiles
       const int btri = __shfl_sync(0xffffffffu, tri, src);
       const unsigned bbb = __shfl_sync(0xffffffffu, bb, src);
       const int sx0 = bbb & 0xff, sx1 = (bbb >> 8) & 0xff, sy0 = (bbb >> 16) & 0xff, sy1 = bbb >> 24;
-      raster_flat(binv, bzc, btri, sx0, sy0, sx1 - sx0 + 1, sy1 - sy0 + 1, lane, 32);
+      if ((sx1 - sx0 + 1) * (sy1 - sy0 + 1) >= V2_HIER_AREA)
+        raster_hier_warp(binv, bzc, (unsigned)btri, sx0, sy0, sx1, sy1, lane, xs, ys, keys_saddr, tile_h, vp22, vp23);
+      else
+        raster_flat(binv, bzc, btri, sx0, sy0, sx1 - sx0 + 1, sy1 - sy0 + 1, lane, 32);
     }
   };
 

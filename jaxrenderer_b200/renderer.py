@@ -124,8 +124,9 @@ class Renderer:
             return Buffers(zbuffer=z, targets=(c,))
         shadow = Shadow.render_shadow_map(
             shadow_map=torch.full_like(buffers.zbuffer, DtypeInfo.create(buffers.zbuffer.dtype).max),
-            verts=model.verts, faces=model.faces, light_direction=ldir_raw,
-            viewport_matrix=camera.viewport, centre=shadow_param.centre, up=shadow_param.up,
+            # no gradient reaches the shadow map (it is only compared against, shadow.py:129-153)
+            verts=model.verts.detach(), faces=model.faces, light_direction=ldir_raw.detach(),
+            viewport_matrix=camera.viewport.detach(), centre=shadow_param.centre, up=shadow_param.up,
             strength=shadow_param.strength, offset=float(shadow_param.offset))
         arrays.update({
             "shadow_map": shadow.shadow_map, "shadow_strength": _f32(shadow.strength, dev),

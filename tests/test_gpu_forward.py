@@ -78,10 +78,11 @@ def test_depth_brax_like(wh):
         assert int((ref.tri_id >= 0).sum()) > W * H // 2  # ground plane covers most of the view
 
 
-def test_depth_triangle0_backfacing_leak():
+@pytest.mark.parametrize("wh", [(40, 36), (300, 200)])
+def test_depth_triangle0_backfacing_leak(wh):
     """a kept back-facing triangle 0 leaks into the depth buffer where
-    no candidate exists (DepthShader has no front-face term)."""
-    W, H = 40, 36
+    no candidate exists (DepthShader has no front-face term).  Single-tile and binned paths."""
+    W, H = wh
     cam, _, extra = smoke_scene(W, H, depth=1.0)
     pos = torch.cat((extra.position, torch.tensor(((-2.0, -1.0, 0.0), (-1.0, -1.0, 0.0), (-1.5, -0.2, 0.3)))))
     faces = torch.tensor(((0, 2, 1), (6, 7, 8)), dtype=torch.int32)  # tri 0 = flipped (0,1,2)
