@@ -293,17 +293,28 @@ struct GlobalOut {
   long long stride[NG];
 };
 
-// one thread per slot: sums the per-block partials in fixed (b, block) order
-__global__ void k_bwd_global_final(const float* __restrict__ partials, int B, int nblk, GlobalOut out) {
-  const int j = threadIdx.x;
-  if (j >= NG || out.ptr[j] == nullptr) return;
+// One CTA per slot.  Shared (stride 0) parameters: the B*nblk partials are summed by 128 threads in a
+// fixed strided order, then a fixed-shape tree.  Batched parameters: thread t sums the nblk partials
+// of images t, t+128, ... in block order.  Deterministic either way.
+__global__ void __launch_bounds__(128) k_bwd_global_final(const float* __restrict__ partials, int B, int nblk,
+                                                          GlobalOut out) {
+  const int j = blockIdx.x;
+  if (out.ptr[j] == nullptr) return;
+  const int tid = threadIdx.x;
   if (out.stride[j] == 0) {
+    __shared__ float red[128];
+    const long long n = (long long)B * nblk;
     float acc = 0.f;
-    for (int b = 0; b < B; ++b)
-      for (int k = 0; k < nblk; ++k) acc += partials[((long long)b * nblk + k) * NG + j];
-    *out.ptr[j] += acc;
+    for (long long i = tid; i < n; i += 128) acc += partials[i * NG + j];
+    red[tid] = acc;
+    __syncthreads();
+    for (int off = 64; off > 0; off >>= 1) {
+      if (tid < off) red[tid] += red[tid + off];
+      __syncthreads();
+    }
+    if (tid == 0) *out.ptr[j] += red[0];
   } else {
-    for (int b = 0; b < B; ++b) {
+    for (int b = tid; b < B; b += 128) {
       float acc = 0.f;
       for (int k = 0; k < nblk; ++k) acc += partials[((long long)b * nblk + k) * NG + j];
       out.ptr[j][(long long)b * out.stride[j]] += acc;
@@ -485,27 +496,44 @@ k_bwd_segreduce(const __grid_constant__ JrRenderArgs a, const __grid_constant__ 
   }
 }
 
-// Resolve segments that straddle chunks: one thread per chunk that STARTS a run.
+// Resolve segments that straddle chunks: one WARP per chunk; the warp whose chunk STARTS a run finds
+// the run's last chunk by binary search in the sorted keys, its lanes sum the per-chunk pieces in a
+// fixed strided order and a fixed butterfly combines them (deterministic, and parallel for the long
+// runs produced by few-key targets such as 1x1 textures).
 template <int MODE, int C>
-__global__ void k_bwd_segfix(KeyedPlan plan, const Carry<C>* __restrict__ carry, int nchunks) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256)
+k_bwd_segfix(KeyedPlan plan, const Carry<C>* __restrict__ carry, const unsigned* __restrict__ keys, int nchunks) {
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (c >= nchunks) return;
   const Carry<C>& me = carry[c];
   if (!me.last_open) return;
   if (me.whole && me.first_open) return;  // continues a run started further left
   const unsigned key = me.last_key;
   if (key == plan.invalid_key) return;
+  // last entry with this key: upper bound over the sorted keys
+  long long lo = (long long)(c + 1) * 256, hi = plan.n_entries;  // keys[lo] == key is known
+  while (lo < hi) {
+    const long long mid = (lo + hi) >> 1;
+    if (keys[mid] <= key) lo = mid + 1; else hi = mid;
+  }
+  const int c_end = (int)((lo - 1) >> 8);  // chunk holding the last entry of the run (> c)
   float acc[C];
 #pragma unroll
-  for (int k = 0; k < C; ++k) acc[k] = me.last_val[k];
-  int j = c + 1;
-  while (j < nchunks) {
+  for (int k = 0; k < C; ++k) acc[k] = 0.f;
+  for (int j = c + 1 + lane; j <= c_end; j += 32) {
     const Carry<C>& nx = carry[j];
 #pragma unroll
     for (int k = 0; k < C; ++k) acc[k] += nx.first_val[k];
-    if (!(nx.whole && nx.last_open)) break;
-    ++j;
   }
+#pragma unroll
+  for (int k = 0; k < C; ++k) {
+    float v = acc[k];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    acc[k] = v + me.last_val[k];
+  }
+  if (lane != 0) return;
   if (MODE == MODE_POS && C > 3) {
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -596,7 +624,7 @@ static int run_keyed(const JrRenderArgs* a, const JrGradArgs* g, const BwdLayout
   const long long nchunks = (plan.n_entries + 255) / 256;
   k_bwd_segreduce<S, MODE, C><<<(unsigned)nchunks, 256, 0, stream>>>(*a, *g, plan, keys_b, vals_b, carry);
   g_launches++;
-  k_bwd_segfix<MODE, C><<<(unsigned)((nchunks + 127) / 128), 128, 0, stream>>>(plan, carry, (int)nchunks);
+  k_bwd_segfix<MODE, C><<<(unsigned)((nchunks + 7) / 8), 256, 0, stream>>>(plan, carry, keys_b, (int)nchunks);
   g_launches++;
   return cudaGetLastError() == cudaSuccess ? JR_OK : JR_ERR_CUDA;
 }
@@ -634,7 +662,7 @@ static int backward_impl(const JrRenderArgs* a, const JrGradArgs* g, cudaStream_
     set(G_DIF, 3, g->d_diffuse, nullptr);
     set(G_SPE, 3, g->d_specular, nullptr);
     set(G_STR, 3, g->d_shadow_strength, nullptr);
-    k_bwd_global_final<<<1, 64, 0, stream>>>(partials, a->B, L.nblk, out);
+    k_bwd_global_final<<<NG, 128, 0, stream>>>(partials, a->B, L.nblk, out);
     g_launches++;
   }
   if (S >= JR_GOURAUD_TEXTURE && g->d_texture.ptr) {

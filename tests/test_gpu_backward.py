@@ -250,3 +250,17 @@ def test_batched_shared_parameter_grads_and_determinism():
     _check("shared light.colour", g1[1], lcol.grad)
     _check("batched position", g1[2], torch.stack([p.grad for p in ps]))
     _check("shared world_to_clip", g1[3], w2c.grad)
+
+
+def test_long_segments_few_keys():
+    """1x1 texture: every covered pixel hits the same texel, so one key spans dozens of 256-entry
+    chunks (the Brax capsule textures are 1x1).  Exercises the cross-chunk carry resolution."""
+    s = random_mesh_scene(21, n_tri=120, W=160, H=120)
+    tex1 = torch.tensor([[[0.7, 0.4, 0.9]]])
+
+    def mk(get):
+        return GouraudTextureExtraInput(s.pos, s.nrm, s.uv_texel,
+                                        jr.LightSource(s.light.direction, get("light_colour", s.light.colour)),
+                                        get("texture", tex1))
+    out = _run_case("gouraud_texture", GouraudTextureShader, mk, s, ("texture", "light_colour", "world_to_clip"))
+    assert int((out.zbuffer != 1.0).sum()) > 2000
