@@ -90,7 +90,11 @@ def dot3(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
 
 
 def norm3(v: torch.Tensor) -> torch.Tensor:
-    return torch.sqrt(dot3(v, v))
+    """IEEE-exact fp32 square root.  ``torch.sqrt`` on CPU float32 tensors is NOT correctly rounded
+    (vectorised approximation, off by 1 ulp on ~1 % of inputs -- found when Gouraud colours with
+    cancelling vertex terms differed from the CUDA kernel in the last place); sqrt in float64
+    followed by rounding to float32 is exact (53 >= 2*24 + 2 bits, so double rounding is harmless)."""
+    return torch.sqrt(dot3(v, v).double()).to(F32)
 
 
 def normalise(v: torch.Tensor) -> torch.Tensor:

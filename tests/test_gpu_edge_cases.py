@@ -1,0 +1,126 @@
+"""GPU parity on edge cases: empty mesh, degenerate triangles, geometry straddling / behind the
+camera (reference examples/behind_camera.py), odd canvas sizes, canvases around the single-tile /
+binned switch, batch broadcast of the camera, buffers with non-default contents."""
+from types import SimpleNamespace as NS
+
+import pytest
+import torch
+
+import jaxrenderer_b200 as jr
+from jaxrenderer_b200.shaders import DepthExtraInput, DepthShader, GouraudExtraInput, GouraudShader
+from oracle import jr_oracle as O
+from tests.helpers import assert_parity, compare, random_mesh_scene
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _cam_d(cam):
+    return type(cam)(*[t.to(DEV) for t in cam])
+
+
+def test_empty_mesh_leaves_buffers_untouched():
+    cam = jr.Renderer.create_camera_from_parameters(jr.CameraParameters(viewWidth=20, viewHeight=12))
+    z0 = torch.rand(20, 12)
+    c0 = torch.rand(20, 12, 3)
+    out, tri = jr.render(_cam_d(cam), DepthShader, jr.Buffers(z0.to(DEV), ()),
+                         torch.zeros(0, 3, dtype=torch.int32, device=DEV),
+                         DepthExtraInput(position=torch.zeros(3, 3, device=DEV)), return_tri_id=True)
+    assert torch.equal(out.zbuffer.cpu(), z0) and bool((tri == -1).all())
+    light = jr.LightSource(torch.tensor((0.0, 0.0, -1.0)), torch.ones(3))
+    out = jr.render(_cam_d(cam), GouraudShader, jr.Buffers(z0.to(DEV), (c0.to(DEV),)),
+                    torch.zeros(0, 3, dtype=torch.int32, device=DEV),
+                    GouraudExtraInput(torch.zeros(3, 3, device=DEV), torch.zeros(3, 3, device=DEV),
+                                      torch.ones(3, 3, device=DEV), light))
+    assert torch.equal(out.zbuffer.cpu(), z0) and torch.equal(out.targets[0].cpu(), c0)
+
+
+def test_degenerate_and_duplicate_triangles():
+    """Zero-area triangles are dropped by |det| > 1e-6; exact duplicates tie on depth and the
+    lowest index wins (shader.py:217)."""
+    s = random_mesh_scene(4, n_tri=30)
+    pos = s.pos.clone()
+    pos[3:6] = pos[3:4]                      # triangle 1 collapses to a point
+    pos[9] = pos[10]                         # triangle 3 has two equal vertices
+    faces = torch.cat((s.faces, s.faces[5:8]))   # duplicates of triangles 5..7 with higher ids
+    z0 = torch.full((s.W, s.H), 1.0)
+    out, tri = jr.render(_cam_d(s.cam), DepthShader, jr.Buffers(z0.to(DEV), ()), faces.to(DEV),
+                         DepthExtraInput(position=pos.to(DEV)), return_tri_id=True)
+    ref = O.render(s.cam, "depth", z0, (), faces, NS(position=pos))
+    rep = compare("degenerate", out.zbuffer, None, tri, ref)
+    print(rep)
+    assert rep["tri_mismatch"] == 0 and rep["z_not_bit_equal"] == 0
+    assert not bool(((tri.cpu() >= 30)).any()), "duplicates must lose the tie to the lower index"
+    assert not bool(((tri.cpu() == 1) | (tri.cpu() == 3)).any())
+
+
+@pytest.mark.parametrize("wh", [(64, 48), (640, 480)])
+def test_geometry_behind_and_straddling_the_camera(wh):
+    """examples/behind_camera.py: a 20 x 20 slab around the eye -- triangles with some or all w <= 0
+    (no clipping in the reference: README.md:115)."""
+    W, H = wh
+    tex = torch.tensor([[[1.0, 0, 0], [0, 1.0, 0]], [[0, 0, 1.0], [1.0, 1.0, 0]]])
+    slab = jr.create_cube(torch.tensor((10.0, 10.0, 0.03)), torch.tensor((160.0, 160.0)), tex, torch.ones(2, 2) * 2)
+    small = jr.create_cube(torch.tensor((1.0, 1.0, 0.03)), torch.tensor((16.0, 16.0)), tex, torch.ones(2, 2) * 2)
+    t = torch.eye(4); t[2, 3] = 0.5
+    model = jr.merge_objects([jr.ModelObject(model=slab), jr.ModelObject(model=small, transform=t)])
+    camp = jr.CameraParameters(viewWidth=W, viewHeight=H, position=torch.tensor([2.5894797, -2.5876467, 1.9174135]),
+                               hfov=58.0, vfov=32.625)
+    cam = jr.Renderer.create_camera_from_parameters(camp)
+    clip_w = (torch.cat((model.verts, torch.ones(len(model.verts), 1)), 1) @ cam.world_to_clip.T)[:, 3]
+    assert bool((clip_w < 0).any()) and bool((clip_w > 0).any()), "scene must straddle w = 0"
+    z0 = torch.full((W, H), 1.0)
+    out, tri = jr.render(_cam_d(cam), DepthShader, jr.Buffers(z0.to(DEV), ()), model.faces.to(DEV),
+                         DepthExtraInput(position=model.verts.to(DEV)), return_tri_id=True)
+    ref = O.render(cam, "depth", z0, (), model.faces, NS(position=model.verts))
+    rep = compare(f"behind{W}", out.zbuffer, None, tri, ref)
+    print(rep)
+    assert_parity(rep)
+    assert int((ref.tri_id >= 0).sum()) > W * H // 3
+    # and through the full renderer (phong_reflection + shadow)
+    img = jr.Renderer.render(type(model)(*[v.to(DEV) if isinstance(v, torch.Tensor) else v for v in model]),
+                             jr.LightParameters(), _cam_d(cam), jr.Renderer.create_buffers(W, H, device=DEV),
+                             shadow_param=jr.ShadowParameters()).targets[0]
+    assert bool(torch.isfinite(img).all())
+
+
+@pytest.mark.parametrize("wh", [(1, 1), (7, 3), (3, 97), (110, 110), (111, 111), (255, 48), (256, 48), (129, 65)])
+def test_odd_canvas_sizes(wh):
+    """Canvas shapes around every internal switch: 1x1, non-square, single tile <-> binned (96 KB of
+    keys, 255-pixel side limit), partial edge tiles."""
+    W, H = wh
+    s = random_mesh_scene(7, n_tri=50, W=W, H=H)
+    z0 = torch.full((W, H), 2.0)
+    c0 = torch.full((W, H, 3), 0.5)
+    ex = GouraudExtraInput(s.pos, s.col, s.nrm, s.light)
+    out, tri = jr.render(_cam_d(s.cam), GouraudShader, jr.Buffers(z0.to(DEV), (c0.to(DEV),)), s.faces.to(DEV),
+                         GouraudExtraInput(s.pos.to(DEV), s.col.to(DEV), s.nrm.to(DEV),
+                                           jr.LightSource(s.light.direction.to(DEV), s.light.colour.to(DEV))),
+                         return_tri_id=True)
+    ref = O.render(s.cam, "gouraud", z0, (c0,), s.faces, ex)
+    rep = compare(f"{W}x{H}", out.zbuffer, out.targets[0], tri, ref)
+    print(rep)
+    assert_parity(rep)
+
+
+def test_many_large_overlapping_triangles():
+    """Stress the warp / hierarchical raster paths and their queue overflow: 300 screen-filling
+    triangles at distinct depths on a single-tile canvas and on a binned canvas."""
+    for (W, H) in ((96, 80), (320, 200)):
+        g = torch.Generator().manual_seed(3)
+        n = 300
+        base = torch.tensor([[-3.0, -3.0, 0.0], [3.0, -3.0, 0.0], [0.0, 3.5, 0.0]])
+        pos = (base[None] + torch.rand(n, 3, 3, generator=g) * 0.5)
+        pos[:, :, 2] = torch.linspace(-1.5, 0.5, n)[:, None] + torch.rand(n, 3, generator=g) * 0.01
+        pos = pos.reshape(-1, 3)
+        faces = torch.arange(3 * n, dtype=torch.int32).reshape(n, 3)
+        cam = jr.Renderer.create_camera_from_parameters(jr.CameraParameters(
+            viewWidth=W, viewHeight=H, position=torch.tensor((0.0, 0.0, 4.0)), up=(0.0, 1.0, 0.0)))
+        z0 = torch.full((W, H), 1.0)
+        out, tri = jr.render(_cam_d(cam), DepthShader, jr.Buffers(z0.to(DEV), ()), faces.to(DEV),
+                             DepthExtraInput(position=pos.to(DEV)), return_tri_id=True)
+        ref = O.render(cam, "depth", z0, (), faces, NS(position=pos))
+        rep = compare(f"large{W}", out.zbuffer, None, tri, ref)
+        print(rep)
+        assert_parity(rep)
+        assert int((ref.tri_id >= 0).sum()) > W * H // 4
