@@ -303,6 +303,43 @@ __global__ void __launch_bounds__(256) k_shade(const __grid_constant__ JrRenderA
   }
 }
 
+// One thread per triangle: vertex stage of the shader -> attribute record (large canvases).
+template <int SHADER>
+__global__ void __launch_bounds__(128) k_tri_attr(const __grid_constant__ JrRenderArgs a, float* __restrict__ attrs) {
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * 128 + threadIdx.x;
+  if (t >= a.T) return;
+  Frag f;
+  frag_vertex<SHADER>(a, b, t, f);
+  attr_store<SHADER>(f, attrs + ((size_t)b * a.T + t) * TA_FLOATS);
+}
+
+// Pixel stage from attribute records (same arithmetic as k_shade, the per-triangle part is shared).
+template <int SHADER>
+__global__ void __launch_bounds__(256) k_shade_rec(const __grid_constant__ JrRenderArgs a,
+                                                   const float* __restrict__ attrs) {
+  const long long npix = (long long)a.W * a.H;
+  const long long total = npix * a.B;
+  for (long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x; gi < total;
+       gi += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(gi / npix);
+    const int pix = (int)(gi - (long long)b * npix);
+    const int tri = a.tri_id[gi];
+    if (tri < 0) continue;
+    const int x = pix / a.H, y = pix - x * a.H;
+    Frag f;
+    attr_load<SHADER>(a, b, attrs + ((size_t)b * a.T + tri) * TA_FLOATS, f);
+    frag_pixel<SHADER>(a, b, x, y, f);
+    if (f.keep) {
+      a.zbuffer[gi] = f.zw;
+      float* o = a.canvas + gi * 3;
+      o[0] = f.col[0]; o[1] = f.col[1]; o[2] = f.col[2];
+    } else {
+      a.tri_id[gi] = -1;
+    }
+  }
+}
+
 __global__ void k_add_scalar(float* data, long long n, float v) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x)
@@ -410,12 +447,24 @@ const char* jr_strerror(int s) {
   }
 }
 
-size_t jr_workspace_bytes(const JrRenderArgs* a) {
-  if (!a || a->B <= 0 || a->W <= 0 || a->H <= 0) return 0;
+// Forward scratch: [binned visibility: triangle records + tile bitmasks][shading attribute records]
+struct FwdLayout { size_t tiled, attr_off, total; bool use_attr; };
+static FwdLayout fwd_layout(const JrRenderArgs* a) {
+  FwdLayout F{};
   int tw, th, nx, ny;
   choose_tiles(a->W, a->H, &tw, &th, &nx, &ny);
-  if (nx * ny == 1) return 0;                       // single shared-memory tile: no scratch
-  return tiled_layout(a->B, a->W, a->H, a->T).total;  // triangle records + per-tile bitmasks
+  F.tiled = (nx * ny == 1) ? 0 : tiled_layout(a->B, a->W, a->H, a->T).total;
+  // per-triangle attribute records pay off when a triangle is shared by several pixels
+  F.use_attr = a->shader != JR_DEPTH && a->shader != JR_PHONG_DARBOUX && a->T > 0 &&
+               (long long)a->W * a->H >= 2LL * a->T && getenv("JR_NO_ATTR") == nullptr;
+  F.attr_off = (F.tiled + 255) & ~(size_t)255;
+  F.total = F.use_attr ? F.attr_off + (size_t)a->B * a->T * TA_FLOATS * 4 : F.tiled;
+  return F;
+}
+
+size_t jr_workspace_bytes(const JrRenderArgs* a) {
+  if (!a || a->B <= 0 || a->W <= 0 || a->H <= 0) return 0;
+  return fwd_layout(a).total;
 }
 
 long long jr_launch_count(void) { return jr::g_launches.load(); }
@@ -480,17 +529,39 @@ int jr_render_forward(const JrRenderArgs* a, jr_stream_t stream_) {
     const int threads = 256;
     long long blocks = (total + threads - 1) / threads;
     if (blocks > 148LL * 64) blocks = 148LL * 64;
-    switch (a->shader) {
-      case JR_GOURAUD: k_shade<JR_GOURAUD><<<(unsigned)blocks, threads, 0, stream>>>(*a); break;
-      case JR_GOURAUD_TEXTURE: k_shade<JR_GOURAUD_TEXTURE><<<(unsigned)blocks, threads, 0, stream>>>(*a); break;
-      case JR_PHONG: k_shade<JR_PHONG><<<(unsigned)blocks, threads, 0, stream>>>(*a); break;
-      case JR_PHONG_DARBOUX: k_shade<JR_PHONG_DARBOUX><<<(unsigned)blocks, threads, 0, stream>>>(*a); break;
-      case JR_PHONG_REFLECTION: k_shade<JR_PHONG_REFLECTION><<<(unsigned)blocks, threads, 0, stream>>>(*a); break;
-      case JR_PHONG_REFLECTION_SHADOW:
-        k_shade<JR_PHONG_REFLECTION_SHADOW><<<(unsigned)blocks, threads, 0, stream>>>(*a); break;
-      default: return JR_ERR_SHADER;
+    const FwdLayout F = fwd_layout(a);
+    if (F.use_attr) {
+      if (!a->workspace || a->workspace_bytes < F.total) return JR_ERR_WORKSPACE;
+      if (a->B > 65535) return JR_ERR_DIMS;
+      float* attrs = (float*)((char*)a->workspace + F.attr_off);
+      dim3 g1((a->T + 127) / 128, a->B);
+#define JR_ATTR_CASE(S)                                                          \
+  case S:                                                                        \
+    k_tri_attr<S><<<g1, 128, 0, stream>>>(*a, attrs);                            \
+    k_shade_rec<S><<<(unsigned)blocks, threads, 0, stream>>>(*a, attrs);         \
+    break;
+      switch (a->shader) {
+        JR_ATTR_CASE(JR_GOURAUD)
+        JR_ATTR_CASE(JR_GOURAUD_TEXTURE)
+        JR_ATTR_CASE(JR_PHONG)
+        JR_ATTR_CASE(JR_PHONG_REFLECTION)
+        JR_ATTR_CASE(JR_PHONG_REFLECTION_SHADOW)
+        default: return JR_ERR_SHADER;
+      }
+      jr::g_launches += 2;
+    } else {
+      switch (a->shader) {
+        case JR_GOURAUD: k_shade<JR_GOURAUD><<<(unsigned)blocks, threads, 0, stream>>>(*a); break;
+        case JR_GOURAUD_TEXTURE: k_shade<JR_GOURAUD_TEXTURE><<<(unsigned)blocks, threads, 0, stream>>>(*a); break;
+        case JR_PHONG: k_shade<JR_PHONG><<<(unsigned)blocks, threads, 0, stream>>>(*a); break;
+        case JR_PHONG_DARBOUX: k_shade<JR_PHONG_DARBOUX><<<(unsigned)blocks, threads, 0, stream>>>(*a); break;
+        case JR_PHONG_REFLECTION: k_shade<JR_PHONG_REFLECTION><<<(unsigned)blocks, threads, 0, stream>>>(*a); break;
+        case JR_PHONG_REFLECTION_SHADOW:
+          k_shade<JR_PHONG_REFLECTION_SHADOW><<<(unsigned)blocks, threads, 0, stream>>>(*a); break;
+        default: return JR_ERR_SHADER;
+      }
+      jr::g_launches++;
     }
-    jr::g_launches++;
   }
   return cudaGetLastError() == cudaSuccess ? JR_OK : JR_ERR_CUDA;
 }

@@ -35,6 +35,10 @@ struct Frag {
   Vec3 mvert[3], tvert[3];     // S4-S7: m = normalise(normalise(n_k)), t = R m (before the last normalise)
   Vec3 nl;                     // normalised light direction (S2-S5) / light_dir_eye (S6,S7)
   float lraw[3];               // raw light vector that was normalised into nl
+  float colv[3][3];            // S2: per-vertex colours (colour * light colour * intensity)
+  float uvv[3][2];             // S3-S7: per-vertex uv
+  float scv[3][4];             // S7: per-vertex shadow coordinates (NDC of the light camera)
+  int ti;                      // S6,S7: texture index of the triangle (first vertex)
   float lc[3];                 // S3: interpolated light colour; S4,S5: lcol * ndl
   long long texel;             // linear texel index (u * tex_h + v), -1 if none
   long long spec_idx;          // linear index into specular_map (S6,S7)
@@ -48,10 +52,9 @@ struct Frag {
   bool lit;
 };
 
-// Common part: setup of triangle `tri` of image b and the pixel's weights.
-__device__ __forceinline__ void frag_setup(const JrRenderArgs& a, int b, int x, int y, int tri, Frag& f) {
+// Per-TRIANGLE part of the common setup (independent of the pixel).
+__device__ __forceinline__ void frag_setup_tri(const JrRenderArgs& a, int b, int tri, Frag& f) {
   const float* __restrict__ w2c = a.world_to_clip.ptr + (long long)b * a.world_to_clip.batch_stride;
-  const float* __restrict__ vp = a.viewport.ptr + (long long)b * a.viewport.batch_stride;
   const float* __restrict__ pos = a.position.ptr + (long long)b * a.position.batch_stride;
   const int32_t* __restrict__ faces = a.faces.ptr + (long long)b * a.faces.batch_stride;
 #pragma unroll
@@ -63,6 +66,12 @@ __device__ __forceinline__ void frag_setup(const JrRenderArgs& a, int b, int x, 
   float M[9];
   tri_matrix(f.cl[0], f.cl[1], f.cl[2], M);
   lu_inverse3(M, f.inv);
+}
+
+// Per-PIXEL part: NDC position, edge functions, 1/w, depth, perspective-correct weights.
+// Needs f.inv and f.cl[k][2].
+__device__ __forceinline__ void frag_setup_pix(const JrRenderArgs& a, int b, int x, int y, Frag& f) {
+  const float* __restrict__ vp = a.viewport.ptr + (long long)b * a.viewport.batch_stride;
   f.xn = ((float)x - vp[3]) / vp[0];
   f.yn = ((float)y - vp[7]) / vp[5];
   clip_coef(f.inv, f.xn, f.yn, f.cc);
@@ -73,16 +82,13 @@ __device__ __forceinline__ void frag_setup(const JrRenderArgs& a, int b, int x, 
   for (int k = 0; k < 3; ++k) f.tc[k] = f.cc[k] / f.w_rec;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Vertex stage of the chosen triangle (reference `Shader.vertex` of each built-in, evaluated for
+// the triangle's three vertices): everything that does not depend on the pixel.
 template <int SHADER>
-__device__ __forceinline__ void shade_pixel(const JrRenderArgs& a, int b, int x, int y, int tri, Frag& f) {
-  frag_setup(a, b, x, y, tri, f);
-  const float* tc = f.tc;
-  f.col[0] = f.col[1] = f.col[2] = 0.f;
-  f.keep = true;
-  f.texel = -1;
-  f.spec_idx = -1;
+__device__ __forceinline__ void frag_vertex(const JrRenderArgs& a, int b, int tri, Frag& f) {
+  frag_setup_tri(a, b, tri, f);
   if (SHADER == JR_DEPTH) return;
-
 #pragma unroll
   for (int k = 0; k < 3; ++k) { f.fn[k] = f.fi[k]; f.fu[k] = f.fi[k]; }
   if (a.faces_norm.ptr) {
@@ -97,6 +103,11 @@ __device__ __forceinline__ void shade_pixel(const JrRenderArgs& a, int b, int x,
   load3(a.light_colour, b, f.lcol);
 #pragma unroll
   for (int k = 0; k < 3; ++k) f.nraw[k] = loadv3(nrm, f.fn[k]);
+  if (SHADER >= JR_GOURAUD_TEXTURE) {
+    const float* __restrict__ uvp = a.uv.ptr + (long long)b * a.uv.batch_stride;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { f.uvv[k][0] = uvp[2 * f.fu[k]]; f.uvv[k][1] = uvp[2 * f.fu[k] + 1]; }
+  }
 
   if (SHADER == JR_GOURAUD || SHADER == JR_GOURAUD_TEXTURE) {
     load3(a.light_direction, b, f.lraw);
@@ -109,35 +120,15 @@ __device__ __forceinline__ void shade_pixel(const JrRenderArgs& a, int b, int x,
     if (SHADER == JR_GOURAUD) {
       const float* __restrict__ cv = a.colour.ptr + (long long)b * a.colour.batch_stride;
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const float v0 = (cv[3 * f.fi[0] + c] * f.lcol[c]) * f.inten[0];
-        const float v1 = (cv[3 * f.fi[1] + c] * f.lcol[c]) * f.inten[1];
-        const float v2 = (cv[3 * f.fi[2] + c] * f.lcol[c]) * f.inten[2];
-        f.col[c] = interp3(tc, v0, v1, v2);
-        f.keep = f.keep && (f.col[c] >= 0.f);
-      }
-    } else {
-      const float* __restrict__ uvp = a.uv.ptr + (long long)b * a.uv.batch_stride;
-      const float* __restrict__ tex = a.texture.ptr + (long long)b * a.texture.batch_stride;
-      const float u = interp3(tc, uvp[2 * f.fu[0]], uvp[2 * f.fu[1]], uvp[2 * f.fu[2]]);
-      const float v = interp3(tc, uvp[2 * f.fu[0] + 1], uvp[2 * f.fu[1] + 1], uvp[2 * f.fu[2] + 1]);
-      const int ui = pymod((int)floorf(u), a.tex_w), vi = pymod((int)floorf(v), a.tex_h);
-      f.texel = (long long)ui * a.tex_h + vi;
+      for (int k = 0; k < 3; ++k)
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        f.tex[c] = tex[f.texel * 3 + c];
-        f.lc[c] = interp3(tc, f.lcol[c] * f.inten[0], f.lcol[c] * f.inten[1], f.lcol[c] * f.inten[2]);
-        f.keep = f.keep && (f.lc[c] >= 0.f);
-        f.col[c] = f.tex[c] * f.lc[c];
-      }
+        for (int c = 0; c < 3; ++c) f.colv[k][c] = (cv[3 * f.fi[k] + c] * f.lcol[c]) * f.inten[k];
     }
     return;
   }
 
   // ---- S4-S7: eye-space normals (phong.py:92-103)
   const float* __restrict__ wen = a.world_to_eye_norm.ptr + (long long)b * a.world_to_eye_norm.batch_stride;
-  const float* __restrict__ uvp = a.uv.ptr + (long long)b * a.uv.batch_stride;
-  const float* __restrict__ tex = a.texture.ptr + (long long)b * a.texture.batch_stride;
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     // Camera.apply_vec(normalise(n), wen): normalise twice, rotate, normalise
@@ -149,11 +140,65 @@ __device__ __forceinline__ void shade_pixel(const JrRenderArgs& a, int b, int x,
     f.mvert[k] = m; f.tvert[k] = t;
     f.nvert[k] = normalise3(t);
   }
+  if (SHADER >= JR_PHONG_REFLECTION) {
+    const int32_t* __restrict__ ftp =
+        a.faces_tex.ptr ? a.faces_tex.ptr + (long long)b * a.faces_tex.batch_stride + 3 * tri : nullptr;
+    const int tv = ftp ? ftp[0] : f.fi[0];
+    f.ti = (a.texture_index.ptr + (long long)b * a.texture_index.batch_stride)[tv];
+  }
+  if (SHADER == JR_PHONG_REFLECTION_SHADOW) {
+    const float* __restrict__ sw2c = a.shadow_world_to_clip.ptr + (long long)b * a.shadow_world_to_clip.batch_stride;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      float sc[4];
+      to_clip(sw2c, f.P[k].x, f.P[k].y, f.P[k].z, sc);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) f.scv[k][j] = sc[j] / sc[3];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Interpolate + fragment + mix for pixel (x, y) given the triangle's vertex-stage outputs in `f`
+// (either just computed by frag_vertex or loaded from a TriAttr record).  `tri` is only used by
+// the Darboux shader.
+template <int SHADER>
+__device__ __forceinline__ void frag_pixel(const JrRenderArgs& a, int b, int x, int y, Frag& f) {
+  frag_setup_pix(a, b, x, y, f);
+  const float* tc = f.tc;
+  f.col[0] = f.col[1] = f.col[2] = 0.f;
+  f.keep = true;
+  f.texel = -1;
+  f.spec_idx = -1;
+  if (SHADER == JR_DEPTH) return;
+
+  if (SHADER == JR_GOURAUD) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      f.col[c] = interp3(tc, f.colv[0][c], f.colv[1][c], f.colv[2][c]);
+      f.keep = f.keep && (f.col[c] >= 0.f);
+    }
+    return;
+  }
+  const float* __restrict__ tex = a.texture.ptr + (long long)b * a.texture.batch_stride;
+  const float u = interp3(tc, f.uvv[0][0], f.uvv[1][0], f.uvv[2][0]);
+  const float v = interp3(tc, f.uvv[0][1], f.uvv[1][1], f.uvv[2][1]);
+  if (SHADER == JR_GOURAUD_TEXTURE) {
+    const int ui = pymod((int)floorf(u), a.tex_w), vi = pymod((int)floorf(v), a.tex_h);
+    f.texel = (long long)ui * a.tex_h + vi;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      f.tex[c] = tex[f.texel * 3 + c];
+      f.lc[c] = interp3(tc, f.lcol[c] * f.inten[0], f.lcol[c] * f.inten[1], f.lcol[c] * f.inten[2]);
+      f.keep = f.keep && (f.lc[c] >= 0.f);
+      f.col[c] = f.tex[c] * f.lc[c];
+    }
+    return;
+  }
+
   f.normal = Vec3{interp3(tc, f.nvert[0].x, f.nvert[1].x, f.nvert[2].x),
                   interp3(tc, f.nvert[0].y, f.nvert[1].y, f.nvert[2].y),
                   interp3(tc, f.nvert[0].z, f.nvert[1].z, f.nvert[2].z)};
-  const float u = interp3(tc, uvp[2 * f.fu[0]], uvp[2 * f.fu[1]], uvp[2 * f.fu[2]]);
-  const float v = interp3(tc, uvp[2 * f.fu[0] + 1], uvp[2 * f.fu[1] + 1], uvp[2 * f.fu[2] + 1]);
   f.nn = normalise3(f.normal);
 
   if (SHADER == JR_PHONG || SHADER == JR_PHONG_DARBOUX) {
@@ -166,6 +211,7 @@ __device__ __forceinline__ void shade_pixel(const JrRenderArgs& a, int b, int x,
       // phong_darboux.py:144-151, :231-262
       const float* __restrict__ w2c = a.world_to_clip.ptr + (long long)b * a.world_to_clip.batch_stride;
       const float* __restrict__ pos = a.position.ptr + (long long)b * a.position.batch_stride;
+      const float* __restrict__ uvp = a.uv.ptr + (long long)b * a.uv.batch_stride;
       const int32_t* __restrict__ i2f = a.id_to_face.ptr + (long long)b * a.id_to_face.batch_stride;
       const int32_t* __restrict__ fidx = a.faces_indices.ptr + (long long)b * a.faces_indices.batch_stride;
       const int face = i2f[f.fi[0]];
@@ -212,10 +258,7 @@ __device__ __forceinline__ void shade_pixel(const JrRenderArgs& a, int b, int x,
   }
 
   // ---- S6 / S7 (phong_reflection.py:175-220, phong_reflection_shadow.py:196-257)
-  const int32_t* __restrict__ ftp =
-      a.faces_tex.ptr ? a.faces_tex.ptr + (long long)b * a.faces_tex.batch_stride + 3 * tri : nullptr;
-  const int tv = ftp ? ftp[0] : f.fi[0];
-  const int ti = (a.texture_index.ptr + (long long)b * a.texture_index.batch_stride)[tv];
+  const int ti = f.ti;
   const int32_t* tsh = a.texture_shape.ptr + (long long)b * a.texture_shape.batch_stride + 2 * ti;
   float fu0 = u - truncf(u), fv0 = v - truncf(v);  // jnp.modf(uv)[0]
   if (fu0 < 0.f) fu0 = fu0 + 1.f;
@@ -242,19 +285,10 @@ __device__ __forceinline__ void shade_pixel(const JrRenderArgs& a, int b, int x,
   f.shadow[0] = f.shadow[1] = f.shadow[2] = 1.f;
   f.lit = true;
   if (SHADER == JR_PHONG_REFLECTION_SHADOW) {
-    const float* __restrict__ sw2c = a.shadow_world_to_clip.ptr + (long long)b * a.shadow_world_to_clip.batch_stride;
     const float* __restrict__ svp = a.shadow_viewport.ptr + (long long)b * a.shadow_viewport.batch_stride;
-    float scv[3][4];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      float s[4];
-      to_clip(sw2c, f.P[k].x, f.P[k].y, f.P[k].z, s);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) scv[k][j] = s[j] / s[3];
-    }
     float sc[4], ss[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) sc[j] = interp3(tc, scv[0][j], scv[1][j], scv[2][j]);
+    for (int j = 0; j < 4; ++j) sc[j] = interp3(tc, f.scv[0][j], f.scv[1][j], f.scv[2][j]);
 #pragma unroll
     for (int r = 0; r < 4; ++r)
       ss[r] = ((svp[4 * r] * sc[0] + svp[4 * r + 1] * sc[1]) + svp[4 * r + 2] * sc[2]) + svp[4 * r + 3] * sc[3];
@@ -284,6 +318,79 @@ __device__ __forceinline__ void shade_pixel(const JrRenderArgs& a, int b, int x,
     else
       f.col[c] = f.amb[c] * f.tex[c] + ((f.shadow[c] * f.ds[c]) * f.tex[c]) * f.lcol[c];
   }
+}
+
+// Both stages for one pixel (backward and small-canvas forward: recompute per pixel).
+template <int SHADER>
+__device__ __forceinline__ void shade_pixel(const JrRenderArgs& a, int b, int x, int y, int tri, Frag& f) {
+  frag_vertex<SHADER>(a, b, tri, f);
+  frag_pixel<SHADER>(a, b, x, y, f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-triangle attribute record: the vertex-stage outputs the pixel stage reads, written once per
+// triangle by k_tri_attr and shared by all pixels of the triangle (large canvases).
+constexpr int TA_FLOATS = 44;  // 176 bytes, 11 x float4
+// layout: [0..8] inv, [9..11] zc, [12..20] nvert (S4-S7) or colv (S2), [21..26] uvv, [27] ti,
+//         [28..39] scv (S7), [40..42] inten (S3), [43] pad
+template <int SHADER>
+__device__ __forceinline__ void attr_store(const Frag& f, float* __restrict__ r) {
+#pragma unroll
+  for (int k = 0; k < 9; ++k) r[k] = f.inv[k];
+  r[9] = f.cl[0][2]; r[10] = f.cl[1][2]; r[11] = f.cl[2][2];
+  if (SHADER == JR_GOURAUD) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) r[12 + 3 * k + c] = f.colv[k][c];
+  }
+  if (SHADER >= JR_PHONG) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { r[12 + 3 * k] = f.nvert[k].x; r[13 + 3 * k] = f.nvert[k].y; r[14 + 3 * k] = f.nvert[k].z; }
+  }
+  if (SHADER >= JR_GOURAUD_TEXTURE) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { r[21 + 2 * k] = f.uvv[k][0]; r[22 + 2 * k] = f.uvv[k][1]; }
+  }
+  if (SHADER >= JR_PHONG_REFLECTION) r[27] = __int_as_float(f.ti);
+  if (SHADER == JR_PHONG_REFLECTION_SHADOW) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) r[28 + 4 * k + j] = f.scv[k][j];
+  }
+  if (SHADER == JR_GOURAUD_TEXTURE) { r[40] = f.inten[0]; r[41] = f.inten[1]; r[42] = f.inten[2]; }
+}
+
+template <int SHADER>
+__device__ __forceinline__ void attr_load(const JrRenderArgs& a, int b, const float* __restrict__ r, Frag& f) {
+#pragma unroll
+  for (int k = 0; k < 9; ++k) f.inv[k] = r[k];
+  f.cl[0][2] = r[9]; f.cl[1][2] = r[10]; f.cl[2][2] = r[11];
+  if (SHADER == JR_DEPTH) return;
+  load3(a.light_colour, b, f.lcol);
+  if (SHADER == JR_GOURAUD) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) f.colv[k][c] = r[12 + 3 * k + c];
+  }
+  if (SHADER >= JR_PHONG) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) f.nvert[k] = Vec3{r[12 + 3 * k], r[13 + 3 * k], r[14 + 3 * k]};
+  }
+  if (SHADER >= JR_GOURAUD_TEXTURE) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { f.uvv[k][0] = r[21 + 2 * k]; f.uvv[k][1] = r[22 + 2 * k]; }
+  }
+  if (SHADER >= JR_PHONG_REFLECTION) f.ti = __float_as_int(r[27]);
+  if (SHADER == JR_PHONG_REFLECTION_SHADOW) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) f.scv[k][j] = r[28 + 4 * k + j];
+  }
+  if (SHADER == JR_GOURAUD_TEXTURE) { f.inten[0] = r[40]; f.inten[1] = r[41]; f.inten[2] = r[42]; }
 }
 
 }  // namespace jr
