@@ -12,7 +12,7 @@ from typing import Any, Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libjr_b200.so")
+LIB_PATH = os.environ.get("JR_B200_LIB") or os.path.join(_HERE, "lib", "libjr_b200.so")  # env: A/B builds
 
 JR_DEPTH, JR_GOURAUD, JR_GOURAUD_TEXTURE, JR_PHONG, JR_PHONG_DARBOUX = 0, 1, 2, 3, 4
 JR_PHONG_REFLECTION, JR_PHONG_REFLECTION_SHADOW = 5, 6

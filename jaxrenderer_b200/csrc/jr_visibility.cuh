@@ -8,7 +8,7 @@
 //   lane = triangle   gather vertices, clip x/y/w (z only for survivors), det,
 //                     back-face / degenerate / behind-camera cull, approximate
 //                     bbox (+-0.5 px), exact LU inverse for survivors.
-//   small  (<= 32 px) rasterised by the owning lane.
+//   small  (<= 16 px) rasterised by the owning lane (threshold swept on B200: 8/16/32/64 px).
 //   medium (<= 1024)  rasterised by the whole warp right away: the owner's
 //                     record is broadcast with shuffles, lanes cover the bbox
 //                     pixels flat (no integer division).
@@ -25,8 +25,14 @@ namespace jr {
 
 constexpr int V2_THREADS = 256;
 constexpr int V2_BIGCAP = 32;
-constexpr int V2_SMALL_AREA = 32;
-constexpr int V2_MEDIUM_AREA = 1024;
+#ifndef JR_SMALL_AREA
+#define JR_SMALL_AREA 16
+#endif
+#ifndef JR_MEDIUM_AREA
+#define JR_MEDIUM_AREA 1024
+#endif
+constexpr int V2_SMALL_AREA = JR_SMALL_AREA;    // boxes up to this many pixels: the owning lane
+constexpr int V2_MEDIUM_AREA = JR_MEDIUM_AREA;  // up to this: the owning warp; above: the whole CTA
 constexpr int V2_HIER_AREA = 256;   // warp-cooperative boxes from this size use the hierarchical raster
 
 struct V2Layout { size_t keys, xs, ys, bigq, total; };
