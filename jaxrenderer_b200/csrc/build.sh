@@ -10,6 +10,6 @@ NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 srcs=("$here"/jr_common.cu "$here"/jr_forward.cu)
 [ -f "$here/jr_backward.cu" ] && srcs+=("$here/jr_backward.cu")
 "$NVCC" -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false \
-  -std=c++17 -Xcompiler -fPIC -shared ${JR_NVCC_EXTRA:-} \
+  -std=c++17 -diag-suppress 128 -Xcompiler -fPIC -shared ${JR_NVCC_EXTRA:-} \
   -o "$out/libjr_b200.so" "${srcs[@]}"
 echo "built $out/libjr_b200.so"

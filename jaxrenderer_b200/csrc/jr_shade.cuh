@@ -59,7 +59,7 @@ __device__ __forceinline__ void frag_setup_tri(const JrRenderArgs& a, int b, int
   const int32_t* __restrict__ faces = a.faces.ptr + (long long)b * a.faces.batch_stride;
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    f.fi[k] = faces[3 * tri + k];
+    f.fi[k] = min(max(faces[3 * tri + k], 0), a.n_pos - 1);  // clamped like the visibility kernels
     f.P[k] = loadv3(pos, f.fi[k]);
     to_clip(w2c, f.P[k].x, f.P[k].y, f.P[k].z, f.cl[k]);
   }
@@ -88,16 +88,22 @@ __device__ __forceinline__ void frag_setup_pix(const JrRenderArgs& a, int b, int
 template <int SHADER>
 __device__ __forceinline__ void frag_vertex(const JrRenderArgs& a, int b, int tri, Frag& f) {
   frag_setup_tri(a, b, tri, f);
-  if (SHADER == JR_DEPTH) return;
+  if constexpr (SHADER == JR_DEPTH) return;
 #pragma unroll
   for (int k = 0; k < 3; ++k) { f.fn[k] = f.fi[k]; f.fu[k] = f.fi[k]; }
   if (a.faces_norm.ptr) {
     const int32_t* q = a.faces_norm.ptr + (long long)b * a.faces_norm.batch_stride + 3 * tri;
     f.fn[0] = q[0]; f.fn[1] = q[1]; f.fn[2] = q[2];
   }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) f.fn[k] = min(max(f.fn[k], 0), a.n_nrm - 1);
   if (a.faces_uv.ptr) {
     const int32_t* q = a.faces_uv.ptr + (long long)b * a.faces_uv.batch_stride + 3 * tri;
     f.fu[0] = q[0]; f.fu[1] = q[1]; f.fu[2] = q[2];
+  }
+  if (SHADER >= JR_GOURAUD_TEXTURE) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) f.fu[k] = min(max(f.fu[k], 0), a.n_uv - 1);
   }
   const float* __restrict__ nrm = a.normal.ptr + (long long)b * a.normal.batch_stride;
   load3(a.light_colour, b, f.lcol);
@@ -143,8 +149,8 @@ __device__ __forceinline__ void frag_vertex(const JrRenderArgs& a, int b, int tr
   if (SHADER >= JR_PHONG_REFLECTION) {
     const int32_t* __restrict__ ftp =
         a.faces_tex.ptr ? a.faces_tex.ptr + (long long)b * a.faces_tex.batch_stride + 3 * tri : nullptr;
-    const int tv = ftp ? ftp[0] : f.fi[0];
-    f.ti = (a.texture_index.ptr + (long long)b * a.texture_index.batch_stride)[tv];
+    const int tv = min(max(ftp ? ftp[0] : f.fi[0], 0), a.n_texidx - 1);
+    f.ti = min(max((a.texture_index.ptr + (long long)b * a.texture_index.batch_stride)[tv], 0), a.n_objects - 1);
   }
   if (SHADER == JR_PHONG_REFLECTION_SHADOW) {
     const float* __restrict__ sw2c = a.shadow_world_to_clip.ptr + (long long)b * a.shadow_world_to_clip.batch_stride;

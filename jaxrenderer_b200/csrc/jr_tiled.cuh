@@ -68,7 +68,9 @@ k_setup_bin(const __grid_constant__ JrRenderArgs a, TriRecord* __restrict__ recs
   bool surv = false;
   int x0 = 0, x1 = a.W - 1, y0 = 0, y1 = a.H - 1;
   if (t < a.T) {
-    const int i0 = faces[3 * t + 0], i1 = faces[3 * t + 1], i2 = faces[3 * t + 2];
+    const int vmax = a.n_pos - 1;  // out-of-range indices are clamped, never read out of bounds
+    const int i0 = min(max(faces[3 * t + 0], 0), vmax), i1 = min(max(faces[3 * t + 1], 0), vmax),
+              i2 = min(max(faces[3 * t + 2], 0), vmax);
     const float p0x = pos[3 * i0], p0y = pos[3 * i0 + 1], p0z = pos[3 * i0 + 2];
     const float p1x = pos[3 * i1], p1y = pos[3 * i1 + 1], p1z = pos[3 * i1 + 2];
     const float p2x = pos[3 * i2], p2y = pos[3 * i2 + 1], p2z = pos[3 * i2 + 2];

@@ -137,8 +137,7 @@ k_vis2(const __grid_constant__ JrRenderArgs a, int tile_w, int tile_h, int tiles
   __shared__ float s_w2c[16];
   __shared__ float s_vp[16];
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr int NW = V2_THREADS / 32;
+  const int tid = threadIdx.x, lane = tid & 31;
   const int tiles = tiles_x * tiles_y;
   const int b = blockIdx.x / tiles;
   const int tile = blockIdx.x - b * tiles;
@@ -262,7 +261,10 @@ k_vis2(const __grid_constant__ JrRenderArgs a, int tile_w, int tile_h, int tiles
     float M[9], zc[3];
     unsigned bb = 0;
     if (t < a.T) {
-      const int i0 = faces[3 * t + 0], i1 = faces[3 * t + 1], i2 = faces[3 * t + 2];
+      // out-of-range indices are clamped (the reference's gathers clamp too) -- never read out of bounds
+      const int vmax = a.n_pos - 1;
+      const int i0 = min(max(faces[3 * t + 0], 0), vmax), i1 = min(max(faces[3 * t + 1], 0), vmax),
+                i2 = min(max(faces[3 * t + 2], 0), vmax);
       const float p0x = pos[3 * i0], p0y = pos[3 * i0 + 1], p0z = pos[3 * i0 + 2];
       const float p1x = pos[3 * i1], p1y = pos[3 * i1 + 1], p1z = pos[3 * i1 + 2];
       const float p2x = pos[3 * i2], p2y = pos[3 * i2 + 1], p2z = pos[3 * i2 + 2];

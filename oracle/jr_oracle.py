@@ -392,6 +392,8 @@ def render(camera: Any, shader: Any, zbuffer: Any, targets: Sequence[Any], face_
     faces = _t(face_indices, torch.int64)
     W, H = zbuffer.shape
     pos = _t(extra.position)
+    # out-of-range vertex indices: jnp gathers clamp them [JAX-semantics]; restated as a plain clamp
+    faces = faces.clamp(0, max(pos.shape[0] - 1, 0))
 
     # ---- vertex stage (pipeline.py:500-518; each shader's `vertex`)
     clip_v = mat4_apply(pos, w2c, w_one=True)

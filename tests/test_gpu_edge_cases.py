@@ -124,3 +124,17 @@ def test_many_large_overlapping_triangles():
         print(rep)
         assert_parity(rep)
         assert int((ref.tri_id >= 0).sum()) > W * H // 4
+
+
+def test_out_of_range_indices_are_clamped_not_read():
+    """Bad face indices never read out of bounds: they are clamped (what the reference's gathers do)."""
+    s = random_mesh_scene(9, n_tri=20)
+    faces = s.faces.clone()
+    faces[3, 1] = 10_000_000
+    faces[7, 0] = -5
+    z0 = torch.full((s.W, s.H), 1.0)
+    out, tri = jr.render(_cam_d(s.cam), DepthShader, jr.Buffers(z0.to(DEV), ()), faces.to(DEV),
+                         DepthExtraInput(position=s.pos.to(DEV)), return_tri_id=True)
+    ref = O.render(s.cam, "depth", z0, (), faces, NS(position=s.pos))
+    rep = compare("clamped", out.zbuffer, None, tri, ref)
+    assert_parity(rep)
