@@ -132,6 +132,7 @@ k_vis2(const __grid_constant__ JrRenderArgs a, int tile_w, int tile_h, int tiles
   float* ys = reinterpret_cast<float*>(smem + L.ys);
   V2Big* bigq = reinterpret_cast<V2Big*>(smem + L.bigq);
   __shared__ int bigq_n;
+  __shared__ int next_chunk;  // dynamic work distribution: next group of 32 triangles
   __shared__ int tri0_flag;
   __shared__ TriSetup tri0;
   __shared__ float s_w2c[16];
@@ -151,7 +152,7 @@ k_vis2(const __grid_constant__ JrRenderArgs a, int tile_w, int tile_h, int tiles
     s_w2c[tid] = a.world_to_clip.ptr[(long long)b * a.world_to_clip.batch_stride + tid];
     s_vp[tid] = a.viewport.ptr[(long long)b * a.viewport.batch_stride + tid];
   }
-  if (tid == 0) { bigq_n = 0; tri0_flag = 0; }
+  if (tid == 0) { bigq_n = 0; tri0_flag = 0; next_chunk = 0; }
   {
     const int nk = tile_w * tile_h;
     ulonglong2* k2 = reinterpret_cast<ulonglong2*>(keys);
@@ -255,8 +256,14 @@ k_vis2(const __grid_constant__ JrRenderArgs a, int tile_w, int tile_h, int tiles
     }
   };
 
-  const int t_end = ((a.T + 31) / 32) * 32;  // whole warps stay in the loop
-  for (int t = tid; t < t_end; t += V2_THREADS) {
+  // Warps claim groups of 32 triangles dynamically (a static stride left warps that drew the
+  // medium / ground triangles far behind the others at the barrier below).
+  for (;;) {
+    int t0 = 0;
+    if (lane == 0) t0 = atomicAdd(&next_chunk, 32);
+    t0 = __shfl_sync(0xffffffffu, t0, 0);
+    if (t0 >= a.T) break;
+    const int t = t0 + lane;
     bool surv = false;
     float M[9], zc[3];
     unsigned bb = 0;
