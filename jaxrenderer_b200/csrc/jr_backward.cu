@@ -339,12 +339,10 @@ template <int S, int MODE>
 __global__ void __launch_bounds__(256)
 k_bwd_keys(const __grid_constant__ JrRenderArgs a, KeyedPlan plan, unsigned* __restrict__ keys,
            unsigned* __restrict__ vals) {
-  const long long npix = (long long)a.W * a.H;
-  const long long total = npix * a.B;
-  for (long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x; gi < total;
-       gi += (long long)gridDim.x * blockDim.x) {
-    const int b = (int)(gi / npix);
-    const int pix = (int)(gi - (long long)b * npix);
+  const int npix = a.W * a.H;
+  for (int b = blockIdx.y; b < a.B; b += gridDim.y)
+  for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += gridDim.x * blockDim.x) {
+    const long long gi = (long long)b * npix + pix;
     const int tri = a.tri_id[gi];
     const unsigned boff = plan.batched ? (unsigned)((long long)b * plan.keys_per_image) : 0u;
     if (MODE == MODE_TEXEL || MODE == MODE_SPEC) {
@@ -407,7 +405,7 @@ k_bwd_segreduce(const __grid_constant__ JrRenderArgs a, const __grid_constant__ 
       int corner = 0;
       if (MODE == MODE_TEXEL || MODE == MODE_SPEC) gi = payload;
       else { gi = payload >> 2; corner = payload & 3; }
-      const int b = (int)(gi / npix);
+      const int b = (int)((unsigned)gi / (unsigned)npix);  // gi < 2^30 (checked by the host side)
       const int pix = (int)(gi - (long long)b * npix);
       const int x = pix / a.H, y = pix - x * a.H;
       Frag f;
@@ -612,10 +610,9 @@ static int run_keyed(const JrRenderArgs* a, const JrGradArgs* g, const BwdLayout
   unsigned* vals_a = (unsigned*)(ws + L.vals_a);
   unsigned* vals_b = (unsigned*)(ws + L.vals_b);
   Carry<C>* carry = (Carry<C>*)(ws + L.carry);
-  const long long total = (long long)a->B * a->W * a->H;
-  long long blocks = (total + 255) / 256;
-  if (blocks > 148LL * 32) blocks = 148LL * 32;
-  k_bwd_keys<S, MODE><<<(unsigned)blocks, 256, 0, stream>>>(*a, plan, keys_a, vals_a);
+  int bx = (a->W * a->H + 255) / 256;
+  if (bx > 4096) bx = 4096;
+  k_bwd_keys<S, MODE><<<dim3(bx, a->B > 65535 ? 65535 : a->B), 256, 0, stream>>>(*a, plan, keys_a, vals_a);
   g_launches++;
   size_t tmp = L.cub_bytes;
   const int end_bit = bit_length((unsigned long long)plan.invalid_key);

@@ -20,18 +20,19 @@
 #include "jr_visibility.cuh"
 #include "jr_tiled.cuh"
 #include <stdlib.h>
+#include <mutex>
 
 namespace jr {
 
 // --------------------------------------------------------------------- shading
 template <int SHADER>
 __global__ void __launch_bounds__(256) k_shade(const __grid_constant__ JrRenderArgs a) {
-  const long long npix = (long long)a.W * a.H;
-  const long long total = npix * a.B;
-  for (long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x; gi < total;
-       gi += (long long)gridDim.x * blockDim.x) {
-    const int b = (int)(gi / npix);
-    const int pix = (int)(gi - (long long)b * npix);
+  // grid = (blocks per image, images): all index arithmetic stays 32-bit (a 64-bit division per
+  // pixel cost ~100 instructions)
+  const int npix = a.W * a.H;
+  for (int b = blockIdx.y; b < a.B; b += gridDim.y)
+  for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += gridDim.x * blockDim.x) {
+    const long long gi = (long long)b * npix + pix;
     const int tri = a.tri_id[gi];
     if (tri < 0) continue;
     const int x = pix / a.H, y = pix - x * a.H;
@@ -62,12 +63,12 @@ __global__ void __launch_bounds__(128) k_tri_attr(const __grid_constant__ JrRend
 template <int SHADER>
 __global__ void __launch_bounds__(256) k_shade_rec(const __grid_constant__ JrRenderArgs a,
                                                    const float* __restrict__ attrs) {
-  const long long npix = (long long)a.W * a.H;
-  const long long total = npix * a.B;
-  for (long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x; gi < total;
-       gi += (long long)gridDim.x * blockDim.x) {
-    const int b = (int)(gi / npix);
-    const int pix = (int)(gi - (long long)b * npix);
+  // grid = (blocks per image, images): all index arithmetic stays 32-bit (a 64-bit division per
+  // pixel cost ~100 instructions)
+  const int npix = a.W * a.H;
+  for (int b = blockIdx.y; b < a.B; b += gridDim.y)
+  for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += gridDim.x * blockDim.x) {
+    const long long gi = (long long)b * npix + pix;
     const int tri = a.tri_id[gi];
     if (tri < 0) continue;
     const int x = pix / a.H, y = pix - x * a.H;
@@ -193,6 +194,10 @@ const char* jr_strerror(int s) {
   }
 }
 
+// debugging / A-B switches, read once at load
+static const bool g_no_attr = getenv("JR_NO_ATTR") != nullptr;  // shade without attribute records
+static const bool g_no_bins = getenv("JR_NO_BINS") != nullptr;  // every tile CTA scans all triangles
+
 // Forward scratch: [binned visibility: triangle records + tile bitmasks][shading attribute records]
 struct FwdLayout { size_t tiled, attr_off, total; bool use_attr; };
 static FwdLayout fwd_layout(const JrRenderArgs* a) {
@@ -202,7 +207,7 @@ static FwdLayout fwd_layout(const JrRenderArgs* a) {
   F.tiled = (nx * ny == 1) ? 0 : tiled_layout(a->B, a->W, a->H, a->T).total;
   // per-triangle attribute records pay off when a triangle is shared by several pixels
   F.use_attr = a->shader != JR_DEPTH && a->shader != JR_PHONG_DARBOUX && a->T > 0 &&
-               (long long)a->W * a->H >= 2LL * a->T && getenv("JR_NO_ATTR") == nullptr;
+               (long long)a->W * a->H >= 2LL * a->T && !g_no_attr;
   F.attr_off = (F.tiled + 255) & ~(size_t)255;
   F.total = F.use_attr ? F.attr_off + (size_t)a->B * a->T * TA_FLOATS * 4 : F.tiled;
   return F;
@@ -223,15 +228,15 @@ int jr_render_forward(const JrRenderArgs* a, jr_stream_t stream_) {
   choose_tiles(a->W, a->H, &tw, &th, &nx, &ny);
   const long long ctas = (long long)a->B * nx * ny;
   if (ctas > 2147483647LL) return JR_ERR_DIMS;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static std::once_flag attr_once;
+  std::call_once(attr_once, [] {
     cudaFuncSetAttribute(k_vis2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(k_vis2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_done = true;
-  }
+    cudaFuncSetAttribute(k_raster_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(k_raster_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  });
   const bool depth = a->shader == JR_DEPTH;
-  static const bool no_bins = getenv("JR_NO_BINS") != nullptr;  // A/B switch: every tile CTA scans all triangles
-  if (nx * ny > 1 && !no_bins) {
+  if (nx * ny > 1 && !g_no_bins) {
     // two-level path: per-triangle records + per-tile bitmasks, then one CTA per (image, tile)
     const TiledLayout TLy = tiled_layout(a->B, a->W, a->H, a->T);
     if (!a->workspace || a->workspace_bytes < TLy.total) return JR_ERR_WORKSPACE;
@@ -240,12 +245,6 @@ int jr_render_forward(const JrRenderArgs* a, jr_stream_t stream_) {
     TriRecord* recs = (TriRecord*)(ws + TLy.rec);
     unsigned* masks = (unsigned*)(ws + TLy.mask);
     cudaMemsetAsync(masks, 0, (size_t)a->B * TLy.tiles * TLy.words * 4, stream);
-    static bool attr2 = false;
-    if (!attr2) {
-      cudaFuncSetAttribute(k_raster_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-      cudaFuncSetAttribute(k_raster_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-      attr2 = true;
-    }
     if (a->T > 0) {
       dim3 g1((a->T + 255) / 256, a->B);
       if (depth) k_setup_bin<true><<<g1, 256, 0, stream>>>(*a, recs, masks, TLy);
@@ -264,10 +263,11 @@ int jr_render_forward(const JrRenderArgs* a, jr_stream_t stream_) {
   }
   jr::g_launches++;
   if (!depth) {
-    const long long total = (long long)a->B * a->W * a->H;
     const int threads = 256;
-    long long blocks = (total + threads - 1) / threads;
-    if (blocks > 148LL * 64) blocks = 148LL * 64;
+    const int npix = a->W * a->H;
+    int bx = (npix + threads - 1) / threads;
+    if (bx > 4096) bx = 4096;
+    const dim3 blocks(bx, a->B > 65535 ? 65535 : a->B);
     const FwdLayout F = fwd_layout(a);
     if (F.use_attr) {
       if (!a->workspace || a->workspace_bytes < F.total) return JR_ERR_WORKSPACE;
@@ -277,7 +277,7 @@ int jr_render_forward(const JrRenderArgs* a, jr_stream_t stream_) {
 #define JR_ATTR_CASE(S)                                                          \
   case S:                                                                        \
     k_tri_attr<S><<<g1, 128, 0, stream>>>(*a, attrs);                            \
-    k_shade_rec<S><<<(unsigned)blocks, threads, 0, stream>>>(*a, attrs);         \
+    k_shade_rec<S><<<blocks, threads, 0, stream>>>(*a, attrs);         \
     break;
       switch (a->shader) {
         JR_ATTR_CASE(JR_GOURAUD)
@@ -290,13 +290,13 @@ int jr_render_forward(const JrRenderArgs* a, jr_stream_t stream_) {
       jr::g_launches += 2;
     } else {
       switch (a->shader) {
-        case JR_GOURAUD: k_shade<JR_GOURAUD><<<(unsigned)blocks, threads, 0, stream>>>(*a); break;
-        case JR_GOURAUD_TEXTURE: k_shade<JR_GOURAUD_TEXTURE><<<(unsigned)blocks, threads, 0, stream>>>(*a); break;
-        case JR_PHONG: k_shade<JR_PHONG><<<(unsigned)blocks, threads, 0, stream>>>(*a); break;
-        case JR_PHONG_DARBOUX: k_shade<JR_PHONG_DARBOUX><<<(unsigned)blocks, threads, 0, stream>>>(*a); break;
-        case JR_PHONG_REFLECTION: k_shade<JR_PHONG_REFLECTION><<<(unsigned)blocks, threads, 0, stream>>>(*a); break;
+        case JR_GOURAUD: k_shade<JR_GOURAUD><<<blocks, threads, 0, stream>>>(*a); break;
+        case JR_GOURAUD_TEXTURE: k_shade<JR_GOURAUD_TEXTURE><<<blocks, threads, 0, stream>>>(*a); break;
+        case JR_PHONG: k_shade<JR_PHONG><<<blocks, threads, 0, stream>>>(*a); break;
+        case JR_PHONG_DARBOUX: k_shade<JR_PHONG_DARBOUX><<<blocks, threads, 0, stream>>>(*a); break;
+        case JR_PHONG_REFLECTION: k_shade<JR_PHONG_REFLECTION><<<blocks, threads, 0, stream>>>(*a); break;
         case JR_PHONG_REFLECTION_SHADOW:
-          k_shade<JR_PHONG_REFLECTION_SHADOW><<<(unsigned)blocks, threads, 0, stream>>>(*a); break;
+          k_shade<JR_PHONG_REFLECTION_SHADOW><<<blocks, threads, 0, stream>>>(*a); break;
         default: return JR_ERR_SHADER;
       }
       jr::g_launches++;
