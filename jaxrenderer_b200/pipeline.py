@@ -50,6 +50,18 @@ _SPEC: Dict[str, Tuple[int, bool]] = {
     "zbuffer": (2, True), "canvas": (3, True),
 }
 
+# required trailing dimensions (None = free)
+_TRAIL: Dict[str, Tuple[Optional[int], ...]] = {
+    "world_to_clip": (4, 4), "viewport": (4, 4), "world_to_eye_norm": (4, 4),
+    "shadow_world_to_clip": (4, 4), "shadow_viewport": (4, 4),
+    "position": (None, 3), "normal": (None, 3), "colour": (None, 3), "uv": (None, 2),
+    "faces": (None, 3), "faces_norm": (None, 3), "faces_uv": (None, 3), "faces_tex": (None, 3),
+    "faces_indices": (None, 3), "texture_shape": (None, 2),
+    "light_direction": (3,), "light_colour": (3,), "light_dir_eye": (3,), "ambient": (3,),
+    "diffuse": (3,), "specular": (3,), "shadow_strength": (3,),
+    "texture": (None, None, 3), "normal_map": (None, None, 3),
+}
+
 # differentiable inputs, in the positional order of _RenderFn
 _DIFF = (
     "zbuffer", "canvas", "position", "normal", "colour", "world_to_clip", "viewport",
@@ -254,29 +266,18 @@ def _render_arrays(sid: int, arrays: Dict[str, Any], zbuffer: Any, canvas: Optio
                    inplace: bool = False, return_tri_id: bool = False):
     """Internal entry: flat C-ABI array names -> (zbuffer, canvas, tri_id)."""
     _native.load()  # fail loudly before anything else when the extension is missing
+    arrays = dict(arrays)
     texture_offset = int(arrays.pop("texture_offset", 0))
-    host_in = not (isinstance(zbuffer, torch.Tensor) and zbuffer.is_cuda)
-    if host_in:
-        if not torch.cuda.is_available():
-            raise RuntimeError("jaxrenderer_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
-        dev = torch.device("cuda", torch.cuda.current_device())
-    else:
-        dev = zbuffer.device
-    tens: Dict[str, Tensor] = {}
-    for name, v in arrays.items():
+    # ---- validate shapes first (host side, before any transfer or launch)
+    raw: Dict[str, Tensor] = {}
+    for name, v in list(arrays.items()) + [("zbuffer", zbuffer), ("canvas", canvas)]:
         if v is None:
             continue
-        tens[name] = _as(v, _SPEC[name][1], dev)
-    z = _as(zbuffer, True, dev)
-    c = _as(canvas, True, dev) if canvas is not None else None
-    # batch size: every leaf is un-batched (rank r) or batched (rank r + 1)
+        raw[name] = v if isinstance(v, torch.Tensor) else torch.as_tensor(
+            v, dtype=torch.float32 if _SPEC[name][1] else torch.int32)
     B = None
     batched: Dict[str, bool] = {}
-    items = dict(tens)
-    items["zbuffer"] = z
-    if c is not None:
-        items["canvas"] = c
-    for name, t in items.items():
+    for name, t in raw.items():
         r = _SPEC[name][0]
         if t.ndim == r:
             batched[name] = False
@@ -288,13 +289,33 @@ def _render_arrays(sid: int, arrays: Dict[str, Any], zbuffer: Any, canvas: Optio
                 raise ValueError(f"inconsistent batch size for `{name}`: {t.shape[0]} vs {B}")
         else:
             raise ValueError(f"`{name}` has rank {t.ndim}, expected {r} or {r + 1}")
+        trail = _TRAIL.get(name)
+        if trail is not None:
+            got = tuple(t.shape[t.ndim - len(trail):])
+            if any(w is not None and w != g for w, g in zip(trail, got)):
+                raise ValueError(f"`{name}` must end in shape {trail}, got {tuple(t.shape)}")
+    if "colour" in raw and raw["colour"].shape[-2] != raw["position"].shape[-2]:
+        raise ValueError("`colour` must have one row per `position` row")
+    if "id_to_face" in raw and raw["id_to_face"].shape[-1] != raw["position"].shape[-2]:
+        raise ValueError("`id_to_face` must have one entry per `position` row")
+    if "normal_map" in raw and raw["normal_map"].shape[-3:-1] != raw["texture"].shape[-3:-1]:
+        raise ValueError("`normal_map` must have the texture's width and height")
+    W, H = raw["zbuffer"].shape[-2], raw["zbuffer"].shape[-1]
+    if canvas is not None and tuple(raw["canvas"].shape[-3:]) != (W, H, 3):
+        raise ValueError(f"canvas must be (..., {W}, {H}, 3), got {tuple(raw['canvas'].shape)}")
+    # ---- device placement
+    host_in = not (isinstance(zbuffer, torch.Tensor) and zbuffer.is_cuda)
+    if host_in:
+        if not torch.cuda.is_available():
+            raise RuntimeError("jaxrenderer_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        dev = torch.device("cuda", torch.cuda.current_device())
+    else:
+        dev = zbuffer.device
+    tens: Dict[str, Tensor] = {n: _as(t, _SPEC[n][1], dev) for n, t in raw.items() if n not in ("zbuffer", "canvas")}
+    z = _as(raw["zbuffer"], True, dev)
+    c = _as(raw["canvas"], True, dev) if canvas is not None else None
     squeeze = B is None
     B = 1 if B is None else B
-    W, H = z.shape[-2], z.shape[-1]
-    if c is not None and tuple(c.shape[-3:]) != (W, H, 3):
-        raise ValueError(f"canvas must be (..., {W}, {H}, 3), got {tuple(c.shape)}")
-    if tens["faces"].shape[-1] != 3:
-        raise ValueError("face_indices must be (T, 3)")
     # buffers always get a batch axis (vmap would broadcast them on output)
     if not batched["zbuffer"]:
         z = z.unsqueeze(0).expand(B, W, H)
@@ -367,7 +388,10 @@ def render(camera: Camera, shader: type, buffers: Buffers, face_indices: Any, ex
         if len(targets) != 1:
             raise ValueError(f"{shader.__name__} renders to exactly one target (canvas)")
         canvas = targets[0]
-    arrays = _collect(shader, camera, face_indices, extra)
+    try:
+        arrays = _collect(shader, camera, face_indices, extra)
+    except AttributeError as e:
+        raise TypeError(f"`extra` / `camera` do not carry the fields {shader.__name__} reads: {e}") from None
     z, c, tri = _render_arrays(sid, arrays, buffers.zbuffer, canvas, inplace=inplace,
                                return_tri_id=return_tri_id)
     out = Buffers(zbuffer=z, targets=() if c is None else (c,))

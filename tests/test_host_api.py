@@ -124,3 +124,23 @@ def test_transpose_for_display():
     a = torch.arange(24.0).reshape(2, 3, 4)
     d = jr.transpose_for_display(a)
     assert d.shape == (3, 2, 4) and torch.equal(d[0], a[:, 2]) and torch.equal(jr.transpose_for_display(a, False)[0], a[:, 0])
+
+
+def test_shape_validation_errors_before_any_launch():
+    cam = jr.Renderer.create_camera_from_parameters(jr.CameraParameters(viewWidth=8, viewHeight=8))
+    f13 = torch.zeros(1, 3, dtype=torch.int32)
+    cases = [
+        (dict(position=torch.zeros(3, 2)), f13, torch.ones(8, 8), "must end in shape"),
+        (dict(position=torch.zeros(2, 3, 3)), torch.zeros(3, 1, 3, dtype=torch.int32), torch.ones(8, 8), "inconsistent batch"),
+        (dict(position=torch.zeros(3, 3)), torch.zeros(1, 4, dtype=torch.int32), torch.ones(8, 8), "must end in shape"),
+        (dict(position=torch.zeros(3, 3)), f13, torch.ones(8), "has rank"),
+    ]
+    for kw, faces, z, msg in cases:
+        with pytest.raises(ValueError, match=msg):
+            jr.render(cam, DepthShader, jr.Buffers(z, ()), faces, DepthExtraInput(**kw))
+    with pytest.raises(ValueError, match="targets must be"):
+        jr.render(cam, DepthShader, jr.Buffers(torch.ones(8, 8), (torch.ones(8, 8, 3),)), f13,
+                  DepthExtraInput(torch.zeros(3, 3)))
+    with pytest.raises(TypeError, match="do not carry the fields"):
+        jr.render(cam, GouraudShader, jr.Buffers(torch.ones(8, 8), (torch.ones(8, 8, 3),)), f13,
+                  DepthExtraInput(torch.zeros(3, 3)))
