@@ -264,3 +264,55 @@ def test_long_segments_few_keys():
                                         get("texture", tex1))
     out = _run_case("gouraud_texture", GouraudTextureShader, mk, s, ("texture", "light_colour", "world_to_clip"))
     assert int((out.zbuffer != 1.0).sum()) > 2000
+
+
+def test_renderer_level_grads_wrt_camera_position_light_and_atlas():
+    """BASELINE config 5 in miniature: Renderer.render with the shadow pass, gradients w.r.t.
+    CameraParameters.position (through the host-side camera builders), LightParameters and the
+    shared diffuse atlas, against the oracle driven by the same (differentiable) host code."""
+    from jaxrenderer_b200 import synthetic
+    W, H = 64, 48
+    sc = synthetic.brax_like_batch(1, n_capsules=2, with_attributes=True)
+    nv, _ = synthetic.scene_sizes(2)
+    g = torch.Generator().manual_seed(5)
+    atlas0 = torch.rand(3 * 8, 8, 3, generator=g)
+    wc = torch.rand(W, H, 3, generator=g) + 0.5
+
+    def run(dev, use_oracle):
+        atlas = _leaf(atlas0, dev)
+        eye = _leaf(sc["eye"][0], dev)
+        ldir = _leaf(torch.tensor((0.57735, -0.57735, 0.57735)), dev)
+        amb = _leaf(torch.tensor((0.8, 0.8, 0.8)), dev)
+        d = dev or "cpu"
+        model = jr.MergedModel(
+            verts=sc["position"][0].to(d), norms=sc["normal"][0].to(d), uvs=sc["uv"].to(d),
+            faces=sc["faces"][0].to(d), faces_norm=sc["faces"][0].to(d), faces_uv=sc["faces"][0].to(d),
+            texture_index=sc["texture_index"].to(d), double_sided=torch.zeros(nv, dtype=torch.bool, device=d),
+            texture_shape=torch.tensor([[8, 8], [1, 1], [1, 1]], dtype=torch.int32, device=d), offset=8,
+            diffuse_map=atlas, specular_map=torch.full((3, 1), 2.0, device=d))
+        cam = jr.Renderer.create_camera_from_parameters(jr.CameraParameters(
+            viewWidth=W, viewHeight=H, hfov=58.0, vfov=58.0 * H / W, position=eye, target=sc["target"][0].to(d)))
+        light = jr.LightParameters(direction=ldir, ambient=amb, diffuse=(0.8,) * 3, specular=(0.6,) * 3)
+        sp = jr.ShadowParameters(centre=sc["target"][0].to(d))
+        if not use_oracle:
+            out = jr.Renderer.render(model, light, cam, jr.Renderer.create_buffers(W, H, device=d), shadow_param=sp)
+            canvas = out.targets[0]
+            shadow_cam = None
+        else:
+            # light camera from the product's own host code so host rounding is shared
+            sh = jr.Shadow.render_shadow_map(
+                torch.full((W, H), torch.finfo(torch.float32).max, device=DEV), model.verts.detach().to(DEV),
+                model.faces.to(DEV), ldir.detach(), cam.viewport.detach().to(DEV), sp.centre, sp.up, sp.strength,
+                offset=sp.offset)
+            scam = NS(world_to_clip=sh.camera.world_to_clip.cpu(), viewport=sh.camera.viewport.cpu())
+            lp = NS(direction=ldir, colour=torch.ones(3), ambient=amb, diffuse=torch.full((3,), 0.8),
+                    specular=torch.full((3,), 0.6))
+            spo = NS(centre=sp.centre, up=torch.tensor(sp.up), strength=torch.tensor(sp.strength), offset=sp.offset)
+            canvas = O.renderer_render(model, lp, cam, torch.ones(W, H), torch.ones(W, H, 3), spo, scam)["out"].targets[0]
+        (canvas * wc.to(canvas.device)).sum().backward()
+        return {"atlas": atlas.grad, "eye": eye.grad, "light.direction": ldir.grad, "ambient": amb.grad}
+
+    got = run(DEV, False)
+    want = run(None, True)
+    for k in want:
+        _check(k, got[k], want[k], rtol=2e-4 if k == "eye" else RTOL)
