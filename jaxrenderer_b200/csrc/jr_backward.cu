@@ -249,9 +249,12 @@ __device__ __forceinline__ void load_cotangent(const JrGradArgs& g, long long gi
 
 // ------------------------------------------------------------ global parameters
 constexpr int BWD_THREADS = 256;
+#ifndef JR_BWD_MIN_BLOCKS
+#define JR_BWD_MIN_BLOCKS 2  // caps k_bwd_global at 128 registers: 2 CTAs/SM beat 1 CTA with 233 registers (measured)
+#endif
 
 template <int S>
-__global__ void __launch_bounds__(BWD_THREADS)
+__global__ void __launch_bounds__(BWD_THREADS, JR_BWD_MIN_BLOCKS)
 k_bwd_global(const __grid_constant__ JrRenderArgs a, const __grid_constant__ JrGradArgs g, float* __restrict__ partials) {
   const int b = blockIdx.y;
   const int npix = a.W * a.H;
