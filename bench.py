@@ -260,6 +260,9 @@ def run_ours(args) -> None:
     # parity guard: the e2e result equals the resident result
     assert torch.equal(z_host, z.cpu()), "e2e output differs from the device-resident output"
 
+    fwd_bwd = None
+    if not args.no_fwd_bwd:
+        fwd_bwd = fwd_bwd_secondary(dev, rank, world)
     if rank == 0:
         nv, ntri = synthetic.scene_sizes(N_CAPSULES)
         alg_bytes = (12 * nv + 12 * ntri + 4 * W * H) * B       # geometry read once + z write
@@ -296,12 +299,73 @@ def run_ours(args) -> None:
                 "launch_ms_avg": avg_ms, "launch_ms_median": med_ms,
             },
         }
+        if fwd_bwd is not None:
+            line["fwd_bwd"] = fwd_bwd
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def fwd_bwd_secondary(dev, rank: int, world: int, steps: int = 5) -> dict:
+    """Secondary line (BASELINE metric: "fwd+bwd images/sec"; configs[4] shape at a reduced batch):
+    Renderer.render with the shadow pass at 480x270, 3276 triangles, 64 images per GPU, loss =
+    mean((canvas - target)^2), gradients w.r.t. light, world_to_clip and the SHARED diffuse atlas;
+    the shared gradients are all-reduced across ranks (NCCL) inside the timed region."""
+    import torch
+    import torch.distributed as dist
+
+    import jaxrenderer_b200 as jr
+    from jaxrenderer_b200 import synthetic
+    from jaxrenderer_b200.distributed import all_reduce_shared_grads
+
+    Wd, Hd, n_caps, Bd = 480, 270, 17, 64
+    sc = synthetic.brax_like_batch(Bd, n_capsules=n_caps, env0=10_000_000 + rank * Bd, with_attributes=True)
+    cam = synthetic.brax_cameras(sc["eye"], sc["target"], Wd, Hd)
+    cam = type(cam)(*[t.to(dev) for t in cam])
+    model = synthetic.merged_model_from_batch(sc, n_caps, dev)
+    light0 = jr.LightParameters(direction=(0.57735, -0.57735, 0.57735), ambient=(0.8,) * 3, diffuse=(0.8,) * 3,
+                                specular=(0.6,) * 3)
+    sp = jr.ShadowParameters(centre=sc["target"].to(dev))
+    target = torch.rand(Bd, Wd, Hd, 3, device=dev)
+    atlas = model.diffuse_map.clone().requires_grad_(True)
+    ldir = torch.tensor(light0.direction, device=dev, requires_grad=True)
+    amb = torch.tensor(light0.ambient, device=dev, requires_grad=True)
+    w2c = cam.world_to_clip.clone().requires_grad_(True)
+
+    def step():
+        for p in (atlas, ldir, amb, w2c):
+            p.grad = None
+        out = jr.Renderer.render(model._replace(diffuse_map=atlas), light0._replace(direction=ldir, ambient=amb),
+                                 cam._replace(world_to_clip=w2c), jr.Renderer.create_buffers(Wd, Hd, batch=Bd, device=dev),
+                                 shadow_param=sp)
+        ((out.targets[0] - target) ** 2).mean().backward()
+        all_reduce_shared_grads([atlas.grad, ldir.grad, amb.grad])   # w2c is per image: no exchange
+
+    for _ in range(3):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / steps
+    return {"value": Bd * world / (ms / 1e3), "unit": "images/s (forward + backward)", "ms_per_step": ms,
+            "steps": steps,
+            "config": {"workload": "configs[4] shape at reduced batch: phong_reflection_shadow 480x270, 3276 triangles, "
+                                   f"{Bd} images per GPU, grads w.r.t. light, world_to_clip, shared diffuse atlas",
+                       "allreduce_floats": int(atlas.numel() + 6) if world > 1 else 0}}
 
 
 def main() -> None:
@@ -312,6 +376,7 @@ def main() -> None:
     ap.add_argument("--impl", choices=("ours", "reference"), default="ours")
     ap.add_argument("--batch", type=int, default=BATCH, help="images per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-fwd-bwd", action="store_true", help="skip the secondary forward+backward measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -107,3 +107,27 @@ def checker_texture(w: int = 100, h: int = 100, cell: int = 10) -> torch.Tensor:
     on = ((ii // cell + jj // cell) % 2).astype(np.float32)
     tex = np.stack([0.2 + 0.6 * on, 0.3 + 0.4 * (1 - on), 0.5 + 0.3 * on], axis=-1)
     return torch.from_numpy(tex.astype(np.float32))
+
+
+def merged_model_from_batch(sc: Dict[str, torch.Tensor], n_capsules: int, device, atlas_tex: int = 100):
+    """``MergedModel`` of a ``brax_like_batch(..., with_attributes=True)``: shared topology, batched
+    world-space attributes, an atlas with a checker texture for the ground and 1x1 textures for the
+    capsules (the layout of the real Brax ant fixture)."""
+    from .model import MergedModel
+
+    nv, _ = scene_sizes(n_capsules)
+    n_obj = n_capsules + 1
+    g = torch.Generator().manual_seed(1)
+    atlas = torch.zeros(n_obj * atlas_tex, atlas_tex, 3)
+    atlas[:atlas_tex] = checker_texture(atlas_tex, atlas_tex)
+    shapes = [[atlas_tex, atlas_tex]] + [[1, 1]] * n_capsules
+    for i in range(1, n_obj):
+        atlas[i * atlas_tex, 0] = torch.rand(3, generator=g)
+    faces = sc["faces"][0].to(device)
+    return MergedModel(
+        verts=sc["position"].to(device), norms=sc["normal"].to(device), uvs=sc["uv"].to(device),
+        faces=faces, faces_norm=faces, faces_uv=faces,
+        texture_index=sc["texture_index"].to(device),
+        double_sided=torch.zeros(nv, dtype=torch.bool, device=device),
+        texture_shape=torch.tensor(shapes, dtype=torch.int32, device=device), offset=atlas_tex,
+        diffuse_map=atlas.to(device), specular_map=torch.full((n_obj, 1), 2.0, device=device))

@@ -40,22 +40,7 @@ def timeit(fn, steps, warmup=3):
 
 
 def merged_model(sc, n_caps, dev, atlas_tex=100):
-    """MergedModel of the synthetic batch (shared topology, batched world-space attributes)."""
-    nv, t = synthetic.scene_sizes(n_caps)
-    n_obj = n_caps + 1
-    g = torch.Generator().manual_seed(1)
-    atlas = torch.zeros(n_obj * atlas_tex, atlas_tex, 3)
-    atlas[:atlas_tex] = synthetic.checker_texture(atlas_tex, atlas_tex)
-    shapes = [[atlas_tex, atlas_tex]] + [[1, 1]] * n_caps
-    for i in range(1, n_obj):
-        atlas[i * atlas_tex, 0] = torch.rand(3, generator=g)
-    faces = sc["faces"][0].to(dev)
-    return jr.MergedModel(
-        verts=sc["position"].to(dev), norms=sc["normal"].to(dev), uvs=sc["uv"].to(dev),
-        faces=faces, faces_norm=faces, faces_uv=faces,
-        texture_index=sc["texture_index"].to(dev), double_sided=torch.zeros(nv, dtype=torch.bool, device=dev),
-        texture_shape=torch.tensor(shapes, dtype=torch.int32, device=dev), offset=atlas_tex,
-        diffuse_map=atlas.to(dev), specular_map=torch.full((n_obj, 1), 2.0, device=dev))
+    return synthetic.merged_model_from_batch(sc, n_caps, dev, atlas_tex)
 
 
 NOTEBOOK_LIGHT = jr.LightParameters(direction=(0.57735, -0.57735, 0.57735), ambient=(0.8,) * 3,
