@@ -737,7 +737,7 @@ size_t jr_backward_workspace_bytes(const JrRenderArgs* a, const JrGradArgs* g) {
 int jr_render_backward(const JrRenderArgs* a, const JrGradArgs* g, jr_stream_t stream_) {
   if (!a || !g) return JR_ERR_NULL;
   if (a->shader < 0 || a->shader >= JR_NUM_SHADERS) return JR_ERR_SHADER;
-  if (a->B <= 0 || a->W <= 0 || a->H <= 0) return JR_ERR_DIMS;
+  if (a->B <= 0 || a->W <= 0 || a->H <= 0 || a->B > 65535) return JR_ERR_DIMS;  // grid.y = batch
   if (!a->tri_id || !a->world_to_clip.ptr || !a->viewport.ptr) return JR_ERR_NULL;
   cudaStream_t stream = (cudaStream_t)stream_;
   switch (a->shader) {

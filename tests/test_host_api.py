@@ -144,3 +144,19 @@ def test_shape_validation_errors_before_any_launch():
     with pytest.raises(TypeError, match="do not carry the fields"):
         jr.render(cam, GouraudShader, jr.Buffers(torch.ones(8, 8), (torch.ones(8, 8, 3),)), f13,
                   DepthExtraInput(torch.zeros(3, 3)))
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/test_resources/pre-gen-brax/inputs-2.zip"),
+                    reason="reference checkout not present (GPU box)")
+def test_brax_pregen_loader_matches_committed_fixture():
+    from jaxrenderer_b200.brax_io import load_pregen
+    objs, cam, targets = load_pregen("/root/reference/test_resources/pre-gen-brax/inputs-30.zip")
+    fix_objs, fix_cam = load_brax_fixture()      # frames 0, 7, 15, 29 extracted at build time
+    assert len(objs) == 18 and targets.shape == (30, 3)
+    assert objs[0].model.verts.shape == (24, 3) and objs[1].model.faces.shape == (192, 3)
+    frames = [0, 7, 15, 29]
+    for o, f in zip(objs, fix_objs):
+        assert torch.equal(o.transform[frames], f.transform) and torch.equal(o.model.verts, f.model.verts)
+    assert torch.equal(cam.position[frames], fix_cam.position)
+    m = jr.merge_objects(objs)
+    assert m.verts.shape == (30, 9816, 3) and m.faces.shape[-2:] == (3276, 3)
