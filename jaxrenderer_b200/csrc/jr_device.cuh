@@ -142,4 +142,27 @@ __device__ __forceinline__ int wrap_clamp(int i, int n) {
   return i < 0 ? 0 : (i > n - 1 ? n - 1 : i);
 }
 
+
+// Conservative bbox margin (pixels).  The fp32 edge functions can include a pixel centre that lies
+// slightly OUTSIDE the exact triangle; the bbox must keep every such pixel.  The excess distance is
+// bounded by ~ eps * W * (L/h)^2 pixels (evaluation error eps*W, amplified by the conditioning L/h of
+// the 3x3 inverse and by 1/sin of the sharpest corner ~ L/h; L = longest edge, h = smallest height).
+// Small, well-shaped triangles therefore get a margin of 1/64 px (with a 64x safety factor on the
+// estimate), growing to the blanket 0.5 px for needles and for anything larger than 8 px (where the
+// margin costs little).  About half of the candidate triangles of a Brax scene at 84x84 contain no
+// sample at all and are dropped here, before the LU inverse (validated bit-for-bit against the
+// brute-force oracle on millions of random small / needle triangles: tests/test_gpu_fuzz.py).
+__device__ __forceinline__ float bbox_margin(float sx0, float sy0, float sx1, float sy1, float sx2, float sy2,
+                                             float view_w) {
+  const float ex = fmaxf(fmaxf(sx0, sx1), sx2) - fminf(fminf(sx0, sx1), sx2);
+  const float ey = fmaxf(fmaxf(sy0, sy1), sy2) - fminf(fminf(sy0, sy1), sy2);
+  if (!(ex < 8.f && ey < 8.f)) return 0.5f;  // also NaN
+  const float ax = sx1 - sx0, ay = sy1 - sy0, bx = sx2 - sx0, by = sy2 - sy0, cx = sx2 - sx1, cy = sy2 - sy1;
+  const float l2 = fmaxf(fmaxf(ax * ax + ay * ay, bx * bx + by * by), cx * cx + cy * cy);
+  const float area2 = fabsf(ax * by - ay * bx);           // twice the area
+  const float asp = l2 / fmaxf(area2, 1e-20f);            // L / h
+  const float m = 3.8e-6f * view_w * asp * asp;           // 64 * eps * W * (L/h)^2
+  return fminf(0.5f, fmaxf(m, 0.015625f));
+}
+
 }  // namespace jr

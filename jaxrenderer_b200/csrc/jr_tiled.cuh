@@ -94,10 +94,11 @@ k_setup_bin(const __grid_constant__ JrRenderArgs a, TriRecord* __restrict__ recs
         const float r0 = __fdividef(1.f, w0), r1 = __fdividef(1.f, w1), r2 = __fdividef(1.f, w2);
         const float sx0 = (M[0] * r0) * vp00 + vp03, sx1 = (M[3] * r1) * vp00 + vp03, sx2 = (M[6] * r2) * vp00 + vp03;
         const float sy0 = (M[1] * r0) * vp11 + vp13, sy1 = (M[4] * r1) * vp11 + vp13, sy2 = (M[7] * r2) * vp11 + vp13;
-        const float mnx = fmaxf(fminf(fminf(sx0, sx1), sx2) - 0.5f, 0.f);
-        const float mxx = fminf(fmaxf(fmaxf(sx0, sx1), sx2) + 0.5f, (float)(a.W - 1));
-        const float mny = fmaxf(fminf(fminf(sy0, sy1), sy2) - 0.5f, 0.f);
-        const float mxy = fminf(fmaxf(fmaxf(sy0, sy1), sy2) + 0.5f, (float)(a.H - 1));
+        const float mg = bbox_margin(sx0, sy0, sx1, sy1, sx2, sy2, 2.f * fmaxf(vp00, vp11));
+        const float mnx = fmaxf(fminf(fminf(sx0, sx1), sx2) - mg, 0.f);
+        const float mxx = fminf(fmaxf(fmaxf(sx0, sx1), sx2) + mg, (float)(a.W - 1));
+        const float mny = fmaxf(fminf(fminf(sy0, sy1), sy2) - mg, 0.f);
+        const float mxy = fminf(fmaxf(fmaxf(sy0, sy1), sy2) + mg, (float)(a.H - 1));
         if (!(mnx <= mxx) || !(mny <= mxy)) surv = false;
         x0 = (int)ceilf(mnx); x1 = (int)floorf(mxx);
         y0 = (int)ceilf(mny); y1 = (int)floorf(mxy);

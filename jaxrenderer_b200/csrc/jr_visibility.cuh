@@ -296,11 +296,12 @@ k_vis2(const __grid_constant__ JrRenderArgs a, int tile_w, int tile_h, int tiles
           const float r0 = __fdividef(1.f, w0), r1 = __fdividef(1.f, w1), r2 = __fdividef(1.f, w2);
           const float sx0 = (M[0] * r0) * vp00 + vp03, sx1 = (M[3] * r1) * vp00 + vp03, sx2 = (M[6] * r2) * vp00 + vp03;
           const float sy0 = (M[1] * r0) * vp11 + vp13, sy1 = (M[4] * r1) * vp11 + vp13, sy2 = (M[7] * r2) * vp11 + vp13;
-          // conservative +-0.5 px margin; fmaxf/fminf drop NaN towards "whole tile"
-          const float mnx = fmaxf(fminf(fminf(sx0, sx1), sx2) - 0.5f, fx_lo);
-          const float mxx = fminf(fmaxf(fmaxf(sx0, sx1), sx2) + 0.5f, fx_hi);
-          const float mny = fmaxf(fminf(fminf(sy0, sy1), sy2) - 0.5f, fy_lo);
-          const float mxy = fminf(fmaxf(fmaxf(sy0, sy1), sy2) + 0.5f, fy_hi);
+          // conservative margin (see bbox_margin); fmaxf/fminf drop NaN towards "whole tile"
+          const float mg = bbox_margin(sx0, sy0, sx1, sy1, sx2, sy2, 2.f * fmaxf(vp00, vp11));
+          const float mnx = fmaxf(fminf(fminf(sx0, sx1), sx2) - mg, fx_lo);
+          const float mxx = fminf(fmaxf(fmaxf(sx0, sx1), sx2) + mg, fx_hi);
+          const float mny = fmaxf(fminf(fminf(sy0, sy1), sy2) - mg, fy_lo);
+          const float mxy = fminf(fmaxf(fmaxf(sy0, sy1), sy2) + mg, fy_hi);
           if (!(mnx <= mxx) || !(mny <= mxy)) surv = false;
           x0 = (int)ceilf(mnx) - tx0; x1 = (int)floorf(mxx) - tx0;
           y0 = (int)ceilf(mny) - ty0; y1 = (int)floorf(mxy) - ty0;
