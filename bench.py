@@ -262,7 +262,9 @@ def run_ours(args) -> None:
 
     fwd_bwd = None
     if not args.no_fwd_bwd:
-        fwd_bwd = fwd_bwd_secondary(dev, rank, world)
+        # the metric's 84x84 scenes, and configs[4]'s 480x270 canvas at a reduced batch
+        fwd_bwd = {"84x84": fwd_bwd_secondary(dev, rank, world, shape=(84, 84, 10, 1024)),
+                   "480x270": fwd_bwd_secondary(dev, rank, world, shape=(480, 270, 17, 64))}
     if rank == 0:
         nv, ntri = synthetic.scene_sizes(N_CAPSULES)
         alg_bytes = (12 * nv + 12 * ntri + 4 * W * H) * B       # geometry read once + z write
@@ -309,7 +311,7 @@ def run_ours(args) -> None:
         dist.destroy_process_group()
 
 
-def fwd_bwd_secondary(dev, rank: int, world: int, steps: int = 5) -> dict:
+def fwd_bwd_secondary(dev, rank: int, world: int, steps: int = 5, shape=(480, 270, 17, 64)) -> dict:
     """Secondary line (BASELINE metric: "fwd+bwd images/sec"; configs[4] shape at a reduced batch):
     Renderer.render with the shadow pass at 480x270, 3276 triangles, 64 images per GPU, loss =
     mean((canvas - target)^2), gradients w.r.t. light, world_to_clip and the SHARED diffuse atlas;
@@ -321,7 +323,7 @@ def fwd_bwd_secondary(dev, rank: int, world: int, steps: int = 5) -> dict:
     from jaxrenderer_b200 import synthetic
     from jaxrenderer_b200.distributed import all_reduce_shared_grads
 
-    Wd, Hd, n_caps, Bd = 480, 270, 17, 64
+    Wd, Hd, n_caps, Bd = shape
     sc = synthetic.brax_like_batch(Bd, n_capsules=n_caps, env0=10_000_000 + rank * Bd, with_attributes=True)
     cam = synthetic.brax_cameras(sc["eye"], sc["target"], Wd, Hd)
     cam = type(cam)(*[t.to(dev) for t in cam])
@@ -363,7 +365,7 @@ def fwd_bwd_secondary(dev, rank: int, world: int, steps: int = 5) -> dict:
     ms = float(t.item()) / steps
     return {"value": Bd * world / (ms / 1e3), "unit": "images/s (forward + backward)", "ms_per_step": ms,
             "steps": steps,
-            "config": {"workload": "configs[4] shape at reduced batch: phong_reflection_shadow 480x270, 3276 triangles, "
+            "config": {"workload": f"phong_reflection_shadow {Wd}x{Hd}, {synthetic.scene_sizes(n_caps)[1]} triangles, "
                                    f"{Bd} images per GPU, grads w.r.t. light, world_to_clip, shared diffuse atlas",
                        "allreduce_floats": int(atlas.numel() + 6) if world > 1 else 0}}
 
