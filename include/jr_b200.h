@@ -190,6 +190,30 @@ int jr_add_scalar(float* data, long long n, float value, jr_stream_t stream);
 int jr_canvas_to_uint8_display(const float* canvas, uint8_t* out, int B, int W, int H,
                                jr_stream_t stream);
 
+/*
+ * merge_objects (renderer/model.py:447-555), fused: world-space vertices and normals of all
+ * objects of all batch elements in two launches instead of ~15 small framework ops per object
+ * (first step).  Meshes are given concatenated in local space with an object id per
+ * vertex / normal; `transform`, `normal_matrix` (= inverse(transform)^T, computed by the host) are
+ * (n_objects,4,4) and `scaling` (n_objects,3), each optionally batched.
+ *   verts  = to_cartesian(to_homogeneous(v * scaling) @ transform^T)            (model.py:489-499)
+ *   norms  = apply_vec(n, normal_matrix) with the reference's whole-array (Frobenius)
+ *            normalisation per object before and after the rotation             (model.py:517-530)
+ */
+typedef struct JrMergeArgs {
+  int32_t B, n_objects, n_verts, n_norms;
+  JrF32 local_verts;      /* (n_verts,3) */
+  JrF32 local_norms;      /* (n_norms,3) */
+  JrI32 vert_object;      /* (n_verts) object id of each vertex */
+  JrI32 norm_start;       /* (n_objects+1) first normal of each object, prefix sums */
+  JrF32 scaling;          /* (n_objects,3) */
+  JrF32 transform;        /* (n_objects,4,4) */
+  JrF32 normal_matrix;    /* (n_objects,4,4) */
+  float* out_verts;       /* (B,n_verts,3) */
+  float* out_norms;       /* (B,n_norms,3) */
+} JrMergeArgs;
+int jr_merge_objects(const JrMergeArgs* args, jr_stream_t stream);
+
 /* Introspection for benchmarks: number of kernel launches issued by this
  * library since load (monotonic). */
 long long jr_launch_count(void);

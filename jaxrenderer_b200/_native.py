@@ -22,7 +22,7 @@ EXPORTS = (
     "jr_render_forward", "jr_render_backward",
     "jr_depth_forward", "jr_gouraud_forward", "jr_gouraud_texture_forward", "jr_phong_forward",
     "jr_phong_darboux_forward", "jr_phong_reflection_forward", "jr_phong_reflection_shadow_forward",
-    "jr_add_scalar", "jr_canvas_to_uint8_display", "jr_launch_count",
+    "jr_add_scalar", "jr_canvas_to_uint8_display", "jr_launch_count", "jr_merge_objects",
 )
 
 
@@ -68,6 +68,15 @@ class JrGradArgs(C.Structure):
     ]
 
 
+class JrMergeArgs(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("n_objects", C.c_int32), ("n_verts", C.c_int32), ("n_norms", C.c_int32),
+        ("local_verts", JrF32), ("local_norms", JrF32), ("vert_object", JrI32), ("norm_start", JrI32),
+        ("scaling", JrF32), ("transform", JrF32), ("normal_matrix", JrF32),
+        ("out_verts", C.c_void_p), ("out_norms", C.c_void_p),
+    ]
+
+
 _lib: Optional[C.CDLL] = None
 
 
@@ -103,6 +112,8 @@ def load() -> C.CDLL:
     lib.jr_canvas_to_uint8_display.restype = C.c_int
     lib.jr_canvas_to_uint8_display.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.jr_launch_count.restype = C.c_longlong
+    lib.jr_merge_objects.restype = C.c_int
+    lib.jr_merge_objects.argtypes = [C.POINTER(JrMergeArgs), C.c_void_p]
     _lib = lib
     return lib
 

@@ -85,6 +85,66 @@ __global__ void __launch_bounds__(256) k_shade_rec(const __grid_constant__ JrRen
   }
 }
 
+// ---------------------------------------------------------------- merge_objects (model.py:447-555)
+__global__ void __launch_bounds__(256) k_merge_verts(const __grid_constant__ JrMergeArgs m) {
+  const int b = blockIdx.y;
+  const int v = blockIdx.x * 256 + threadIdx.x;
+  if (v >= m.n_verts) return;
+  const float* lv = m.local_verts.ptr + (long long)b * m.local_verts.batch_stride + 3 * v;
+  const int o = (m.vert_object.ptr + (long long)b * m.vert_object.batch_stride)[v];
+  const float* s = m.scaling.ptr + (long long)b * m.scaling.batch_stride + 3 * o;
+  const float* T = m.transform.ptr + (long long)b * m.transform.batch_stride + 16 * o;
+  const float x = lv[0] * s[0], y = lv[1] * s[1], z = lv[2] * s[2];
+  float h[4];
+  to_clip(T, x, y, z, h);  // to_homogeneous(p) @ T^T
+  float* out = m.out_verts + ((long long)b * m.n_verts + v) * 3;
+  const bool w0 = h[3] == 0.0f;  // to_cartesian (geometry.py:183-202)
+  out[0] = w0 ? h[0] : h[0] / h[3];
+  out[1] = w0 ? h[1] : h[1] / h[3];
+  out[2] = w0 ? h[2] : h[2] / h[3];
+}
+
+__device__ __forceinline__ float block_sum_256(float v, float* red) {
+  // fixed-shape reduction: butterfly inside each warp, warps in order
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) t += red[w];
+  __syncthreads();
+  return t;
+}
+
+// one CTA per (object, batch element): Camera.apply_vec with whole-array normalisation
+__global__ void __launch_bounds__(256) k_merge_norms(const __grid_constant__ JrMergeArgs m) {
+  __shared__ float red[8];
+  const int b = blockIdx.y, o = blockIdx.x;
+  const int32_t* ns = m.norm_start.ptr + (long long)b * m.norm_start.batch_stride;
+  const int n0 = ns[o], n1 = ns[o + 1];
+  const float* ln = m.local_norms.ptr + (long long)b * m.local_norms.batch_stride;
+  const float* R = m.normal_matrix.ptr + (long long)b * m.normal_matrix.batch_stride + 16 * o;
+  float ss = 0.f;
+  for (int i = n0 + threadIdx.x; i < n1; i += 256) ss += dot3(ln[3 * i], ln[3 * i + 1], ln[3 * i + 2], ln[3 * i], ln[3 * i + 1], ln[3 * i + 2]);
+  const float f1 = sqrtf(block_sum_256(ss, red));
+  float ss2 = 0.f;
+  for (int i = n0 + threadIdx.x; i < n1; i += 256) {
+    const float x = ln[3 * i] / f1, y = ln[3 * i + 1] / f1, z = ln[3 * i + 2] / f1;
+    const float tx = (x * R[0] + y * R[1]) + z * R[2], ty = (x * R[4] + y * R[5]) + z * R[6],
+                tz = (x * R[8] + y * R[9]) + z * R[10];
+    ss2 += dot3(tx, ty, tz, tx, ty, tz);
+  }
+  const float f2 = sqrtf(block_sum_256(ss2, red));
+  float* out = m.out_norms + (long long)b * m.n_norms * 3;
+  for (int i = n0 + threadIdx.x; i < n1; i += 256) {
+    const float x = ln[3 * i] / f1, y = ln[3 * i + 1] / f1, z = ln[3 * i + 2] / f1;
+    out[3 * i] = ((x * R[0] + y * R[1]) + z * R[2]) / f2;
+    out[3 * i + 1] = ((x * R[4] + y * R[5]) + z * R[6]) / f2;
+    out[3 * i + 2] = ((x * R[8] + y * R[9]) + z * R[10]) / f2;
+  }
+}
+
 __global__ void k_add_scalar(float* data, long long n, float v) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x)
@@ -318,6 +378,24 @@ JR_SHADER_ENTRY(jr_phong_forward, JR_PHONG)
 JR_SHADER_ENTRY(jr_phong_darboux_forward, JR_PHONG_DARBOUX)
 JR_SHADER_ENTRY(jr_phong_reflection_forward, JR_PHONG_REFLECTION)
 JR_SHADER_ENTRY(jr_phong_reflection_shadow_forward, JR_PHONG_REFLECTION_SHADOW)
+
+int jr_merge_objects(const JrMergeArgs* m, jr_stream_t stream_) {
+  if (!m) return JR_ERR_NULL;
+  if (m->B <= 0 || m->B > 65535 || m->n_objects <= 0 || m->n_verts < 0 || m->n_norms < 0) return JR_ERR_DIMS;
+  if (!m->scaling.ptr || !m->transform.ptr || !m->normal_matrix.ptr) return JR_ERR_NULL;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (m->n_verts > 0) {
+    if (!m->local_verts.ptr || !m->vert_object.ptr || !m->out_verts) return JR_ERR_NULL;
+    k_merge_verts<<<dim3((m->n_verts + 255) / 256, m->B), 256, 0, stream>>>(*m);
+    jr::g_launches++;
+  }
+  if (m->n_norms > 0) {
+    if (!m->local_norms.ptr || !m->norm_start.ptr || !m->out_norms) return JR_ERR_NULL;
+    k_merge_norms<<<dim3(m->n_objects, m->B), 256, 0, stream>>>(*m);
+    jr::g_launches++;
+  }
+  return cudaGetLastError() == cudaSuccess ? JR_OK : JR_ERR_CUDA;
+}
 
 int jr_add_scalar(float* data, long long n, float value, jr_stream_t stream) {
   if (!data) return JR_ERR_NULL;

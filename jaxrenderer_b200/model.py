@@ -169,9 +169,70 @@ def _frob_normalise(x: Tensor) -> Tensor:
     return x / torch.linalg.norm(x, dim=(-2, -1), keepdim=True)
 
 
+def _merge_geometry_fused(objects: Sequence[ModelObject], dev: torch.device):
+    """CUDA fast path of the vertex / normal part of ``merge_objects``: two launches of
+    ``jr_merge_objects`` (``csrc/jr_forward.cu``) instead of ~15 framework ops per object."""
+    import ctypes as C
+
+    from . import _native
+    from ._native import JrF32, JrI32, JrMergeArgs
+
+    models = [o.model for o in objects]
+    n_obj = len(objects)
+
+    def cat(parts, base_rank):
+        if any(p.ndim > base_rank for p in parts):
+            batch = torch.broadcast_shapes(*[p.shape[: p.ndim - base_rank] for p in parts])
+            parts = [p.expand(*batch, *p.shape[p.ndim - base_rank:]) for p in parts]
+        return torch.cat(parts, dim=-base_rank).contiguous()
+
+    lv = cat([_f32(m.verts, dev) for m in models], 2)
+    ln = cat([_f32(m.norms, dev) for m in models], 2)
+    counts_v = [m.verts.shape[-2] for m in models]
+    counts_n = [m.norms.shape[-2] for m in models]
+    vobj = torch.repeat_interleave(torch.arange(n_obj, dtype=torch.int32, device=dev),
+                                   torch.tensor(counts_v, device=dev))
+    nstart = torch.tensor([0] + list(torch.tensor(counts_n).cumsum(0)), dtype=torch.int32, device=dev)
+
+    def stack(vals, base_rank, shape):
+        ts = [_f32(v, dev) for v in vals]
+        if any(t.ndim > base_rank for t in ts):
+            batch = torch.broadcast_shapes(*[t.shape[: t.ndim - base_rank] for t in ts])
+            ts = [t.expand(*batch, *shape) for t in ts]
+        return torch.stack(ts, dim=-(base_rank + 1)).contiguous()
+
+    scaling = stack([o.local_scaling for o in objects], 1, (3,))
+    transform = stack([o.transform for o in objects], 2, (4, 4))
+    nmat = torch.linalg.inv(transform).transpose(-1, -2).contiguous()
+    B = None
+    for t, r in ((lv, 2), (ln, 2), (scaling, 2), (transform, 3)):
+        if t.ndim == r + 1:
+            B = t.shape[0]
+    squeeze = B is None
+    B = 1 if B is None else B
+    V, Nn = lv.shape[-2], ln.shape[-2]
+    out_v = torch.empty((B, V, 3), dtype=torch.float32, device=dev)
+    out_n = torch.empty((B, Nn, 3), dtype=torch.float32, device=dev)
+
+    def f32(t, r):
+        return JrF32(t.data_ptr(), int(t[0].numel()) if t.ndim == r + 1 else 0)
+
+    a = JrMergeArgs()
+    a.B, a.n_objects, a.n_verts, a.n_norms = B, n_obj, V, Nn
+    a.local_verts, a.local_norms = f32(lv, 2), f32(ln, 2)
+    a.vert_object, a.norm_start = JrI32(vobj.data_ptr(), 0), JrI32(nstart.data_ptr(), 0)
+    a.scaling, a.transform, a.normal_matrix = f32(scaling, 2), f32(transform, 3), f32(nmat, 3)
+    a.out_verts, a.out_norms = out_v.data_ptr(), out_n.data_ptr()
+    lib = _native.load()
+    with torch.cuda.device(dev):
+        _native.check(lib.jr_merge_objects(C.byref(a), _native.stream_ptr(dev)))
+    return (out_v[0], out_n[0]) if squeeze else (out_v, out_n)
+
+
 def merge_objects(objects: Sequence[ModelObject]) -> MergedModel:
     """World-space merge of all objects into one mesh + texture atlas
-    (``model.py:447-555``)."""
+    (``model.py:447-555``).  On CUDA inputs (and when no gradient is requested through the
+    transforms) the vertex / normal transforms run in the fused ``jr_merge_objects`` kernels."""
     models = [obj.model for obj in objects]
     dev = models[0].verts.device
     counts = [m.verts.shape[-2] for m in models]
@@ -198,12 +259,24 @@ def merge_objects(objects: Sequence[ModelObject]) -> MergedModel:
         t = (to_homogeneous(n, 0.0) @ m.transpose(-1, -2))[..., :3]
         return _frob_normalise(t)
 
-    verts, faces = MergedModel.merge_verts(
-        [transform_vert(o.model.verts, o.local_scaling, o.transform) for o in objects],
-        [m.faces for m in models])
-    norms, faces_norm = MergedModel.merge_verts(
-        [transform_normals(o.model.norms, o.transform) for o in objects],
-        [m.faces_norm for m in models])
+    needs_grad = torch.is_grad_enabled() and any(
+        isinstance(t, torch.Tensor) and t.requires_grad
+        for o in objects for t in (o.model.verts, o.model.norms, o.local_scaling, o.transform))
+    if dev.type == "cuda" and not needs_grad:
+        verts, norms = _merge_geometry_fused(objects, dev)
+        cum_v, cum_n = [0], [0]
+        for m in models[:-1]:
+            cum_v.append(cum_v[-1] + m.verts.shape[-2])
+            cum_n.append(cum_n[-1] + m.norms.shape[-2])
+        faces = torch.cat([m.faces + cum_v[i] for i, m in enumerate(models)], dim=-2).to(torch.int32)
+        faces_norm = torch.cat([m.faces_norm + cum_n[i] for i, m in enumerate(models)], dim=-2).to(torch.int32)
+    else:
+        verts, faces = MergedModel.merge_verts(
+            [transform_vert(o.model.verts, o.local_scaling, o.transform) for o in objects],
+            [m.faces for m in models])
+        norms, faces_norm = MergedModel.merge_verts(
+            [transform_normals(o.model.norms, o.transform) for o in objects],
+            [m.faces_norm for m in models])
     uvs, faces_uv = MergedModel.merge_verts([_f32(m.uvs) for m in models],
                                             [m.faces_uv for m in models])
     return MergedModel(
