@@ -49,14 +49,24 @@ __global__ void __launch_bounds__(256) k_shade(const __grid_constant__ JrRenderA
 }
 
 // One thread per triangle: vertex stage of the shader -> attribute record (large canvases).
+// Records are staged in shared memory and written out with coalesced 128-bit stores (a thread
+// writing its own 176-byte record directly touches 44 different cache lines per warp store).
 template <int SHADER>
 __global__ void __launch_bounds__(128) k_tri_attr(const __grid_constant__ JrRenderArgs a, float* __restrict__ attrs) {
+  __shared__ __align__(16) float stage[128 * TA_FLOATS];
   const int b = blockIdx.y;
-  const int t = blockIdx.x * 128 + threadIdx.x;
-  if (t >= a.T) return;
-  Frag f;
-  frag_vertex<SHADER>(a, b, t, f);
-  attr_store<SHADER>(f, attrs + ((size_t)b * a.T + t) * TA_FLOATS);
+  const int t0 = blockIdx.x * 128;
+  const int t = t0 + threadIdx.x;
+  if (t < a.T) {
+    Frag f;
+    frag_vertex<SHADER>(a, b, t, f);
+    attr_store<SHADER>(f, stage + threadIdx.x * TA_FLOATS);
+  }
+  __syncthreads();
+  const int n = min(128, a.T - t0) * (TA_FLOATS / 4);
+  float4* dst = reinterpret_cast<float4*>(attrs + ((size_t)b * a.T + t0) * TA_FLOATS);
+  const float4* src = reinterpret_cast<const float4*>(stage);
+  for (int i = threadIdx.x; i < n; i += 128) dst[i] = src[i];
 }
 
 // Pixel stage from attribute records (same arithmetic as k_shade, the per-triangle part is shared).
@@ -257,6 +267,7 @@ const char* jr_strerror(int s) {
 // debugging / A-B switches, read once at load
 static const bool g_no_attr = getenv("JR_NO_ATTR") != nullptr;  // shade without attribute records
 static const bool g_no_bins = getenv("JR_NO_BINS") != nullptr;  // every tile CTA scans all triangles
+static const bool g_key64 = getenv("JR_KEY64") != nullptr;      // depth shader: keep packed 64-bit keys
 
 // Forward scratch: [binned visibility: triangle records + tile bitmasks][shading attribute records]
 struct FwdLayout { size_t tiled, attr_off, total; bool use_attr; };
@@ -290,8 +301,9 @@ int jr_render_forward(const JrRenderArgs* a, jr_stream_t stream_) {
   if (ctas > 2147483647LL) return JR_ERR_DIMS;
   static std::once_flag attr_once;
   std::call_once(attr_once, [] {
-    cudaFuncSetAttribute(k_vis2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(k_vis2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_vis2<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_vis2<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_vis2<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(k_raster_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     cudaFuncSetAttribute(k_raster_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   });
@@ -317,9 +329,12 @@ int jr_render_forward(const JrRenderArgs* a, jr_stream_t stream_) {
     if (depth) k_raster_tile<true><<<(unsigned)ctas2, TL_THREADS, sm, stream>>>(*a, recs, masks, TLy);
     else k_raster_tile<false><<<(unsigned)ctas2, TL_THREADS, sm, stream>>>(*a, recs, masks, TLy);
   } else {
-    const V2Layout L = v2_layout(tw, th);
-    if (depth) k_vis2<true><<<(unsigned)ctas, V2_THREADS, L.total, stream>>>(*a, tw, th, nx, ny);
-    else k_vis2<false><<<(unsigned)ctas, V2_THREADS, L.total, stream>>>(*a, tw, th, nx, ny);
+    // depth shader without a triangle-id output: z-only 32-bit keys (half the shared memory, native atomic min)
+    const bool k32 = depth && !a->tri_id && !g_key64;
+    const V2Layout L = v2_layout(tw, th, k32 ? 4 : 8);
+    if (k32) k_vis2<true, true><<<(unsigned)ctas, V2_THREADS, L.total, stream>>>(*a, tw, th, nx, ny);
+    else if (depth) k_vis2<true, false><<<(unsigned)ctas, V2_THREADS, L.total, stream>>>(*a, tw, th, nx, ny);
+    else k_vis2<false, false><<<(unsigned)ctas, V2_THREADS, L.total, stream>>>(*a, tw, th, nx, ny);
   }
   jr::g_launches++;
   if (!depth) {

@@ -251,7 +251,7 @@ k_raster_tile(const __grid_constant__ JrRenderArgs a, const TriRecord* __restric
       const int n = __shfl_sync(0xffffffffu, area, src);
       if (n >= V2_HIER_AREA) {
         const int sx1 = __shfl_sync(0xffffffffu, x1, src), sy1 = __shfl_sync(0xffffffffu, y1, src);
-        raster_hier_warp(binv, bzc, btri, sx0, sy0, sx1, sy1, lane, xs, ys, keys_saddr, TL_TILE, vp22, vp23);
+        raster_hier_warp<false>(binv, bzc, btri, sx0, sy0, sx1, sy1, lane, xs, ys, keys_saddr, TL_TILE, vp22, vp23);
       } else {
         const float rbh = 1.0f / (float)sbh;
         for (int i = lane; i < n; i += 32) {

@@ -18,6 +18,12 @@
 //
 // The 64-bit shared atomicMin is an explicit ld.shared / atom.shared.cas.b64 loop on
 // a 32-bit shared-window address (the compiler's generic-pointer emulation costs ~3x).
+//
+// K32 variant (depth shader, no triangle-id output: the bench workload and every shadow pass): the
+// key is the orderable z alone -> half the shared memory, so 5 CTAs (40 warps) fit an SM instead
+// of 3.  The kernel is issue/latency bound and the extra warps are what pays (measured on B200,
+// 84x84 x 4096: 0.484 ms with 64-bit keys, 0.506 with 32-bit keys at the same 3 CTAs/SM, 0.442 at
+// 4, 0.436 at 5 with 76 B of register spill, 0.454 at 6).
 #pragma once
 #include "jr_device.cuh"
 
@@ -31,15 +37,23 @@ constexpr int V2_BIGCAP = 32;
 #ifndef JR_MEDIUM_AREA
 #define JR_MEDIUM_AREA 1024
 #endif
+#ifndef JR_K32_CTAS
+#define JR_K32_CTAS 5
+#endif
+#ifndef JR_K64_CTAS
+#define JR_K64_CTAS 4
+#endif
+constexpr int V2_K32_CTAS = JR_K32_CTAS;        // resident CTAs per SM targeted by the z-only-key variant
 constexpr int V2_SMALL_AREA = JR_SMALL_AREA;    // boxes up to this many pixels: the owning lane
 constexpr int V2_MEDIUM_AREA = JR_MEDIUM_AREA;  // up to this: the owning warp; above: the whole CTA
 constexpr int V2_HIER_AREA = 256;   // warp-cooperative boxes from this size use the hierarchical raster
 
 struct V2Layout { size_t keys, xs, ys, bigq, total; };
-__host__ __device__ inline V2Layout v2_layout(int tile_w, int tile_h) {
+// key_bytes: 8 for packed (z | triangle id) keys, 4 for the z-only keys of the depth shader
+__host__ __device__ inline V2Layout v2_layout(int tile_w, int tile_h, int key_bytes) {
   V2Layout L;
   L.keys = 0;
-  L.xs = (size_t)tile_w * tile_h * 8;
+  L.xs = ((size_t)tile_w * tile_h * key_bytes + 15) & ~(size_t)15;
   L.ys = L.xs + (size_t)tile_w * 4;
   size_t e = L.ys + (size_t)tile_h * 4;
   L.bigq = (e + 15) & ~(size_t)15;
@@ -58,12 +72,30 @@ __device__ __forceinline__ void key_min(uint32_t saddr, unsigned long long key) 
   }
 }
 
+// One fragment into the tile's key buffer.  K32 (depth shader without a triangle-id output): the key is
+// the orderable depth alone and the update is ONE native shared-memory atomic min; equal depths need no
+// tie-break because only z is written.  0xFFFFFFFF is the "empty" mark, so the canonical NaN (whose
+// orderable image it is) is stored as 0xFFFFFFFE -- still a NaN after from_orderable.
+template <bool K32>
+__device__ __forceinline__ void put_key(uint32_t keys_saddr, int idx, float zw, unsigned tri) {
+  if (K32) {
+    const uint32_t k = min(orderable(zw), 0xFFFFFFFEu);
+    const uint32_t addr = keys_saddr + (uint32_t)idx * 4u;
+    uint32_t old;  // plain load first: occluded fragments (most of them) never reach the atomic unit
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(old) : "r"(addr));
+    if (k < old) asm volatile("red.shared.min.u32 [%0], %1;" ::"r"(addr), "r"(k) : "memory");
+  } else {
+    key_min(keys_saddr + (uint32_t)idx * 8u, ((unsigned long long)orderable(zw) << 32) | tri);
+  }
+}
+
 // Warp-cooperative, EXACT hierarchical rasterisation of one triangle's bbox (tile-local, inclusive).
 // Every rounded fp32 op is monotone, so fl(fl(xn*i0 + yn*i1) + i2) is monotone in xn and in yn and,
 // over a block of pixels, attains its max / min at one of the 4 block corners: a 4x8 block whose
 // corner max is < 0 for some edge has no inside pixel (skipped); one whose corner min is >= 0 for
 // all edges is fully inside (edge tests skipped).  One lane classifies one block (32 blocks per
 // round); surviving blocks get one lane per pixel.  Pays off from ~8 blocks (256 px) upwards.
+template <bool K32>
 __device__ __forceinline__ void raster_hier_warp(const float* inv, const float* zc, unsigned tri, int x0, int y0,
                                                  int x1, int y1, int lane, const float* xs, const float* ys,
                                                  uint32_t keys_saddr, int key_stride, float vp22, float vp23) {
@@ -107,7 +139,7 @@ __device__ __forceinline__ void raster_hier_warp(const float* inv, const float* 
         if (((m_full >> j) & 1u) || (c0 >= 0.f && c1 >= 0.f && c2 >= 0.f)) {
           const float z = (c0 * zc[0] + c1 * zc[1]) + c2 * zc[2];
           const float zw = z * vp22 + vp23;
-          key_min(keys_saddr + (uint32_t)(x * key_stride + y) * 8u, ((unsigned long long)orderable(zw) << 32) | tri);
+          put_key<K32>(keys_saddr, x * key_stride + y, zw, tri);
         }
       }
     }
@@ -122,12 +154,14 @@ struct V2Big {  // 64 bytes
   int pad;
 };
 
-template <bool DEPTH>
-__global__ void __launch_bounds__(V2_THREADS, 3)
+template <bool DEPTH, bool K32>
+__global__ void __launch_bounds__(V2_THREADS, K32 ? V2_K32_CTAS : JR_K64_CTAS)
 k_vis2(const __grid_constant__ JrRenderArgs a, int tile_w, int tile_h, int tiles_x, int tiles_y) {
+  static_assert(DEPTH || !K32, "z-only keys are for the depth shader");
   extern __shared__ __align__(16) unsigned char smem[];
-  const V2Layout L = v2_layout(tile_w, tile_h);
+  const V2Layout L = v2_layout(tile_w, tile_h, K32 ? 4 : 8);
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem + L.keys);
+  uint32_t* keys32 = reinterpret_cast<uint32_t*>(smem + L.keys);
   float* xs = reinterpret_cast<float*>(smem + L.xs);
   float* ys = reinterpret_cast<float*>(smem + L.ys);
   V2Big* bigq = reinterpret_cast<V2Big*>(smem + L.bigq);
@@ -154,10 +188,10 @@ k_vis2(const __grid_constant__ JrRenderArgs a, int tile_w, int tile_h, int tiles
   }
   if (tid == 0) { bigq_n = 0; tri0_flag = 0; next_chunk = 0; }
   {
-    const int nk = tile_w * tile_h;
-    ulonglong2* k2 = reinterpret_cast<ulonglong2*>(keys);
-    for (int i = tid; i < (nk >> 1); i += V2_THREADS) k2[i] = make_ulonglong2(~0ull, ~0ull);
-    if ((nk & 1) && tid == 0) keys[nk - 1] = ~0ull;
+    // all-ones = empty, whatever the key width (the layout rounds the buffer up to 16 bytes)
+    const int n16 = (int)(L.xs >> 4);
+    uint4* k4 = reinterpret_cast<uint4*>(smem + L.keys);
+    for (int i = tid; i < n16; i += V2_THREADS) k4[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
   }
   __syncthreads();
   for (int i = tid; i < tw; i += V2_THREADS) xs[i] = ((float)(tx0 + i) - s_vp[3]) / s_vp[0];
@@ -184,8 +218,7 @@ k_vis2(const __grid_constant__ JrRenderArgs a, int tile_w, int tile_h, int tiles
         if (c0 >= 0.f && c1 >= 0.f && c2 >= 0.f) {
           const float z = (c0 * zc[0] + c1 * zc[1]) + c2 * zc[2];
           const float zw = z * vp22 + vp23;
-          key_min(keys_saddr + (uint32_t)(x * tile_h + y) * 8u,
-                  ((unsigned long long)orderable(zw) << 32) | (unsigned)tri);
+          put_key<K32>(keys_saddr, x * tile_h + y, zw, (unsigned)tri);
         }
       }
     }
@@ -207,8 +240,7 @@ k_vis2(const __grid_constant__ JrRenderArgs a, int tile_w, int tile_h, int tiles
       if (c0 >= 0.f && c1 >= 0.f && c2 >= 0.f) {
         const float z = (c0 * zc[0] + c1 * zc[1]) + c2 * zc[2];
         const float zw = z * vp22 + vp23;
-        key_min(keys_saddr + (uint32_t)(x * tile_h + y) * 8u,
-                ((unsigned long long)orderable(zw) << 32) | (unsigned)tri);
+        put_key<K32>(keys_saddr, x * tile_h + y, zw, (unsigned)tri);
       }
     }
   };
@@ -250,7 +282,7 @@ k_vis2(const __grid_constant__ JrRenderArgs a, int tile_w, int tile_h, int tiles
       const unsigned bbb = __shfl_sync(0xffffffffu, bb, src);
       const int sx0 = bbb & 0xff, sx1 = (bbb >> 8) & 0xff, sy0 = (bbb >> 16) & 0xff, sy1 = bbb >> 24;
       if ((sx1 - sx0 + 1) * (sy1 - sy0 + 1) >= V2_HIER_AREA)
-        raster_hier_warp(binv, bzc, (unsigned)btri, sx0, sy0, sx1, sy1, lane, xs, ys, keys_saddr, tile_h, vp22, vp23);
+        raster_hier_warp<K32>(binv, bzc, (unsigned)btri, sx0, sy0, sx1, sy1, lane, xs, ys, keys_saddr, tile_h, vp22, vp23);
       else
         raster_flat(binv, bzc, btri, sx0, sy0, sx1 - sx0 + 1, sy1 - sy0 + 1, lane, 32);
     }
@@ -356,9 +388,15 @@ k_vis2(const __grid_constant__ JrRenderArgs a, int tile_w, int tile_h, int tiles
         if (c0 >= 0.f && c1 >= 0.f && c2 >= 0.f) {
           const float z = (c0 * z0 + c1 * z1) + c2 * z2;
           const float zw = z * vp22 + vp23;
-          const unsigned long long key = ((unsigned long long)orderable(zw) << 32) | tri;
-          unsigned long long* slot = &keys[x * tile_h + y];
-          if (key < *slot) *slot = key;
+          if (K32) {
+            const uint32_t key = min(orderable(zw), 0xFFFFFFFEu);
+            uint32_t* slot = &keys32[x * tile_h + y];
+            if (key < *slot) *slot = key;
+          } else {
+            const unsigned long long key = ((unsigned long long)orderable(zw) << 32) | tri;
+            unsigned long long* slot = &keys[x * tile_h + y];
+            if (key < *slot) *slot = key;
+          }
         }
       }
       __syncthreads();
@@ -369,7 +407,22 @@ k_vis2(const __grid_constant__ JrRenderArgs a, int tile_w, int tile_h, int tiles
   float* __restrict__ z_out = DEPTH ? a.zbuffer + (long long)b * a.W * a.H : nullptr;
   const bool use0 = DEPTH && tri0_flag;
   const int npix_img = a.W * a.H;
-  if (tiles == 1 && !use0 && !(npix_img & 1)) {
+  if (K32 && tiles == 1 && !use0 && !(npix_img & 3)) {
+    // z-only keys, single tile: four pixels per thread, 128-bit LDS / STG when all four are covered
+    const uint4* k4 = reinterpret_cast<const uint4*>(keys32);
+    for (int i = tid; i < (npix_img >> 2); i += V2_THREADS) {
+      const uint4 kk = k4[i];
+      if ((kk.x & kk.y & kk.z & kk.w) != ~0u && kk.x != ~0u && kk.y != ~0u && kk.z != ~0u && kk.w != ~0u) {
+        reinterpret_cast<float4*>(z_out)[i] =
+            make_float4(from_orderable(kk.x), from_orderable(kk.y), from_orderable(kk.z), from_orderable(kk.w));
+      } else {
+        if (kk.x != ~0u) z_out[4 * i] = from_orderable(kk.x);
+        if (kk.y != ~0u) z_out[4 * i + 1] = from_orderable(kk.y);
+        if (kk.z != ~0u) z_out[4 * i + 2] = from_orderable(kk.z);
+        if (kk.w != ~0u) z_out[4 * i + 3] = from_orderable(kk.w);
+      }
+    }
+  } else if (!K32 && tiles == 1 && !use0 && !(npix_img & 1)) {
     // single tile: tile-local index == pixel index; two pixels per thread, 128-bit LDS / 64-bit STG
     const ulonglong2* k2 = reinterpret_cast<const ulonglong2*>(keys);
     for (int i = tid; i < (npix_img >> 1); i += V2_THREADS) {
@@ -392,12 +445,22 @@ k_vis2(const __grid_constant__ JrRenderArgs a, int tile_w, int tile_h, int tiles
     int lx = tid / th, ly = tid - lx * th;
     for (; lx < tw; lx += dq, ly += dr) {
       if (ly >= th) { ly -= th; ++lx; if (lx >= tw) break; }
-      const unsigned long long key = keys[lx * tile_h + ly];
       const long long pix = (long long)(tx0 + lx) * a.H + (ty0 + ly);
       int tri = -1;
-      if (key != ~0ull) {
-        tri = (int)(unsigned)(key & 0xFFFFFFFFull);
-        if (DEPTH) z_out[pix] = from_orderable((uint32_t)(key >> 32));
+      bool covered;
+      if (K32) {
+        const uint32_t key = keys32[lx * tile_h + ly];
+        covered = key != ~0u;
+        if (covered) z_out[pix] = from_orderable(key);
+      } else {
+        const unsigned long long key = keys[lx * tile_h + ly];
+        covered = key != ~0ull;
+        if (covered) {
+          tri = (int)(unsigned)(key & 0xFFFFFFFFull);
+          if (DEPTH) z_out[pix] = from_orderable((uint32_t)(key >> 32));
+        }
+      }
+      if (covered) {
       } else if (use0) {
         float c[3];
         clip_coef(tri0.inv, xs[lx], ys[ly], c);

@@ -173,34 +173,31 @@ class Camera(NamedTuple):
         return side, up, forward
 
     @classmethod
-    def view_matrix(cls, eye: Any, centre: Any, up: Any) -> View:
-        """``lookAt`` (``geometry.py:536-575``)."""
+    def _look_at(cls, eye: Any, centre: Any, up: Any):
         eye, centre, up = _f32(eye), _f32(centre), _f32(up)
         eye, centre, up = torch.broadcast_tensors(eye, centre.to(eye.device), up.to(eye.device))
         side, up2, forward = cls._look_at_basis(eye, centre, up)
-        batch = eye.shape[:-1]
-        m = _eye4(eye, batch)
-        m[..., 0, :3] = side
-        m[..., 1, :3] = up2
-        m[..., 2, :3] = -forward
-        t = _eye4(eye, batch)
-        t[..., :3, 3] = -eye
-        return m @ t
+        rot = torch.stack((side, up2, -forward), dim=-2)          # (..., 3, 3), rows = camera axes
+        return eye, rot
+
+    @staticmethod
+    def _affine(rot: Tensor, trans: Tensor) -> Tensor:
+        """[[rot, trans], [0, 0, 0, 1]] built with two concatenations (few kernels)."""
+        top = torch.cat((rot, trans.unsqueeze(-1)), dim=-1)
+        bottom = torch.tensor((0.0, 0.0, 0.0, 1.0), device=rot.device).expand(*rot.shape[:-2], 1, 4)
+        return torch.cat((top, bottom), dim=-2)
+
+    @classmethod
+    def view_matrix(cls, eye: Any, centre: Any, up: Any) -> View:
+        """``lookAt`` (``geometry.py:536-575``): ``rotation @ translation(-eye)``."""
+        eye, rot = cls._look_at(eye, centre, up)
+        return cls._affine(rot, -(rot @ eye.unsqueeze(-1)).squeeze(-1))
 
     @classmethod
     def view_matrix_inv(cls, eye: Any, centre: Any, up: Any) -> View:
-        """``geometry.py:577-636``."""
-        eye, centre, up = _f32(eye), _f32(centre), _f32(up)
-        eye, centre, up = torch.broadcast_tensors(eye, centre.to(eye.device), up.to(eye.device))
-        side, up2, forward = cls._look_at_basis(eye, centre, up)
-        batch = eye.shape[:-1]
-        m = _eye4(eye, batch)
-        m[..., 0, :3] = side
-        m[..., 1, :3] = up2
-        m[..., 2, :3] = -forward
-        t_inv = _eye4(eye, batch)
-        t_inv[..., :3, 3] = eye
-        return t_inv @ m.transpose(-1, -2)
+        """``geometry.py:577-636``: ``translation(eye) @ rotation^T``."""
+        eye, rot = cls._look_at(eye, centre, up)
+        return cls._affine(rot.transpose(-1, -2), eye)
 
     @staticmethod
     def perspective_projection_matrix(fovy: Any, aspect: Any, z_near: Any, z_far: Any) -> Projection:

@@ -37,9 +37,13 @@ class Shadow(NamedTuple):
         centre = _f32(centre, dev)
         ld = _f32(light_direction, dev)
         up = _f32(up, dev)
-        view = Camera.view_matrix(eye=centre + ld * distance, centre=centre, up=up)
+        eye = centre + ld * distance
+        view = Camera.view_matrix(eye=eye, centre=centre, up=up)
         proj = Camera.orthographic_projection_matrix(-1.0, 1.0, -1.0, 1.0, -1.0, 1.0).to(view.device)
-        cam = Camera.create(view=view, projection=proj, viewport=_f32(viewport_matrix, dev))
+        # The reference inverts `view` numerically here (Camera.create without view_inv); the analytic
+        # inverse only enters fields of the light camera that the path never reads.
+        cam = Camera.create(view=view, projection=proj, viewport=_f32(viewport_matrix, dev),
+                            view_inv=Camera.view_matrix_inv(eye=eye, centre=centre, up=up))
         arrays = {"world_to_clip": cam.world_to_clip, "viewport": cam.viewport,
                   "position": verts, "faces": faces}
         z, _, _ = _render_arrays(_native.JR_DEPTH, arrays, shadow_map, None, inplace=False)

@@ -1,0 +1,103 @@
+#!/usr/bin/env python
+"""Secondary measurement: the whole ``Renderer.get_camera_image`` facade (merge_objects -> camera ->
+shadow pass -> Phong pass -> uint8-ready canvas) on the real Brax ant scene of the reference's
+``test_resources/pre-gen-brax`` fixture (tests/golden/brax_ant_frames.npz, 4 frames tiled to ``--batch``
+environments), inputs resident on the device.
+
+  python tools/bench_facade.py [--batch 1024] [--width 84 --height 84] [--steps 20] [--profile]
+
+Prints one JSON line: total ms / step plus the split merge / camera / render, and the native launch count.
+``--profile`` adds the torch-profiler kernel table (CPU vs GPU time of the step) on stderr.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+import jaxrenderer_b200 as jr  # noqa: E402
+from jaxrenderer_b200 import _native  # noqa: E402
+from tests.helpers import load_brax_fixture  # noqa: E402
+
+
+def tile(t: torch.Tensor, B: int, dev) -> torch.Tensor:
+    reps = (B + t.shape[0] - 1) // t.shape[0]
+    return t.repeat((reps,) + (1,) * (t.ndim - 1))[:B].contiguous().to(dev)
+
+
+def timeit(fn, steps, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=1024)
+    ap.add_argument("--width", type=int, default=84)
+    ap.add_argument("--height", type=int, default=84)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--profile", action="store_true")
+    args = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    B, W, H = args.batch, args.width, args.height
+    objs, cam = load_brax_fixture()
+    n_frames = objs[0].transform.shape[0]
+    objs = [jr.ModelObject(model=type(o.model)(*[t.to(dev) for t in o.model]),
+                           local_scaling=tile(o.local_scaling, B, dev), transform=tile(o.transform, B, dev),
+                           double_sided=tile(o.double_sided, B, dev)) for o in objs]
+    cam = type(cam)(*[tile(v, B, dev) if isinstance(v, torch.Tensor) and v.ndim >= 1 and v.shape[0] == n_frames
+                      else v for v in cam])
+    cam = cam._replace(viewWidth=W, viewHeight=H)
+    light = jr.LightParameters()
+    sp = jr.ShadowParameters(centre=cam.target)
+
+    def full():
+        return jr.Renderer.get_camera_image(objs, light, cam, W, H, shadow_param=sp)
+
+    def merge():
+        return jr.merge_objects(objs)
+
+    def camera():
+        return jr.Renderer.create_camera_from_parameters(cam)
+
+    model, camera_obj = merge(), camera()
+    bufs = jr.Renderer.create_buffers(W, H, batch=B, device=dev)
+
+    def render():
+        return jr.Renderer.render(model, light, camera_obj, bufs, shadow_param=sp)
+
+    out = {"workload": f"get_camera_image brax-ant fixture B={B} {W}x{H}", "T": int(model.faces.shape[-2])}
+    l0 = _native.launch_count()
+    full()
+    out["launches"] = _native.launch_count() - l0
+    out["ms_total"] = timeit(full, args.steps)
+    out["ms_merge"] = timeit(merge, args.steps)
+    out["ms_camera"] = timeit(camera, args.steps)
+    out["ms_render"] = timeit(render, args.steps)
+    out["images_per_s"] = B / out["ms_total"] * 1e3
+    print(json.dumps(out))
+    if args.profile:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+            for _ in range(5):
+                full()
+            torch.cuda.synchronize()
+        print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25), file=sys.stderr)
+
+
+if __name__ == "__main__":
+    main()
