@@ -214,6 +214,31 @@ typedef struct JrMergeArgs {
 } JrMergeArgs;
 int jr_merge_objects(const JrMergeArgs* args, jr_stream_t stream);
 
+/* Fused camera construction: all 8 matrices of `Camera` (geometry.py:205-278) per
+ * batch element in ONE launch.
+ *   mode JR_CAMERA_PERSPECTIVE  Renderer.create_camera_from_parameters (renderer.py:141-196):
+ *        lookAt view + analytic inverse (geometry.py:536-636), gluPerspective projection with
+ *        aspect = tan(hfov/2) / tan(vfov/2) (geometry.py:638-684), viewport matrix (geometry.py:813-845).
+ *        params row: position(3) target(3) up(3) vfov hfov near far viewWidth viewHeight viewDepth
+ *   mode JR_CAMERA_LIGHT        the orthographic light camera of Shadow.render_shadow_map
+ *        (shadow.py:73-98): eye = centre + light_direction * distance, glOrtho (geometry.py:720-763),
+ *        viewport matrix taken from `viewport` (the main camera's).
+ *        params row: centre(3) light_direction(3) up(3) distance left right bottom top near far
+ * Both: world_to_clip = projection @ view, world_to_eye_norm = view_inv^T, world_to_screen =
+ * (viewport @ projection) @ view, screen_to_world = (view_inv @ projection_inv) @ viewport_inv with the
+ * closed-form inverses of geometry.py:472-511, :686-718 chosen by isclose(projection[3][3], 0)
+ * (geometry.py:248-262).  out: (8, B, 4, 4) in the field order of `Camera`:
+ * view, projection, viewport, world_to_clip, world_to_eye_norm, world_to_screen, view_inv, screen_to_world. */
+#define JR_CAMERA_PERSPECTIVE 0
+#define JR_CAMERA_LIGHT 1
+typedef struct JrCameraArgs {
+  int32_t B, mode;
+  JrF32 params;     /* (16) per batch element, see above */
+  JrF32 viewport;   /* (4,4), JR_CAMERA_LIGHT only */
+  float* out;       /* (8,B,4,4) */
+} JrCameraArgs;
+int jr_camera_build(const JrCameraArgs* args, jr_stream_t stream);
+
 /* Introspection for benchmarks: number of kernel launches issued by this
  * library since load (monotonic). */
 long long jr_launch_count(void);

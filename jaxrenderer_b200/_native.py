@@ -22,7 +22,7 @@ EXPORTS = (
     "jr_render_forward", "jr_render_backward",
     "jr_depth_forward", "jr_gouraud_forward", "jr_gouraud_texture_forward", "jr_phong_forward",
     "jr_phong_darboux_forward", "jr_phong_reflection_forward", "jr_phong_reflection_shadow_forward",
-    "jr_add_scalar", "jr_canvas_to_uint8_display", "jr_launch_count", "jr_merge_objects",
+    "jr_add_scalar", "jr_canvas_to_uint8_display", "jr_launch_count", "jr_merge_objects", "jr_camera_build",
 )
 
 
@@ -77,6 +77,13 @@ class JrMergeArgs(C.Structure):
     ]
 
 
+class JrCameraArgs(C.Structure):
+    _fields_ = [("B", C.c_int32), ("mode", C.c_int32), ("params", JrF32), ("viewport", JrF32),
+                ("out", C.c_void_p)]
+
+
+JR_CAMERA_PERSPECTIVE, JR_CAMERA_LIGHT = 0, 1
+
 _lib: Optional[C.CDLL] = None
 
 
@@ -114,6 +121,8 @@ def load() -> C.CDLL:
     lib.jr_launch_count.restype = C.c_longlong
     lib.jr_merge_objects.restype = C.c_int
     lib.jr_merge_objects.argtypes = [C.POINTER(JrMergeArgs), C.c_void_p]
+    lib.jr_camera_build.restype = C.c_int
+    lib.jr_camera_build.argtypes = [C.POINTER(JrCameraArgs), C.c_void_p]
     _lib = lib
     return lib
 

@@ -12,11 +12,13 @@ from __future__ import annotations
 
 import enum
 import math
-from typing import Any, NamedTuple, Optional
+from typing import Any, NamedTuple, Optional, Sequence, Tuple
+
+import numpy as np
 
 import torch
 
-from .types import Tensor, _f32
+from .types import Tensor, _device_constant, _f32
 
 View = Tensor
 Projection = Tensor
@@ -274,6 +276,71 @@ class Camera(NamedTuple):
         b = torch.eye(4); b[0, 0] = width; b[1, 1] = height
         c = torch.eye(4); c[:2, -1] = 1
         return a @ b @ c
+
+
+def camera_build_native(mode: int, fields: Sequence[Tuple[Any, int]], dev: torch.device,
+                        viewport: Optional[Tensor] = None) -> Optional[Camera]:
+    """All 8 ``Camera`` matrices in ONE launch of ``jr_camera_build`` (``csrc/jr_camera.cu``) instead of
+    ~120 framework ops.  ``fields`` are the (value, width) pairs of the 16-float parameter row described
+    in ``include/jr_b200.h``; every value is un-batched or carries ONE leading batch axis.  Returns
+    ``None`` when the fast path does not apply (gradients requested, deeper batch nesting): the caller
+    then uses the differentiable torch builders above."""
+    import ctypes as C
+
+    from . import _native
+
+    host = np.zeros(16, dtype=np.float32)
+    dev_parts = []
+    batch: Optional[int] = None
+    tensors = [v for v, _ in fields] + [viewport]
+    if torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors):
+        return None
+    off = 0
+    for v, w in fields:
+        base = 1 if w > 1 else 0
+        nd = v.ndim if isinstance(v, torch.Tensor) else np.ndim(v)
+        if nd > base + 1:
+            return None
+        if nd == base + 1 or (isinstance(v, torch.Tensor) and v.is_cuda):
+            t = _f32(v, dev).reshape(-1, w)
+            if t.shape[0] > 1:
+                if batch not in (None, t.shape[0]):
+                    raise ValueError(f"inconsistent batch sizes {batch} and {t.shape[0]}")
+                batch = t.shape[0]
+            dev_parts.append((off, w, t))
+        else:
+            host[off:off + w] = np.asarray(v, dtype=np.float32).reshape(-1)
+        off += w
+    assert off == 16
+    vp = None
+    if viewport is not None:
+        vp = _f32(viewport, dev).contiguous()
+        if vp.ndim > 3:
+            return None
+        if vp.ndim == 3 and vp.shape[0] > 1:
+            if batch not in (None, vp.shape[0]):
+                raise ValueError(f"inconsistent batch sizes {batch} and {vp.shape[0]}")
+            batch = vp.shape[0]
+    B = batch or 1
+    rows = _device_constant(host, dev if dev.index is not None else torch.device('cuda', torch.cuda.current_device()))
+    if dev_parts:
+        rows = rows.expand(B, 16).clone()
+        for o, w, t in dev_parts:
+            rows[:, o:o + w] = t
+    out = torch.empty((8, B, 4, 4), dtype=torch.float32, device=dev)
+    a = _native.JrCameraArgs()
+    a.B, a.mode = B, mode
+    a.params = _native.JrF32(rows.data_ptr(), 16 if rows.ndim == 2 else 0)
+    if vp is not None:
+        a.viewport = _native.JrF32(vp.data_ptr(), 16 if (vp.ndim == 3 and vp.shape[0] > 1) else 0)
+    a.out = out.data_ptr()
+    lib = _native.load()
+    with torch.cuda.device(dev):
+        _native.check(lib.jr_camera_build(C.byref(a), _native.stream_ptr(dev)))
+    mats = out.unbind(0)
+    if batch is None:
+        mats = tuple(m[0] for m in mats)
+    return Camera(*mats)
 
 
 def compute_normal(triangle_verts: Tensor) -> Tensor:

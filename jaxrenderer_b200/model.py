@@ -9,6 +9,8 @@ reference gets this from ``jax.vmap``); ``merge_objects`` broadcasts them.
 """
 from __future__ import annotations
 
+import collections
+
 from typing import Any, List, NamedTuple, Optional, Sequence, Tuple
 
 import torch
@@ -169,7 +171,75 @@ def _frob_normalise(x: Tensor) -> Tensor:
     return x / torch.linalg.norm(x, dim=(-2, -1), keepdim=True)
 
 
-def _merge_geometry_fused(objects: Sequence[ModelObject], dev: torch.device):
+_STATIC_FIELDS = ("verts", "norms", "uvs", "faces", "faces_norm", "faces_uv", "diffuse_map", "specular_map")
+_STATIC_RANK = (2, 2, 2, 2, 2, 2, 3, 2)
+_STATIC_CACHE: "collections.OrderedDict[tuple, tuple]" = collections.OrderedDict()
+_STATIC_CACHE_SIZE = 8
+
+
+def _merge_static(models: Sequence[Model], dev: torch.device) -> dict:
+    """The part of ``merge_objects`` that depends only on the objects' meshes and maps, not on their
+    per-frame transforms: concatenated index buffers / UVs / local vertices, the texture atlas and the
+    per-vertex object tables (``model.py:447-555``).  The reference gets this for free from ``jax.jit``
+    (constant folding at trace time); here the result is memoised on the identity + in-place version of
+    the model tensors (entries keep the tensors alive, so an id cannot be recycled).  Batched or
+    gradient-carrying mesh tensors bypass the cache."""
+    tensors = [getattr(m, f) for m in models for f in _STATIC_FIELDS]
+    cacheable = all(isinstance(t, torch.Tensor) and not t.requires_grad and t.ndim == r
+                    for t, r in zip(tensors, _STATIC_RANK * len(models)))
+    key = (dev, tuple((id(t), t._version) for t in tensors)) if cacheable else None
+    if key is not None:
+        hit = _STATIC_CACHE.get(key)
+        if hit is not None:
+            _STATIC_CACHE.move_to_end(key)
+            return hit[1]
+    n_obj = len(models)
+    counts_v = [m.verts.shape[-2] for m in models]
+    counts_n = [m.norms.shape[-2] for m in models]
+    counts_uv = [m.uvs.shape[-2] for m in models]
+
+    def starts(counts):
+        out = [0]
+        for c in counts:
+            out.append(out[-1] + c)
+        return out
+
+    def cat_faces(fs, counts):
+        off = starts(counts)
+        fb = torch.broadcast_shapes(*[f.shape[:-2] for f in fs])
+        return torch.cat([(f.to(dev) + off[i]).expand(*fb, *f.shape[-2:]) for i, f in enumerate(fs)],
+                         dim=-2).to(torch.int32)
+
+    def cat_attr(parts):
+        parts = [_f32(p, dev) for p in parts]
+        batch = torch.broadcast_shapes(*[p.shape[:-2] for p in parts])
+        return torch.cat([p.expand(*batch, *p.shape[-2:]) for p in parts], dim=-2).contiguous()
+
+    diffuse_map, single = MergedModel.merge_maps([m.diffuse_map for m in models], rank=3)
+    st = {
+        "counts": counts_v,
+        "vert_object": torch.repeat_interleave(torch.arange(n_obj, dtype=torch.int32),
+                                               torch.tensor(counts_v)).to(dev),
+        "norm_start": torch.tensor(starts(counts_n), dtype=torch.int32).to(dev),
+        "local_verts": cat_attr([m.verts for m in models]),
+        "local_norms": cat_attr([m.norms for m in models]),
+        "uvs": cat_attr([m.uvs for m in models]),
+        "faces": cat_faces([m.faces for m in models], counts_v),
+        "faces_norm": cat_faces([m.faces_norm for m in models], counts_n),
+        "faces_uv": cat_faces([m.faces_uv for m in models], counts_uv),
+        "texture_shape": torch.tensor([tuple(m.diffuse_map.shape[-3:-1]) for m in models],
+                                      dtype=torch.int32).to(dev),
+        "diffuse_map": diffuse_map.to(dev), "offset": int(single[0]),
+        "specular_map": MergedModel.merge_maps([m.specular_map for m in models], rank=2)[0].to(dev),
+    }
+    if key is not None:
+        _STATIC_CACHE[key] = (tensors, st)
+        while len(_STATIC_CACHE) > _STATIC_CACHE_SIZE:
+            _STATIC_CACHE.popitem(last=False)
+    return st
+
+
+def _merge_geometry_fused(objects: Sequence[ModelObject], dev: torch.device, st: dict):
     """CUDA fast path of the vertex / normal part of ``merge_objects``: two launches of
     ``jr_merge_objects`` (``csrc/jr_forward.cu``) instead of ~15 framework ops per object."""
     import ctypes as C
@@ -177,22 +247,8 @@ def _merge_geometry_fused(objects: Sequence[ModelObject], dev: torch.device):
     from . import _native
     from ._native import JrF32, JrI32, JrMergeArgs
 
-    models = [o.model for o in objects]
     n_obj = len(objects)
-
-    def cat(parts, base_rank):
-        if any(p.ndim > base_rank for p in parts):
-            batch = torch.broadcast_shapes(*[p.shape[: p.ndim - base_rank] for p in parts])
-            parts = [p.expand(*batch, *p.shape[p.ndim - base_rank:]) for p in parts]
-        return torch.cat(parts, dim=-base_rank).contiguous()
-
-    lv = cat([_f32(m.verts, dev) for m in models], 2)
-    ln = cat([_f32(m.norms, dev) for m in models], 2)
-    counts_v = [m.verts.shape[-2] for m in models]
-    counts_n = [m.norms.shape[-2] for m in models]
-    vobj = torch.repeat_interleave(torch.arange(n_obj, dtype=torch.int32, device=dev),
-                                   torch.tensor(counts_v, device=dev))
-    nstart = torch.tensor([0] + list(torch.tensor(counts_n).cumsum(0)), dtype=torch.int32, device=dev)
+    lv, ln = st["local_verts"], st["local_norms"]
 
     def stack(vals, base_rank, shape):
         ts = [_f32(v, dev) for v in vals]
@@ -203,7 +259,9 @@ def _merge_geometry_fused(objects: Sequence[ModelObject], dev: torch.device):
 
     scaling = stack([o.local_scaling for o in objects], 1, (3,))
     transform = stack([o.transform for o in objects], 2, (4, 4))
-    nmat = torch.linalg.inv(transform).transpose(-1, -2).contiguous()
+    # inv_ex: no host synchronisation on the singularity check (a singular transform gives inf / nan
+    # normals, as in the reference)
+    nmat = torch.linalg.inv_ex(transform, check_errors=False).inverse.transpose(-1, -2).contiguous()
     B = None
     for t, r in ((lv, 2), (ln, 2), (scaling, 2), (transform, 3)):
         if t.ndim == r + 1:
@@ -220,7 +278,7 @@ def _merge_geometry_fused(objects: Sequence[ModelObject], dev: torch.device):
     a = JrMergeArgs()
     a.B, a.n_objects, a.n_verts, a.n_norms = B, n_obj, V, Nn
     a.local_verts, a.local_norms = f32(lv, 2), f32(ln, 2)
-    a.vert_object, a.norm_start = JrI32(vobj.data_ptr(), 0), JrI32(nstart.data_ptr(), 0)
+    a.vert_object, a.norm_start = JrI32(st["vert_object"].data_ptr(), 0), JrI32(st["norm_start"].data_ptr(), 0)
     a.scaling, a.transform, a.normal_matrix = f32(scaling, 2), f32(transform, 3), f32(nmat, 3)
     a.out_verts, a.out_norms = out_v.data_ptr(), out_n.data_ptr()
     lib = _native.load()
@@ -229,22 +287,29 @@ def _merge_geometry_fused(objects: Sequence[ModelObject], dev: torch.device):
     return (out_v[0], out_n[0]) if squeeze else (out_v, out_n)
 
 
+def _double_sided_per_vertex(objects: Sequence[ModelObject], st: dict, dev: torch.device) -> Tensor:
+    """One flag per merged vertex (``model.py:492-497``), without reading device values on the host."""
+    flags = [o.double_sided for o in objects]
+    if any(isinstance(f, torch.Tensor) and f.is_cuda for f in flags):
+        if all(isinstance(f, torch.Tensor) and f.shape == flags[0].shape and f.device == flags[0].device
+               for f in flags):
+            per_obj = torch.stack(flags).reshape(len(flags), -1)[:, 0].to(device=dev, dtype=torch.bool)
+        else:
+            per_obj = torch.stack([torch.as_tensor(f, device=dev).reshape(-1)[0].to(torch.bool) for f in flags])
+        return per_obj[st["vert_object"].long()]
+    return MergedModel.generate_object_vert_info(
+        st["counts"], [bool(torch.as_tensor(f).reshape(-1)[0]) for f in flags]).to(dev)
+
+
 def merge_objects(objects: Sequence[ModelObject]) -> MergedModel:
     """World-space merge of all objects into one mesh + texture atlas
     (``model.py:447-555``).  On CUDA inputs (and when no gradient is requested through the
-    transforms) the vertex / normal transforms run in the fused ``jr_merge_objects`` kernels."""
+    transforms) the vertex / normal transforms run in the fused ``jr_merge_objects`` kernels; the
+    transform-independent part is memoised (``_merge_static``)."""
     models = [obj.model for obj in objects]
     dev = models[0].verts.device
-    counts = [m.verts.shape[-2] for m in models]
-    map_indices = MergedModel.generate_object_vert_info(counts, list(range(len(models)))).to(
-        torch.int32).to(dev)
-    map_wh = torch.tensor([tuple(m.diffuse_map.shape[-3:-1]) for m in models], dtype=torch.int32,
-                          device=dev)
-    double_sided = MergedModel.generate_object_vert_info(
-        counts, [bool(torch.as_tensor(o.double_sided).reshape(-1)[0]) for o in objects]).to(dev)
-
-    diffuse_map, single = MergedModel.merge_maps([m.diffuse_map for m in models], rank=3)
-    specular_map = MergedModel.merge_maps([m.specular_map for m in models], rank=2)[0]
+    st = _merge_static(models, dev)
+    double_sided = _double_sided_per_vertex(objects, st, dev)
 
     def transform_vert(verts: Tensor, local_scaling: Any, transform: Any) -> Tensor:
         ls = _f32(local_scaling, dev)
@@ -263,24 +328,16 @@ def merge_objects(objects: Sequence[ModelObject]) -> MergedModel:
         isinstance(t, torch.Tensor) and t.requires_grad
         for o in objects for t in (o.model.verts, o.model.norms, o.local_scaling, o.transform))
     if dev.type == "cuda" and not needs_grad:
-        verts, norms = _merge_geometry_fused(objects, dev)
-        cum_v, cum_n = [0], [0]
-        for m in models[:-1]:
-            cum_v.append(cum_v[-1] + m.verts.shape[-2])
-            cum_n.append(cum_n[-1] + m.norms.shape[-2])
-        faces = torch.cat([m.faces + cum_v[i] for i, m in enumerate(models)], dim=-2).to(torch.int32)
-        faces_norm = torch.cat([m.faces_norm + cum_n[i] for i, m in enumerate(models)], dim=-2).to(torch.int32)
+        verts, norms = _merge_geometry_fused(objects, dev, st)
     else:
-        verts, faces = MergedModel.merge_verts(
+        verts, _ = MergedModel.merge_verts(
             [transform_vert(o.model.verts, o.local_scaling, o.transform) for o in objects],
             [m.faces for m in models])
-        norms, faces_norm = MergedModel.merge_verts(
+        norms, _ = MergedModel.merge_verts(
             [transform_normals(o.model.norms, o.transform) for o in objects],
             [m.faces_norm for m in models])
-    uvs, faces_uv = MergedModel.merge_verts([_f32(m.uvs) for m in models],
-                                            [m.faces_uv for m in models])
     return MergedModel(
-        verts=verts, norms=norms, uvs=uvs, faces=faces, faces_norm=faces_norm,
-        faces_uv=faces_uv, texture_shape=map_wh, texture_index=map_indices,
-        double_sided=double_sided, offset=int(single[0]), diffuse_map=diffuse_map,
-        specular_map=specular_map)
+        verts=verts, norms=norms, uvs=st["uvs"], faces=st["faces"], faces_norm=st["faces_norm"],
+        faces_uv=st["faces_uv"], texture_shape=st["texture_shape"], texture_index=st["vert_object"],
+        double_sided=double_sided, offset=st["offset"], diffuse_map=st["diffuse_map"],
+        specular_map=st["specular_map"])

@@ -33,7 +33,7 @@ from ._native import JrF32, JrGradArgs, JrI32, JrRenderArgs
 from .geometry import Camera
 from .shader import Shader, UnsupportedShaderError
 from .shaders import BUILTIN_SHADERS
-from .types import Buffers, Tensor
+from .types import Buffers, Tensor, _f32, _i32
 
 # name -> (un-batched rank, is_float)
 _SPEC: Dict[str, Tuple[int, bool]] = {
@@ -71,10 +71,14 @@ _DIFF = (
 _GRAD_FIELD = {n: "d_" + n for n in _DIFF if n not in ("zbuffer", "canvas")}
 
 
-def _as(t: Any, is_float: bool, device: torch.device) -> Tensor:
+def _as(t: Any, is_float: bool, device: torch.device, written: bool = False) -> Tensor:
+    """Device placement of one input.  ``written`` marks the buffers the kernels update in place: they
+    never alias the memoised constants."""
     dt = torch.float32 if is_float else torch.int32
-    if not isinstance(t, torch.Tensor):
+    if written and not isinstance(t, torch.Tensor):
         t = torch.as_tensor(t, dtype=dt)
+    if not written and (not isinstance(t, torch.Tensor) or (not t.is_cuda and t.numel() <= 64)):
+        return (_f32 if is_float else _i32)(t, device).contiguous()   # small host constants: memoised copy
     if t.dtype != dt:
         t = t.to(dt)
     if t.device != device:
@@ -312,8 +316,8 @@ def _render_arrays(sid: int, arrays: Dict[str, Any], zbuffer: Any, canvas: Optio
     else:
         dev = zbuffer.device
     tens: Dict[str, Tensor] = {n: _as(t, _SPEC[n][1], dev) for n, t in raw.items() if n not in ("zbuffer", "canvas")}
-    z = _as(raw["zbuffer"], True, dev)
-    c = _as(raw["canvas"], True, dev) if canvas is not None else None
+    z = _as(raw["zbuffer"], True, dev, written=True)
+    c = _as(raw["canvas"], True, dev, written=True) if canvas is not None else None
     squeeze = B is None
     B = 1 if B is None else B
     # buffers always get a batch axis (vmap would broadcast them on output)

@@ -17,7 +17,7 @@ from typing import Any, NamedTuple, Optional, Sequence, Tuple, Union
 import torch
 
 from . import _native
-from .geometry import Camera, _deg_tan_half, _normalise_last
+from .geometry import Camera, _deg_tan_half, _normalise_last, camera_build_native
 from .model import MergedModel, ModelObject, merge_objects
 from .pipeline import _render_arrays
 from .shadow import Shadow
@@ -64,7 +64,18 @@ class ShadowParameters(NamedTuple):
 class Renderer:
     @staticmethod
     def create_camera_from_parameters(camera: CameraParameters, device: Any = None) -> Camera:
-        """``renderer.py:141-196``."""
+        """``renderer.py:141-196``.  On a CUDA device (``device`` argument or where ``position`` lives)
+        all 8 matrices come from one ``jr_camera_build`` launch; the torch builders below are the
+        differentiable / host form of the same formulas."""
+        dev = torch.device(device) if device is not None else (
+            camera.position.device if isinstance(camera.position, torch.Tensor) else None)
+        if dev is not None and dev.type == "cuda":
+            cam = camera_build_native(_native.JR_CAMERA_PERSPECTIVE, (
+                (camera.position, 3), (camera.target, 3), (camera.up, 3), (camera.vfov, 1), (camera.hfov, 1),
+                (camera.near, 1), (camera.far, 1), (camera.viewWidth, 1), (camera.viewHeight, 1),
+                (camera.viewDepth, 1)), dev)
+            if cam is not None:
+                return cam
         eye, centre, up = _f32(camera.position, device), _f32(camera.target, device), _f32(camera.up, device)
         view = Camera.view_matrix(eye=eye, centre=centre, up=up)
         view_inv = Camera.view_matrix_inv(eye=eye, centre=centre, up=up)
@@ -86,7 +97,8 @@ class Renderer:
         b = (batch,) if batch is not None else ()
         colour_default = _f32(colour_default, device)
         z = torch.full((*b, width, height), float(zbuffer_default), dtype=torch.float32, device=device)
-        c = colour_default.expand(*b, width, height, colour_default.numel()).contiguous()
+        c = torch.empty((*b, width, height, colour_default.numel()), dtype=torch.float32,
+                        device=colour_default.device).copy_(colour_default)   # never aliases the constant
         return Buffers(zbuffer=z, targets=(c,))
 
     @classmethod

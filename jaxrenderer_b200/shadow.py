@@ -13,7 +13,7 @@ from typing import Any, NamedTuple
 import torch
 
 from . import _native
-from .geometry import Camera
+from .geometry import Camera, camera_build_native
 from .types import Tensor, _f32
 
 
@@ -31,21 +31,37 @@ class Shadow(NamedTuple):
                           loop_unroll: int = 1) -> "Shadow":
         """``shadow.py:49-125``.  NB the light direction is used as given
         (un-normalised), exactly like the reference (``renderer.py:357``)."""
-        from .pipeline import _render_arrays  # local: pipeline imports this module's users
-
         dev = shadow_map.device if isinstance(shadow_map, torch.Tensor) else None
         centre = _f32(centre, dev)
         ld = _f32(light_direction, dev)
         up = _f32(up, dev)
+        cam = None
+        if dev is not None and dev.type == "cuda":   # one launch instead of ~100 framework ops
+            cam = camera_build_native(_native.JR_CAMERA_LIGHT, (
+                (centre, 3), (ld, 3), (up, 3), (float(distance), 1), (-1.0, 1), (1.0, 1), (-1.0, 1), (1.0, 1),
+                (-1.0, 1), (1.0, 1)), dev, viewport=viewport_matrix)
+        if cam is None:
+            cam = Shadow._light_camera(centre, ld, up, distance, viewport_matrix, dev)
+        arrays = {"world_to_clip": cam.world_to_clip, "viewport": cam.viewport,
+                  "position": verts, "faces": faces}
+        return Shadow._finish(cam, arrays, shadow_map, strength, offset)
+
+    @staticmethod
+    def _light_camera(centre: Tensor, ld: Tensor, up: Tensor, distance: float, viewport_matrix: Tensor,
+                      dev: Any) -> Camera:
+        """Torch form of the light camera (``shadow.py:73-98``); differentiable / host inputs."""
         eye = centre + ld * distance
         view = Camera.view_matrix(eye=eye, centre=centre, up=up)
         proj = Camera.orthographic_projection_matrix(-1.0, 1.0, -1.0, 1.0, -1.0, 1.0).to(view.device)
         # The reference inverts `view` numerically here (Camera.create without view_inv); the analytic
         # inverse only enters fields of the light camera that the path never reads.
-        cam = Camera.create(view=view, projection=proj, viewport=_f32(viewport_matrix, dev),
-                            view_inv=Camera.view_matrix_inv(eye=eye, centre=centre, up=up))
-        arrays = {"world_to_clip": cam.world_to_clip, "viewport": cam.viewport,
-                  "position": verts, "faces": faces}
+        return Camera.create(view=view, projection=proj, viewport=_f32(viewport_matrix, dev),
+                             view_inv=Camera.view_matrix_inv(eye=eye, centre=centre, up=up))
+
+    @staticmethod
+    def _finish(cam: Camera, arrays: dict, shadow_map: Tensor, strength: Any, offset: float) -> "Shadow":
+        from .pipeline import _render_arrays  # local: pipeline imports this module's users
+
         z, _, _ = _render_arrays(_native.JR_DEPTH, arrays, shadow_map, None, inplace=False)
         if z.is_cuda:
             lib = _native.load()

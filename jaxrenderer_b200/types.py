@@ -10,8 +10,10 @@ reference's ``jax.vmap`` idiom (``examples/batch_rendering.py:87-95``).
 """
 from __future__ import annotations
 
+import collections
 from typing import Any, Generic, NamedTuple, Tuple, TypeVar
 
+import numpy as np
 import torch
 
 Tensor = torch.Tensor
@@ -19,19 +21,55 @@ Tensor = torch.Tensor
 _TargetsT = TypeVar("_TargetsT", bound=Tuple[Any, ...])
 
 
+_CONST_CACHE: "collections.OrderedDict[tuple, Tensor]" = collections.OrderedDict()
+_CONST_CACHE_SIZE = 512
+_CONST_MAX_ELEMS = 64
+
+
+def _device_constant(arr: np.ndarray, device: torch.device) -> Tensor:
+    """Device copy of a small host constant (light parameters, camera intrinsics given as Python
+    numbers...), memoised by VALUE.  A copy from pageable host memory makes the host wait for the
+    stream, which would serialise the host with all queued kernels once per parameter and per call;
+    this way the wait is paid once per distinct value.  The returned tensor is shared: read-only."""
+    key = (arr.dtype.str, arr.shape, arr.tobytes(), device.type, device.index)
+    t = _CONST_CACHE.get(key)
+    if t is None:
+        t = torch.from_numpy(arr.copy()).to(device)
+        _CONST_CACHE[key] = t
+        while len(_CONST_CACHE) > _CONST_CACHE_SIZE:
+            _CONST_CACHE.popitem(last=False)
+    else:
+        _CONST_CACHE.move_to_end(key)
+    return t
+
+
+def _as_dtype(x: Any, dtype: torch.dtype, np_dtype: Any, device: Any) -> Tensor:
+    dev = torch.device(device) if device is not None else None
+    to_cuda = dev is not None and dev.type == "cuda"
+    if isinstance(x, torch.Tensor):
+        if to_cuda and not x.is_cuda and x.numel() <= _CONST_MAX_ELEMS and not x.requires_grad:
+            if dev.index is None:
+                dev = torch.device("cuda", torch.cuda.current_device())
+            return _device_constant(x.detach().to(dtype).numpy(), dev)
+        t = x if x.dtype == dtype else x.to(dtype)
+        return t if dev is None else t.to(dev)
+    if to_cuda:
+        arr = np.asarray(x, dtype=np_dtype)
+        if arr.size <= _CONST_MAX_ELEMS:
+            if dev.index is None:
+                dev = torch.device("cuda", torch.cuda.current_device())
+            return _device_constant(arr, dev)
+        return torch.from_numpy(arr.copy()).to(dev)
+    return torch.as_tensor(x, dtype=dtype, device=dev)
+
+
 def _f32(x: Any, device: Any = None) -> Tensor:
     """``jnp.asarray(x, dtype=float32)`` equivalent."""
-    if isinstance(x, torch.Tensor):
-        t = x if x.dtype == torch.float32 else x.to(torch.float32)
-        return t if device is None else t.to(device)
-    return torch.as_tensor(x, dtype=torch.float32, device=device)
+    return _as_dtype(x, torch.float32, np.float32, device)
 
 
 def _i32(x: Any, device: Any = None) -> Tensor:
-    if isinstance(x, torch.Tensor):
-        t = x if x.dtype == torch.int32 else x.to(torch.int32)
-        return t if device is None else t.to(device)
-    return torch.as_tensor(x, dtype=torch.int32, device=device)
+    return _as_dtype(x, torch.int32, np.int32, device)
 
 
 class LightSource(NamedTuple):

@@ -138,3 +138,53 @@ def test_out_of_range_indices_are_clamped_not_read():
     ref = O.render(s.cam, "depth", z0, (), faces, NS(position=s.pos))
     rep = compare("clamped", out.zbuffer, None, tri, ref)
     assert_parity(rep)
+
+
+# ------------------------------------------------------------------ fused camera construction (8f-2)
+def _torch_camera(cp):
+    """The differentiable torch builders (forced by a requires_grad leaf)."""
+    pos = torch.as_tensor(cp.position, dtype=torch.float32).clone().requires_grad_(True)
+    return jr.Renderer.create_camera_from_parameters(cp._replace(position=pos))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("batched", [False, True])
+def test_camera_kernel_matches_torch_builders(batched):
+    dev = torch.device("cuda", 0)
+    g = torch.Generator().manual_seed(5)
+    B = 37
+    shape = (B,) if batched else ()
+    cp = jr.CameraParameters(
+        viewWidth=84, viewHeight=60, viewDepth=1.0, near=0.1, far=(torch.rand(shape, generator=g) * 50 + 20).to(dev),
+        hfov=58.0, vfov=(torch.rand(shape, generator=g) * 20 + 30).to(dev),
+        position=(torch.rand(*shape, 3, generator=g) * 4 + 1).to(dev),
+        target=(torch.rand(*shape, 3, generator=g) - 0.5).to(dev), up=(0.0, 0.0, 1.0))
+    fused = jr.Renderer.create_camera_from_parameters(cp)
+    ref = _torch_camera(cp)
+    for name, a, b in zip(fused._fields, fused, ref):
+        assert a.shape == b.shape or a.shape == b.shape[-2:] or b.shape == a.shape[-2:], (name, a.shape, b.shape)
+        torch.testing.assert_close(a.expand_as(b) if a.ndim < b.ndim else a, b.detach().expand_as(a),
+                                   rtol=2e-5, atol=1e-6, msg=lambda m: f"{name}: {m}")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("batched", [False, True])
+def test_light_camera_kernel_matches_torch_builders(batched):
+    from jaxrenderer_b200.geometry import camera_build_native
+    from jaxrenderer_b200.shadow import Shadow
+    from jaxrenderer_b200 import _native
+
+    dev = torch.device("cuda", 0)
+    g = torch.Generator().manual_seed(6)
+    shape = (19,) if batched else ()
+    centre = (torch.rand(*shape, 3, generator=g) - 0.5).to(dev)
+    ld = torch.tensor((0.3, -0.6, 0.9), device=dev)
+    up = torch.tensor((0.0, 1.0, 0.0), device=dev)
+    viewport = jr.Camera.viewport_matrix(torch.zeros(2), torch.tensor((84.0, 60.0)), torch.tensor(1.0)).to(dev)
+    fused = camera_build_native(_native.JR_CAMERA_LIGHT, (
+        (centre, 3), (ld, 3), (up, 3), (10.0, 1), (-1.0, 1), (1.0, 1), (-1.0, 1), (1.0, 1), (-1.0, 1), (1.0, 1)),
+        dev, viewport=viewport)
+    ref = Shadow._light_camera(centre, ld, up, 10.0, viewport, dev)
+    for name, a, b in zip(fused._fields, fused, ref):
+        b = b.expand_as(a) if b.ndim < a.ndim else b
+        torch.testing.assert_close(a, b, rtol=2e-5, atol=1e-6, msg=lambda m: f"{name}: {m}")

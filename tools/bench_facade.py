@@ -15,6 +15,7 @@ import argparse
 import json
 import os
 import sys
+import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -37,11 +38,13 @@ def timeit(fn, steps, warmup=3):
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    t0 = time.perf_counter()
     for _ in range(steps):
         fn()
+    host_ms = (time.perf_counter() - t0) * 1e3 / steps   # time the host needs to enqueue one step
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / steps
+    return e0.elapsed_time(e1) / steps, host_ms
 
 
 def main():
@@ -84,10 +87,8 @@ def main():
     l0 = _native.launch_count()
     full()
     out["launches"] = _native.launch_count() - l0
-    out["ms_total"] = timeit(full, args.steps)
-    out["ms_merge"] = timeit(merge, args.steps)
-    out["ms_camera"] = timeit(camera, args.steps)
-    out["ms_render"] = timeit(render, args.steps)
+    for name, fn in (("total", full), ("merge", merge), ("camera", camera), ("render", render)):
+        out[f"ms_{name}"], out[f"ms_{name}_host"] = (round(v, 4) for v in timeit(fn, args.steps))
     out["images_per_s"] = B / out["ms_total"] * 1e3
     print(json.dumps(out))
     if args.profile:
@@ -97,6 +98,7 @@ def main():
                 full()
             torch.cuda.synchronize()
         print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25), file=sys.stderr)
+        print(prof.key_averages().table(sort_by="self_cpu_time_total", row_limit=25), file=sys.stderr)
 
 
 if __name__ == "__main__":
