@@ -25,6 +25,7 @@
 // 84x84 x 4096: 0.484 ms with 64-bit keys, 0.506 with 32-bit keys at the same 3 CTAs/SM, 0.442 at
 // 4, 0.436 at 5 with 76 B of register spill, 0.454 at 6).
 #pragma once
+#include <type_traits>
 #include "jr_device.cuh"
 
 namespace jr {
@@ -365,9 +366,20 @@ k_vis2(const __grid_constant__ JrRenderArgs a, int tile_w, int tile_h, int tiles
     if (__ballot_sync(0xffffffffu, surv)) fire(surv, M, zc, t, bb);
   }
   __syncthreads();
+  const bool use0 = DEPTH && tri0_flag;
+  const int npix_img = a.W * a.H;
+  constexpr int PX = K32 ? 4 : 2;  // pixels per thread of the vectorised resolve
+  // Single tile (tile-local index == pixel index), no triangle-0 fallback, column height a multiple of
+  // PX (a thread's PX pixels share their x): the large triangles are folded into the resolve loop
+  // below, against keys held in registers.
+#ifdef JR_NO_FUSED_BIG
+  const bool fused = false;
+#else
+  const bool fused = tiles == 1 && !use0 && (a.H % PX) == 0;
+#endif
   // ---------------- large triangles: whole CTA, one at a time (a barrier between two entries makes
   // every pixel single-writer, so plain read-modify-write instead of a CAS loop)
-  {
+  if (!fused) {
     const int nbig = min(bigq_n, V2_BIGCAP);
     for (int e = 0; e < nbig; ++e) {
       const V2Big& q = bigq[e];
@@ -405,40 +417,83 @@ k_vis2(const __grid_constant__ JrRenderArgs a, int tile_w, int tile_h, int tiles
   // ---------------- resolve
   int32_t* __restrict__ tri_out = a.tri_id ? a.tri_id + (long long)b * a.W * a.H : nullptr;
   float* __restrict__ z_out = DEPTH ? a.zbuffer + (long long)b * a.W * a.H : nullptr;
-  const bool use0 = DEPTH && tri0_flag;
-  const int npix_img = a.W * a.H;
-  if (K32 && tiles == 1 && !use0 && !(npix_img & 3)) {
-    // z-only keys, single tile: four pixels per thread, 128-bit LDS / STG when all four are covered
-    const uint4* k4 = reinterpret_cast<const uint4*>(keys32);
-    for (int i = tid; i < (npix_img >> 2); i += V2_THREADS) {
-      const uint4 kk = k4[i];
-      if ((kk.x & kk.y & kk.z & kk.w) != ~0u && kk.x != ~0u && kk.y != ~0u && kk.z != ~0u && kk.w != ~0u) {
-        reinterpret_cast<float4*>(z_out)[i] =
-            make_float4(from_orderable(kk.x), from_orderable(kk.y), from_orderable(kk.z), from_orderable(kk.w));
+  if (fused) {
+    // PX consecutive pixels per thread (128-bit LDS of their keys).  Each queued large triangle (the
+    // ground plane of a Brax scene) is evaluated here, once per pixel, with the keys in registers:
+    // no shared-memory read-modify-write, no barrier per triangle, the pixel coordinates are computed
+    // once for all of them.  Same expressions, hence the same bits, as the rasterisers above.
+    const int nbig = min(bigq_n, V2_BIGCAP);
+    const int H = a.H;
+    const float rH = 1.0f / (float)H;
+    typedef typename std::conditional<K32, uint32_t, unsigned long long>::type KeyT;
+    for (int i = tid; i < npix_img / PX; i += V2_THREADS) {
+      KeyT k[PX];
+      if (K32) {
+        const uint4 kk = reinterpret_cast<const uint4*>(keys32)[i];
+        k[0] = kk.x; k[1] = kk.y; k[2 % PX] = kk.z; k[3 % PX] = kk.w;
       } else {
-        if (kk.x != ~0u) z_out[4 * i] = from_orderable(kk.x);
-        if (kk.y != ~0u) z_out[4 * i + 1] = from_orderable(kk.y);
-        if (kk.z != ~0u) z_out[4 * i + 2] = from_orderable(kk.z);
-        if (kk.w != ~0u) z_out[4 * i + 3] = from_orderable(kk.w);
+        const ulonglong2 kk = reinterpret_cast<const ulonglong2*>(keys)[i];
+        k[0] = (KeyT)kk.x; k[1] = (KeyT)kk.y;
       }
-    }
-  } else if (!K32 && tiles == 1 && !use0 && !(npix_img & 1)) {
-    // single tile: tile-local index == pixel index; two pixels per thread, 128-bit LDS / 64-bit STG
-    const ulonglong2* k2 = reinterpret_cast<const ulonglong2*>(keys);
-    for (int i = tid; i < (npix_img >> 1); i += V2_THREADS) {
-      const ulonglong2 kk = k2[i];
-      const bool e0 = kk.x == ~0ull, e1 = kk.y == ~0ull;
-      if (DEPTH) {
-        if (!e0 && !e1) {
-          reinterpret_cast<float2*>(z_out)[i] =
-              make_float2(from_orderable((uint32_t)(kk.x >> 32)), from_orderable((uint32_t)(kk.y >> 32)));
-        } else {
-          if (!e0) z_out[2 * i] = from_orderable((uint32_t)(kk.x >> 32));
-          if (!e1) z_out[2 * i + 1] = from_orderable((uint32_t)(kk.y >> 32));
+      if (nbig) {
+        const int p0 = i * PX;
+        const int x = (int)(((float)p0 + 0.5f) * rH);  // exact for p0 < 2^16 (see raster_flat)
+        const int y = p0 - x * H;                       // multiple of PX: the PX pixels are (x, y..y+PX-1)
+        const float xn = xs[x];
+        float yn[PX];
+#pragma unroll
+        for (int p = 0; p < PX; ++p) yn[p] = ys[y + p];
+        for (int e = 0; e < nbig; ++e) {
+          const V2Big& q = bigq[e];
+          if (x < q.x0 || x > q.x1) continue;
+          const float i3 = q.inv[3], i4 = q.inv[4], i5 = q.inv[5], i6 = q.inv[6], i7 = q.inv[7], i8 = q.inv[8];
+          const float px0 = xn * q.inv[0], px1 = xn * q.inv[1], px2 = xn * q.inv[2];
+          const float z0 = q.zc[0], z1 = q.zc[1], z2 = q.zc[2];
+          const unsigned tri = (unsigned)q.tri;
+          const int qy0 = q.y0;
+          const unsigned qdy = (unsigned)(q.y1 - qy0);
+#pragma unroll
+          for (int p = 0; p < PX; ++p) {
+            if ((unsigned)(y + p - qy0) > qdy) continue;
+            const float c0 = (px0 + yn[p] * i3) + i6;
+            const float c1 = (px1 + yn[p] * i4) + i7;
+            const float c2 = (px2 + yn[p] * i5) + i8;
+            if (c0 >= 0.f && c1 >= 0.f && c2 >= 0.f) {
+              const float z = (c0 * z0 + c1 * z1) + c2 * z2;
+              const float zw = z * vp22 + vp23;
+              const KeyT key = K32 ? (KeyT)min(orderable(zw), 0xFFFFFFFEu)
+                                   : (KeyT)(((unsigned long long)orderable(zw) << 32) | tri);
+              if (key < k[p]) k[p] = key;
+            }
+          }
         }
       }
-      if (tri_out)
-        reinterpret_cast<int2*>(tri_out)[i] = make_int2(e0 ? -1 : (int)(unsigned)kk.x, e1 ? -1 : (int)(unsigned)kk.y);
+      if (K32) {
+        const uint32_t k0 = (uint32_t)k[0], k1 = (uint32_t)k[1], k2 = (uint32_t)k[2 % PX], k3 = (uint32_t)k[3 % PX];
+        if (k0 != ~0u && k1 != ~0u && k2 != ~0u && k3 != ~0u) {
+          reinterpret_cast<float4*>(z_out)[i] =
+              make_float4(from_orderable(k0), from_orderable(k1), from_orderable(k2), from_orderable(k3));
+        } else {
+          if (k0 != ~0u) z_out[4 * i] = from_orderable(k0);
+          if (k1 != ~0u) z_out[4 * i + 1] = from_orderable(k1);
+          if (k2 != ~0u) z_out[4 * i + 2] = from_orderable(k2);
+          if (k3 != ~0u) z_out[4 * i + 3] = from_orderable(k3);
+        }
+      } else {
+        const unsigned long long q0 = k[0], q1 = k[1];
+        const bool e0 = q0 == ~0ull, e1 = q1 == ~0ull;
+        if (DEPTH) {
+          if (!e0 && !e1) {
+            reinterpret_cast<float2*>(z_out)[i] =
+                make_float2(from_orderable((uint32_t)(q0 >> 32)), from_orderable((uint32_t)(q1 >> 32)));
+          } else {
+            if (!e0) z_out[2 * i] = from_orderable((uint32_t)(q0 >> 32));
+            if (!e1) z_out[2 * i + 1] = from_orderable((uint32_t)(q1 >> 32));
+          }
+        }
+        if (tri_out)
+          reinterpret_cast<int2*>(tri_out)[i] = make_int2(e0 ? -1 : (int)(unsigned)q0, e1 ? -1 : (int)(unsigned)q1);
+      }
     }
   } else {
     const int dq = V2_THREADS / th, dr = V2_THREADS - dq * th;
