@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define JR_ABI_VERSION 1
+#define JR_ABI_VERSION 2
 
 typedef void* jr_stream_t; /* cudaStream_t */
 
@@ -154,6 +154,8 @@ typedef struct JrGradArgs {
   JrF32Out d_texture;          /* (tex_w,tex_h,3) deterministic scatter */
   JrF32Out d_specular_map;     /* (spec_w,spec_h) */
   JrF32Out d_shadow_strength;  /* (3) */
+  JrF32Out d_uv;               /* (n_uv,2)  phong_darboux only: through the tangent frame (phong_darboux.py:231-262) */
+  JrF32Out d_normal_map;       /* (tex_w,tex_h,3) phong_darboux only, deterministic scatter */
   void* workspace;
   size_t workspace_bytes;
 } JrGradArgs;

@@ -64,6 +64,7 @@ class JrGradArgs(C.Structure):
         ("d_light_direction", JrF32), ("d_light_colour", JrF32), ("d_light_dir_eye", JrF32),
         ("d_ambient", JrF32), ("d_diffuse", JrF32), ("d_specular", JrF32),
         ("d_texture", JrF32), ("d_specular_map", JrF32), ("d_shadow_strength", JrF32),
+        ("d_uv", JrF32), ("d_normal_map", JrF32),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
     ]
 

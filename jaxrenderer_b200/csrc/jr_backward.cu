@@ -35,7 +35,8 @@ enum : int {
   NG = 52
 };
 
-enum : int { MODE_TEXEL = 0, MODE_SPEC = 1, MODE_POS = 2, MODE_NRM = 3 };
+enum : int { MODE_TEXEL = 0, MODE_SPEC = 1, MODE_POS = 2, MODE_NRM = 3,
+              MODE_NMAP = 4, MODE_UV = 5, MODE_POS2 = 6 };  // phong_darboux: normal map, uv and tangent-triangle positions
 
 struct PixGrad {
   float g[NG];
@@ -44,6 +45,10 @@ struct PixGrad {
   float d_pos[3][3];
   float d_col[3][3];
   float d_nrm[3][3];
+  // phong_darboux
+  float d_nmap[3];
+  float d_uv[3][2];
+  float d_pos2[3][3];
 };
 
 __device__ __forceinline__ Vec3 normalise_bwd(Vec3 v, Vec3 dy) {
@@ -112,7 +117,107 @@ __device__ __forceinline__ void backprop_pixel(const JrRenderArgs& a, int b, con
   } else if (S >= JR_PHONG) {
     Vec3 d_nn = {0.f, 0.f, 0.f};
     bool active = true;
-    if (S == JR_PHONG) {
+    if (S == JR_PHONG_DARBOUX) {
+      // phong_darboux.py:231-262 in reverse: normal = normalise(B @ nm), B = [i | j | n],
+      // i, j = normalise(AI[:, :2] @ (du | dv)), AI = inv([tr1 - tr0; tr2 - tr0; n])
+      active = f.ok;
+      if (WT) { o.d_nmap[0] = o.d_nmap[1] = o.d_nmap[2] = 0.f; }
+      if (WV) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          o.d_uv[k][0] = o.d_uv[k][1] = 0.f;
+          o.d_pos2[k][0] = o.d_pos2[k][1] = o.d_pos2[k][2] = 0.f;
+        }
+      }
+      if (active) {
+        float d_ndl = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          if (WT) o.d_tex[c] = d_col[c] * f.lc[c];
+          const float d_lc = d_col[c] * f.tex[c];
+          if (WG) o.g[G_LCOL + c] += d_lc * f.ndl;
+          d_ndl += d_lc * f.lcol[c];
+        }
+        const Vec3 n2 = f.dn2;
+        if (WG) {
+          const Vec3 dl = normalise_bwd(Vec3{f.lraw[0], f.lraw[1], f.lraw[2]},
+                                        Vec3{d_ndl * n2.x, d_ndl * n2.y, d_ndl * n2.z});
+          o.g[G_LDIR] += dl.x; o.g[G_LDIR + 1] += dl.y; o.g[G_LDIR + 2] += dl.z;
+        }
+        const Vec3 d_bn = normalise_bwd(f.dbn, Vec3{d_ndl * f.nl.x, d_ndl * f.nl.y, d_ndl * f.nl.z});
+        const Vec3 iv = f.div_, jv = f.djv, nn = f.nn;
+        if (WT) {
+          o.d_nmap[0] = iv.x * d_bn.x + iv.y * d_bn.y + iv.z * d_bn.z;
+          o.d_nmap[1] = jv.x * d_bn.x + jv.y * d_bn.y + jv.z * d_bn.z;
+          o.d_nmap[2] = nn.x * d_bn.x + nn.y * d_bn.y + nn.z * d_bn.z;
+        }
+        d_nn = Vec3{f.dnm[2] * d_bn.x, f.dnm[2] * d_bn.y, f.dnm[2] * d_bn.z};
+        const Vec3 d_ivr = normalise_bwd(f.divr, Vec3{f.dnm[0] * d_bn.x, f.dnm[0] * d_bn.y, f.dnm[0] * d_bn.z});
+        const Vec3 d_jvr = normalise_bwd(f.djvr, Vec3{f.dnm[1] * d_bn.x, f.dnm[1] * d_bn.y, f.dnm[1] * d_bn.z});
+        const float di[3] = {d_ivr.x, d_ivr.y, d_ivr.z}, dj[3] = {d_jvr.x, d_jvr.y, d_jvr.z};
+        const float du0 = f.dduv[0], du1 = f.dduv[1], dv0 = f.dduv[2], dv1 = f.dduv[3];
+        const float* AI = f.dAI;
+        float dAI[9];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          dAI[3 * r] = di[r] * du0 + dj[r] * dv0;
+          dAI[3 * r + 1] = di[r] * du1 + dj[r] * dv1;
+          dAI[3 * r + 2] = 0.f;
+        }
+        if (WV) {
+          const float d_du0 = di[0] * AI[0] + di[1] * AI[3] + di[2] * AI[6];
+          const float d_du1 = di[0] * AI[1] + di[1] * AI[4] + di[2] * AI[7];
+          const float d_dv0 = dj[0] * AI[0] + dj[1] * AI[3] + dj[2] * AI[6];
+          const float d_dv1 = dj[0] * AI[1] + dj[1] * AI[4] + dj[2] * AI[7];
+          o.d_uv[1][0] = d_du0; o.d_uv[1][1] = d_dv0;
+          o.d_uv[2][0] = d_du1; o.d_uv[2][1] = d_dv1;
+          o.d_uv[0][0] = -(d_du0 + d_du1); o.d_uv[0][1] = -(d_dv0 + d_dv1);
+        }
+        // d_A = -(AI^T dAI AI^T)
+        float T1[9], dA[9];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int l = 0; l < 3; ++l) T1[3 * i + l] = AI[i] * dAI[l] + AI[3 + i] * dAI[3 + l] + AI[6 + i] * dAI[6 + l];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int j = 0; j < 3; ++j)
+            dA[3 * i + j] = -(T1[3 * i] * AI[3 * j] + T1[3 * i + 1] * AI[3 * j + 1] + T1[3 * i + 2] * AI[3 * j + 2]);
+        d_nn.x += dA[6]; d_nn.y += dA[7]; d_nn.z += dA[8];
+        if (WG || WV) {
+          const float* __restrict__ w2c = a.world_to_clip.ptr + (long long)b * a.world_to_clip.batch_stride;
+          float d_tr[3][3];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            d_tr[1][c] = dA[c]; d_tr[2][c] = dA[3 + c]; d_tr[0][c] = -(dA[c] + dA[3 + c]);
+          }
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const float w = f.dtw[k];
+            float dc[4];
+            if (w != 0.0f) {
+              dc[0] = d_tr[k][0] / w; dc[1] = d_tr[k][1] / w; dc[2] = d_tr[k][2] / w;
+              dc[3] = -(d_tr[k][0] * f.dtr[k][0] + d_tr[k][1] * f.dtr[k][1] + d_tr[k][2] * f.dtr[k][2]) / w;
+            } else {
+              dc[0] = d_tr[k][0]; dc[1] = d_tr[k][1]; dc[2] = d_tr[k][2]; dc[3] = 0.f;
+            }
+            const float ph[4] = {f.dP[k].x, f.dP[k].y, f.dP[k].z, 1.f};
+            if (WG) {
+#pragma unroll
+              for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) o.g[G_W2C + 4 * r + c] += dc[r] * ph[c];
+            }
+            if (WV) {
+#pragma unroll
+              for (int c = 0; c < 3; ++c)
+                o.d_pos2[k][c] = w2c[c] * dc[0] + w2c[4 + c] * dc[1] + w2c[8 + c] * dc[2] + w2c[12 + c] * dc[3];
+            }
+          }
+        }
+      }
+    } else if (S == JR_PHONG) {
       active = f.ok;
       if (active) {
         float d_ndl = 0.f;
@@ -348,13 +453,13 @@ k_bwd_keys(const __grid_constant__ JrRenderArgs a, KeyedPlan plan, unsigned* __r
     const long long gi = (long long)b * npix + pix;
     const int tri = a.tri_id[gi];
     const unsigned boff = plan.batched ? (unsigned)((long long)b * plan.keys_per_image) : 0u;
-    if (MODE == MODE_TEXEL || MODE == MODE_SPEC) {
+    if (MODE == MODE_TEXEL || MODE == MODE_SPEC || MODE == MODE_NMAP) {
       unsigned key = plan.invalid_key;
       if (tri >= 0) {
         const int x = pix / a.H, y = pix - x * a.H;
         Frag f;
         shade_pixel<S>(a, b, x, y, tri, f);
-        const long long k = (MODE == MODE_TEXEL) ? f.texel : f.spec_idx;
+        const long long k = (MODE == MODE_SPEC) ? f.spec_idx : f.texel;
         bool contributes = true;
         if (S == JR_PHONG || S == JR_PHONG_DARBOUX) contributes = f.ok;
         if (k >= 0 && contributes) key = boff + (unsigned)k;
@@ -369,7 +474,15 @@ k_bwd_keys(const __grid_constant__ JrRenderArgs a, KeyedPlan plan, unsigned* __r
           const int32_t* fp = a.faces.ptr + (long long)b * a.faces.batch_stride + 3 * tri;
           if (MODE == MODE_NRM && a.faces_norm.ptr)
             fp = a.faces_norm.ptr + (long long)b * a.faces_norm.batch_stride + 3 * tri;
-          key = boff + (unsigned)fp[k];
+          int v = fp[k];
+          if (MODE == MODE_UV || MODE == MODE_POS2) {
+            // vertices of the tangent-frame triangle of the chosen triangle's first vertex
+            const int v0 = min(max(fp[0], 0), a.n_pos - 1);
+            const int face = (a.id_to_face.ptr + (long long)b * a.id_to_face.batch_stride)[v0];
+            v = (a.faces_indices.ptr + (long long)b * a.faces_indices.batch_stride)[3 * face + k];
+          }
+          v = min(max(v, 0), (int)plan.keys_per_image - 1);
+          key = boff + (unsigned)v;
         }
         keys[gi * 3 + k] = key;
         vals[gi * 3 + k] = (unsigned)(gi * 4 + k);
@@ -406,7 +519,7 @@ k_bwd_segreduce(const __grid_constant__ JrRenderArgs a, const __grid_constant__ 
       const unsigned payload = vals[i];
       long long gi;
       int corner = 0;
-      if (MODE == MODE_TEXEL || MODE == MODE_SPEC) gi = payload;
+      if (MODE == MODE_TEXEL || MODE == MODE_SPEC || MODE == MODE_NMAP) gi = payload;
       else { gi = payload >> 2; corner = payload & 3; }
       const int b = (int)((unsigned)gi / (unsigned)npix);  // gi < 2^30 (checked by the host side)
       const int pix = (int)(gi - (long long)b * npix);
@@ -416,8 +529,22 @@ k_bwd_segreduce(const __grid_constant__ JrRenderArgs a, const __grid_constant__ 
       float d_zw, d_col[3];
       load_cotangent(g, gi, S != JR_DEPTH, d_zw, d_col);
       PixGrad o;
-      backprop_pixel<S, false, (MODE == MODE_TEXEL || MODE == MODE_SPEC), (MODE == MODE_POS || MODE == MODE_NRM)>(
+      backprop_pixel<S, false, (MODE == MODE_TEXEL || MODE == MODE_SPEC || MODE == MODE_NMAP),
+                     (MODE == MODE_POS || MODE == MODE_NRM || MODE == MODE_UV || MODE == MODE_POS2)>(
           a, b, f, d_zw, d_col, o);
+      if (S == JR_PHONG_DARBOUX) {
+        if (MODE == MODE_NMAP) { v[0] = o.d_nmap[0]; v[1] = o.d_nmap[1]; v[2] = o.d_nmap[2]; }
+        if (MODE == MODE_UV) {
+#pragma unroll
+          for (int k = 0; k < 3; ++k)
+            if (k == corner) { v[0] = o.d_uv[k][0]; v[1] = o.d_uv[k][1]; }
+        }
+        if (MODE == MODE_POS2) {
+#pragma unroll
+          for (int k = 0; k < 3; ++k)
+            if (k == corner) { v[0] = o.d_pos2[k][0]; v[1] = o.d_pos2[k][1]; v[2] = o.d_pos2[k][2]; }
+        }
+      }
       if (MODE == MODE_TEXEL) { v[0] = o.d_tex[0]; v[1] = o.d_tex[1]; v[2] = o.d_tex[2]; }
       if (MODE == MODE_SPEC) v[0] = o.d_sexp;
       if (MODE == MODE_POS) {
@@ -581,8 +708,8 @@ static BwdLayout bwd_layout(const JrRenderArgs* a, const JrGradArgs* g) {
   L.nblk = (int)((npix + BWD_THREADS * 8 - 1) / (BWD_THREADS * 8));
   if (L.nblk < 1) L.nblk = 1;
   if (L.nblk > 64) L.nblk = 64;
-  const bool keyed1 = g->d_texture.ptr || g->d_specular_map.ptr;
-  const bool keyed3 = g->d_position.ptr || g->d_colour.ptr || g->d_normal.ptr;
+  const bool keyed1 = g->d_texture.ptr || g->d_specular_map.ptr || g->d_normal_map.ptr;
+  const bool keyed3 = g->d_position.ptr || g->d_colour.ptr || g->d_normal.ptr || g->d_uv.ptr;
   L.max_entries = keyed3 ? npix * a->B * 3 : (keyed1 ? npix * a->B : 0);
   size_t off = 0;
   L.partials = off; off += align256(sizeof(float) * NG * (size_t)L.nblk * a->B);
@@ -712,6 +839,41 @@ static int backward_impl(const JrRenderArgs* a, const JrGradArgs* g, cudaStream_
     rc = run_keyed<S, MODE_NRM, 3>(a, g, L, p, stream);
     if (rc != JR_OK) return rc;
   }
+  if (S == JR_PHONG_DARBOUX) {
+    if (g->d_normal_map.ptr) {
+      KeyedPlan p{};
+      p.mode = MODE_NMAP; p.per_pixel = 1; p.n_entries = total;
+      p.keys_per_image = (long long)a->tex_w * a->tex_h;
+      p.batched = g->d_normal_map.batch_stride != 0;
+      const long long nk = p.keys_per_image * (p.batched ? a->B : 1);
+      if (nk >= 0x7FFFFFFFLL) return JR_ERR_DIMS;
+      p.invalid_key = (unsigned)nk; p.C = 3; p.out = g->d_normal_map.ptr; p.out2 = nullptr;
+      rc = run_keyed<S, MODE_NMAP, 3>(a, g, L, p, stream);
+      if (rc != JR_OK) return rc;
+    }
+    if (g->d_uv.ptr) {
+      KeyedPlan p{};
+      p.mode = MODE_UV; p.per_pixel = 3; p.n_entries = total * 3;
+      p.keys_per_image = a->n_uv;
+      p.batched = g->d_uv.batch_stride != 0;
+      const long long nk = p.keys_per_image * (p.batched ? a->B : 1);
+      if (nk >= 0x7FFFFFFFLL || p.n_entries >= 0x7FFFFFFFLL) return JR_ERR_DIMS;
+      p.invalid_key = (unsigned)nk; p.C = 2; p.out = g->d_uv.ptr; p.out2 = nullptr;
+      rc = run_keyed<S, MODE_UV, 2>(a, g, L, p, stream);
+      if (rc != JR_OK) return rc;
+    }
+    if (g->d_position.ptr) {  // second position pass: the tangent-frame triangle's vertices
+      KeyedPlan p{};
+      p.mode = MODE_POS2; p.per_pixel = 3; p.n_entries = total * 3;
+      p.keys_per_image = a->n_pos;
+      p.batched = g->d_position.batch_stride != 0;
+      const long long nk = p.keys_per_image * (p.batched ? a->B : 1);
+      if (nk >= 0x7FFFFFFFLL || p.n_entries >= 0x7FFFFFFFLL) return JR_ERR_DIMS;
+      p.invalid_key = (unsigned)nk; p.C = 3; p.out = g->d_position.ptr; p.out2 = nullptr;
+      rc = run_keyed<S, MODE_POS2, 3>(a, g, L, p, stream);
+      if (rc != JR_OK) return rc;
+    }
+  }
   // cotangent of the incoming buffers
   if (g->d_zbuffer || g->d_canvas) {
     long long blocks = (total + 255) / 256;
@@ -747,7 +909,9 @@ int jr_render_backward(const JrRenderArgs* a, const JrGradArgs* g, jr_stream_t s
     case JR_PHONG: return backward_impl<JR_PHONG>(a, g, stream);
     case JR_PHONG_REFLECTION: return backward_impl<JR_PHONG_REFLECTION>(a, g, stream);
     case JR_PHONG_REFLECTION_SHADOW: return backward_impl<JR_PHONG_REFLECTION_SHADOW>(a, g, stream);
-    case JR_PHONG_DARBOUX: return JR_ERR_UNSUPPORTED;  // gradients of the Darboux shader: not yet
+    case JR_PHONG_DARBOUX:
+      if (!a->id_to_face.ptr || !a->faces_indices.ptr || !a->normal_map.ptr || !a->uv.ptr) return JR_ERR_NULL;
+      return backward_impl<JR_PHONG_DARBOUX>(a, g, stream);
     default: return JR_ERR_SHADER;
   }
 }

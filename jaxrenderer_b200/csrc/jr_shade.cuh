@@ -50,6 +50,15 @@ struct Frag {
   Vec3 rv;                     // 2 ndl nn - ld (before normalise)
   float ds[3], shadow[3], amb[3], dif[3], spe[3], str[3];
   bool lit;
+  // S5 (Darboux) intermediates, kept for backward
+  int dvtx[3];                 // vertices of the tangent-frame triangle (faces_indices[id_to_face[v0]])
+  Vec3 dP[3];                  // their world positions
+  float dtr[3][3], dtw[3];     // their NDC positions and clip w
+  float dAI[9];                // inverse of [tr1 - tr0; tr2 - tr0; n]
+  float dduv[4];               // du0, du1, dv0, dv1
+  Vec3 divr, djvr, div_, djv;  // tangent / bitangent before and after normalisation
+  float dnm[3];                // normal-map texel
+  Vec3 dbn, dn2;               // B @ nm and its normalisation (the shading normal)
 };
 
 // Per-TRIANGLE part of the common setup (independent of the pixel).
@@ -232,6 +241,10 @@ __device__ __forceinline__ void frag_pixel(const JrRenderArgs& a, int b, int x, 
         tr[k][1] = w0 ? tcq[1] : tcq[1] / tcq[3];
         tr[k][2] = w0 ? tcq[2] : tcq[2] / tcq[3];
         tuv[k][0] = uvp[2 * vtx]; tuv[k][1] = uvp[2 * vtx + 1];
+        f.dvtx[k] = vtx;
+        f.dP[k] = Vec3{pos[3 * vtx], pos[3 * vtx + 1], pos[3 * vtx + 2]};
+        f.dtr[k][0] = tr[k][0]; f.dtr[k][1] = tr[k][1]; f.dtr[k][2] = tr[k][2];
+        f.dtw[k] = tcq[3];
       }
       const float A[9] = {tr[1][0] - tr[0][0], tr[1][1] - tr[0][1], tr[1][2] - tr[0][2],
                           tr[2][0] - tr[0][0], tr[2][1] - tr[0][1], tr[2][2] - tr[0][2],
@@ -240,15 +253,21 @@ __device__ __forceinline__ void frag_pixel(const JrRenderArgs& a, int b, int x, 
       lu_inverse3(A, AI);
       const float du0 = tuv[1][0] - tuv[0][0], du1 = tuv[2][0] - tuv[0][0];
       const float dv0 = tuv[1][1] - tuv[0][1], dv1 = tuv[2][1] - tuv[0][1];
-      const Vec3 iv = normalise3(Vec3{AI[0] * du0 + AI[1] * du1, AI[3] * du0 + AI[4] * du1,
-                                      AI[6] * du0 + AI[7] * du1});
-      const Vec3 jv = normalise3(Vec3{AI[0] * dv0 + AI[1] * dv1, AI[3] * dv0 + AI[4] * dv1,
-                                      AI[6] * dv0 + AI[7] * dv1});
+      const Vec3 ivr = {AI[0] * du0 + AI[1] * du1, AI[3] * du0 + AI[4] * du1, AI[6] * du0 + AI[7] * du1};
+      const Vec3 jvr = {AI[0] * dv0 + AI[1] * dv1, AI[3] * dv0 + AI[4] * dv1, AI[6] * dv0 + AI[7] * dv1};
+      const Vec3 iv = normalise3(ivr);
+      const Vec3 jv = normalise3(jvr);
       const float* nm = a.normal_map.ptr + (long long)b * a.normal_map.batch_stride + f.texel * 3;
       const Vec3 bn = {(iv.x * nm[0] + jv.x * nm[1]) + nn.x * nm[2],
                        (iv.y * nm[0] + jv.y * nm[1]) + nn.y * nm[2],
                        (iv.z * nm[0] + jv.z * nm[1]) + nn.z * nm[2]};
       nn = normalise3(bn);
+#pragma unroll
+      for (int k = 0; k < 9; ++k) f.dAI[k] = AI[k];
+      f.dduv[0] = du0; f.dduv[1] = du1; f.dduv[2] = dv0; f.dduv[3] = dv1;
+      f.divr = ivr; f.djvr = jvr; f.div_ = iv; f.djv = jv;
+      f.dnm[0] = nm[0]; f.dnm[1] = nm[1]; f.dnm[2] = nm[2];
+      f.dbn = bn; f.dn2 = nn;
     }
     f.ndl = dot3(nn.x, nn.y, nn.z, f.nl.x, f.nl.y, f.nl.z);
     f.ok = true;

@@ -67,6 +67,7 @@ _DIFF = (
     "zbuffer", "canvas", "position", "normal", "colour", "world_to_clip", "viewport",
     "world_to_eye_norm", "light_direction", "light_colour", "light_dir_eye", "ambient",
     "diffuse", "specular", "texture", "specular_map", "shadow_strength",
+    "uv", "normal_map",   # phong_darboux only (through the tangent frame); zero for the other shaders
 )
 _GRAD_FIELD = {n: "d_" + n for n in _DIFF if n not in ("zbuffer", "canvas")}
 
@@ -228,9 +229,6 @@ class _RenderFn(torch.autograd.Function):
         g = JrGradArgs()
         g.d_zbuffer = d_z.data_ptr()
         g.d_canvas = d_c.data_ptr() if has_canvas else None
-        if call.sid == _native.JR_PHONG_DARBOUX:
-            raise UnsupportedShaderError(
-                "gradients through PhongTextureDarbouxShader are not implemented in jaxrenderer_b200")
         outs: Dict[str, Tensor] = {}
         wanted = []
         for i, name in enumerate(_DIFF):

@@ -16,7 +16,8 @@ import jaxrenderer_b200 as jr
 from jaxrenderer_b200.shaders import (
     DepthExtraInput, DepthShader, GouraudExtraInput, GouraudShader, GouraudTextureExtraInput,
     GouraudTextureShader, PhongReflectionShadowTextureExtraInput, PhongReflectionShadowTextureShader,
-    PhongReflectionTextureExtraInput, PhongReflectionTextureShader, PhongTextureExtraInput, PhongTextureShader,
+    PhongReflectionTextureExtraInput, PhongReflectionTextureShader, PhongTextureDarbouxExtraInput,
+    PhongTextureDarbouxShader, PhongTextureExtraInput, PhongTextureShader,
 )
 from oracle import jr_oracle as O
 from tests.helpers import random_mesh_scene, smoke_scene
@@ -163,6 +164,25 @@ def test_gouraud_texture_and_phong_grads():
                                                      get("light_colour", s.light.colour)),
                                       get("texture", s.texture))
     _run_case("phong", PhongTextureShader, mk_p, s, names + ("world_to_eye_norm",))
+
+
+@pytest.mark.parametrize("shift", [0, 1])
+def test_phong_darboux_grads(shift):
+    """Normal mapping through the Darboux frame (phong_darboux.py:231-262): gradients also reach uv
+    and the normal map, and positions through the tangent-frame triangle -- which for ``shift=1``
+    is NOT the shaded triangle (id_to_face points at the next face)."""
+    s = random_mesh_scene(4 + shift)
+    n_tri = s.faces.shape[0]
+    id_to_face = ((torch.arange(n_tri, dtype=torch.int32) + shift) % n_tri).repeat_interleave(3)
+
+    def mk(get):
+        return PhongTextureDarbouxExtraInput(
+            get("position", s.pos), get("normal", s.nrm), get("uv", s.uv_texel),
+            jr.LightSource(get("light_direction", s.light.direction), get("light_colour", s.light.colour)),
+            get("texture", s.texture), get("normal_map", s.normal_map), id_to_face, s.faces)
+    _run_case("phong_darboux", PhongTextureDarbouxShader, mk, s,
+              ALL_CAM + ("position", "normal", "uv", "light_direction", "light_colour", "texture", "normal_map",
+                         "canvas"))
 
 
 def _reflection_inputs(s):

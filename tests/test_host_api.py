@@ -24,7 +24,7 @@ def test_abi_library_exports_every_declared_symbol():
     assert declared == set(_native.EXPORTS), declared ^ set(_native.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.jr_abi_version() == 1
+    assert lib.jr_abi_version() == 2
     assert lib.jr_strerror(-4).decode() == "workspace too small"
     # struct layout agreed between Python and C: a NULL args pointer is reported, not crashed on
     assert lib.jr_render_forward(None, None) == -1
