@@ -358,9 +358,24 @@ constexpr int BWD_THREADS = 256;
 #define JR_BWD_MIN_BLOCKS 2  // caps k_bwd_global at 128 registers: 2 CTAs/SM beat 1 CTA with 233 registers (measured)
 #endif
 
+// Per-pixel outputs of the pixel pass for the one-entry-per-pixel keyed targets (diffuse texture,
+// specular map, normal map): key + value are produced HERE, while the pixel's fragment is live, so the
+// keyed passes only sort and reduce -- they do not shade the pixel again.
+struct PixelEmit {
+  unsigned* iota;       // (B*W*H) payload = pixel index (sort values)
+  unsigned* key_tex;    // texel key (shared by texture and normal map), or null
+  unsigned* key_spec;   // specular-map key, or null
+  float* val_tex;       // (B*W*H,3) d colour / d texel
+  float* val_spec;      // (B*W*H)   d colour / d specular exponent
+  float* val_nmap;      // (B*W*H,3) d colour / d normal-map texel (phong_darboux)
+  unsigned inv_tex, inv_spec;            // "no contribution" keys
+  long long per_image_tex, per_image_spec;  // key offset per image when the target is batched, else 0
+};
+
 template <int S>
 __global__ void __launch_bounds__(BWD_THREADS, JR_BWD_MIN_BLOCKS)
-k_bwd_global(const __grid_constant__ JrRenderArgs a, const __grid_constant__ JrGradArgs g, float* __restrict__ partials) {
+k_bwd_global(const __grid_constant__ JrRenderArgs a, const __grid_constant__ JrGradArgs g, float* __restrict__ partials,
+             const __grid_constant__ PixelEmit em) {
   const int b = blockIdx.y;
   const int npix = a.W * a.H;
   PixGrad o;
@@ -369,13 +384,33 @@ k_bwd_global(const __grid_constant__ JrRenderArgs a, const __grid_constant__ JrG
   for (int pix = blockIdx.x * BWD_THREADS + threadIdx.x; pix < npix; pix += gridDim.x * BWD_THREADS) {
     const long long gi = (long long)b * npix + pix;
     const int tri = a.tri_id[gi];
-    if (tri < 0) continue;
+    if (em.iota) em.iota[gi] = (unsigned)gi;
+    if (tri < 0) {
+      if (em.key_tex) em.key_tex[gi] = em.inv_tex;
+      if (em.key_spec) em.key_spec[gi] = em.inv_spec;
+      continue;
+    }
     const int x = pix / a.H, y = pix - x * a.H;
     Frag f;
     shade_pixel<S>(a, b, x, y, tri, f);
     float d_zw, d_col[3];
     load_cotangent(g, gi, S != JR_DEPTH, d_zw, d_col);
-    backprop_pixel<S, true, false, false>(a, b, f, d_zw, d_col, o);
+    backprop_pixel<S, true, true, false>(a, b, f, d_zw, d_col, o);
+    if (S >= JR_GOURAUD_TEXTURE) {
+      if (em.key_tex) {
+        bool contributes = f.texel >= 0;
+        if (S == JR_PHONG || S == JR_PHONG_DARBOUX) contributes = contributes && f.ok;
+        em.key_tex[gi] = contributes ? (unsigned)(b * em.per_image_tex + f.texel) : em.inv_tex;
+        if (em.val_tex) { em.val_tex[gi * 3] = o.d_tex[0]; em.val_tex[gi * 3 + 1] = o.d_tex[1]; em.val_tex[gi * 3 + 2] = o.d_tex[2]; }
+        if (S == JR_PHONG_DARBOUX && em.val_nmap) {
+          em.val_nmap[gi * 3] = o.d_nmap[0]; em.val_nmap[gi * 3 + 1] = o.d_nmap[1]; em.val_nmap[gi * 3 + 2] = o.d_nmap[2];
+        }
+      }
+      if (S >= JR_PHONG_REFLECTION && em.key_spec) {
+        em.key_spec[gi] = f.spec_idx >= 0 ? (unsigned)(b * em.per_image_spec + f.spec_idx) : em.inv_spec;
+        em.val_spec[gi] = o.d_sexp;
+      }
+    }
   }
   // fixed-shape block reduction: xor-butterfly inside each warp, then warps in order
   __shared__ float red[BWD_THREADS / 32][NG];
@@ -441,6 +476,8 @@ struct KeyedPlan {
   int C;                // channels reduced
   float* out;           // target base
   float* out2;          // MODE_POS: d_colour (may be null)
+  const float* pix_vals;      // one-entry-per-pixel modes: values emitted by the pixel pass (C per pixel)
+  const unsigned* pix_keys;   // ... and their keys (sort input); payload = PixelEmit::iota
 };
 
 template <int S, int MODE>
@@ -515,7 +552,11 @@ k_bwd_segreduce(const __grid_constant__ JrRenderArgs a, const __grid_constant__ 
   for (int c = 0; c < C; ++c) v[c] = 0.f;
   if (i < plan.n_entries) {
     key = keys[i];
-    if (key != plan.invalid_key) {
+    if (key != plan.invalid_key && plan.pix_vals) {
+      const long long gi = vals[i];
+#pragma unroll
+      for (int c = 0; c < C; ++c) v[c] = plan.pix_vals[gi * C + c];
+    } else if (key != plan.invalid_key) {
       const unsigned payload = vals[i];
       long long gi;
       int corner = 0;
@@ -692,6 +733,7 @@ static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 struct BwdLayout {
   int nblk;             // global pass blocks per image
   size_t partials, keys_a, keys_b, vals_a, vals_b, cub_temp, carry, total;
+  size_t em_iota, em_key_tex, em_key_spec, em_val_tex, em_val_spec, em_val_nmap;  // PixelEmit buffers
   size_t cub_bytes;
   long long max_entries;
 };
@@ -727,6 +769,17 @@ static BwdLayout bwd_layout(const JrRenderArgs* a, const JrGradArgs* g) {
     const size_t nchunks = (n + 255) / 256;
     L.carry = off; off += align256(nchunks * sizeof(Carry<6>));
   }
+  if (keyed1) {
+    const size_t np = (size_t)npix * a->B;
+    L.em_iota = off; off += align256(np * 4);
+    if (g->d_texture.ptr || g->d_normal_map.ptr) { L.em_key_tex = off; off += align256(np * 4); }
+    if (g->d_texture.ptr) { L.em_val_tex = off; off += align256(np * 12); }
+    if (g->d_normal_map.ptr) { L.em_val_nmap = off; off += align256(np * 12); }
+    if (g->d_specular_map.ptr) {
+      L.em_key_spec = off; off += align256(np * 4);
+      L.em_val_spec = off; off += align256(np * 4);
+    }
+  }
   L.total = off;
   return L;
 }
@@ -742,11 +795,18 @@ static int run_keyed(const JrRenderArgs* a, const JrGradArgs* g, const BwdLayout
   Carry<C>* carry = (Carry<C>*)(ws + L.carry);
   int bx = (a->W * a->H + 255) / 256;
   if (bx > 4096) bx = 4096;
-  k_bwd_keys<S, MODE><<<dim3(bx, a->B > 65535 ? 65535 : a->B), 256, 0, stream>>>(*a, plan, keys_a, vals_a);
-  g_launches++;
+  const unsigned* keys_in = keys_a;
+  const unsigned* vals_in = vals_a;
+  if (plan.pix_keys) {  // emitted by the pixel pass
+    keys_in = plan.pix_keys;
+    vals_in = (const unsigned*)(ws + L.em_iota);
+  } else {
+    k_bwd_keys<S, MODE><<<dim3(bx, a->B > 65535 ? 65535 : a->B), 256, 0, stream>>>(*a, plan, keys_a, vals_a);
+    g_launches++;
+  }
   size_t tmp = L.cub_bytes;
   const int end_bit = bit_length((unsigned long long)plan.invalid_key);
-  cub::DeviceRadixSort::SortPairs(ws + L.cub_temp, tmp, keys_a, keys_b, vals_a, vals_b, (int)plan.n_entries, 0,
+  cub::DeviceRadixSort::SortPairs(ws + L.cub_temp, tmp, keys_in, keys_b, vals_in, vals_b, (int)plan.n_entries, 0,
                                   end_bit, stream);
   const long long nchunks = (plan.n_entries + 255) / 256;
   k_bwd_segreduce<S, MODE, C><<<(unsigned)nchunks, 256, 0, stream>>>(*a, *g, plan, keys_b, vals_b, carry);
@@ -765,11 +825,45 @@ static int backward_impl(const JrRenderArgs* a, const JrGradArgs* g, cudaStream_
   const long long total = npix * a->B;
   if (total * 4 > 0xFFFFFFFFLL) return JR_ERR_DIMS;  // payload packing (gi * 4 + corner) is 32-bit
   int rc = JR_OK;
-  if (wants_global(g)) {
+  // ---- pixel pass: scene-global partial sums + keys / values of the one-entry-per-pixel targets
+  const bool want_tex = S >= JR_GOURAUD_TEXTURE && g->d_texture.ptr;
+  const bool want_spec = S >= JR_PHONG_REFLECTION && g->d_specular_map.ptr;
+  const bool want_nmap = S == JR_PHONG_DARBOUX && g->d_normal_map.ptr;
+  PixelEmit em{};
+  long long nk_tex = 0, nk_spec = 0;
+  if (want_tex || want_nmap) {
+    const long long per = (long long)a->tex_w * a->tex_h;
+    const long long bs_t = g->d_texture.ptr ? g->d_texture.batch_stride : 0;
+    const long long bs_n = g->d_normal_map.ptr ? g->d_normal_map.batch_stride : 0;
+    if (want_tex && want_nmap && ((bs_t != 0) != (bs_n != 0))) return JR_ERR_UNSUPPORTED;  // one key space
+    const bool batched = (want_tex ? bs_t : bs_n) != 0;
+    nk_tex = per * (batched ? a->B : 1);
+    if (nk_tex >= 0x7FFFFFFFLL) return JR_ERR_DIMS;
+    em.key_tex = (unsigned*)(ws + L.em_key_tex);
+    em.inv_tex = (unsigned)nk_tex;
+    em.per_image_tex = batched ? per : 0;
+    if (want_tex) em.val_tex = (float*)(ws + L.em_val_tex);
+    if (want_nmap) em.val_nmap = (float*)(ws + L.em_val_nmap);
+  }
+  if (want_spec) {
+    const long long per = (long long)a->spec_w * a->spec_h;
+    const bool batched = g->d_specular_map.batch_stride != 0;
+    nk_spec = per * (batched ? a->B : 1);
+    if (nk_spec >= 0x7FFFFFFFLL) return JR_ERR_DIMS;
+    em.key_spec = (unsigned*)(ws + L.em_key_spec);
+    em.val_spec = (float*)(ws + L.em_val_spec);
+    em.inv_spec = (unsigned)nk_spec;
+    em.per_image_spec = batched ? per : 0;
+  }
+  if (want_tex || want_nmap || want_spec) em.iota = (unsigned*)(ws + L.em_iota);
+  if (wants_global(g) || em.iota) {
     float* partials = (float*)(ws + L.partials);
     dim3 grid(L.nblk, a->B);
-    k_bwd_global<S><<<grid, BWD_THREADS, 0, stream>>>(*a, *g, partials);
+    k_bwd_global<S><<<grid, BWD_THREADS, 0, stream>>>(*a, *g, partials, em);
     g_launches++;
+  }
+  if (wants_global(g)) {
+    float* partials = (float*)(ws + L.partials);
     GlobalOut out{};
     auto set = [&](int base, int n, const JrF32Out& t, const int* offs) {
       for (int j = 0; j < n; ++j) {
@@ -792,25 +886,23 @@ static int backward_impl(const JrRenderArgs* a, const JrGradArgs* g, cudaStream_
     k_bwd_global_final<<<NG, 128, 0, stream>>>(partials, a->B, L.nblk, out);
     g_launches++;
   }
-  if (S >= JR_GOURAUD_TEXTURE && g->d_texture.ptr) {
+  if (want_tex) {
     KeyedPlan p{};
     p.mode = MODE_TEXEL; p.per_pixel = 1; p.n_entries = total;
     p.keys_per_image = (long long)a->tex_w * a->tex_h;
     p.batched = g->d_texture.batch_stride != 0;
-    const long long nk = p.keys_per_image * (p.batched ? a->B : 1);
-    if (nk >= 0x7FFFFFFFLL) return JR_ERR_DIMS;
-    p.invalid_key = (unsigned)nk; p.C = 3; p.out = g->d_texture.ptr; p.out2 = nullptr;
+    p.invalid_key = em.inv_tex; p.C = 3; p.out = g->d_texture.ptr; p.out2 = nullptr;
+    p.pix_keys = em.key_tex; p.pix_vals = em.val_tex;
     rc = run_keyed<S, MODE_TEXEL, 3>(a, g, L, p, stream);
     if (rc != JR_OK) return rc;
   }
-  if (S >= JR_PHONG_REFLECTION && g->d_specular_map.ptr) {
+  if (want_spec) {
     KeyedPlan p{};
     p.mode = MODE_SPEC; p.per_pixel = 1; p.n_entries = total;
     p.keys_per_image = (long long)a->spec_w * a->spec_h;
     p.batched = g->d_specular_map.batch_stride != 0;
-    const long long nk = p.keys_per_image * (p.batched ? a->B : 1);
-    if (nk >= 0x7FFFFFFFLL) return JR_ERR_DIMS;
-    p.invalid_key = (unsigned)nk; p.C = 1; p.out = g->d_specular_map.ptr; p.out2 = nullptr;
+    p.invalid_key = em.inv_spec; p.C = 1; p.out = g->d_specular_map.ptr; p.out2 = nullptr;
+    p.pix_keys = em.key_spec; p.pix_vals = em.val_spec;
     rc = run_keyed<S, MODE_SPEC, 1>(a, g, L, p, stream);
     if (rc != JR_OK) return rc;
   }
@@ -840,14 +932,13 @@ static int backward_impl(const JrRenderArgs* a, const JrGradArgs* g, cudaStream_
     if (rc != JR_OK) return rc;
   }
   if (S == JR_PHONG_DARBOUX) {
-    if (g->d_normal_map.ptr) {
+    if (want_nmap) {
       KeyedPlan p{};
       p.mode = MODE_NMAP; p.per_pixel = 1; p.n_entries = total;
       p.keys_per_image = (long long)a->tex_w * a->tex_h;
       p.batched = g->d_normal_map.batch_stride != 0;
-      const long long nk = p.keys_per_image * (p.batched ? a->B : 1);
-      if (nk >= 0x7FFFFFFFLL) return JR_ERR_DIMS;
-      p.invalid_key = (unsigned)nk; p.C = 3; p.out = g->d_normal_map.ptr; p.out2 = nullptr;
+      p.invalid_key = em.inv_tex; p.C = 3; p.out = g->d_normal_map.ptr; p.out2 = nullptr;
+      p.pix_keys = em.key_tex; p.pix_vals = em.val_nmap;
       rc = run_keyed<S, MODE_NMAP, 3>(a, g, L, p, stream);
       if (rc != JR_OK) return rc;
     }

@@ -52,6 +52,9 @@ def main():
     ap.add_argument("--cfg", type=int, required=True, choices=(3, 4, 5))
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--size", type=str, default="", help="cfg 4/5: override WxH, e.g. 84x84")
+    ap.add_argument("--caps", type=int, default=0, help="cfg 4/5: override the number of capsules")
+    ap.add_argument("--profile", action="store_true", help="cfg 5: torch-profiler kernel table on stderr")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     out = {"cfg": args.cfg}
@@ -81,6 +84,9 @@ def main():
         else:
             W, H, n_caps = 480, 270, 17   # T = 3276
             B = args.batch or 128
+        if args.size:
+            W, H = (int(v) for v in args.size.split("x"))
+        n_caps = args.caps or n_caps
         sc = synthetic.brax_like_batch(B, n_capsules=n_caps, with_attributes=True)
         cam = synthetic.brax_cameras(sc["eye"], sc["target"], W, H)
         cam = type(cam)(*[t.to(dev) for t in cam])
@@ -119,6 +125,13 @@ def main():
                 loss.backward()
             ms_f, l_f = timeit(step_fwd, args.steps)
             ms, launches = timeit(step, args.steps)
+            if args.profile:
+                from torch.profiler import ProfilerActivity, profile
+                with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+                    for _ in range(3):
+                        step()
+                    torch.cuda.synchronize()
+                print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=30), file=sys.stderr)
             out.update(shader="phong_reflection_shadow fwd+bwd (grads: light, world_to_clip, shared diffuse atlas)",
                        W=W, H=H, B=B, T=synthetic.scene_sizes(n_caps)[1], ms_per_step=ms, ms_forward_only=ms_f,
                        images_per_s=B / ms * 1e3, launches=launches, launches_forward=l_f,
