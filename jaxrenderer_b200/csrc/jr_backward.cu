@@ -38,8 +38,15 @@ enum : int {
 enum : int { MODE_TEXEL = 0, MODE_SPEC = 1, MODE_POS = 2, MODE_NRM = 3,
               MODE_NMAP = 4, MODE_UV = 5, MODE_POS2 = 6 };  // phong_darboux: normal map, uv and tangent-triangle positions
 
+// Scene-global accumulators of one thread: a column of a [NG][BWD_THREADS] shared-memory array
+// (conflict-free; keeps 52 values out of the register file, which is what limits occupancy here).
+struct GAcc {
+  float* p;
+  __device__ __forceinline__ float& operator[](int j) const { return p[j * 256]; }
+};
+
 struct PixGrad {
-  float g[NG];
+  GAcc g;
   float d_tex[3];
   float d_sexp;
   float d_pos[3][3];
@@ -355,7 +362,7 @@ __device__ __forceinline__ void load_cotangent(const JrGradArgs& g, long long gi
 // ------------------------------------------------------------ global parameters
 constexpr int BWD_THREADS = 256;
 #ifndef JR_BWD_MIN_BLOCKS
-#define JR_BWD_MIN_BLOCKS 2  // caps k_bwd_global at 128 registers: 2 CTAs/SM beat 1 CTA with 233 registers (measured)
+#define JR_BWD_MIN_BLOCKS 3  // register cap of k_bwd_global (accumulators live in shared memory)
 #endif
 
 // Per-pixel outputs of the pixel pass for the one-entry-per-pixel keyed targets (diffuse texture,
@@ -376,9 +383,11 @@ template <int S>
 __global__ void __launch_bounds__(BWD_THREADS, JR_BWD_MIN_BLOCKS)
 k_bwd_global(const __grid_constant__ JrRenderArgs a, const __grid_constant__ JrGradArgs g, float* __restrict__ partials,
              const __grid_constant__ PixelEmit em) {
+  extern __shared__ float s_acc[];  // [NG][BWD_THREADS]
   const int b = blockIdx.y;
   const int npix = a.W * a.H;
   PixGrad o;
+  o.g.p = s_acc + threadIdx.x;
 #pragma unroll
   for (int j = 0; j < NG; ++j) o.g[j] = 0.f;
   for (int pix = blockIdx.x * BWD_THREADS + threadIdx.x; pix < npix; pix += gridDim.x * BWD_THREADS) {
@@ -569,7 +578,7 @@ k_bwd_segreduce(const __grid_constant__ JrRenderArgs a, const __grid_constant__ 
       shade_pixel<S>(a, b, x, y, a.tri_id[gi], f);
       float d_zw, d_col[3];
       load_cotangent(g, gi, S != JR_DEPTH, d_zw, d_col);
-      PixGrad o;
+      PixGrad o; o.g.p = nullptr;
       backprop_pixel<S, false, (MODE == MODE_TEXEL || MODE == MODE_SPEC || MODE == MODE_NMAP),
                      (MODE == MODE_POS || MODE == MODE_NRM || MODE == MODE_UV || MODE == MODE_POS2)>(
           a, b, f, d_zw, d_col, o);
@@ -859,7 +868,8 @@ static int backward_impl(const JrRenderArgs* a, const JrGradArgs* g, cudaStream_
   if (wants_global(g) || em.iota) {
     float* partials = (float*)(ws + L.partials);
     dim3 grid(L.nblk, a->B);
-    k_bwd_global<S><<<grid, BWD_THREADS, 0, stream>>>(*a, *g, partials, em);
+    cudaFuncSetAttribute(k_bwd_global<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, NG * BWD_THREADS * 4);
+    k_bwd_global<S><<<grid, BWD_THREADS, NG * BWD_THREADS * 4, stream>>>(*a, *g, partials, em);
     g_launches++;
   }
   if (wants_global(g)) {
