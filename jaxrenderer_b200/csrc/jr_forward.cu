@@ -301,9 +301,9 @@ int jr_render_forward(const JrRenderArgs* a, jr_stream_t stream_) {
   if (ctas > 2147483647LL) return JR_ERR_DIMS;
   static std::once_flag attr_once;
   std::call_once(attr_once, [] {
-    cudaFuncSetAttribute(k_vis2<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(k_vis2<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(k_vis2<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_vis2<true, true, V2_K32_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_vis2<true, false, V2_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_vis2<false, false, V2_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(k_raster_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     cudaFuncSetAttribute(k_raster_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   });
@@ -332,9 +332,9 @@ int jr_render_forward(const JrRenderArgs* a, jr_stream_t stream_) {
     // depth shader without a triangle-id output: z-only 32-bit keys (half the shared memory, native atomic min)
     const bool k32 = depth && !a->tri_id && !g_key64;
     const V2Layout L = v2_layout(tw, th, k32 ? 4 : 8);
-    if (k32) k_vis2<true, true><<<(unsigned)ctas, V2_THREADS, L.total, stream>>>(*a, tw, th, nx, ny);
-    else if (depth) k_vis2<true, false><<<(unsigned)ctas, V2_THREADS, L.total, stream>>>(*a, tw, th, nx, ny);
-    else k_vis2<false, false><<<(unsigned)ctas, V2_THREADS, L.total, stream>>>(*a, tw, th, nx, ny);
+    if (k32) k_vis2<true, true, V2_K32_THREADS><<<(unsigned)ctas, V2_K32_THREADS, L.total, stream>>>(*a, tw, th, nx, ny);
+    else if (depth) k_vis2<true, false, V2_THREADS><<<(unsigned)ctas, V2_THREADS, L.total, stream>>>(*a, tw, th, nx, ny);
+    else k_vis2<false, false, V2_THREADS><<<(unsigned)ctas, V2_THREADS, L.total, stream>>>(*a, tw, th, nx, ny);
   }
   jr::g_launches++;
   if (!depth) {

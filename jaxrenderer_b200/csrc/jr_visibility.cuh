@@ -31,6 +31,10 @@
 namespace jr {
 
 constexpr int V2_THREADS = 256;
+#ifndef JR_K32_THREADS
+#define JR_K32_THREADS 256
+#endif
+constexpr int V2_K32_THREADS = JR_K32_THREADS;  // CTA size of the z-only-key variant
 constexpr int V2_BIGCAP = 32;
 #ifndef JR_SMALL_AREA
 #define JR_SMALL_AREA 16
@@ -155,8 +159,8 @@ struct V2Big {  // 64 bytes
   int pad;
 };
 
-template <bool DEPTH, bool K32>
-__global__ void __launch_bounds__(V2_THREADS, K32 ? V2_K32_CTAS : JR_K64_CTAS)
+template <bool DEPTH, bool K32, int THREADS>
+__global__ void __launch_bounds__(THREADS, K32 ? V2_K32_CTAS : JR_K64_CTAS)
 k_vis2(const __grid_constant__ JrRenderArgs a, int tile_w, int tile_h, int tiles_x, int tiles_y) {
   static_assert(DEPTH || !K32, "z-only keys are for the depth shader");
   extern __shared__ __align__(16) unsigned char smem[];
@@ -192,11 +196,11 @@ k_vis2(const __grid_constant__ JrRenderArgs a, int tile_w, int tile_h, int tiles
     // all-ones = empty, whatever the key width (the layout rounds the buffer up to 16 bytes)
     const int n16 = (int)(L.xs >> 4);
     uint4* k4 = reinterpret_cast<uint4*>(smem + L.keys);
-    for (int i = tid; i < n16; i += V2_THREADS) k4[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
+    for (int i = tid; i < n16; i += THREADS) k4[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
   }
   __syncthreads();
-  for (int i = tid; i < tw; i += V2_THREADS) xs[i] = ((float)(tx0 + i) - s_vp[3]) / s_vp[0];
-  for (int i = tid; i < th; i += V2_THREADS) ys[i] = ((float)(ty0 + i) - s_vp[7]) / s_vp[5];
+  for (int i = tid; i < tw; i += THREADS) xs[i] = ((float)(tx0 + i) - s_vp[3]) / s_vp[0];
+  for (int i = tid; i < th; i += THREADS) ys[i] = ((float)(ty0 + i) - s_vp[7]) / s_vp[5];
   __syncthreads();
 
   const float vp00 = s_vp[0], vp03 = s_vp[3], vp11 = s_vp[5], vp13 = s_vp[7];
@@ -390,7 +394,7 @@ k_vis2(const __grid_constant__ JrRenderArgs a, int tile_w, int tile_h, int tiles
       const int qx0 = q.x0, qy0 = q.y0, bh = q.y1 - q.y0 + 1;
       const int n = (q.x1 - q.x0 + 1) * bh;
       const float rbh = 1.0f / (float)bh;
-      for (int i = tid; i < n; i += V2_THREADS) {
+      for (int i = tid; i < n; i += THREADS) {
         const int dx = (int)(((float)i + 0.5f) * rbh);
         const int x = qx0 + dx, y = qy0 + (i - dx * bh);
         const float xn = xs[x], yn = ys[y];
@@ -426,7 +430,7 @@ k_vis2(const __grid_constant__ JrRenderArgs a, int tile_w, int tile_h, int tiles
     const int H = a.H;
     const float rH = 1.0f / (float)H;
     typedef typename std::conditional<K32, uint32_t, unsigned long long>::type KeyT;
-    for (int i = tid; i < npix_img / PX; i += V2_THREADS) {
+    for (int i = tid; i < npix_img / PX; i += THREADS) {
       KeyT k[PX];
       if (K32) {
         const uint4 kk = reinterpret_cast<const uint4*>(keys32)[i];
@@ -496,7 +500,7 @@ k_vis2(const __grid_constant__ JrRenderArgs a, int tile_w, int tile_h, int tiles
       }
     }
   } else {
-    const int dq = V2_THREADS / th, dr = V2_THREADS - dq * th;
+    const int dq = THREADS / th, dr = THREADS - dq * th;
     int lx = tid / th, ly = tid - lx * th;
     for (; lx < tw; lx += dq, ly += dr) {
       if (ly >= th) { ly -= th; ++lx; if (lx >= tw) break; }
