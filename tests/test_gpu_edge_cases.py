@@ -188,3 +188,44 @@ def test_light_camera_kernel_matches_torch_builders(batched):
     for name, a, b in zip(fused._fields, fused, ref):
         b = b.expand_as(a) if b.ndim < a.ndim else b
         torch.testing.assert_close(a, b, rtol=2e-5, atol=1e-6, msg=lambda m: f"{name}: {m}")
+
+
+# ------------------------------------------------------------------ CUDA graph capture of the facade
+@pytest.mark.gpu
+def test_facade_captures_into_a_cuda_graph():
+    """After warm-up the whole ``get_camera_image`` call neither allocates outside the caching allocator nor
+    synchronises, so it captures into one CUDA graph; the replay re-reads the (updated) input tensors."""
+    from tests.helpers import load_brax_fixture
+
+    dev = torch.device("cuda", 0)
+    objs, cam = load_brax_fixture()
+    objs = [jr.ModelObject(model=type(o.model)(*[t.to(dev) for t in o.model]), local_scaling=o.local_scaling.to(dev),
+                           transform=o.transform.to(dev), double_sided=o.double_sided.to(dev)) for o in objs]
+    cam = type(cam)(*[v.to(dev) if isinstance(v, torch.Tensor) else v for v in cam])._replace(viewWidth=84, viewHeight=84)
+    light = jr.LightParameters()
+    sp = jr.ShadowParameters(centre=cam.target)
+
+    def full():
+        return jr.Renderer.get_camera_image(objs, light, cam, 84, 84, shadow_param=sp)
+
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            full()
+    torch.cuda.current_stream(dev).wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        img = full()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(img, full())
+    # move the robot: same graph, new transforms
+    with torch.no_grad():
+        for o in objs[1:]:
+            o.transform[..., 2, 3] += 0.05
+    graph.replay()
+    torch.cuda.synchronize()
+    moved = full()
+    assert torch.equal(img, moved)
+    assert img.shape == (4, 84, 84, 3) and bool(torch.isfinite(img).all())

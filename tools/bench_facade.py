@@ -54,6 +54,8 @@ def main():
     ap.add_argument("--height", type=int, default=84)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--profile", action="store_true")
+    ap.add_argument("--graph", action="store_true",
+                    help="also capture the whole facade call in a CUDA graph and time its replay")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     B, W, H = args.batch, args.width, args.height
@@ -90,6 +92,23 @@ def main():
     for name, fn in (("total", full), ("merge", merge), ("camera", camera), ("render", render)):
         out[f"ms_{name}"], out[f"ms_{name}_host"] = (round(v, 4) for v in timeit(fn, args.steps))
     out["images_per_s"] = B / out["ms_total"] * 1e3
+    if args.graph:
+        # launch-bound at small batches: the call is allocation- and sync-free after warm-up, so it captures
+        # into one CUDA graph (inputs are read from the same device tensors at every replay)
+        graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            full()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        with torch.cuda.graph(graph):
+            img = full()
+        ref = full()
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(img, ref), "graph replay differs from the eager call"
+        out["ms_total_graph"], out["ms_total_graph_host"] = (round(v, 4) for v in timeit(graph.replay, args.steps))
+        out["images_per_s_graph"] = B / out["ms_total_graph"] * 1e3
     print(json.dumps(out))
     if args.profile:
         from torch.profiler import ProfilerActivity, profile
