@@ -42,7 +42,7 @@ def test_shard_ranges_cover_the_batch():
 
 def test_gloo_world2_shared_grad_allreduce():
     world = 2
-    mgr = mp.Manager()
+    mgr = mp.get_context("spawn").Manager()
     out = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
     assert out[0] == (True, 4) and out[1] == (True, 3)
