@@ -20,6 +20,10 @@ namespace jr {
 constexpr int TL_TILE = 64;
 constexpr int TL_THREADS = 256;
 constexpr int TL_BIGCAP = 32;
+#ifndef JR_TL_BIG_AREA
+#define JR_TL_BIG_AREA 1024
+#endif
+constexpr int TL_BIG_AREA = JR_TL_BIG_AREA;  // bbox (clipped to the tile) above this: the whole CTA sweeps it
 constexpr int TL_MASKCAP = 2048;  // bitmask words staged in shared memory per chunk (65536 triangles)
 
 struct __align__(16) TriRecord {  // 64 bytes
@@ -229,9 +233,23 @@ k_raster_tile(const __grid_constant__ JrRenderArgs a, const TriRecord* __restric
     }
     const int bw = x1 - x0 + 1, bh = y1 - y0 + 1;
     const int area = (valid && bw > 0 && bh > 0) ? bw * bh : 0;
-    // everything above the per-lane size is rasterised by the whole warp (hierarchically from
-    // V2_HIER_AREA pixels); with hundreds of triangles per tile the warps stay balanced
-    const bool is_medium = area > V2_SMALL_AREA;
+    // above the per-lane size the whole warp rasterises the triangle (hierarchically from V2_HIER_AREA
+    // pixels); triangles covering a large part of the tile (the ground plane: most tiles of a Brax
+    // frame hold nothing else) are queued for the whole CTA -- one warp sweeping 2 x 4096 pixels while
+    // the other seven idle was the critical path of those tiles
+    bool is_medium = area > V2_SMALL_AREA;
+    if (area > TL_BIG_AREA) {
+      const int slot = atomicAdd(&bigq_n, 1);
+      if (slot < TL_BIGCAP) {
+        V2Big& q = bigq[slot];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) q.inv[k] = inv[k];
+        q.zc[0] = zc[0]; q.zc[1] = zc[1]; q.zc[2] = zc[2];
+        q.tri = t;
+        q.x0 = (short)x0; q.x1 = (short)x1; q.y0 = (short)y0; q.y1 = (short)y1;
+        is_medium = false;
+      }
+    }
     if (area > 0 && area <= V2_SMALL_AREA) {
       for (int x = x0; x <= x1; ++x)
         for (int y = y0; y <= y1; ++y) put(x, y, inv, zc, (unsigned)t);

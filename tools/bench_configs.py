@@ -54,7 +54,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--size", type=str, default="", help="cfg 4/5: override WxH, e.g. 84x84")
     ap.add_argument("--caps", type=int, default=0, help="cfg 4/5: override the number of capsules")
-    ap.add_argument("--profile", action="store_true", help="cfg 5: torch-profiler kernel table on stderr")
+    ap.add_argument("--profile", action="store_true", help="cfg 4/5: torch-profiler kernel table on stderr")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     out = {"cfg": args.cfg}
@@ -97,6 +97,13 @@ def main():
             def step():
                 jr.Renderer.render(model, NOTEBOOK_LIGHT, cam, bufs, shadow_param=sp, inplace=True)
             ms, launches = timeit(step, args.steps)
+            if args.profile:
+                from torch.profiler import ProfilerActivity, profile
+                with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+                    for _ in range(3):
+                        step()
+                    torch.cuda.synchronize()
+                print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=14), file=sys.stderr)
             out.update(shader="phong_reflection_shadow", W=W, H=H, B=B, T=synthetic.scene_sizes(n_caps)[1],
                        ms_per_step=ms, images_per_s=B / ms * 1e3, launches=launches)
         else:
