@@ -304,8 +304,9 @@ int jr_render_forward(const JrRenderArgs* a, jr_stream_t stream_) {
     cudaFuncSetAttribute(k_vis2<true, true, V2_K32_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(k_vis2<true, false, V2_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(k_vis2<false, false, V2_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(k_raster_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    cudaFuncSetAttribute(k_raster_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(k_raster_tile<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(k_raster_tile<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(k_raster_tile<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   });
   const bool depth = a->shader == JR_DEPTH;
   if (nx * ny > 1 && !g_no_bins) {
@@ -325,9 +326,11 @@ int jr_render_forward(const JrRenderArgs* a, jr_stream_t stream_) {
     }
     const long long ctas2 = (long long)a->B * TLy.tiles;
     if (ctas2 > 2147483647LL) return JR_ERR_DIMS;
-    const size_t sm = tl_smem().total;
-    if (depth) k_raster_tile<true><<<(unsigned)ctas2, TL_THREADS, sm, stream>>>(*a, recs, masks, TLy);
-    else k_raster_tile<false><<<(unsigned)ctas2, TL_THREADS, sm, stream>>>(*a, recs, masks, TLy);
+    const bool k32t = depth && !a->tri_id && !g_key64;
+    const size_t sm = tl_smem(k32t ? 4 : 8).total;
+    if (k32t) k_raster_tile<true, true><<<(unsigned)ctas2, TL_THREADS, sm, stream>>>(*a, recs, masks, TLy);
+    else if (depth) k_raster_tile<true, false><<<(unsigned)ctas2, TL_THREADS, sm, stream>>>(*a, recs, masks, TLy);
+    else k_raster_tile<false, false><<<(unsigned)ctas2, TL_THREADS, sm, stream>>>(*a, recs, masks, TLy);
   } else {
     // depth shader without a triangle-id output: z-only 32-bit keys (half the shared memory, native atomic min)
     const bool k32 = depth && !a->tri_id && !g_key64;

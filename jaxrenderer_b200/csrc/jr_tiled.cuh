@@ -24,7 +24,16 @@ constexpr int TL_BIGCAP = 32;
 #define JR_TL_BIG_AREA 1024
 #endif
 constexpr int TL_BIG_AREA = JR_TL_BIG_AREA;  // bbox (clipped to the tile) above this: the whole CTA sweeps it
-constexpr int TL_MASKCAP = 2048;  // bitmask words staged in shared memory per chunk (65536 triangles)
+#ifndef JR_TL_MASKCAP
+#define JR_TL_MASKCAP 1024
+#endif
+#ifndef JR_TL_CTAS
+#define JR_TL_CTAS 4
+#endif
+#ifndef JR_TL_K32_CTAS
+#define JR_TL_K32_CTAS 5
+#endif
+constexpr int TL_MASKCAP = JR_TL_MASKCAP;  // bitmask words staged in shared memory per chunk (x32 triangles)
 
 struct __align__(16) TriRecord {  // 64 bytes
   float inv[9];
@@ -150,10 +159,10 @@ k_setup_bin(const __grid_constant__ JrRenderArgs a, TriRecord* __restrict__ recs
 }
 
 struct TLSmem { size_t keys, xs, ys, ring, bigq, mask, total; };
-__host__ __device__ inline TLSmem tl_smem() {
+__host__ __device__ inline TLSmem tl_smem(int key_bytes) {
   TLSmem S;
   S.keys = 0;
-  S.xs = (size_t)TL_TILE * TL_TILE * 8;
+  S.xs = (size_t)TL_TILE * TL_TILE * key_bytes;
   S.ys = S.xs + TL_TILE * 4;
   S.ring = S.ys + TL_TILE * 4;
   S.bigq = S.ring + (TL_THREADS / 32) * 64 * 4;
@@ -162,13 +171,16 @@ __host__ __device__ inline TLSmem tl_smem() {
   return S;
 }
 
-template <bool DEPTH>
-__global__ void __launch_bounds__(TL_THREADS)
+// K32: depth shader without a triangle-id output (shadow passes) -- z-only 32-bit keys, see k_vis2.
+template <bool DEPTH, bool K32>
+__global__ void __launch_bounds__(TL_THREADS, K32 ? JR_TL_K32_CTAS : JR_TL_CTAS)
 k_raster_tile(const __grid_constant__ JrRenderArgs a, const TriRecord* __restrict__ recs,
               const unsigned* __restrict__ masks, TiledLayout L) {
+  static_assert(DEPTH || !K32, "z-only keys are for the depth shader");
   extern __shared__ __align__(16) unsigned char smem[];
-  const TLSmem S = tl_smem();
+  const TLSmem S = tl_smem(K32 ? 4 : 8);
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem + S.keys);
+  uint32_t* keys32 = reinterpret_cast<uint32_t*>(smem + S.keys);
   float* xs = reinterpret_cast<float*>(smem + S.xs);
   float* ys = reinterpret_cast<float*>(smem + S.ys);
   V2Big* bigq = reinterpret_cast<V2Big*>(smem + S.bigq);
@@ -196,8 +208,8 @@ k_raster_tile(const __grid_constant__ JrRenderArgs a, const TriRecord* __restric
     tri0_flag = 0;
   }
   {
-    ulonglong2* k2 = reinterpret_cast<ulonglong2*>(keys);
-    for (int i = tid; i < TL_TILE * TL_TILE / 2; i += TL_THREADS) k2[i] = make_ulonglong2(~0ull, ~0ull);
+    uint4* k4 = reinterpret_cast<uint4*>(smem + S.keys);
+    for (int i = tid; i < (int)(S.xs >> 4); i += TL_THREADS) k4[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
   }
   __syncthreads();
   for (int i = tid; i < tw; i += TL_THREADS) xs[i] = ((float)(tx0 + i) - s_vp[3]) / s_vp[0];
@@ -213,7 +225,7 @@ k_raster_tile(const __grid_constant__ JrRenderArgs a, const TriRecord* __restric
     if (c0 >= 0.f && c1 >= 0.f && c2 >= 0.f) {
       const float z = (c0 * zc[0] + c1 * zc[1]) + c2 * zc[2];
       const float zw = z * vp22 + vp23;
-      key_min(keys_saddr + (uint32_t)(x * TL_TILE + y) * 8u, ((unsigned long long)orderable(zw) << 32) | tri);
+      put_key<K32>(keys_saddr, x * TL_TILE + y, zw, tri);
     }
   };
 
@@ -269,7 +281,7 @@ k_raster_tile(const __grid_constant__ JrRenderArgs a, const TriRecord* __restric
       const int n = __shfl_sync(0xffffffffu, area, src);
       if (n >= V2_HIER_AREA) {
         const int sx1 = __shfl_sync(0xffffffffu, x1, src), sy1 = __shfl_sync(0xffffffffu, y1, src);
-        raster_hier_warp<false>(binv, bzc, btri, sx0, sy0, sx1, sy1, lane, xs, ys, keys_saddr, TL_TILE, vp22, vp23);
+        raster_hier_warp<K32>(binv, bzc, btri, sx0, sy0, sx1, sy1, lane, xs, ys, keys_saddr, TL_TILE, vp22, vp23);
       } else {
         const float rbh = 1.0f / (float)sbh;
         for (int i = lane; i < n; i += 32) {
@@ -344,9 +356,15 @@ k_raster_tile(const __grid_constant__ JrRenderArgs a, const TriRecord* __restric
         if (c0 >= 0.f && c1 >= 0.f && c2 >= 0.f) {
           const float z = (c0 * z0 + c1 * z1) + c2 * z2;
           const float zw = z * vp22 + vp23;
-          const unsigned long long key = ((unsigned long long)orderable(zw) << 32) | tri;
-          unsigned long long* slot = &keys[x * TL_TILE + y];
-          if (key < *slot) *slot = key;
+          if (K32) {
+            const uint32_t key = min(orderable(zw), 0xFFFFFFFEu);
+            uint32_t* slot = &keys32[x * TL_TILE + y];
+            if (key < *slot) *slot = key;
+          } else {
+            const unsigned long long key = ((unsigned long long)orderable(zw) << 32) | tri;
+            unsigned long long* slot = &keys[x * TL_TILE + y];
+            if (key < *slot) *slot = key;
+          }
         }
       }
       __syncthreads();
@@ -359,12 +377,22 @@ k_raster_tile(const __grid_constant__ JrRenderArgs a, const TriRecord* __restric
   for (int i = tid; i < tw * TL_TILE; i += TL_THREADS) {
     const int lx = i >> 6, ly = i & 63;
     if (ly >= th) continue;
-    const unsigned long long key = keys[i];
     const long long pix = (long long)(tx0 + lx) * a.H + (ty0 + ly);
     int tri = -1;
-    if (key != ~0ull) {
-      tri = (int)(unsigned)(key & 0xFFFFFFFFull);
-      if (DEPTH) z_out[pix] = from_orderable((uint32_t)(key >> 32));
+    bool covered;
+    if (K32) {
+      const uint32_t key = keys32[i];
+      covered = key != ~0u;
+      if (covered) z_out[pix] = from_orderable(key);
+    } else {
+      const unsigned long long key = keys[i];
+      covered = key != ~0ull;
+      if (covered) {
+        tri = (int)(unsigned)(key & 0xFFFFFFFFull);
+        if (DEPTH) z_out[pix] = from_orderable((uint32_t)(key >> 32));
+      }
+    }
+    if (covered) {
     } else if (use0) {
       float c[3];
       clip_coef(tri0.inv, xs[lx], ys[ly], c);
