@@ -377,9 +377,15 @@ struct PixelEmit {
   float* val_nmap;      // (B*W*H,3) d colour / d normal-map texel (phong_darboux)
   unsigned inv_tex, inv_spec;            // "no contribution" keys
   long long per_image_tex, per_image_spec;  // key offset per image when the target is batched, else 0
+  // three-entries-per-pixel targets (one per triangle corner): values only, keys come from k_bwd_keys
+  float* val_pos;       // (B*W*H,3,pos_c) d / d position (+ d / d vertex colour for gouraud: pos_c = 6)
+  float* val_nrm;       // (B*W*H,3,3)
+  float* val_uv;        // (B*W*H,3,2)  phong_darboux
+  float* val_pos2;      // (B*W*H,3,3)  phong_darboux: tangent-frame triangle
+  int pos_c;
 };
 
-template <int S>
+template <int S, bool WV>
 __global__ void __launch_bounds__(BWD_THREADS, JR_BWD_MIN_BLOCKS)
 k_bwd_global(const __grid_constant__ JrRenderArgs a, const __grid_constant__ JrGradArgs g, float* __restrict__ partials,
              const __grid_constant__ PixelEmit em) {
@@ -404,7 +410,28 @@ k_bwd_global(const __grid_constant__ JrRenderArgs a, const __grid_constant__ JrG
     shade_pixel<S>(a, b, x, y, tri, f);
     float d_zw, d_col[3];
     load_cotangent(g, gi, S != JR_DEPTH, d_zw, d_col);
-    backprop_pixel<S, true, true, false>(a, b, f, d_zw, d_col, o);
+    backprop_pixel<S, true, true, WV>(a, b, f, d_zw, d_col, o);
+    if (WV) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        if (em.val_pos) {
+          float* dst = em.val_pos + (gi * 3 + k) * em.pos_c;
+          dst[0] = o.d_pos[k][0]; dst[1] = o.d_pos[k][1]; dst[2] = o.d_pos[k][2];
+          if (S == JR_GOURAUD && em.pos_c == 6) { dst[3] = o.d_col[k][0]; dst[4] = o.d_col[k][1]; dst[5] = o.d_col[k][2]; }
+        }
+        if (S != JR_DEPTH && em.val_nrm) {
+          float* dst = em.val_nrm + (gi * 3 + k) * 3;
+          dst[0] = o.d_nrm[k][0]; dst[1] = o.d_nrm[k][1]; dst[2] = o.d_nrm[k][2];
+        }
+        if (S == JR_PHONG_DARBOUX) {
+          if (em.val_uv) { em.val_uv[(gi * 3 + k) * 2] = o.d_uv[k][0]; em.val_uv[(gi * 3 + k) * 2 + 1] = o.d_uv[k][1]; }
+          if (em.val_pos2) {
+            float* dst = em.val_pos2 + (gi * 3 + k) * 3;
+            dst[0] = o.d_pos2[k][0]; dst[1] = o.d_pos2[k][1]; dst[2] = o.d_pos2[k][2];
+          }
+        }
+      }
+    }
     if (S >= JR_GOURAUD_TEXTURE) {
       if (em.key_tex) {
         bool contributes = f.texel >= 0;
@@ -499,20 +526,7 @@ k_bwd_keys(const __grid_constant__ JrRenderArgs a, KeyedPlan plan, unsigned* __r
     const long long gi = (long long)b * npix + pix;
     const int tri = a.tri_id[gi];
     const unsigned boff = plan.batched ? (unsigned)((long long)b * plan.keys_per_image) : 0u;
-    if (MODE == MODE_TEXEL || MODE == MODE_SPEC || MODE == MODE_NMAP) {
-      unsigned key = plan.invalid_key;
-      if (tri >= 0) {
-        const int x = pix / a.H, y = pix - x * a.H;
-        Frag f;
-        shade_pixel<S>(a, b, x, y, tri, f);
-        const long long k = (MODE == MODE_SPEC) ? f.spec_idx : f.texel;
-        bool contributes = true;
-        if (S == JR_PHONG || S == JR_PHONG_DARBOUX) contributes = f.ok;
-        if (k >= 0 && contributes) key = boff + (unsigned)k;
-      }
-      keys[gi] = key;
-      vals[gi] = (unsigned)gi;
-    } else {
+    {
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
         unsigned key = plan.invalid_key;
@@ -544,7 +558,8 @@ struct Carry {
   float first_val[C], last_val[C];
 };
 
-// One thread per sorted entry, fixed chunks of 256 entries per CTA.
+// One thread per sorted entry (it gathers the value the pixel pass emitted for its pixel / corner),
+// fixed chunks of 256 entries per CTA.
 template <int S, int MODE, int C>
 __global__ void __launch_bounds__(256)
 k_bwd_segreduce(const __grid_constant__ JrRenderArgs a, const __grid_constant__ JrGradArgs g, KeyedPlan plan,
@@ -554,7 +569,6 @@ k_bwd_segreduce(const __grid_constant__ JrRenderArgs a, const __grid_constant__ 
   __shared__ float s_val[C][256];
   const int tid = threadIdx.x;
   const long long i = (long long)blockIdx.x * 256 + tid;
-  const long long npix = (long long)a.W * a.H;
   unsigned key = plan.invalid_key;
   float v[C];
 #pragma unroll
@@ -562,54 +576,11 @@ k_bwd_segreduce(const __grid_constant__ JrRenderArgs a, const __grid_constant__ 
   if (i < plan.n_entries) {
     key = keys[i];
     if (key != plan.invalid_key && plan.pix_vals) {
-      const long long gi = vals[i];
-#pragma unroll
-      for (int c = 0; c < C; ++c) v[c] = plan.pix_vals[gi * C + c];
-    } else if (key != plan.invalid_key) {
       const unsigned payload = vals[i];
-      long long gi;
-      int corner = 0;
-      if (MODE == MODE_TEXEL || MODE == MODE_SPEC || MODE == MODE_NMAP) gi = payload;
-      else { gi = payload >> 2; corner = payload & 3; }
-      const int b = (int)((unsigned)gi / (unsigned)npix);  // gi < 2^30 (checked by the host side)
-      const int pix = (int)(gi - (long long)b * npix);
-      const int x = pix / a.H, y = pix - x * a.H;
-      Frag f;
-      shade_pixel<S>(a, b, x, y, a.tri_id[gi], f);
-      float d_zw, d_col[3];
-      load_cotangent(g, gi, S != JR_DEPTH, d_zw, d_col);
-      PixGrad o; o.g.p = nullptr;
-      backprop_pixel<S, false, (MODE == MODE_TEXEL || MODE == MODE_SPEC || MODE == MODE_NMAP),
-                     (MODE == MODE_POS || MODE == MODE_NRM || MODE == MODE_UV || MODE == MODE_POS2)>(
-          a, b, f, d_zw, d_col, o);
-      if (S == JR_PHONG_DARBOUX) {
-        if (MODE == MODE_NMAP) { v[0] = o.d_nmap[0]; v[1] = o.d_nmap[1]; v[2] = o.d_nmap[2]; }
-        if (MODE == MODE_UV) {
+      // one entry per pixel: payload = pixel; one per corner: payload = pixel * 4 + corner
+      const long long e = (plan.per_pixel == 1) ? (long long)payload : (long long)(payload >> 2) * 3 + (payload & 3);
 #pragma unroll
-          for (int k = 0; k < 3; ++k)
-            if (k == corner) { v[0] = o.d_uv[k][0]; v[1] = o.d_uv[k][1]; }
-        }
-        if (MODE == MODE_POS2) {
-#pragma unroll
-          for (int k = 0; k < 3; ++k)
-            if (k == corner) { v[0] = o.d_pos2[k][0]; v[1] = o.d_pos2[k][1]; v[2] = o.d_pos2[k][2]; }
-        }
-      }
-      if (MODE == MODE_TEXEL) { v[0] = o.d_tex[0]; v[1] = o.d_tex[1]; v[2] = o.d_tex[2]; }
-      if (MODE == MODE_SPEC) v[0] = o.d_sexp;
-      if (MODE == MODE_POS) {
-#pragma unroll
-        for (int k = 0; k < 3; ++k)
-          if (k == corner) {
-#pragma unroll
-            for (int c = 0; c < 3; ++c) { v[c] = o.d_pos[k][c]; if (C > 3) v[3 + c] = o.d_col[k][c]; }
-          }
-      }
-      if (MODE == MODE_NRM) {
-#pragma unroll
-        for (int k = 0; k < 3; ++k)
-          if (k == corner) { v[0] = o.d_nrm[k][0]; v[1] = o.d_nrm[k][1]; v[2] = o.d_nrm[k][2]; }
-      }
+      for (int c = 0; c < C; ++c) v[c] = plan.pix_vals[e * C + c];
     }
   }
   s_key[tid] = key;
@@ -743,6 +714,8 @@ struct BwdLayout {
   int nblk;             // global pass blocks per image
   size_t partials, keys_a, keys_b, vals_a, vals_b, cub_temp, carry, total;
   size_t em_iota, em_key_tex, em_key_spec, em_val_tex, em_val_spec, em_val_nmap;  // PixelEmit buffers
+  size_t em_val_pos, em_val_nrm, em_val_uv, em_val_pos2;
+  int pos_c;
   size_t cub_bytes;
   long long max_entries;
 };
@@ -787,6 +760,16 @@ static BwdLayout bwd_layout(const JrRenderArgs* a, const JrGradArgs* g) {
     if (g->d_specular_map.ptr) {
       L.em_key_spec = off; off += align256(np * 4);
       L.em_val_spec = off; off += align256(np * 4);
+    }
+  }
+  if (keyed3) {
+    const size_t np = (size_t)npix * a->B;
+    L.pos_c = (a->shader == JR_GOURAUD && g->d_colour.ptr) ? 6 : 3;
+    if (g->d_position.ptr || g->d_colour.ptr) { L.em_val_pos = off; off += align256(np * 3 * L.pos_c * 4); }
+    if (g->d_normal.ptr) { L.em_val_nrm = off; off += align256(np * 36); }
+    if (a->shader == JR_PHONG_DARBOUX) {
+      if (g->d_uv.ptr) { L.em_val_uv = off; off += align256(np * 24); }
+      if (g->d_position.ptr) { L.em_val_pos2 = off; off += align256(np * 36); }
     }
   }
   L.total = off;
@@ -865,11 +848,28 @@ static int backward_impl(const JrRenderArgs* a, const JrGradArgs* g, cudaStream_
     em.per_image_spec = batched ? per : 0;
   }
   if (want_tex || want_nmap || want_spec) em.iota = (unsigned*)(ws + L.em_iota);
-  if (wants_global(g) || em.iota) {
+  const bool want_pos = g->d_position.ptr || (S == JR_GOURAUD && g->d_colour.ptr);
+  const bool want_nrm = S != JR_DEPTH && g->d_normal.ptr;
+  const bool want_uv = S == JR_PHONG_DARBOUX && g->d_uv.ptr;
+  const bool want_vertex = want_pos || want_nrm || want_uv;
+  if (want_pos) {
+    if (!g->d_position.ptr) return JR_ERR_UNSUPPORTED;  // d_colour alone: ask for d_position too
+    em.val_pos = (float*)(ws + L.em_val_pos);
+    em.pos_c = L.pos_c;
+    if (S == JR_PHONG_DARBOUX) em.val_pos2 = (float*)(ws + L.em_val_pos2);
+  }
+  if (want_nrm) em.val_nrm = (float*)(ws + L.em_val_nrm);
+  if (want_uv) em.val_uv = (float*)(ws + L.em_val_uv);
+  if (wants_global(g) || em.iota || want_vertex) {
     float* partials = (float*)(ws + L.partials);
     dim3 grid(L.nblk, a->B);
-    cudaFuncSetAttribute(k_bwd_global<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, NG * BWD_THREADS * 4);
-    k_bwd_global<S><<<grid, BWD_THREADS, NG * BWD_THREADS * 4, stream>>>(*a, *g, partials, em);
+    if (want_vertex) {
+      cudaFuncSetAttribute(k_bwd_global<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NG * BWD_THREADS * 4);
+      k_bwd_global<S, true><<<grid, BWD_THREADS, NG * BWD_THREADS * 4, stream>>>(*a, *g, partials, em);
+    } else {
+      cudaFuncSetAttribute(k_bwd_global<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NG * BWD_THREADS * 4);
+      k_bwd_global<S, false><<<grid, BWD_THREADS, NG * BWD_THREADS * 4, stream>>>(*a, *g, partials, em);
+    }
     g_launches++;
   }
   if (wants_global(g)) {
@@ -924,10 +924,10 @@ static int backward_impl(const JrRenderArgs* a, const JrGradArgs* g, cudaStream_
     p.batched = bs != 0;
     const long long nk = p.keys_per_image * (p.batched ? a->B : 1);
     if (nk >= 0x7FFFFFFFLL || p.n_entries >= 0x7FFFFFFFLL) return JR_ERR_DIMS;
-    p.invalid_key = (unsigned)nk; p.C = 6;
+    p.invalid_key = (unsigned)nk; p.C = L.pos_c;
     p.out = g->d_position.ptr; p.out2 = (S == JR_GOURAUD) ? g->d_colour.ptr : nullptr;
-    if (!p.out) return JR_ERR_UNSUPPORTED;  // d_colour alone: ask for d_position too
-    rc = run_keyed<S, MODE_POS, 6>(a, g, L, p, stream);
+    p.pix_vals = em.val_pos;
+    rc = (L.pos_c == 6) ? run_keyed<S, MODE_POS, 6>(a, g, L, p, stream) : run_keyed<S, MODE_POS, 3>(a, g, L, p, stream);
     if (rc != JR_OK) return rc;
   }
   if (S != JR_DEPTH && g->d_normal.ptr) {
@@ -938,6 +938,7 @@ static int backward_impl(const JrRenderArgs* a, const JrGradArgs* g, cudaStream_
     const long long nk = p.keys_per_image * (p.batched ? a->B : 1);
     if (nk >= 0x7FFFFFFFLL || p.n_entries >= 0x7FFFFFFFLL) return JR_ERR_DIMS;
     p.invalid_key = (unsigned)nk; p.C = 3; p.out = g->d_normal.ptr; p.out2 = nullptr;
+    p.pix_vals = em.val_nrm;
     rc = run_keyed<S, MODE_NRM, 3>(a, g, L, p, stream);
     if (rc != JR_OK) return rc;
   }
@@ -960,6 +961,7 @@ static int backward_impl(const JrRenderArgs* a, const JrGradArgs* g, cudaStream_
       const long long nk = p.keys_per_image * (p.batched ? a->B : 1);
       if (nk >= 0x7FFFFFFFLL || p.n_entries >= 0x7FFFFFFFLL) return JR_ERR_DIMS;
       p.invalid_key = (unsigned)nk; p.C = 2; p.out = g->d_uv.ptr; p.out2 = nullptr;
+      p.pix_vals = em.val_uv;
       rc = run_keyed<S, MODE_UV, 2>(a, g, L, p, stream);
       if (rc != JR_OK) return rc;
     }
@@ -971,6 +973,7 @@ static int backward_impl(const JrRenderArgs* a, const JrGradArgs* g, cudaStream_
       const long long nk = p.keys_per_image * (p.batched ? a->B : 1);
       if (nk >= 0x7FFFFFFFLL || p.n_entries >= 0x7FFFFFFFLL) return JR_ERR_DIMS;
       p.invalid_key = (unsigned)nk; p.C = 3; p.out = g->d_position.ptr; p.out2 = nullptr;
+      p.pix_vals = em.val_pos2;
       rc = run_keyed<S, MODE_POS2, 3>(a, g, L, p, stream);
       if (rc != JR_OK) return rc;
     }

@@ -54,6 +54,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--size", type=str, default="", help="cfg 4/5: override WxH, e.g. 84x84")
     ap.add_argument("--caps", type=int, default=0, help="cfg 4/5: override the number of capsules")
+    ap.add_argument("--vertex-grads", action="store_true",
+                    help="cfg 5: also request gradients w.r.t. vertex positions and normals")
     ap.add_argument("--profile", action="store_true", help="cfg 4/5: torch-profiler kernel table on stderr")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
@@ -112,9 +114,11 @@ def main():
             ldir = torch.tensor(NOTEBOOK_LIGHT.direction, device=dev, requires_grad=True)
             amb = torch.tensor(NOTEBOOK_LIGHT.ambient, device=dev, requires_grad=True)
             w2c = cam.world_to_clip.clone().requires_grad_(True)
+            verts = model.verts.clone().requires_grad_(args.vertex_grads)
+            norms = model.norms.clone().requires_grad_(args.vertex_grads)
 
             def fwd():
-                m = model._replace(diffuse_map=atlas)
+                m = model._replace(diffuse_map=atlas, verts=verts, norms=norms)
                 light = NOTEBOOK_LIGHT._replace(direction=ldir, ambient=amb)
                 c = cam._replace(world_to_clip=w2c)
                 b0 = jr.Renderer.create_buffers(W, H, batch=B, device=dev)
@@ -125,7 +129,7 @@ def main():
                     fwd()
 
             def step():
-                for p in (atlas, ldir, amb, w2c):
+                for p in (atlas, ldir, amb, w2c, verts, norms):
                     p.grad = None
                 o = fwd()
                 loss = ((o.targets[0] - target) ** 2).mean()
