@@ -262,9 +262,9 @@ def run_ours(args) -> None:
 
     fwd_bwd = None
     if not args.no_fwd_bwd:
-        # the metric's 84x84 scenes, and configs[4]'s 480x270 canvas at a reduced batch
-        fwd_bwd = {"84x84": fwd_bwd_secondary(dev, rank, world, shape=(84, 84, 10, 1024)),
-                   "480x270": fwd_bwd_secondary(dev, rank, world, shape=(480, 270, 17, 64))}
+        # the metric's 84x84 scenes at the metric's batch, and configs[4] as named (480x270, T = 3276, B = 512)
+        fwd_bwd = {"84x84": fwd_bwd_secondary(dev, rank, world, shape=(84, 84, 10, 4096)),
+                   "480x270": fwd_bwd_secondary(dev, rank, world, shape=(480, 270, 17, 512))}
     if rank == 0:
         nv, ntri = synthetic.scene_sizes(N_CAPSULES)
         alg_bytes = (12 * nv + 12 * ntri + 4 * W * H) * B       # geometry read once + z write
@@ -324,8 +324,8 @@ def run_ours(args) -> None:
 
 
 def fwd_bwd_secondary(dev, rank: int, world: int, steps: int = 5, shape=(480, 270, 17, 64)) -> dict:
-    """Secondary line (BASELINE metric: "fwd+bwd images/sec"; configs[4] shape at a reduced batch):
-    Renderer.render with the shadow pass at 480x270, 3276 triangles, 64 images per GPU, loss =
+    """Secondary line (BASELINE metric: "fwd+bwd images/sec"; configs[4]):
+    Renderer.render with the shadow pass at 480x270, 3276 triangles, 512 images per GPU, loss =
     mean((canvas - target)^2), gradients w.r.t. light, world_to_clip and the SHARED diffuse atlas;
     the shared gradients are all-reduced across ranks (NCCL) inside the timed region."""
     import torch
