@@ -51,25 +51,60 @@ __global__ void __launch_bounds__(256) k_shade(const __grid_constant__ JrRenderA
 // One thread per triangle: vertex stage of the shader -> attribute record (large canvases).
 // Records are staged in shared memory and written out with coalesced 128-bit stores (a thread
 // writing its own 176-byte record directly touches 44 different cache lines per warp store).
+// Visible-triangle list: only triangles that won at least one pixel get an attribute record (at 84x84
+// about one Brax triangle in eight; writing all records was the one HBM-bound kernel of the facade).
+// The first pixel to flag a triangle (atomicOr on the flag's 32-bit word) appends it to the image's
+// list; the order of the list is irrelevant, every record goes to its own slot.
+__global__ void __launch_bounds__(256) k_mark_visible(const int32_t* __restrict__ tri_id, unsigned* __restrict__ flag_words,
+                                                      int* __restrict__ list, int* __restrict__ count, int npix, int T,
+                                                      int B) {
+  for (int b = blockIdx.y; b < B; b += gridDim.y)
+    for (int p0 = blockIdx.x * 256; p0 < npix; p0 += gridDim.x * 256) {
+      const int pix = p0 + threadIdx.x;
+      const int tri = pix < npix ? tri_id[(long long)b * npix + pix] : -1;
+      // neighbouring pixels mostly share their triangle: one lane per run of equal ids goes on
+      const int prev = __shfl_up_sync(0xffffffffu, tri, 1);
+      if (tri < 0 || ((threadIdx.x & 31) != 0 && prev == tri)) continue;
+      const long long bit = (long long)b * T + tri;
+      unsigned* w = flag_words + (bit >> 5);
+      const unsigned m = 1u << (bit & 31);
+      if (*w & m) continue;                    // already listed (plain load first: most pixels stop here)
+      if (atomicOr(w, m) & m) continue;
+      list[(long long)b * T + atomicAdd(&count[b], 1)] = tri;
+    }
+}
+
 template <int SHADER>
-__global__ void __launch_bounds__(128) k_tri_attr(const __grid_constant__ JrRenderArgs a, float* __restrict__ attrs) {
+__global__ void __launch_bounds__(128) k_tri_attr(const __grid_constant__ JrRenderArgs a, float* __restrict__ attrs,
+                                                  const int* __restrict__ list, const int* __restrict__ count) {
+  // records are staged in shared memory and written out as coalesced float4 (a thread writing its
+  // own 176 B record with scalar stores made this kernel 4x slower)
   __shared__ __align__(16) float stage[128 * TA_FLOATS];
+  __shared__ int s_tri[128];
   const int b = blockIdx.y;
-  const int t0 = blockIdx.x * 128;
-  const int t = t0 + threadIdx.x;
-  if (t < a.T) {
+  const int n_vis = count[b];
+  const int i0 = blockIdx.x * 128;
+  if (i0 >= n_vis) return;
+  const int i = i0 + threadIdx.x;
+  int t = -1;
+  if (i < n_vis) {
+    t = list[(long long)b * a.T + i];
     Frag f;
     frag_vertex<SHADER>(a, b, t, f);
     attr_store<SHADER>(f, stage + threadIdx.x * TA_FLOATS);
   }
+  s_tri[threadIdx.x] = t;
   __syncthreads();
-  const int n = min(128, a.T - t0) * (TA_FLOATS / 4);
-  float4* dst = reinterpret_cast<float4*>(attrs + ((size_t)b * a.T + t0) * TA_FLOATS);
+  constexpr int Q = TA_FLOATS / 4;
+  const int n = min(128, n_vis - i0) * Q;
   const float4* src = reinterpret_cast<const float4*>(stage);
-  for (int i = threadIdx.x; i < n; i += 128) dst[i] = src[i];
+  float4* base = reinterpret_cast<float4*>(attrs + (size_t)b * a.T * TA_FLOATS);
+  for (int j = threadIdx.x; j < n; j += 128) {
+    const int r = j / Q;
+    base[(size_t)s_tri[r] * Q + (j - r * Q)] = src[j];
+  }
 }
 
-// Pixel stage from attribute records (same arithmetic as k_shade, the per-triangle part is shared).
 template <int SHADER>
 __global__ void __launch_bounds__(256) k_shade_rec(const __grid_constant__ JrRenderArgs a,
                                                    const float* __restrict__ attrs) {
@@ -270,7 +305,7 @@ static const bool g_no_bins = getenv("JR_NO_BINS") != nullptr;  // every tile CT
 static const bool g_key64 = getenv("JR_KEY64") != nullptr;      // depth shader: keep packed 64-bit keys
 
 // Forward scratch: [binned visibility: triangle records + tile bitmasks][shading attribute records]
-struct FwdLayout { size_t tiled, attr_off, total; bool use_attr; };
+struct FwdLayout { size_t tiled, attr_off, flags_off, list_off, total; bool use_attr; };
 static FwdLayout fwd_layout(const JrRenderArgs* a) {
   FwdLayout F{};
   int tw, th, nx, ny;
@@ -280,7 +315,11 @@ static FwdLayout fwd_layout(const JrRenderArgs* a) {
   F.use_attr = a->shader != JR_DEPTH && a->shader != JR_PHONG_DARBOUX && a->T > 0 &&
                (long long)a->W * a->H >= 2LL * a->T && !g_no_attr;
   F.attr_off = (F.tiled + 255) & ~(size_t)255;
-  F.total = F.use_attr ? F.attr_off + (size_t)a->B * a->T * TA_FLOATS * 4 : F.tiled;
+  F.flags_off = F.attr_off + (size_t)a->B * a->T * TA_FLOATS * 4;
+  // [flag bits (B*T) | per-image counters (B)] zeroed per call, then the visible-triangle lists (B*T ints)
+  const size_t flag_bytes = ((((size_t)a->B * a->T + 31) / 32) * 4 + (size_t)a->B * 4 + 255) & ~(size_t)255;
+  F.list_off = F.flags_off + flag_bytes;
+  F.total = F.use_attr ? F.list_off + (size_t)a->B * a->T * 4 : F.tiled;
   return F;
 }
 
@@ -351,10 +390,17 @@ int jr_render_forward(const JrRenderArgs* a, jr_stream_t stream_) {
       if (!a->workspace || a->workspace_bytes < F.total) return JR_ERR_WORKSPACE;
       if (a->B > 65535) return JR_ERR_DIMS;
       float* attrs = (float*)((char*)a->workspace + F.attr_off);
+      unsigned* flag_words = (unsigned*)((char*)a->workspace + F.flags_off);
+      const size_t n_words = ((size_t)a->B * a->T + 31) / 32;
+      int* count = (int*)(flag_words + n_words);
+      int* list = (int*)((char*)a->workspace + F.list_off);
+      cudaMemsetAsync(flag_words, 0, n_words * 4 + (size_t)a->B * 4, stream);
+      k_mark_visible<<<dim3(bx > 64 ? 64 : bx, blocks.y), 256, 0, stream>>>(a->tri_id, flag_words, list, count, npix,
+                                                                           a->T, a->B);
       dim3 g1((a->T + 127) / 128, a->B);
 #define JR_ATTR_CASE(S)                                                          \
   case S:                                                                        \
-    k_tri_attr<S><<<g1, 128, 0, stream>>>(*a, attrs);                            \
+    k_tri_attr<S><<<g1, 128, 0, stream>>>(*a, attrs, list, count);               \
     k_shade_rec<S><<<blocks, threads, 0, stream>>>(*a, attrs);         \
     break;
       switch (a->shader) {
@@ -365,7 +411,7 @@ int jr_render_forward(const JrRenderArgs* a, jr_stream_t stream_) {
         JR_ATTR_CASE(JR_PHONG_REFLECTION_SHADOW)
         default: return JR_ERR_SHADER;
       }
-      jr::g_launches += 2;
+      jr::g_launches += 3;
     } else {
       switch (a->shader) {
         case JR_GOURAUD: k_shade<JR_GOURAUD><<<blocks, threads, 0, stream>>>(*a); break;
