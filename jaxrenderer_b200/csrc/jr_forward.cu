@@ -173,8 +173,23 @@ __global__ void __launch_bounds__(256) k_merge_norms(const __grid_constant__ JrM
   float ss = 0.f;
   for (int i = n0 + threadIdx.x; i < n1; i += 256) ss += dot3(ln[3 * i], ln[3 * i + 1], ln[3 * i + 2], ln[3 * i], ln[3 * i + 1], ln[3 * i + 2]);
   const float f1 = sqrtf(block_sum_256(ss, red));
+  // rotated normals of this thread stay in registers between the second reduction and the final
+  // division (objects of up to 256 * KEEP normals; larger ones recompute)
+  constexpr int KEEP = 4;
+  float keep[KEEP][3];
   float ss2 = 0.f;
-  for (int i = n0 + threadIdx.x; i < n1; i += 256) {
+#pragma unroll
+  for (int kk = 0; kk < KEEP; ++kk) {
+    const int i = n0 + threadIdx.x + 256 * kk;
+    if (i < n1) {
+      const float x = ln[3 * i] / f1, y = ln[3 * i + 1] / f1, z = ln[3 * i + 2] / f1;
+      const float tx = (x * R[0] + y * R[1]) + z * R[2], ty = (x * R[4] + y * R[5]) + z * R[6],
+                  tz = (x * R[8] + y * R[9]) + z * R[10];
+      ss2 += dot3(tx, ty, tz, tx, ty, tz);
+      keep[kk][0] = tx; keep[kk][1] = ty; keep[kk][2] = tz;
+    }
+  }
+  for (int i = n0 + threadIdx.x + 256 * KEEP; i < n1; i += 256) {
     const float x = ln[3 * i] / f1, y = ln[3 * i + 1] / f1, z = ln[3 * i + 2] / f1;
     const float tx = (x * R[0] + y * R[1]) + z * R[2], ty = (x * R[4] + y * R[5]) + z * R[6],
                 tz = (x * R[8] + y * R[9]) + z * R[10];
@@ -182,7 +197,16 @@ __global__ void __launch_bounds__(256) k_merge_norms(const __grid_constant__ JrM
   }
   const float f2 = sqrtf(block_sum_256(ss2, red));
   float* out = m.out_norms + (long long)b * m.n_norms * 3;
-  for (int i = n0 + threadIdx.x; i < n1; i += 256) {
+#pragma unroll
+  for (int kk = 0; kk < KEEP; ++kk) {
+    const int i = n0 + threadIdx.x + 256 * kk;
+    if (i < n1) {
+      out[3 * i] = keep[kk][0] / f2;
+      out[3 * i + 1] = keep[kk][1] / f2;
+      out[3 * i + 2] = keep[kk][2] / f2;
+    }
+  }
+  for (int i = n0 + threadIdx.x + 256 * KEEP; i < n1; i += 256) {
     const float x = ln[3 * i] / f1, y = ln[3 * i + 1] / f1, z = ln[3 * i + 2] / f1;
     out[3 * i] = ((x * R[0] + y * R[1]) + z * R[2]) / f2;
     out[3 * i + 1] = ((x * R[4] + y * R[5]) + z * R[6]) / f2;
