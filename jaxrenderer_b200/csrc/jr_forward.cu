@@ -25,8 +25,11 @@
 namespace jr {
 
 // --------------------------------------------------------------------- shading
+#ifndef JR_SHADE_CTAS
+#define JR_SHADE_CTAS 4
+#endif
 template <int SHADER>
-__global__ void __launch_bounds__(256) k_shade(const __grid_constant__ JrRenderArgs a) {
+__global__ void __launch_bounds__(256, JR_SHADE_CTAS) k_shade(const __grid_constant__ JrRenderArgs a) {
   // grid = (blocks per image, images): all index arithmetic stays 32-bit (a 64-bit division per
   // pixel cost ~100 instructions)
   const int npix = a.W * a.H;
@@ -106,7 +109,7 @@ __global__ void __launch_bounds__(128) k_tri_attr(const __grid_constant__ JrRend
 }
 
 template <int SHADER>
-__global__ void __launch_bounds__(256) k_shade_rec(const __grid_constant__ JrRenderArgs a,
+__global__ void __launch_bounds__(256, JR_SHADE_CTAS) k_shade_rec(const __grid_constant__ JrRenderArgs a,
                                                    const float* __restrict__ attrs) {
   // grid = (blocks per image, images): all index arithmetic stays 32-bit (a 64-bit division per
   // pixel cost ~100 instructions)
