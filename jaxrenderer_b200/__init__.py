@@ -9,11 +9,11 @@ from .renderer import CameraParameters, LightParameters, Renderer, ShadowParamet
 from .shader import MixerOutput, PerFragment, PerVertex, Shader, UnsupportedShaderError
 from .shadow import Shadow
 from .shapes import UpAxis, create_capsule, create_cube
-from .types import Buffers, LightSource
+from .types import Buffers, Colour, LightSource, SpecularMap, Texture, Vec3f
 from .utils import build_texture_from_PyTinyrenderer, canvas_to_uint8_display, transpose_for_display
 
 __all__ = [
-    "Buffers", "Camera", "CameraParameters", "LightParameters", "LightSource", "MergedModel",
+    "Buffers", "Camera", "CameraParameters", "Colour", "SpecularMap", "Texture", "Vec3f", "LightParameters", "LightSource", "MergedModel",
     "MixerOutput", "Model", "ModelObject", "PerFragment", "PerVertex", "Renderer", "Shader",
     "Shadow", "ShadowParameters", "UnsupportedShaderError", "UpAxis", "batch_models",
     "build_texture_from_PyTinyrenderer", "canvas_to_uint8_display", "create_capsule", "create_cube",

@@ -17,6 +17,8 @@ import numpy as np
 import torch
 
 Tensor = torch.Tensor
+# array aliases of the reference (``renderer/types.py``): all plain fp32 tensors here
+Colour = Vec3f = Texture = SpecularMap = Tensor
 
 _TargetsT = TypeVar("_TargetsT", bound=Tuple[Any, ...])
 

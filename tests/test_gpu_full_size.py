@@ -85,3 +85,38 @@ def test_config4_canvas_960x540_humanoid_19980_triangles():
     print("960x540 tri-id mismatches:", mism)
     assert mism == 0
     assert np.array_equal(out.zbuffer.cpu().numpy(), zo)
+
+
+@pytest.mark.parametrize("n_caps", [3, 7, 17, 20])
+def test_config3_gouraud_texture_32x32_mixed_envs(n_caps):
+    """configs[2]: GouraudTextureShader at 32x32 over Brax-like environments of different sizes (T = 588 ... 3852,
+    `32x32 A100 Various Envs.ipynb`): tri-ids, z and colours against the torch oracle for a few images per size,
+    batch independence for the whole group."""
+    from jaxrenderer_b200.shaders import GouraudTextureExtraInput, GouraudTextureShader
+    from oracle import jr_oracle as O
+    from tests.helpers import assert_parity, cam_at, compare
+
+    B, W, H = 64, 32, 32
+    sc = synthetic.brax_like_batch(B, n_capsules=n_caps, env0=7000 * n_caps, with_attributes=True)
+    cam = synthetic.brax_cameras(sc["eye"], sc["target"], W, H)
+    tex = synthetic.checker_texture()
+    light = jr.LightSource(torch.tensor((0.57735, -0.57735, 0.57735)), torch.ones(3))
+    uv = sc["uv"] * 100
+    extra = GouraudTextureExtraInput(sc["position"].to(DEV), sc["normal"].to(DEV), uv.to(DEV),
+                                     jr.LightSource(light.direction.to(DEV), light.colour.to(DEV)), tex.to(DEV))
+    bufs = jr.Buffers(torch.full((B, W, H), 1.0, device=DEV), (torch.zeros(B, W, H, 3, device=DEV),))
+    out, tri = jr.render(_cam_d(cam), GouraudTextureShader, bufs, sc["faces"].to(DEV), extra, return_tri_id=True)
+    assert sc["faces"].shape[1] == 12 + 192 * n_caps
+    for b in (0, 31, B - 1):
+        ex_b = GouraudTextureExtraInput(sc["position"][b], sc["normal"][b], uv, light, tex)
+        ref = O.render(cam_at(cam, b), "gouraud_texture", torch.full((W, H), 1.0), (torch.zeros(W, H, 3),),
+                       sc["faces"][b], ex_b)
+        rep = compare(f"cfg3 T={sc['faces'].shape[1]} b={b}", out.zbuffer[b], out.targets[0][b], tri[b], ref)
+        assert_parity(rep)
+    # batch independence
+    b = 17
+    one = jr.render(_cam_d(cam)._replace(world_to_clip=cam.world_to_clip[b].to(DEV)), GouraudTextureShader,
+                    jr.Buffers(torch.full((W, H), 1.0, device=DEV), (torch.zeros(W, H, 3, device=DEV),)),
+                    sc["faces"][b].to(DEV),
+                    GouraudTextureExtraInput(extra.position[b], extra.normal[b], extra.uv, extra.light, extra.texture))
+    assert torch.equal(one.zbuffer, out.zbuffer[b]) and torch.equal(one.targets[0], out.targets[0][b])
