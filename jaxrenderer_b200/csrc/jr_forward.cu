@@ -135,6 +135,7 @@ __global__ void __launch_bounds__(256, JR_SHADE_CTAS) k_shade_rec(const __grid_c
 
 // ---------------------------------------------------------------- merge_objects (model.py:447-555)
 __global__ void __launch_bounds__(256) k_merge_verts(const __grid_constant__ JrMergeArgs m) {
+  // (staging the block's 3 KB in shared memory for 128-bit stores was measured slower: 292 vs 231 us)
   const int b = blockIdx.y;
   const int v = blockIdx.x * 256 + threadIdx.x;
   if (v >= m.n_verts) return;
@@ -165,55 +166,65 @@ __device__ __forceinline__ float block_sum_256(float v, float* red) {
   return t;
 }
 
-// one CTA per (object, batch element): Camera.apply_vec with whole-array normalisation
+// one CTA per (object, group of MN_GROUP batch elements): Camera.apply_vec with whole-array normalisation.
+// The first Frobenius norm depends only on the object's local normals: computed once per CTA when the
+// local mesh is shared by the batch (the usual case), and reused for the group's batch elements.
+constexpr int MN_GROUP = 8;
 __global__ void __launch_bounds__(256) k_merge_norms(const __grid_constant__ JrMergeArgs m) {
   __shared__ float red[8];
-  const int b = blockIdx.y, o = blockIdx.x;
-  const int32_t* ns = m.norm_start.ptr + (long long)b * m.norm_start.batch_stride;
-  const int n0 = ns[o], n1 = ns[o + 1];
-  const float* ln = m.local_norms.ptr + (long long)b * m.local_norms.batch_stride;
-  const float* R = m.normal_matrix.ptr + (long long)b * m.normal_matrix.batch_stride + 16 * o;
-  float ss = 0.f;
-  for (int i = n0 + threadIdx.x; i < n1; i += 256) ss += dot3(ln[3 * i], ln[3 * i + 1], ln[3 * i + 2], ln[3 * i], ln[3 * i + 1], ln[3 * i + 2]);
-  const float f1 = sqrtf(block_sum_256(ss, red));
-  // rotated normals of this thread stay in registers between the second reduction and the final
-  // division (objects of up to 256 * KEEP normals; larger ones recompute)
-  constexpr int KEEP = 4;
-  float keep[KEEP][3];
-  float ss2 = 0.f;
+  const int o = blockIdx.x;
+  const bool shared_mesh = m.local_norms.batch_stride == 0 && m.norm_start.batch_stride == 0;
+  float f1 = 0.f;
+  for (int b = blockIdx.y * MN_GROUP; b < min(m.B, (blockIdx.y + 1) * MN_GROUP); ++b) {
+    const int32_t* ns = m.norm_start.ptr + (long long)b * m.norm_start.batch_stride;
+    const int n0 = ns[o], n1 = ns[o + 1];
+    const float* ln = m.local_norms.ptr + (long long)b * m.local_norms.batch_stride;
+    const float* R = m.normal_matrix.ptr + (long long)b * m.normal_matrix.batch_stride + 16 * o;
+    if (!shared_mesh || b == blockIdx.y * MN_GROUP) {
+      float ss = 0.f;
+      for (int i = n0 + threadIdx.x; i < n1; i += 256)
+        ss += dot3(ln[3 * i], ln[3 * i + 1], ln[3 * i + 2], ln[3 * i], ln[3 * i + 1], ln[3 * i + 2]);
+      f1 = sqrtf(block_sum_256(ss, red));
+    }
+    // rotated normals of this thread stay in registers between the second reduction and the final
+    // division (objects of up to 256 * KEEP normals; larger ones recompute)
+    constexpr int KEEP = 4;
+    float keep[KEEP][3];
+    float ss2 = 0.f;
 #pragma unroll
-  for (int kk = 0; kk < KEEP; ++kk) {
-    const int i = n0 + threadIdx.x + 256 * kk;
-    if (i < n1) {
+    for (int kk = 0; kk < KEEP; ++kk) {
+      const int i = n0 + threadIdx.x + 256 * kk;
+      if (i < n1) {
+        const float x = ln[3 * i] / f1, y = ln[3 * i + 1] / f1, z = ln[3 * i + 2] / f1;
+        const float tx = (x * R[0] + y * R[1]) + z * R[2], ty = (x * R[4] + y * R[5]) + z * R[6],
+                    tz = (x * R[8] + y * R[9]) + z * R[10];
+        ss2 += dot3(tx, ty, tz, tx, ty, tz);
+        keep[kk][0] = tx; keep[kk][1] = ty; keep[kk][2] = tz;
+      }
+    }
+    for (int i = n0 + threadIdx.x + 256 * KEEP; i < n1; i += 256) {
       const float x = ln[3 * i] / f1, y = ln[3 * i + 1] / f1, z = ln[3 * i + 2] / f1;
       const float tx = (x * R[0] + y * R[1]) + z * R[2], ty = (x * R[4] + y * R[5]) + z * R[6],
                   tz = (x * R[8] + y * R[9]) + z * R[10];
       ss2 += dot3(tx, ty, tz, tx, ty, tz);
-      keep[kk][0] = tx; keep[kk][1] = ty; keep[kk][2] = tz;
     }
-  }
-  for (int i = n0 + threadIdx.x + 256 * KEEP; i < n1; i += 256) {
-    const float x = ln[3 * i] / f1, y = ln[3 * i + 1] / f1, z = ln[3 * i + 2] / f1;
-    const float tx = (x * R[0] + y * R[1]) + z * R[2], ty = (x * R[4] + y * R[5]) + z * R[6],
-                tz = (x * R[8] + y * R[9]) + z * R[10];
-    ss2 += dot3(tx, ty, tz, tx, ty, tz);
-  }
-  const float f2 = sqrtf(block_sum_256(ss2, red));
-  float* out = m.out_norms + (long long)b * m.n_norms * 3;
+    const float f2 = sqrtf(block_sum_256(ss2, red));
+    float* out = m.out_norms + (long long)b * m.n_norms * 3;
 #pragma unroll
-  for (int kk = 0; kk < KEEP; ++kk) {
-    const int i = n0 + threadIdx.x + 256 * kk;
-    if (i < n1) {
-      out[3 * i] = keep[kk][0] / f2;
-      out[3 * i + 1] = keep[kk][1] / f2;
-      out[3 * i + 2] = keep[kk][2] / f2;
+    for (int kk = 0; kk < KEEP; ++kk) {
+      const int i = n0 + threadIdx.x + 256 * kk;
+      if (i < n1) {
+        out[3 * i] = keep[kk][0] / f2;
+        out[3 * i + 1] = keep[kk][1] / f2;
+        out[3 * i + 2] = keep[kk][2] / f2;
+      }
     }
-  }
-  for (int i = n0 + threadIdx.x + 256 * KEEP; i < n1; i += 256) {
-    const float x = ln[3 * i] / f1, y = ln[3 * i + 1] / f1, z = ln[3 * i + 2] / f1;
-    out[3 * i] = ((x * R[0] + y * R[1]) + z * R[2]) / f2;
-    out[3 * i + 1] = ((x * R[4] + y * R[5]) + z * R[6]) / f2;
-    out[3 * i + 2] = ((x * R[8] + y * R[9]) + z * R[10]) / f2;
+    for (int i = n0 + threadIdx.x + 256 * KEEP; i < n1; i += 256) {
+      const float x = ln[3 * i] / f1, y = ln[3 * i + 1] / f1, z = ln[3 * i + 2] / f1;
+      out[3 * i] = ((x * R[0] + y * R[1]) + z * R[2]) / f2;
+      out[3 * i + 1] = ((x * R[4] + y * R[5]) + z * R[6]) / f2;
+      out[3 * i + 2] = ((x * R[8] + y * R[9]) + z * R[10]) / f2;
+    }
   }
 }
 
@@ -482,7 +493,7 @@ int jr_merge_objects(const JrMergeArgs* m, jr_stream_t stream_) {
   }
   if (m->n_norms > 0) {
     if (!m->local_norms.ptr || !m->norm_start.ptr || !m->out_norms) return JR_ERR_NULL;
-    k_merge_norms<<<dim3(m->n_objects, m->B), 256, 0, stream>>>(*m);
+    k_merge_norms<<<dim3(m->n_objects, (m->B + MN_GROUP - 1) / MN_GROUP), 256, 0, stream>>>(*m);
     jr::g_launches++;
   }
   return cudaGetLastError() == cudaSuccess ? JR_OK : JR_ERR_CUDA;
