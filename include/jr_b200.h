@@ -158,6 +158,8 @@ typedef struct JrGradArgs {
   JrF32Out d_normal_map;       /* (tex_w,tex_h,3) phong_darboux only, deterministic scatter */
   void* workspace;
   size_t workspace_bytes;
+  int32_t no_buffer_grads;     /* non-zero: d_zbuffer / d_canvas are read-only inputs (may be NULL = zero); the
+                                  cotangents of the incoming buffers are not wanted and not written */
 } JrGradArgs;
 
 int jr_abi_version(void);

@@ -65,7 +65,7 @@ class JrGradArgs(C.Structure):
         ("d_ambient", JrF32), ("d_diffuse", JrF32), ("d_specular", JrF32),
         ("d_texture", JrF32), ("d_specular_map", JrF32), ("d_shadow_strength", JrF32),
         ("d_uv", JrF32), ("d_normal_map", JrF32),
-        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("no_buffer_grads", C.c_int32),
     ]
 
 

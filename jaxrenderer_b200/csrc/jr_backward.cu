@@ -979,7 +979,7 @@ static int backward_impl(const JrRenderArgs* a, const JrGradArgs* g, cudaStream_
     }
   }
   // cotangent of the incoming buffers
-  if (g->d_zbuffer || g->d_canvas) {
+  if (!g->no_buffer_grads && (g->d_zbuffer || g->d_canvas)) {
     long long blocks = (total + 255) / 256;
     if (blocks > 148LL * 16) blocks = 148LL * 16;
     k_bwd_mask<<<(unsigned)blocks, 256, 0, stream>>>(a->tri_id, g->d_zbuffer, S != JR_DEPTH ? g->d_canvas : nullptr,

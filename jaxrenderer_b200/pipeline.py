@@ -223,12 +223,23 @@ class _RenderFn(torch.autograd.Function):
         d_c = grads[1] if has_canvas else None
         dev = call.tri_id.device
         zshape = (call.B, call.W, call.H)
-        d_z = torch.zeros(zshape, device=dev) if d_z is None else d_z.reshape(zshape).contiguous().clone()
-        if has_canvas:
-            d_c = torch.zeros(zshape + (3,), device=dev) if d_c is None else d_c.reshape(zshape + (3,)).contiguous().clone()
+        # The kernels overwrite d_zbuffer / d_canvas in place with the cotangents of the INCOMING buffers
+        # (d out / d old = 1 - keep).  When nobody asks for those (the usual case: fresh buffers), the
+        # incoming cotangents are passed read-only -- no clone, no zero-fill, no mask launch.
+        zi, ci = _DIFF.index("zbuffer") + 1, _DIFF.index("canvas") + 1
+        buffer_grads = bool(ctx.needs_input_grad[zi] or (has_canvas and ctx.needs_input_grad[ci]))
+        if buffer_grads:
+            d_z = torch.zeros(zshape, device=dev) if d_z is None else d_z.reshape(zshape).contiguous().clone()
+            if has_canvas:
+                d_c = (torch.zeros(zshape + (3,), device=dev) if d_c is None
+                       else d_c.reshape(zshape + (3,)).contiguous().clone())
+        else:
+            d_z = None if d_z is None else d_z.reshape(zshape).contiguous()
+            d_c = None if (d_c is None or not has_canvas) else d_c.reshape(zshape + (3,)).contiguous()
         g = JrGradArgs()
-        g.d_zbuffer = d_z.data_ptr()
-        g.d_canvas = d_c.data_ptr() if has_canvas else None
+        g.no_buffer_grads = 0 if buffer_grads else 1
+        g.d_zbuffer = d_z.data_ptr() if d_z is not None else None
+        g.d_canvas = d_c.data_ptr() if (has_canvas and d_c is not None) else None
         outs: Dict[str, Tensor] = {}
         wanted = []
         for i, name in enumerate(_DIFF):
@@ -243,7 +254,7 @@ class _RenderFn(torch.autograd.Function):
             buf = torch.zeros_like(t)
             outs[name] = buf
             setattr(g, _GRAD_FIELD[name], JrF32(buf.data_ptr(), call.stride(name)))
-        args = call.fill(d_z, d_c, call.tri_id)  # zbuffer/canvas slots are unused by backward
+        args = call.fill(call.tri_id, None, call.tri_id)  # zbuffer/canvas slots are unused by backward
         need = lib.jr_backward_workspace_bytes(C.byref(args), C.byref(g))
         ws = None
         if need:
