@@ -16,6 +16,7 @@
 //     resolution across chunks).
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <cub/device/device_radix_sort.cuh>
 
@@ -385,10 +386,41 @@ struct PixelEmit {
   int pos_c;
 };
 
-template <int S, bool WV>
+// Extended records of the visible triangles (see rec_store): the vertex stage runs once per triangle
+// instead of once per covered pixel of the pixel pass.
+template <int S>
+__global__ void __launch_bounds__(128) k_bwd_records(const __grid_constant__ JrRenderArgs a, float* __restrict__ recs,
+                                                     const int* __restrict__ list, const int* __restrict__ count) {
+  __shared__ __align__(16) float stage[128 * TE_FLOATS];
+  __shared__ int s_tri[128];
+  const int b = blockIdx.y;
+  const int n_vis = count[b];
+  const int i0 = blockIdx.x * 128;
+  if (i0 >= n_vis) return;
+  const int i = i0 + threadIdx.x;
+  int t = -1;
+  if (i < n_vis) {
+    t = list[(long long)b * a.T + i];
+    Frag f;
+    frag_vertex<S>(a, b, t, f);
+    rec_store<S>(f, stage + threadIdx.x * TE_FLOATS);
+  }
+  s_tri[threadIdx.x] = t;
+  __syncthreads();
+  constexpr int Q = TE_FLOATS / 4;
+  const int n = min(128, n_vis - i0) * Q;
+  const float4* src = reinterpret_cast<const float4*>(stage);
+  float4* base = reinterpret_cast<float4*>(recs + (size_t)b * a.T * TE_FLOATS);
+  for (int j = threadIdx.x; j < n; j += 128) {
+    const int r = j / Q;
+    base[(size_t)s_tri[r] * Q + (j - r * Q)] = src[j];
+  }
+}
+
+template <int S, bool WV, bool REC>
 __global__ void __launch_bounds__(BWD_THREADS, JR_BWD_MIN_BLOCKS)
 k_bwd_global(const __grid_constant__ JrRenderArgs a, const __grid_constant__ JrGradArgs g, float* __restrict__ partials,
-             const __grid_constant__ PixelEmit em) {
+             const __grid_constant__ PixelEmit em, const float* __restrict__ recs) {
   extern __shared__ float s_acc[];  // [NG][BWD_THREADS]
   const int b = blockIdx.y;
   const int npix = a.W * a.H;
@@ -407,7 +439,12 @@ k_bwd_global(const __grid_constant__ JrRenderArgs a, const __grid_constant__ JrG
     }
     const int x = pix / a.H, y = pix - x * a.H;
     Frag f;
-    shade_pixel<S>(a, b, x, y, tri, f);
+    if (REC) {
+      rec_load<S>(a, b, recs + ((size_t)b * a.T + tri) * TE_FLOATS, f);
+      frag_pixel<S>(a, b, x, y, f);
+    } else {
+      shade_pixel<S>(a, b, x, y, tri, f);
+    }
     float d_zw, d_col[3];
     load_cotangent(g, gi, S != JR_DEPTH, d_zw, d_col);
     backprop_pixel<S, true, true, WV>(a, b, f, d_zw, d_col, o);
@@ -716,6 +753,8 @@ struct BwdLayout {
   size_t em_iota, em_key_tex, em_key_spec, em_val_tex, em_val_spec, em_val_nmap;  // PixelEmit buffers
   size_t em_val_pos, em_val_nrm, em_val_uv, em_val_pos2;
   int pos_c;
+  bool use_rec;
+  size_t rec_off, rec_flags, rec_list;  // extended records of the visible triangles + their list
   size_t cub_bytes;
   long long max_entries;
 };
@@ -771,6 +810,14 @@ static BwdLayout bwd_layout(const JrRenderArgs* a, const JrGradArgs* g) {
       if (g->d_uv.ptr) { L.em_val_uv = off; off += align256(np * 24); }
       if (g->d_position.ptr) { L.em_val_pos2 = off; off += align256(np * 36); }
     }
+  }
+  // records pay off when a triangle is shared by several pixels (the forward's rule for attribute records)
+  L.use_rec = (a->shader == JR_PHONG_REFLECTION || a->shader == JR_PHONG_REFLECTION_SHADOW) && a->T > 0 &&
+              npix >= 2LL * a->T && getenv("JR_NO_BWD_REC") == nullptr;
+  if (L.use_rec) {
+    L.rec_off = off; off += align256((size_t)a->B * a->T * TE_FLOATS * 4);
+    L.rec_flags = off; off += align256((((size_t)a->B * a->T + 31) / 32) * 4 + (size_t)a->B * 4);
+    L.rec_list = off; off += align256((size_t)a->B * a->T * 4);
   }
   L.total = off;
   return L;
@@ -863,13 +910,34 @@ static int backward_impl(const JrRenderArgs* a, const JrGradArgs* g, cudaStream_
   if (wants_global(g) || em.iota || want_vertex) {
     float* partials = (float*)(ws + L.partials);
     dim3 grid(L.nblk, a->B);
-    if (want_vertex) {
-      cudaFuncSetAttribute(k_bwd_global<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NG * BWD_THREADS * 4);
-      k_bwd_global<S, true><<<grid, BWD_THREADS, NG * BWD_THREADS * 4, stream>>>(*a, *g, partials, em);
-    } else {
-      cudaFuncSetAttribute(k_bwd_global<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NG * BWD_THREADS * 4);
-      k_bwd_global<S, false><<<grid, BWD_THREADS, NG * BWD_THREADS * 4, stream>>>(*a, *g, partials, em);
+    const float* recs = nullptr;
+    constexpr bool CAN_REC = (S == JR_PHONG_REFLECTION || S == JR_PHONG_REFLECTION_SHADOW);
+    if (CAN_REC && L.use_rec) {
+      unsigned* flag_words = (unsigned*)(ws + L.rec_flags);
+      const size_t n_words = ((size_t)a->B * a->T + 31) / 32;
+      int* count = (int*)(flag_words + n_words);
+      int* list = (int*)(ws + L.rec_list);
+      cudaMemsetAsync(flag_words, 0, n_words * 4 + (size_t)a->B * 4, stream);
+      int bx = (int)((npix + 255) / 256);
+      if (bx > 64) bx = 64;
+      k_mark_visible<0><<<dim3(bx, a->B), 256, 0, stream>>>(a->tri_id, flag_words, list, count, (int)npix, a->T, a->B);
+      k_bwd_records<CAN_REC ? S : JR_PHONG_REFLECTION><<<dim3((a->T + 127) / 128, a->B), 128, 0, stream>>>(
+          *a, (float*)(ws + L.rec_off), list, count);
+      g_launches += 2;
+      recs = (const float*)(ws + L.rec_off);
     }
+    const size_t sm = NG * BWD_THREADS * 4;
+#define JR_PIXEL_PASS(WV_, REC_)                                                                                 \
+  do {                                                                                                            \
+    cudaFuncSetAttribute(k_bwd_global<S, WV_, REC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);       \
+    k_bwd_global<S, WV_, REC_><<<grid, BWD_THREADS, sm, stream>>>(*a, *g, partials, em, recs);                    \
+  } while (0)
+    if (CAN_REC && recs) {
+      if (want_vertex) JR_PIXEL_PASS(true, CAN_REC); else JR_PIXEL_PASS(false, CAN_REC);
+    } else {
+      if (want_vertex) JR_PIXEL_PASS(true, false); else JR_PIXEL_PASS(false, false);
+    }
+#undef JR_PIXEL_PASS
     g_launches++;
   }
   if (wants_global(g)) {

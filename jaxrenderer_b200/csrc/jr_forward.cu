@@ -54,29 +54,6 @@ __global__ void __launch_bounds__(256, JR_SHADE_CTAS) k_shade(const __grid_const
 // One thread per triangle: vertex stage of the shader -> attribute record (large canvases).
 // Records are staged in shared memory and written out with coalesced 128-bit stores (a thread
 // writing its own 176-byte record directly touches 44 different cache lines per warp store).
-// Visible-triangle list: only triangles that won at least one pixel get an attribute record (at 84x84
-// about one Brax triangle in eight; writing all records was the one HBM-bound kernel of the facade).
-// The first pixel to flag a triangle (atomicOr on the flag's 32-bit word) appends it to the image's
-// list; the order of the list is irrelevant, every record goes to its own slot.
-__global__ void __launch_bounds__(256) k_mark_visible(const int32_t* __restrict__ tri_id, unsigned* __restrict__ flag_words,
-                                                      int* __restrict__ list, int* __restrict__ count, int npix, int T,
-                                                      int B) {
-  for (int b = blockIdx.y; b < B; b += gridDim.y)
-    for (int p0 = blockIdx.x * 256; p0 < npix; p0 += gridDim.x * 256) {
-      const int pix = p0 + threadIdx.x;
-      const int tri = pix < npix ? tri_id[(long long)b * npix + pix] : -1;
-      // neighbouring pixels mostly share their triangle: one lane per run of equal ids goes on
-      const int prev = __shfl_up_sync(0xffffffffu, tri, 1);
-      if (tri < 0 || ((threadIdx.x & 31) != 0 && prev == tri)) continue;
-      const long long bit = (long long)b * T + tri;
-      unsigned* w = flag_words + (bit >> 5);
-      const unsigned m = 1u << (bit & 31);
-      if (*w & m) continue;                    // already listed (plain load first: most pixels stop here)
-      if (atomicOr(w, m) & m) continue;
-      list[(long long)b * T + atomicAdd(&count[b], 1)] = tri;
-    }
-}
-
 template <int SHADER>
 __global__ void __launch_bounds__(128) k_tri_attr(const __grid_constant__ JrRenderArgs a, float* __restrict__ attrs,
                                                   const int* __restrict__ list, const int* __restrict__ count) {
@@ -433,7 +410,7 @@ int jr_render_forward(const JrRenderArgs* a, jr_stream_t stream_) {
       int* count = (int*)(flag_words + n_words);
       int* list = (int*)((char*)a->workspace + F.list_off);
       cudaMemsetAsync(flag_words, 0, n_words * 4 + (size_t)a->B * 4, stream);
-      k_mark_visible<<<dim3(bx > 64 ? 64 : bx, blocks.y), 256, 0, stream>>>(a->tri_id, flag_words, list, count, npix,
+      k_mark_visible<0><<<dim3(bx > 64 ? 64 : bx, blocks.y), 256, 0, stream>>>(a->tri_id, flag_words, list, count, npix,
                                                                            a->T, a->B);
       dim3 g1((a->T + 127) / 128, a->B);
 #define JR_ATTR_CASE(S)                                                          \

@@ -418,4 +418,56 @@ __device__ __forceinline__ void attr_load(const JrRenderArgs& a, int b, const fl
   if (SHADER == JR_GOURAUD_TEXTURE) { f.inten[0] = r[40]; f.inten[1] = r[41]; f.inten[2] = r[42]; }
 }
 
+// Visible-triangle list: only triangles that won at least one pixel get an attribute record (at 84x84
+// about one Brax triangle in eight; writing all records was the one HBM-bound kernel of the facade).
+// The first pixel to flag a triangle (atomicOr on the flag's 32-bit word) appends it to the image's
+// list; the order of the list is irrelevant, every record goes to its own slot.
+template <int UNUSED>  // template only for inline linkage (two translation units include this header)
+__global__ void __launch_bounds__(256) k_mark_visible(const int32_t* __restrict__ tri_id, unsigned* __restrict__ flag_words,
+                                                      int* __restrict__ list, int* __restrict__ count, int npix, int T,
+                                                      int B) {
+  for (int b = blockIdx.y; b < B; b += gridDim.y)
+    for (int p0 = blockIdx.x * 256; p0 < npix; p0 += gridDim.x * 256) {
+      const int pix = p0 + threadIdx.x;
+      const int tri = pix < npix ? tri_id[(long long)b * npix + pix] : -1;
+      // neighbouring pixels mostly share their triangle: one lane per run of equal ids goes on
+      const int prev = __shfl_up_sync(0xffffffffu, tri, 1);
+      if (tri < 0 || ((threadIdx.x & 31) != 0 && prev == tri)) continue;
+      const long long bit = (long long)b * T + tri;
+      unsigned* w = flag_words + (bit >> 5);
+      const unsigned m = 1u << (bit & 31);
+      if (*w & m) continue;                    // already listed (plain load first: most pixels stop here)
+      if (atomicOr(w, m) & m) continue;
+      list[(long long)b * T + atomicAdd(&count[b], 1)] = tri;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Extended record for the backward pass of the phong_reflection* shaders: the attribute record plus the
+// vertex-stage intermediates that only the reverse pass reads (world positions, raw / rotated normals).
+constexpr int TE_FLOATS = 80;  // 320 bytes, 20 x float4: [0..43] attribute record, [44..52] P, [53..61] nraw,
+                               // [62..70] mvert, [71..79] tvert
+template <int SHADER>
+__device__ __forceinline__ void rec_store(const Frag& f, float* __restrict__ r) {
+  attr_store<SHADER>(f, r);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    r[44 + 3 * k] = f.P[k].x; r[45 + 3 * k] = f.P[k].y; r[46 + 3 * k] = f.P[k].z;
+    r[53 + 3 * k] = f.nraw[k].x; r[54 + 3 * k] = f.nraw[k].y; r[55 + 3 * k] = f.nraw[k].z;
+    r[62 + 3 * k] = f.mvert[k].x; r[63 + 3 * k] = f.mvert[k].y; r[64 + 3 * k] = f.mvert[k].z;
+    r[71 + 3 * k] = f.tvert[k].x; r[72 + 3 * k] = f.tvert[k].y; r[73 + 3 * k] = f.tvert[k].z;
+  }
+}
+template <int SHADER>
+__device__ __forceinline__ void rec_load(const JrRenderArgs& a, int b, const float* __restrict__ r, Frag& f) {
+  attr_load<SHADER>(a, b, r, f);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    f.P[k] = Vec3{r[44 + 3 * k], r[45 + 3 * k], r[46 + 3 * k]};
+    f.nraw[k] = Vec3{r[53 + 3 * k], r[54 + 3 * k], r[55 + 3 * k]};
+    f.mvert[k] = Vec3{r[62 + 3 * k], r[63 + 3 * k], r[64 + 3 * k]};
+    f.tvert[k] = Vec3{r[71 + 3 * k], r[72 + 3 * k], r[73 + 3 * k]};
+  }
+}
+
 }  // namespace jr
