@@ -4,9 +4,9 @@
 //               shared-memory tile; k_setup_bin + k_raster_tile (jr_tiled.cuh) otherwise.
 //               Both produce the triangle-id G-buffer (and z for the depth shader).
 //   shading     k_shade<SHADER>: one thread per pixel, vertex + pixel stage recomputed per pixel
-//               (small canvases);  k_tri_attr<SHADER> + k_shade_rec<SHADER>: vertex stage once
-//               per triangle into an attribute record shared by the triangle's pixels (large
-//               canvases).  Same arithmetic either way (jr_shade.cuh).
+//               (Darboux shader);  k_mark_visible + k_tri_attr<SHADER> + k_shade_rec<SHADER>: vertex stage once
+//               per VISIBLE triangle into an attribute record shared by the triangle's pixels (all other
+//               shaders).  Same arithmetic either way (jr_shade.cuh).
 //
 // Compiled with -fmad=false (see jr_device.cuh).
 #include <cuda_runtime.h>
@@ -56,7 +56,8 @@ __global__ void __launch_bounds__(256, JR_SHADE_CTAS) k_shade(const __grid_const
 // writing its own 176-byte record directly touches 44 different cache lines per warp store).
 template <int SHADER>
 __global__ void __launch_bounds__(128) k_tri_attr(const __grid_constant__ JrRenderArgs a, float* __restrict__ attrs,
-                                                  const int* __restrict__ list, const int* __restrict__ count) {
+                                                  const int* __restrict__ list, const int* __restrict__ count,
+                                                  int rec_stride, bool compact) {
   // records are staged in shared memory and written out as coalesced float4 (a thread writing its
   // own 176 B record with scalar stores made this kernel 4x slower)
   __shared__ __align__(16) float stage[128 * TA_FLOATS];
@@ -73,12 +74,13 @@ __global__ void __launch_bounds__(128) k_tri_attr(const __grid_constant__ JrRend
     frag_vertex<SHADER>(a, b, t, f);
     attr_store<SHADER>(f, stage + threadIdx.x * TA_FLOATS);
   }
-  s_tri[threadIdx.x] = t;
+  // record slot: the triangle id, or (compact layout, more triangles than pixels) the list position
+  s_tri[threadIdx.x] = compact ? i : t;
   __syncthreads();
   constexpr int Q = TA_FLOATS / 4;
   const int n = min(128, n_vis - i0) * Q;
   const float4* src = reinterpret_cast<const float4*>(stage);
-  float4* base = reinterpret_cast<float4*>(attrs + (size_t)b * a.T * TA_FLOATS);
+  float4* base = reinterpret_cast<float4*>(attrs + (size_t)b * rec_stride * TA_FLOATS);
   for (int j = threadIdx.x; j < n; j += 128) {
     const int r = j / Q;
     base[(size_t)s_tri[r] * Q + (j - r * Q)] = src[j];
@@ -87,7 +89,8 @@ __global__ void __launch_bounds__(128) k_tri_attr(const __grid_constant__ JrRend
 
 template <int SHADER>
 __global__ void __launch_bounds__(256, JR_SHADE_CTAS) k_shade_rec(const __grid_constant__ JrRenderArgs a,
-                                                   const float* __restrict__ attrs) {
+                                                   const float* __restrict__ attrs, int rec_stride,
+                                                   const int* __restrict__ slot_map) {
   // grid = (blocks per image, images): all index arithmetic stays 32-bit (a 64-bit division per
   // pixel cost ~100 instructions)
   const int npix = a.W * a.H;
@@ -98,7 +101,8 @@ __global__ void __launch_bounds__(256, JR_SHADE_CTAS) k_shade_rec(const __grid_c
     if (tri < 0) continue;
     const int x = pix / a.H, y = pix - x * a.H;
     Frag f;
-    attr_load<SHADER>(a, b, attrs + ((size_t)b * a.T + tri) * TA_FLOATS, f);
+    const int slot = slot_map ? slot_map[(long long)b * a.T + tri] : tri;
+    attr_load<SHADER>(a, b, attrs + ((size_t)b * rec_stride + slot) * TA_FLOATS, f);
     frag_pixel<SHADER>(a, b, x, y, f);
     if (f.keep) {
       a.zbuffer[gi] = f.zw;
@@ -320,21 +324,27 @@ static const bool g_no_bins = getenv("JR_NO_BINS") != nullptr;  // every tile CT
 static const bool g_key64 = getenv("JR_KEY64") != nullptr;      // depth shader: keep packed 64-bit keys
 
 // Forward scratch: [binned visibility: triangle records + tile bitmasks][shading attribute records]
-struct FwdLayout { size_t tiled, attr_off, flags_off, list_off, total; bool use_attr; };
+struct FwdLayout { size_t tiled, attr_off, flags_off, list_off, map_off, total; bool use_attr, compact; int rec_stride; };
 static FwdLayout fwd_layout(const JrRenderArgs* a) {
   FwdLayout F{};
   int tw, th, nx, ny;
   choose_tiles(a->W, a->H, &tw, &th, &nx, &ny);
   F.tiled = (nx * ny == 1) ? 0 : tiled_layout(a->B, a->W, a->H, a->T).total;
   // per-triangle attribute records pay off when a triangle is shared by several pixels
-  F.use_attr = a->shader != JR_DEPTH && a->shader != JR_PHONG_DARBOUX && a->T > 0 &&
-               (long long)a->W * a->H >= 2LL * a->T && !g_no_attr;
+  // Per-triangle attribute records, built for the VISIBLE triangles only.  More pixels than triangles: the
+  // record of triangle t sits in slot t.  More triangles than pixels (32x32 Brax frames): at most W*H
+  // triangles are visible, records are packed in list order and a triangle -> slot map is kept.
+  const long long npix = (long long)a->W * a->H;
+  F.use_attr = a->shader != JR_DEPTH && a->shader != JR_PHONG_DARBOUX && a->T > 0 && !g_no_attr;
+  F.compact = npix < a->T;
+  F.rec_stride = F.compact ? (int)npix : a->T;
   F.attr_off = (F.tiled + 255) & ~(size_t)255;
-  F.flags_off = F.attr_off + (size_t)a->B * a->T * TA_FLOATS * 4;
+  F.flags_off = F.attr_off + (((size_t)a->B * F.rec_stride * TA_FLOATS * 4 + 255) & ~(size_t)255);
   // [flag bits (B*T) | per-image counters (B)] zeroed per call, then the visible-triangle lists (B*T ints)
   const size_t flag_bytes = ((((size_t)a->B * a->T + 31) / 32) * 4 + (size_t)a->B * 4 + 255) & ~(size_t)255;
   F.list_off = F.flags_off + flag_bytes;
-  F.total = F.use_attr ? F.list_off + (size_t)a->B * a->T * 4 : F.tiled;
+  F.map_off = F.list_off + (((size_t)a->B * a->T * 4 + 255) & ~(size_t)255);
+  F.total = F.use_attr ? F.map_off + (F.compact ? (size_t)a->B * a->T * 4 : 0) : F.tiled;
   return F;
 }
 
@@ -410,13 +420,16 @@ int jr_render_forward(const JrRenderArgs* a, jr_stream_t stream_) {
       int* count = (int*)(flag_words + n_words);
       int* list = (int*)((char*)a->workspace + F.list_off);
       cudaMemsetAsync(flag_words, 0, n_words * 4 + (size_t)a->B * 4, stream);
+      int* slot_map = F.compact ? (int*)((char*)a->workspace + F.map_off) : nullptr;
       k_mark_visible<0><<<dim3(bx > 64 ? 64 : bx, blocks.y), 256, 0, stream>>>(a->tri_id, flag_words, list, count, npix,
-                                                                           a->T, a->B);
+                                                                           a->T, a->B, slot_map);
+      const int rec_stride = F.rec_stride;
+      const bool compact = F.compact;
       dim3 g1((a->T + 127) / 128, a->B);
 #define JR_ATTR_CASE(S)                                                          \
   case S:                                                                        \
-    k_tri_attr<S><<<g1, 128, 0, stream>>>(*a, attrs, list, count);               \
-    k_shade_rec<S><<<blocks, threads, 0, stream>>>(*a, attrs);         \
+    k_tri_attr<S><<<g1, 128, 0, stream>>>(*a, attrs, list, count, rec_stride, compact); \
+    k_shade_rec<S><<<blocks, threads, 0, stream>>>(*a, attrs, rec_stride, slot_map); \
     break;
       switch (a->shader) {
         JR_ATTR_CASE(JR_GOURAUD)

@@ -425,7 +425,7 @@ __device__ __forceinline__ void attr_load(const JrRenderArgs& a, int b, const fl
 template <int UNUSED>  // template only for inline linkage (two translation units include this header)
 __global__ void __launch_bounds__(256) k_mark_visible(const int32_t* __restrict__ tri_id, unsigned* __restrict__ flag_words,
                                                       int* __restrict__ list, int* __restrict__ count, int npix, int T,
-                                                      int B) {
+                                                      int B, int* __restrict__ slot_map = nullptr) {
   for (int b = blockIdx.y; b < B; b += gridDim.y)
     for (int p0 = blockIdx.x * 256; p0 < npix; p0 += gridDim.x * 256) {
       const int pix = p0 + threadIdx.x;
@@ -438,7 +438,9 @@ __global__ void __launch_bounds__(256) k_mark_visible(const int32_t* __restrict_
       const unsigned m = 1u << (bit & 31);
       if (*w & m) continue;                    // already listed (plain load first: most pixels stop here)
       if (atomicOr(w, m) & m) continue;
-      list[(long long)b * T + atomicAdd(&count[b], 1)] = tri;
+      const int slot = atomicAdd(&count[b], 1);
+      list[(long long)b * T + slot] = tri;
+      if (slot_map) slot_map[(long long)b * T + tri] = slot;  // compact records: triangle -> record slot
     }
 }
 
