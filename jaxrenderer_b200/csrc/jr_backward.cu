@@ -747,6 +747,8 @@ __global__ void k_bwd_mask(const int32_t* __restrict__ tri_id, float* d_z, float
 static int bit_length(unsigned long long v) { int n = 0; while (v) { ++n; v >>= 1; } return n; }
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
+static const bool g_no_bwd_rec = getenv("JR_NO_BWD_REC") != nullptr;  // A/B switch: pixel pass recomputes the vertex stage
+
 struct BwdLayout {
   int nblk;             // global pass blocks per image
   size_t partials, keys_a, keys_b, vals_a, vals_b, cub_temp, carry, total;
@@ -813,7 +815,7 @@ static BwdLayout bwd_layout(const JrRenderArgs* a, const JrGradArgs* g) {
   }
   // records pay off when a triangle is shared by several pixels (the forward's rule for attribute records)
   L.use_rec = (a->shader == JR_PHONG_REFLECTION || a->shader == JR_PHONG_REFLECTION_SHADOW) && a->T > 0 &&
-              npix >= 2LL * a->T && getenv("JR_NO_BWD_REC") == nullptr;
+              npix >= 2LL * a->T && !g_no_bwd_rec;
   if (L.use_rec) {
     L.rec_off = off; off += align256((size_t)a->B * a->T * TE_FLOATS * 4);
     L.rec_flags = off; off += align256((((size_t)a->B * a->T + 31) / 32) * 4 + (size_t)a->B * 4);
