@@ -707,6 +707,9 @@ k_bwd_segfix(KeyedPlan plan, const Carry<C>* __restrict__ carry, const unsigned*
   float acc[C];
 #pragma unroll
   for (int k = 0; k < C; ++k) acc[k] = 0.f;
+  // (unrolled: the loads of 8 iterations are in flight together -- a shared 1x1 texture gives runs of
+  // tens of thousands of chunks, and one round trip per iteration made this kernel latency-bound)
+#pragma unroll 8
   for (int j = c + 1 + lane; j <= c_end; j += 32) {
     const Carry<C>& nx = carry[j];
 #pragma unroll

@@ -18,6 +18,7 @@ from .shapes.capsule import _tables as _capsule_tables
 from .shapes.cube import _tables as _cube_tables
 
 SEED0 = 20230701
+GROUND_TEXTURE_SCALING = 8192.0
 
 
 def _quat_to_mat(q: np.ndarray) -> np.ndarray:
@@ -85,7 +86,9 @@ def brax_like_batch(B: int, n_capsules: int = 10, env0: int = 0,
         "eye": torch.from_numpy(eye), "target": torch.from_numpy(tgt),
     }
     if with_attributes:
-        uv = np.concatenate([cube["uvs"].numpy()] + [cap["uvs"].numpy()] * n_capsules, axis=0)
+        # ground uvs carry the Brax glue's texture scaling (8192 repeats of the 100x100 grid over the plane,
+        # notebooks/Generate Data.ipynb), as in the real fixture; shaders taking texel-space uvs rescale them
+        uv = np.concatenate([cube["uvs"].numpy() * GROUND_TEXTURE_SCALING] + [cap["uvs"].numpy()] * n_capsules, axis=0)
         tix = np.concatenate([np.zeros(24, np.int32)] + [np.full(576, i + 1, np.int32) for i in range(n_capsules)])
         out.update({"normal": torch.from_numpy(nrm), "uv": torch.from_numpy(uv.astype(np.float32)),
                     "texture_index": torch.from_numpy(tix)})
