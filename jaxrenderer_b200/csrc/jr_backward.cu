@@ -773,7 +773,14 @@ static bool wants_global(const JrGradArgs* g) {
 static BwdLayout bwd_layout(const JrRenderArgs* a, const JrGradArgs* g) {
   BwdLayout L{};
   const long long npix = (long long)a->W * a->H;
-  L.nblk = (int)((npix + BWD_THREADS * 8 - 1) / (BWD_THREADS * 8));
+  // blocks per image of the pixel pass: 8 to 32 pixels per thread -- few enough blocks that the 52-slot block
+  // reduction at the end is amortised (it cost ~5 % of the pass at 7 pixels per thread), enough of them
+  // (about 2048 CTAs in total) to fill the GPU when the batch is small
+  const int nblk_max = (int)((npix + BWD_THREADS * 8 - 1) / (BWD_THREADS * 8));
+  const int nblk_min = (int)((npix + BWD_THREADS * 32 - 1) / (BWD_THREADS * 32));
+  L.nblk = (2048 + a->B - 1) / a->B;
+  if (L.nblk > nblk_max) L.nblk = nblk_max;
+  if (L.nblk < nblk_min) L.nblk = nblk_min;
   if (L.nblk < 1) L.nblk = 1;
   if (L.nblk > 64) L.nblk = 64;
   const bool keyed1 = g->d_texture.ptr || g->d_specular_map.ptr || g->d_normal_map.ptr;
