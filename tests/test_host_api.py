@@ -160,3 +160,10 @@ def test_brax_pregen_loader_matches_committed_fixture():
     assert torch.equal(cam.position[frames], fix_cam.position)
     m = jr.merge_objects(objs)
     assert m.verts.shape == (30, 9816, 3) and m.faces.shape[-2:] == (3276, 3)
+
+
+def test_graft_entry_check_matches_header():
+    """The driver's build hook verifies ABI version + exports against the header (without recompiling here)."""
+    import __graft_entry__ as g
+
+    g.check()
