@@ -17,11 +17,11 @@ class PhongReflectionShadowTextureExtraInput(NamedTuple):
     texture_offset: Any
     texture: Any
     specular_map: Any
+    shadow: Any   # shadow.Shadow
+    camera: Any   # geometry.Camera
     ambient: Any
     diffuse: Any
     specular: Any
-    shadow: Any   # shadow.Shadow
-    camera: Any   # geometry.Camera
 
 
 class PhongReflectionShadowTextureExtraFragmentData(NamedTuple):
