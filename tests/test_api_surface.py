@@ -60,3 +60,21 @@ def test_namedtuple_fields_and_defaults():
             got = defaults.get(f)
             got = list(got) if isinstance(got, tuple) else got
             assert got == d, f"{name}.{f}: default {got!r} != reference {d!r}"
+
+
+def test_literal_parameter_defaults():
+    where = {"render": jr, "transpose_for_display": utils}
+    classes = {"Renderer": jr.Renderer, "Shadow": shadow.Shadow, "Camera": geometry.Camera,
+               "ModelObject": model.ModelObject, "Model": model.Model, "MergedModel": model.MergedModel}
+    for qual, defaults in GOLDEN["defaults"].items():
+        if not defaults:
+            continue
+        if "." in qual:
+            cls, meth = qual.split(".")
+            fn = inspect.getattr_static(classes[cls], meth)
+            fn = fn.__func__ if isinstance(fn, (classmethod, staticmethod)) else fn
+        else:
+            fn = getattr(where[qual], qual)
+        sig = inspect.signature(fn).parameters
+        for name, value in defaults.items():
+            assert sig[name].default == value, f"{qual}({name}=...): {sig[name].default!r} != reference {value!r}"

@@ -54,6 +54,24 @@ def params(fn: ast.FunctionDef):
     return [n for n in names if n not in ("self", "cls")]
 
 
+def param_defaults(fn: ast.FunctionDef):
+    """{name: literal default} for parameters whose default is a plain literal."""
+    a = fn.args
+    pos = a.posonlyargs + a.args
+    out = {}
+    for p_, d in zip(pos[len(pos) - len(a.defaults):], a.defaults):
+        v = literal(d)
+        if isinstance(v, tuple):
+            v = list(v)
+        if isinstance(v, (int, float, bool, list)):
+            out[p_.arg] = v
+    for p_, d in zip(a.kwonlyargs, a.kw_defaults):
+        v = literal(d) if d is not None else None
+        if isinstance(v, (int, float, bool)):
+            out[p_.arg] = v
+    return out
+
+
 def literal(node):
     try:
         return ast.literal_eval(node)
@@ -62,17 +80,19 @@ def literal(node):
 
 
 def main(root: str) -> None:
-    out = {"functions": {}, "methods": {}, "tuples": {}}
+    out = {"functions": {}, "methods": {}, "tuples": {}, "defaults": {}}
     for rel in sorted(set(FUNCS) | set(METHODS) | set(TUPLES)):
         tree = ast.parse(open(os.path.join(root, rel)).read())
         for node in tree.body:
             if isinstance(node, ast.FunctionDef) and node.name in FUNCS.get(rel, []):
                 out["functions"][node.name] = params(node)
+                out["defaults"][node.name] = param_defaults(node)
             if isinstance(node, ast.ClassDef):
                 if node.name in METHODS.get(rel, {}):
                     for sub in node.body:
                         if isinstance(sub, ast.FunctionDef) and sub.name in METHODS[rel][node.name]:
                             out["methods"][f"{node.name}.{sub.name}"] = params(sub)
+                            out["defaults"][f"{node.name}.{sub.name}"] = param_defaults(sub)
                 if node.name in TUPLES.get(rel, []):
                     fields = []
                     for sub in node.body:
