@@ -97,6 +97,44 @@ def test_oracle_matches_reference_run_all_shaders(p):
     assert float((sm - smf)[smf < 1e30].abs().max()) < 2e-5
 
 
+EDGE = ("tri0_backfacing", "tri0_frontfacing", "behind_and_straddling", "degenerate_and_duplicates", "old_z_closer")
+
+
+def _edge_check(tag, z, name):
+    zi = float(D[f"edge/{name}/z_init"])
+    zf = T(f"edge/{name}/zbuffer")
+    z = z.detach().cpu()
+    flips = int(((zf != zi) != (z != zi)).sum())
+    dz = float((z - zf).abs()[(zf != zi) == (z != zi)].max())
+    print(f"[{tag}] edge/{name}: reference wrote {int((zf != zi).sum())} pixels, coverage flips {flips}, max |dz| {dz:.3g}")
+    assert flips == 0 and dz <= Z_ATOL
+    assert int((zf != zi).sum()) > 20
+
+
+@pytest.mark.parametrize("name", EDGE)
+def test_oracle_matches_reference_run_edge_cases(name):
+    """Conventions restated from reading the reference, checked against its behaviour: a back-facing triangle 0
+    still fills pixels nothing else covers, geometry behind / across the camera plane, degenerate and
+    duplicate triangles (first index wins), no depth test against the incoming z-buffer."""
+    cam = NS(world_to_clip=T("edge/world_to_clip"), viewport=T("edge/viewport"))
+    W, H = int(D["edge/W"]), int(D["edge/H"])
+    ref = O.render(cam, "depth", torch.full((W, H), float(D[f"edge/{name}/z_init"])), (), T(f"edge/{name}/faces"),
+                   NS(position=T(f"edge/{name}/position")))
+    _edge_check("oracle", ref.zbuffer, name)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", EDGE)
+def test_cuda_path_matches_reference_run_edge_cases(name):
+    dev = torch.device("cuda", 0)
+    W, H = int(D["edge/W"]), int(D["edge/H"])
+    camera = jr.Camera(*[None] * 8)._replace(world_to_clip=T("edge/world_to_clip", dev), viewport=T("edge/viewport", dev))
+    z0 = torch.full((W, H), float(D[f"edge/{name}/z_init"]), device=dev)
+    out = jr.render(camera, S.DepthShader, jr.Buffers(z0, ()), T(f"edge/{name}/faces", dev),
+                    S.DepthExtraInput(position=T(f"edge/{name}/position", dev)))
+    _edge_check("cuda", out.zbuffer, name)
+
+
 def _facade_objects(dev=None):
     objs = []
     for i in range(3):

@@ -176,8 +176,46 @@ def run_facade():
         print(f"  {pre}/{name}: {time.time() - t:.1f}s", flush=True)
 
 
+def run_edge_cases():
+    """Depth-shader scenes for the conventions that were restated from reading the reference: the back-facing
+    triangle 0 quirk, geometry behind / straddling the camera plane, degenerate and duplicate triangles, incoming
+    z-buffer values closer than the new fragments (no depth test against the old buffer), an empty face list."""
+    W, H = 16, 12
+    cp = R.CameraParameters(viewWidth=W, viewHeight=H, position=jnp.array((0.0, -3.0, 0.5)), target=jnp.zeros(3),
+                            up=jnp.array((0.0, 0.0, 1.0)))
+    cam = R.Renderer.create_camera_from_parameters(cp)
+    put("edge", world_to_clip=cam.world_to_clip, viewport=cam.viewport, W=W, H=H)
+    scenes = {}
+    # triangle 0 back-facing (clockwise seen from the camera), triangle 1 front-facing, partly overlapping
+    scenes["tri0_backfacing"] = (
+        np.array([[-1.2, 0.0, -0.8], [0.0, 0.0, 1.2], [1.2, 0.0, -0.8],
+                  [-0.2, -0.5, -0.6], [1.4, -0.5, -0.6], [0.6, -0.5, 0.9]], np.float32),
+        np.array([[0, 1, 2], [3, 4, 5]], np.int32), 1.0)
+    # same with the winding of triangle 0 flipped (front-facing): the control
+    scenes["tri0_frontfacing"] = (scenes["tri0_backfacing"][0], np.array([[0, 2, 1], [3, 4, 5]], np.int32), 1.0)
+    # behind the camera, straddling the camera plane, and a normal one
+    scenes["behind_and_straddling"] = (
+        np.array([[-1.0, -6.0, -0.5], [1.0, -6.0, -0.5], [0.0, -6.0, 1.0],       # entirely behind
+                  [-0.8, -4.0, -0.4], [0.9, 1.0, -0.4], [0.0, 1.0, 0.9],          # crosses the camera plane
+                  [-0.5, 0.5, -0.3], [0.7, 0.5, -0.3], [0.1, 0.5, 0.8]], np.float32),
+        np.array([[0, 1, 2], [3, 4, 5], [6, 7, 8]], np.int32), 1.0)
+    # zero-area, repeated-vertex and duplicate triangles around a regular one
+    scenes["degenerate_and_duplicates"] = (
+        np.array([[-0.9, 0.0, -0.6], [0.9, 0.0, -0.6], [0.0, 0.0, 0.9], [0.3, 0.0, 0.1]], np.float32),
+        np.array([[3, 3, 3], [0, 1, 1], [0, 1, 2], [0, 1, 2], [0, 2, 1]], np.int32), 1.0)
+    # incoming z-buffer already closer than every fragment
+    scenes["old_z_closer"] = (scenes["tri0_frontfacing"][0], scenes["tri0_frontfacing"][1], 0.25)
+    for name, (pos, faces, z_init) in scenes.items():
+        out = R.render(cam, DepthShader, R.Buffers(zbuffer=jnp.full((W, H), z_init), targets=()), J(faces),
+                       DepthExtraInput(position=J(pos)))
+        put(f"edge/{name}", position=pos, faces=faces, z_init=np.float32(z_init), zbuffer=out.zbuffer)
+        z = np.asarray(out.zbuffer)
+        print(f"  edge/{name}: written {(z != z_init).sum()} of {z.size}", flush=True)
+
+
 def main():
     t0 = time.time()
+    run_edge_cases()
     for seed in (0, 1):
         run_soup(seed)
     run_facade()

@@ -231,7 +231,13 @@ def finfo(d):
 class _Linalg:
     @staticmethod
     def inv(a):
-        return _wrap(_np.linalg.inv(_np.asarray(a, dtype=_np.float32)))
+        a = _np.asarray(a, dtype=_np.float32)
+        try:
+            return _wrap(_np.linalg.inv(a))
+        except _np.linalg.LinAlgError:
+            # jax returns inf / nan for a singular input instead of raising (the reference masks such
+            # triangles with `keep = |det| > 1e-6`)
+            return _wrap(_np.full(a.shape, _np.nan, dtype=_np.float32))
 
     @staticmethod
     def det(a):
