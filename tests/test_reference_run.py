@@ -198,3 +198,53 @@ def test_cuda_facade_matches_reference_run(shadow):
     print(f"facade shadow={shadow}: max |dcolour| {float(diff.max()):.3g}, pixels off by > 2e-5: {bad} of {diff.numel()}")
     # a pixel may flip triangle / shadow state where the reference's own edge or depth comparison is within rounding
     assert bad <= 3
+
+
+def test_host_helpers_match_reference_run():
+    """Shapes, quaternion / rotation helpers, camera matrix builders and display utilities against the outputs of
+    the reference's own functions for the same arguments."""
+    from jaxrenderer_b200 import utils as U  # noqa: F401
+
+    def close(name, got, want, tol=2e-6):
+        got = np.asarray(got.detach().cpu() if isinstance(got, torch.Tensor) else got)
+        want = np.asarray(want)
+        assert got.shape == want.shape, (name, got.shape, want.shape)
+        if want.dtype.kind == "f":
+            assert np.abs(got - want).max() <= tol * max(1.0, np.abs(want).max()), name
+        else:
+            assert np.array_equal(got.astype(np.int64), want.astype(np.int64)), name
+
+    tex = T("helpers/cube/diffuse_map")
+    cube = jr.create_cube(half_extents=torch.tensor((0.5, 1.5, 2.0)), texture_scaling=torch.tensor((2.0, 3.0)),
+                          diffuse_map=tex, specular_map=torch.ones(3, 4) * 2.5)
+    for k in cube._fields:
+        close("cube." + k, getattr(cube, k), D["helpers/cube/" + k])
+    for ax in (jr.UpAxis.X, jr.UpAxis.Y, jr.UpAxis.Z):
+        cap = jr.create_capsule(radius=torch.tensor(0.25), half_height=torch.tensor(0.75), up_axis=ax, diffuse_map=tex,
+                                specular_map=torch.ones(3, 4) * 2.5)
+        for k in ("verts", "norms", "uvs", "faces"):
+            close(f"capsule[{int(ax)}].{k}", getattr(cap, k), D[f"helpers/capsule_{int(ax)}/{k}"])
+    axis, angle = T("helpers/rotation/axis"), T("helpers/rotation/angle")
+    q1, q2 = jr.quaternion(axis, angle), T("helpers/rotation/quaternion2")
+    close("quaternion", q1, D["helpers/rotation/quaternion"])
+    close("quaternion_mul", jr.quaternion_mul(q1, q2), D["helpers/rotation/quaternion_mul"])
+    close("rotation_matrix", jr.rotation_matrix(axis, angle), D["helpers/rotation/rotation_matrix"])
+    close("normalise", jr.normalise(torch.tensor((3.0, -4.0, 12.0))), D["helpers/rotation/normalise"])
+    mo = jr.ModelObject(model=cube).replace_with_orientation(q1).replace_with_position(torch.tensor((1.0, 2.0, 3.0)))
+    close("ModelObject.transform", mo.transform, D["helpers/model_object/transform"])
+    eye, centre, up = T("helpers/camera/eye"), T("helpers/camera/centre"), T("helpers/camera/up")
+    C = jr.Camera
+    close("view_matrix", C.view_matrix(eye, centre, up), D["helpers/camera/view"])
+    close("view_matrix_inv", C.view_matrix_inv(eye, centre, up), D["helpers/camera/view_inv"])
+    close("perspective", C.perspective_projection_matrix(40.0, 1.6, 0.1, 50.0), D["helpers/camera/perspective"])
+    close("orthographic", C.orthographic_projection_matrix(-2.0, 3.0, -1.0, 1.5, 0.5, 20.0),
+          D["helpers/camera/orthographic"])
+    close("viewport", C.viewport_matrix(torch.tensor((1.0, 2.0)), torch.tensor((640.0, 480.0)), torch.tensor(2.0)),
+          D["helpers/camera/viewport"])
+    close("world_to_screen", C.world_to_screen_matrix(320, 200), D["helpers/camera/world_to_screen"])
+    canvas = T("helpers/utils/canvas")
+    close("transpose_for_display", jr.transpose_for_display(canvas), D["helpers/utils/transposed"])
+    close("transpose_for_display(noflip)", jr.transpose_for_display(canvas, flip_vertical=False),
+          D["helpers/utils/transposed_noflip"])
+    close("build_texture_from_PyTinyrenderer", jr.build_texture_from_PyTinyrenderer(T("helpers/utils/pytiny_raw"), 4, 3),
+          D["helpers/utils/pytiny_texture"])

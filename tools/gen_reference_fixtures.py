@@ -213,8 +213,44 @@ def run_edge_cases():
         print(f"  edge/{name}: written {(z != z_init).sum()} of {z.size}", flush=True)
 
 
+def run_host_helpers():
+    """Outputs of the reference's host-side helpers (shapes, quaternions / rotations, camera matrix builders,
+    display utilities) for fixed arguments."""
+    rng = np.random.default_rng(11)
+    tex = rng.random((3, 4, 3), dtype=np.float32)
+    cube = R.create_cube(half_extents=jnp.array((0.5, 1.5, 2.0)), texture_scaling=jnp.array((2.0, 3.0)),
+                         diffuse_map=J(tex), specular_map=jnp.ones((3, 4)) * 2.5)
+    put("helpers/cube", **{k: getattr(cube, k) for k in cube._fields})
+    for axis in (R.UpAxis.X, R.UpAxis.Y, R.UpAxis.Z):
+        cap = R.create_capsule(radius=jnp.array(0.25), half_height=jnp.array(0.75), up_axis=axis, diffuse_map=J(tex),
+                               specular_map=jnp.ones((3, 4)) * 2.5)
+        put(f"helpers/capsule_{int(axis)}", verts=cap.verts, norms=cap.norms, uvs=cap.uvs, faces=cap.faces)
+    axis, angle = jnp.array((0.3, -0.5, 0.8)), jnp.array(37.0)
+    q1, q2 = R.quaternion(axis, angle), R.quaternion(jnp.array((1.0, 0.2, 0.1)), jnp.array(-110.0))
+    put("helpers/rotation", axis=axis, angle=angle, quaternion=q1, quaternion2=q2, quaternion_mul=R.quaternion_mul(q1, q2),
+        rotation_matrix=R.rotation_matrix(axis, angle), normalise=R.normalise(jnp.array((3.0, -4.0, 12.0))))
+    mo = R.ModelObject(model=cube).replace_with_orientation(q1).replace_with_position(jnp.array((1.0, 2.0, 3.0)))
+    put("helpers/model_object", transform=mo.transform)
+    eye, centre, up = jnp.array((1.0, -2.0, 3.0)), jnp.array((0.2, 0.1, -0.3)), jnp.array((0.0, 0.0, 1.0))
+    C = R.Camera
+    put("helpers/camera", eye=eye, centre=centre, up=up, view=C.view_matrix(eye, centre, up),
+        view_inv=C.view_matrix_inv(eye, centre, up),
+        perspective=C.perspective_projection_matrix(jnp.array(40.0), jnp.array(1.6), jnp.array(0.1), jnp.array(50.0)),
+        orthographic=C.orthographic_projection_matrix(jnp.array(-2.0), jnp.array(3.0), jnp.array(-1.0), jnp.array(1.5),
+                                                       jnp.array(0.5), jnp.array(20.0)),
+        viewport=C.viewport_matrix(jnp.array((1.0, 2.0)), jnp.array((640.0, 480.0)), jnp.array(2.0)),
+        world_to_screen=C.world_to_screen_matrix(320, 200))
+    canvas = rng.random((5, 7, 3), dtype=np.float32) * 1.4 - 0.2
+    put("helpers/utils", canvas=canvas, transposed=R.transpose_for_display(J(canvas)),
+        transposed_noflip=R.transpose_for_display(J(canvas), flip_vertical=False))
+    raw = (rng.integers(0, 256, 4 * 3 * 3)).astype(np.float32)
+    put("helpers/utils", pytiny_raw=raw, pytiny_texture=R.build_texture_from_PyTinyrenderer(J(raw), 4, 3))
+    print("  helpers done", flush=True)
+
+
 def main():
     t0 = time.time()
+    run_host_helpers()
     run_edge_cases()
     for seed in (0, 1):
         run_soup(seed)
