@@ -282,16 +282,16 @@ def _oracle_facade(objs, cp, light, sp, W, H):
     merged = jr.merge_objects(objs)
     cam = jr.Renderer.create_camera_from_parameters(cp)
     res = O.renderer_render(merged, light, cam, torch.ones(W, H), torch.ones(W, H, 3), shadow_param=sp)
-    return res["out"].targets[0]
+    return res["out"].targets[0], res["out"].gap
 
 
 @pytest.mark.parametrize("shadow", [True, False])
 def test_oracle_facade_matches_reference_run(shadow):
     objs, cp, sp = _facade_objects()
-    canvas = _oracle_facade(objs, cp, jr.LightParameters(), sp if shadow else None, cp.viewWidth, cp.viewHeight)
+    canvas, gap = _oracle_facade(objs, cp, jr.LightParameters(), sp if shadow else None, cp.viewWidth, cp.viewHeight)
     want = T("facade/with_shadow/canvas" if shadow else "facade/no_shadow/canvas")
     diff = (canvas - want).abs().amax(-1)
-    assert int((diff > 2e-5).sum()) <= 3, float(diff.max())
+    assert int((diff > 2e-5).sum()) == 0, float(diff.max())
 
 
 def test_oracle_facade_matches_reference_run_brax_frame():
@@ -307,8 +307,10 @@ def test_oracle_facade_matches_reference_run_brax_frame():
                              position=cam.position[f], target=cam.target[f], up=cam.up[f])
     light = jr.LightParameters(direction=torch.from_numpy(B["light_direction"]), ambient=torch.from_numpy(B["ambient"]),
                                diffuse=torch.from_numpy(B["diffuse"]), specular=torch.from_numpy(B["specular"]))
-    canvas = _oracle_facade(objs, cp, light, jr.ShadowParameters(centre=cam.target[f]), W, H)
+    canvas, gap = _oracle_facade(objs, cp, light, jr.ShadowParameters(centre=cam.target[f]), W, H)
     diff = (canvas - torch.from_numpy(B["canvas"])).abs().amax(-1)
-    bad = int((diff > 2e-5).sum())
-    print(f"oracle, brax frame {f} at {W}x{H}: max |dcolour| {float(diff.max()):.3g}, pixels off by > 2e-5: {bad}")
-    assert bad <= 4
+    bad = diff > 2e-5
+    print(f"oracle, brax frame {f} at {W}x{H}: max |dcolour| {float(diff.max()):.3g}, pixels off by > 2e-5: "
+          f"{int(bad.sum())}, of which depth ties (< 1e-6 between the competing triangles): {int((bad & (gap < 1e-6)).sum())}")
+    # BASELINE.json: the chosen triangle may differ only where the competing depths differ by < 1e-6 -- counted
+    assert int((bad & ~(gap < 1e-6)).sum()) == 0 and int(bad.sum()) <= 4
