@@ -16,7 +16,7 @@ import sys
 import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-REF = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
+REF = sys.argv[1] if (len(sys.argv) > 1 and os.path.isdir(sys.argv[1])) else "/root/reference"
 sys.path.insert(0, os.path.join(ROOT, "tools", "jax_numpy_shim"))
 sys.path.insert(0, REF)
 sys.path.insert(1, ROOT)

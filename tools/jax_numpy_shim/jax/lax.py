@@ -5,7 +5,7 @@ import builtins as _bi
 
 import numpy as _np
 
-from .numpy import _wrap, _canon
+from .numpy import _wrap, _canon, _FLOAT
 from .tree_util import tree_map
 
 
@@ -133,16 +133,16 @@ class _Linalg:
     @staticmethod
     def triangular_solve(a, b, left_side=False, lower=False, transpose_a=False, conjugate_a=False,
                          unit_diagonal=False):
-        a, b = _np.asarray(a, dtype=_np.float32), _np.asarray(b, dtype=_np.float32)
+        a, b = _np.asarray(a, dtype=_FLOAT), _np.asarray(b, dtype=_FLOAT)
         tri = _np.tril(a) if lower else _np.triu(a)
         if unit_diagonal:
             tri = tri - _np.diag(_np.diag(tri)) + _np.eye(a.shape[-1], dtype=a.dtype)
         if transpose_a:
             tri = tri.T
         if left_side:      # solve tri @ x = b
-            return _wrap(_np.linalg.solve(tri, b).astype(_np.float32))
+            return _wrap(_np.linalg.solve(tri, b).astype(_FLOAT))
         # solve x @ tri = b
-        return _wrap(_np.linalg.solve(tri.T, b.T).T.astype(_np.float32))
+        return _wrap(_np.linalg.solve(tri.T, b.T).T.astype(_FLOAT))
 
 
 linalg = _Linalg()

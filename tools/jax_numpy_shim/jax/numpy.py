@@ -2,6 +2,7 @@
 from __future__ import annotations
 
 import builtins as _bi
+import os as _os
 
 import numpy as _np
 
@@ -17,10 +18,17 @@ newaxis = None
 ndarray = _np.ndarray
 
 
+# JAX_SHIM_X64=1: keep float64 (the analogue of jax_enable_x64) -- used for finite-difference gradient references
+X64 = _os.environ.get("JAX_SHIM_X64", "0") == "1"
+_FLOAT = _np.float64 if X64 else _np.float32
+
+
 def _canon(dtype):
     dtype = _np.dtype(dtype)
     if dtype == _np.float64:
-        return _np.dtype(_np.float32)
+        return _np.dtype(_FLOAT)
+    if X64 and dtype == _np.float32:
+        return _np.dtype(_np.float64)
     if dtype == _np.int64:
         return _np.dtype(_np.int32)
     if dtype == _np.uint64:
@@ -126,11 +134,11 @@ def asarray(x, dtype=None):
 
 
 def zeros(shape, dtype=None):
-    return _wrap(_np.zeros(shape, dtype=dtype or _np.float32))
+    return _wrap(_np.zeros(shape, dtype=dtype or _FLOAT))
 
 
 def ones(shape, dtype=None):
-    return _wrap(_np.ones(shape, dtype=dtype or _np.float32))
+    return _wrap(_np.ones(shape, dtype=dtype or _FLOAT))
 
 
 def full(shape, fill_value, dtype=None):
@@ -146,11 +154,11 @@ def zeros_like(x, dtype=None):
 
 
 def identity(n, dtype=None):
-    return _wrap(_np.identity(n, dtype=dtype or _np.float32))
+    return _wrap(_np.identity(n, dtype=dtype or _FLOAT))
 
 
 def eye(n, dtype=None):
-    return _wrap(_np.eye(n, dtype=dtype or _np.float32))
+    return _wrap(_np.eye(n, dtype=dtype or _FLOAT))
 
 
 def arange(*a, dtype=None):
@@ -231,18 +239,18 @@ def finfo(d):
 class _Linalg:
     @staticmethod
     def inv(a):
-        a = _np.asarray(a, dtype=_np.float32)
+        a = _np.asarray(a, dtype=_FLOAT)
         try:
             return _wrap(_np.linalg.inv(a))
         except _np.linalg.LinAlgError:
             # jax returns inf / nan for a singular input instead of raising (the reference masks such
             # triangles with `keep = |det| > 1e-6`)
-            return _wrap(_np.full(a.shape, _np.nan, dtype=_np.float32))
+            return _wrap(_np.full(a.shape, _np.nan, dtype=_FLOAT))
 
     @staticmethod
     def det(a):
         """3x3: the closed form jax lowers to (`_det_3x3`), same term order."""
-        a = _np.asarray(a, dtype=_np.float32)
+        a = _np.asarray(a, dtype=_FLOAT)
         if a.shape[-2:] == (3, 3):
             return _wrap(a[..., 0, 0] * a[..., 1, 1] * a[..., 2, 2] + a[..., 0, 1] * a[..., 1, 2] * a[..., 2, 0]
                          + a[..., 0, 2] * a[..., 1, 0] * a[..., 2, 1] - a[..., 0, 2] * a[..., 1, 1] * a[..., 2, 0]
