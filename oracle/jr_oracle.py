@@ -30,7 +30,9 @@ cannot run on XLA here.  It DOES run on a NumPy stand-in for jax
 the UNMODIFIED reference sources for all seven shaders, the shadow pass and the
 ``get_camera_image`` facade (``tools/gen_reference_fixtures.py``), and this oracle
 reproduces them (``tests/test_reference_run.py``: no coverage flips, |dz| <= 2e-6,
-|dcolour| <= 1.1e-6).  What remains UNPINNED is XLA's last-bit rounding, i.e. the
+|dcolour| <= 1.1e-6; ``tests/test_reference_grad.py``: its autograd gradients
+match float64 finite differences of the reference's forward code within 4e-6).
+What remains UNPINNED is XLA's last-bit rounding, i.e. the
 outcome for pixels whose edge / depth comparisons are within rounding (the
 reference holds no golden vectors, images or gradient values).  It is also
 checked against every assertion of the reference's own tests for this path
