@@ -2,8 +2,8 @@
 
 `tests/golden/reference_grad.npz` (tools/gen_reference_grad_fixtures.py): central finite differences, in FLOAT64, of
 `loss = sum(wz * zbuffer) + sum(wc * canvas)` computed by the UNMODIFIED reference (run on the NumPy stand-in for jax in
-double precision) on scene `soup0` of `reference_run.npz`, for single entries of the differentiable inputs of three
-shaders.  The CPU test checks the oracle's autograd gradients against them, the GPU test the CUDA backward kernels.
+double precision) on scene `soup0` of `reference_run.npz`, for single entries of the differentiable inputs of the built-in
+shaders (two fixture files: depth / gouraud / phong_reflection_shadow, and the four others).  The CPU test checks the oracle's autograd gradients against them, the GPU test the CUDA backward kernels.
 
 Tolerance: BASELINE.json's 1e-4, relative to the largest reference entry of the same input array (position: 5e-4 --
 d z / d position is a cancellation of O(100)-sized terms in fp32, see tests/test_gpu_backward.py).  Measured: every
@@ -18,18 +18,22 @@ import jaxrenderer_b200 as jr
 from oracle import jr_oracle as O
 from tests import test_reference_run as RR
 
-_PATH = os.path.join(os.path.dirname(__file__), "golden", "reference_grad.npz")
-if not os.path.exists(_PATH):   # generated by tools/gen_reference_grad_fixtures.py (~40 minutes)
-    pytest.skip("tests/golden/reference_grad.npz has not been generated", allow_module_level=True)
-G = np.load(_PATH)
+_DIR = os.path.join(os.path.dirname(__file__), "golden")
+G = {}
+for _f in ("reference_grad.npz", "reference_grad_more.npz"):   # tools/gen_reference_grad_fixtures.py [more]
+    if os.path.exists(os.path.join(_DIR, _f)):
+        _z = np.load(os.path.join(_DIR, _f))
+        G.update({k: _z[k] for k in _z.files})
+if not G:
+    pytest.skip("tests/golden/reference_grad*.npz have not been generated", allow_module_level=True)
 P = "soup0"
-SHADERS = ("depth", "gouraud", "phong_reflection_shadow")
+SHADERS = tuple(k.split("/")[0] for k in G if k.endswith("/names"))
 RTOL = {"position": 5e-4}
 DEFAULT_RTOL = 1e-4
 # reference_grad name -> (attribute path used to fetch the gradient from the leaves dict)
 LEAF_KEYS = ("position", "normal", "colour", "light_direction", "light_colour", "world_to_clip", "viewport",
              "world_to_eye_norm", "atlas", "specular_map", "light_dir_eye", "ambient", "diffuse", "specular",
-             "shadow_strength")
+             "shadow_strength", "uv_texel", "texture", "normal_map")
 
 
 def _leaves(dev=None):
@@ -51,6 +55,22 @@ def _extra(name, L, dev=None):
     if name == "gouraud":
         return cam, S.GouraudShader, S.GouraudExtraInput(L["position"], L["colour"], L["normal"], light)
     T = RR.T
+    if name in ("gouraud_texture", "phong"):
+        cls = (S.GouraudTextureShader, S.GouraudTextureExtraInput) if name == "gouraud_texture" else (
+            S.PhongTextureShader, S.PhongTextureExtraInput)
+        return cam, cls[0], cls[1](L["position"], L["normal"], L["uv_texel"], light, L["texture"])
+    if name == "phong_darboux":
+        faces = T(P + "/faces", dev)
+        i2f = torch.arange(faces.shape[0], dtype=torch.int32, device=dev).repeat_interleave(3)
+        return cam, S.PhongTextureDarbouxShader, S.PhongTextureDarbouxExtraInput(
+            L["position"], L["normal"], L["uv_texel"], light, L["texture"], L["normal_map"], i2f, faces)
+    if name == "phong_reflection":
+        return cam, S.PhongReflectionTextureShader, S.PhongReflectionTextureExtraInput(
+            position=L["position"], normal=L["normal"], uv=T(P + "/uv01", dev), light=light,
+            light_dir_eye=L["light_dir_eye"], texture_shape=T(P + "/texture_shape", dev),
+            texture_index=T(P + "/texture_index", dev), texture_offset=int(RR.D[P + "/texture_offset"]),
+            texture=L["atlas"], specular_map=L["specular_map"], ambient=L["ambient"], diffuse=L["diffuse"],
+            specular=L["specular"])
     shadow_cam = NS(world_to_clip=T(P + "/shadow_world_to_clip", dev), viewport=T(P + "/shadow_viewport", dev))
     shadow = jr.Shadow(shadow_map=T(P + "/shadow_map", dev), strength=L["shadow_strength"], camera=shadow_cam)
     extra = S.PhongReflectionShadowTextureExtraInput(
@@ -71,7 +91,7 @@ def _compare(tag, name, L):
         if scale == 0.0:
             continue
         g = L[arr].grad
-        assert g is not None, (name, arr)
+        g = torch.zeros_like(L[arr]) if g is None else g      # an input the shader does not differentiate
         g = g.detach().cpu().double().numpy()
         errs = []
         for idx, w in zip(index[sel], want[sel]):

@@ -8,7 +8,8 @@ differentiable inputs by +-h (h = 1e-6) and stores `(loss(+h) - loss(-h)) / 2h`;
 is not O(h^2) -- a visibility, texel or shadow change inside the step -- are dropped.  Output:
 `tests/golden/reference_grad.npz`.  About 20 minutes.
 
-  python tools/gen_reference_grad_fixtures.py [/root/reference]
+  python tools/gen_reference_grad_fixtures.py          # depth, gouraud, phong_reflection_shadow
+  python tools/gen_reference_grad_fixtures.py more     # gouraud_texture, phong, phong_darboux, phong_reflection
 """
 from __future__ import annotations
 
@@ -35,7 +36,7 @@ WC = rng.random((W, H, 3)) + 0.5
 
 
 def inputs():
-    keys = ["position", "normal", "colour", "uv01", "light_direction", "light_colour", "world_to_clip", "viewport",
+    keys = ["uv_texel", "texture", "normal_map", "position", "normal", "colour", "uv01", "light_direction", "light_colour", "world_to_clip", "viewport",
             "world_to_eye_norm", "view", "atlas", "specular_map", "light_dir_eye", "ambient", "diffuse", "specular",
             "shadow_strength", "shadow_map", "shadow_world_to_clip", "shadow_viewport", "texture_shape",
             "texture_index", "faces"]
@@ -57,9 +58,30 @@ def loss(shader_name, v):
         out = R.render(cam, G.DepthShader, R.Buffers(zbuffer=z0, targets=()), faces,
                        G.DepthExtraInput(position=J(v["position"])))
         return float((np.asarray(out.zbuffer) * WZ).sum())
+    n_tri = v["faces"].shape[0]
     if shader_name == "gouraud":
         extra = G.GouraudExtraInput(position=J(v["position"]), colour=J(v["colour"]), normal=J(v["normal"]), light=light)
         shader = G.GouraudShader
+    elif shader_name == "gouraud_texture":
+        extra = G.GouraudTextureExtraInput(position=J(v["position"]), normal=J(v["normal"]), uv=J(v["uv_texel"]),
+                                           light=light, texture=J(v["texture"]))
+        shader = G.GouraudTextureShader
+    elif shader_name == "phong":
+        extra = G.PhongTextureExtraInput(position=J(v["position"]), normal=J(v["normal"]), uv=J(v["uv_texel"]),
+                                         light=light, texture=J(v["texture"]))
+        shader = G.PhongTextureShader
+    elif shader_name == "phong_darboux":
+        extra = G.PhongTextureDarbouxExtraInput(
+            position=J(v["position"]), normal=J(v["normal"]), uv=J(v["uv_texel"]), light=light, texture=J(v["texture"]),
+            normal_map=J(v["normal_map"]), id_to_face=J(np.repeat(np.arange(n_tri, dtype=np.int32), 3)), faces_indices=faces)
+        shader = G.PhongTextureDarbouxShader
+    elif shader_name == "phong_reflection":
+        extra = G.PhongReflectionTextureExtraInput(
+            position=J(v["position"]), normal=J(v["normal"]), uv=J(v["uv01"]), light=light,
+            light_dir_eye=J(v["light_dir_eye"]), texture_shape=J(v["texture_shape"]), texture_index=J(v["texture_index"]),
+            texture_offset=J(np.int32(D[P + "/texture_offset"])), texture=J(v["atlas"]), specular_map=J(v["specular_map"]),
+            ambient=J(v["ambient"]), diffuse=J(v["diffuse"]), specular=J(v["specular"]))
+        shader = G.PhongReflectionTextureShader
     else:
         scam = R.Camera(view=jnp.identity(4), projection=jnp.identity(4), viewport=J(v["shadow_viewport"]),
                         world_to_clip=J(v["shadow_world_to_clip"]), world_to_eye_norm=jnp.identity(4),
@@ -119,6 +141,17 @@ def main():
                                     ("world_to_eye_norm", (0, 0)), ("world_to_eye_norm", (1, 2)),
                                     ("world_to_eye_norm", (2, 1)), ("viewport", (0, 3))],
     }
+    second = len(sys.argv) > 1 and sys.argv[-1] == "more"
+    if second:   # the four remaining shaders -> tests/golden/reference_grad_more.npz
+        common = [("light_colour", (0,)), ("light_direction", (1,)), ("light_direction", (2,)),
+                  ("world_to_clip", (0, 0)), ("world_to_clip", (3, 1)), ("viewport", (1, 1))]
+        plans = {
+            "gouraud_texture": list(common),
+            "phong": common + [("world_to_eye_norm", (0, 1)), ("world_to_eye_norm", (2, 2))],
+            "phong_darboux": common + [("world_to_eye_norm", (1, 1)), ("world_to_eye_norm", (0, 2))],
+            "phong_reflection": [("light_colour", (2,)), ("light_dir_eye", (1,)), ("ambient", (2,)), ("diffuse", (0,)),
+                                 ("specular", (1,)), ("world_to_clip", (1, 1)), ("world_to_eye_norm", (2, 0))],
+        }
     # vertex attributes of the triangles that cover most pixels (one coordinate per vertex, cycled)
     tris = visible_triangles(base)
     print("  most visible triangles:", tris, flush=True)
@@ -126,6 +159,14 @@ def main():
         for k in range(3):
             vtx = int(base["faces"][t][k])
             c = (j + k) % 3
+            if second:
+                if j >= 4:
+                    continue
+                for sh in ("gouraud_texture", "phong", "phong_darboux", "phong_reflection"):
+                    plans[sh].append(("position", (vtx, (c + 1) % 3)))
+                    plans[sh].append(("normal", (vtx, c)))
+                plans["phong_darboux"].append(("uv_texel", (vtx, k % 2)))
+                continue
             plans["depth"].append(("position", (vtx, c)))
             plans["gouraud"].append(("position", (vtx, (c + 1) % 3)))
             plans["gouraud"].append(("normal", (vtx, (c + 2) % 3)))
@@ -133,10 +174,21 @@ def main():
             plans["phong_reflection_shadow"].append(("position", (vtx, (c + 2) % 3)))
             plans["phong_reflection_shadow"].append(("normal", (vtx, c)))
     # texture / specular-map entries: all texels of the small atlas rows that are likely hit are too many; sample
-    for u in range(0, base["atlas"].shape[0], 3):
-        plans["phong_reflection_shadow"].append(("atlas", (u, (u // 3) % base["atlas"].shape[1], u % 3)))
-    for u in range(base["specular_map"].shape[0]):
-        plans["phong_reflection_shadow"].append(("specular_map", (u, u % 2)))
+    if second:
+        tw, th = base["texture"].shape[:2]
+        for u in range(tw):
+            for sh in ("gouraud_texture", "phong", "phong_darboux"):
+                plans[sh].append(("texture", (u, (3 * u + 1) % th, u % 3)))
+            plans["phong_darboux"].append(("normal_map", (u, (5 * u + 2) % th, (u + 1) % 3)))
+        for u in range(0, base["atlas"].shape[0], 4):
+            plans["phong_reflection"].append(("atlas", (u, (u // 4) % base["atlas"].shape[1], u % 3)))
+        for u in range(0, base["specular_map"].shape[0], 2):
+            plans["phong_reflection"].append(("specular_map", (u, u % 2)))
+    else:
+        for u in range(0, base["atlas"].shape[0], 3):
+            plans["phong_reflection_shadow"].append(("atlas", (u, (u // 3) % base["atlas"].shape[1], u % 3)))
+        for u in range(base["specular_map"].shape[0]):
+            plans["phong_reflection_shadow"].append(("specular_map", (u, u % 2)))
     out = {"wz": WZ.astype(np.float32), "wc": WC.astype(np.float32)}
     for shader_name, plan in plans.items():
         names, idxs, grads = [], [], []
@@ -159,7 +211,7 @@ def main():
         out[f"{shader_name}/index"] = np.array(idxs, dtype=np.int32)
         out[f"{shader_name}/grad"] = np.array(grads, dtype=np.float64)
         out[f"{shader_name}/loss"] = np.float64(l0)
-    dst = os.path.join(ROOT, "tests", "golden", "reference_grad.npz")
+    dst = os.path.join(ROOT, "tests", "golden", "reference_grad_more.npz" if second else "reference_grad.npz")
     np.savez_compressed(dst, **out)
     print(f"wrote {dst} in {time.time() - t0:.0f}s")
 
