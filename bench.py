@@ -12,7 +12,9 @@ collective).  One "step" = one `pipeline.render` of the whole per-GPU batch.
 `value`   images/s with inputs resident in HBM (device-timed, max over ranks).
 `e2e`     images/s through the public API with HOST (pinned) geometry: H2D of
           positions/faces/camera and D2H of the z-buffers inside the timed region.
-`roofline` HBM roofline of the dominant kernel (k_visibility<depth>).
+`roofline` HBM roofline of the dominant kernel (jr::k_vis2<true,true>) + `roofline.issue`, the issue-slot figure
+          that actually binds it.
+`fwd_bwd` secondary lines: forward + backward images/s (phong_reflection_shadow, 84x84 x 4096 and 480x270 x 512).
 `cpu_baseline` / `--impl reference`: the reference's brute-force algorithm
           (C port, oracle/jr_oracle_c.c) on the host cores, bounded sample.
 """
