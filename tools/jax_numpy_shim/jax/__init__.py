@@ -56,7 +56,6 @@ def vmap(f, in_axes=0, out_axes=0):
         for arg, ax in zip(args, axes):
             leaves, treedef = tree_flatten(arg)
             if isinstance(ax, (tuple, list)) or (ax is not None and not isinstance(ax, int)):
-                ax_leaves, _ = tree_flatten(ax, is_leaf=lambda x: x is None)
                 # a pytree of axes matching the argument (one entry per top-level field)
                 ax_leaves = _broadcast_axes(arg, ax)
             else:
