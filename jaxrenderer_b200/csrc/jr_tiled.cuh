@@ -17,7 +17,12 @@
 
 namespace jr {
 
-constexpr int TL_TILE = 64;
+#ifndef JR_TL_TILE
+#define JR_TL_TILE 64
+#endif
+constexpr int TL_TILE = JR_TL_TILE;  // power of two
+constexpr int TL_SHIFT = (TL_TILE == 64) ? 6 : (TL_TILE == 32) ? 5 : (TL_TILE == 128) ? 7 : -1;
+static_assert(TL_SHIFT > 0, "tile size must be 32, 64 or 128");
 constexpr int TL_THREADS = 256;
 constexpr int TL_BIGCAP = 32;
 #ifndef JR_TL_BIG_AREA
@@ -375,7 +380,7 @@ k_raster_tile(const __grid_constant__ JrRenderArgs a, const TriRecord* __restric
   float* __restrict__ z_out = DEPTH ? a.zbuffer + (long long)b * a.W * a.H : nullptr;
   const bool use0 = DEPTH && tri0_flag;
   for (int i = tid; i < tw * TL_TILE; i += TL_THREADS) {
-    const int lx = i >> 6, ly = i & 63;
+    const int lx = i >> TL_SHIFT, ly = i & (TL_TILE - 1);
     if (ly >= th) continue;
     const long long pix = (long long)(tx0 + lx) * a.H + (ty0 + ly);
     int tri = -1;
