@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define JR_ABI_VERSION 2
+#define JR_ABI_VERSION 3
 
 typedef void* jr_stream_t; /* cudaStream_t */
 
@@ -130,6 +130,13 @@ typedef struct JrRenderArgs {
 
   void* workspace;         /* >= jr_workspace_bytes(args) bytes, or NULL if that is 0 */
   size_t workspace_bytes;
+
+  /* Optional measurement counters (device, 8 x uint64, caller zero-fills; NULL = off, the normal case).
+   * When set, the visibility kernels run their counting variant and ADD: [0] triangles visited,
+   * [1] triangles passed by the filter phase, [2] triangles kept by the exact cull, [3] N_test = edge-function
+   * evaluations (pixel x triangle tests; the reference's count is W*H*T, pipeline.py:163-279), [4] fragments
+   * that passed the inside test, [5] exact-phase warp rounds, [6] batches. */
+  unsigned long long* stats;
 } JrRenderArgs;
 
 /*

@@ -53,6 +53,7 @@ class JrRenderArgs(C.Structure):
         ("shadow_strength", JrF32), ("shadow_world_to_clip", JrF32), ("shadow_viewport", JrF32),
         ("zbuffer", C.c_void_p), ("canvas", C.c_void_p), ("tri_id", C.c_void_p),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("stats", C.c_void_p),
     ]
 
 

@@ -20,25 +20,44 @@ from .model import Model, ModelObject
 from .renderer import CameraParameters
 
 
+def _np_reconstruct(*args: Any):
+    from numpy._core.multiarray import _reconstruct   # numpy >= 2 (``numpy.core`` in older pickles)
+
+    return _reconstruct(*args)
+
+
 def _reconstruct_array(fun, args, arr_state, aval_state):  # jax._src.array._reconstruct_array
+    # `fun` comes out of the pickle stream: only numpy's own array reconstructor may be called
+    if fun is not _np_reconstruct:
+        raise pickle.UnpicklingError("refusing to call a non-numpy array constructor from a pickle")
     a = fun(*args)
+    if not isinstance(a, np.ndarray):
+        raise pickle.UnpicklingError("array reconstruction did not yield a numpy array")
     a.__setstate__(arr_state)
     return a
 
 
+# Exact (module, name) pairs the pre-generated files reference; everything else is refused.  (Whole-module
+# allow-lists would expose builtins.eval / numpy helpers that execute code.)
+_ALLOWED = {
+    ("renderer.model", "Model"): Model,
+    ("renderer.model", "ModelObject"): ModelObject,
+    ("renderer.renderer", "CameraParameters"): CameraParameters,
+    ("jax._src.array", "_reconstruct_array"): _reconstruct_array,
+    ("numpy", "ndarray"): np.ndarray,
+    ("numpy", "dtype"): np.dtype,
+    ("numpy.core.multiarray", "_reconstruct"): _np_reconstruct,
+    ("numpy._core.multiarray", "_reconstruct"): _np_reconstruct,
+    ("collections", "OrderedDict"): __import__("collections").OrderedDict,
+}
+
+
 class _Unpickler(pickle.Unpickler):
     def find_class(self, module: str, name: str):
-        if module == "renderer.model":
-            return {"Model": Model, "ModelObject": ModelObject}[name]
-        if module == "renderer.renderer":
-            return {"CameraParameters": CameraParameters}[name]
-        if module == "jax._src.array" and name == "_reconstruct_array":
-            return _reconstruct_array
-        if module.startswith("numpy.core"):
-            module = module.replace("numpy.core", "numpy._core", 1)
-        if module.split(".")[0] not in ("numpy", "builtins", "collections"):
-            raise pickle.UnpicklingError(f"refusing to load {module}.{name}")
-        return super().find_class(module, name)
+        try:
+            return _ALLOWED[(module, name)]
+        except KeyError:
+            raise pickle.UnpicklingError(f"refusing to load {module}.{name}") from None
 
 
 def _to_torch(x: Any) -> Any:

@@ -575,8 +575,10 @@ k_bwd_keys(const __grid_constant__ JrRenderArgs a, KeyedPlan plan, unsigned* __r
           if (MODE == MODE_UV || MODE == MODE_POS2) {
             // vertices of the tangent-frame triangle of the chosen triangle's first vertex
             const int v0 = min(max(fp[0], 0), a.n_pos - 1);
-            const int face = (a.id_to_face.ptr + (long long)b * a.id_to_face.batch_stride)[v0];
-            v = (a.faces_indices.ptr + (long long)b * a.faces_indices.batch_stride)[3 * face + k];
+            // wrap one negative, then clamp: the forward's gathers (jr_shade.cuh, frag_pixel Darboux branch)
+            const int face = wrap_clamp((a.id_to_face.ptr + (long long)b * a.id_to_face.batch_stride)[v0], a.n_faces_indices);
+            v = wrap_clamp((a.faces_indices.ptr + (long long)b * a.faces_indices.batch_stride)[3 * face + k],
+                           (int)plan.keys_per_image);
           }
           v = min(max(v, 0), (int)plan.keys_per_image - 1);
           key = boff + (unsigned)v;

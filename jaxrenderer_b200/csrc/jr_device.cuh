@@ -98,12 +98,11 @@ __device__ __forceinline__ void lu_inverse3(const float A[9], float inv[9]) {
 
 // Monotone map float -> uint32 (-0 canonicalised to +0 first).
 __device__ __forceinline__ uint32_t orderable(float z) {
-  uint32_t f = __float_as_uint(z + 0.0f);
-  return f ^ ((f >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+  const uint32_t f = __float_as_uint(z + 0.0f);
+  return f ^ ((uint32_t)((int32_t)f >> 31) | 0x80000000u);  // negative: flip all bits; else: set the sign bit
 }
 __device__ __forceinline__ float from_orderable(uint32_t u) {
-  uint32_t f = u ^ ((u >> 31) ? 0x80000000u : 0xFFFFFFFFu);
-  return __uint_as_float(f);
+  return __uint_as_float(u ^ (~(uint32_t)((int32_t)u >> 31) | 0x80000000u));
 }
 
 // Per-triangle raster record (PerPrimitive, pipeline.py:49-113).

@@ -18,6 +18,7 @@
 #include "jr_common.cuh"
 #include "jr_shade.cuh"
 #include "jr_visibility.cuh"
+#include "jr_vis3.cuh"
 #include "jr_tiled.cuh"
 #include <stdlib.h>
 #include <mutex>
@@ -301,6 +302,29 @@ static void choose_tiles(int W, int H, int* tw, int* th, int* nx, int* ny) {
   *ny = (H + *th - 1) / *th;
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per device: set it once per device this process renders on
+template <typename K>
+static void smem_attr(K kernel, int bytes) { cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); }
+static void set_kernel_attributes_once() {
+  static std::once_flag once[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::call_once(once[dev & 63], [] {
+    smem_attr(k_vis2<true, true, V2_K32_THREADS>, 200 * 1024);
+    smem_attr(k_vis2<true, false, V2_THREADS>, 200 * 1024);
+    smem_attr(k_vis2<false, false, V2_THREADS>, 200 * 1024);
+    smem_attr(k_vis3<true, true, false>, 200 * 1024);
+    smem_attr(k_vis3<true, false, false>, 200 * 1024);
+    smem_attr(k_vis3<false, false, false>, 200 * 1024);
+    smem_attr(k_vis3<true, true, true>, 200 * 1024);
+    smem_attr(k_vis3<true, false, true>, 200 * 1024);
+    smem_attr(k_vis3<false, false, true>, 200 * 1024);
+    smem_attr(k_raster_tile<true, true>, 64 * 1024);
+    smem_attr(k_raster_tile<true, false>, 64 * 1024);
+    smem_attr(k_raster_tile<false, false>, 64 * 1024);
+  });
+}
+
 extern "C" {
 
 int jr_abi_version(void) { return JR_ABI_VERSION; }
@@ -322,6 +346,7 @@ const char* jr_strerror(int s) {
 static const bool g_no_attr = getenv("JR_NO_ATTR") != nullptr;  // shade without attribute records
 static const bool g_no_bins = getenv("JR_NO_BINS") != nullptr;  // every tile CTA scans all triangles
 static const bool g_key64 = getenv("JR_KEY64") != nullptr;      // depth shader: keep packed 64-bit keys
+static const bool g_vis2 = getenv("JR_VIS2") != nullptr;        // single-tile canvases: the one-phase kernel k_vis2
 
 // Forward scratch: [binned visibility: triangle records + tile bitmasks][shading attribute records]
 struct FwdLayout { size_t tiled, attr_off, flags_off, list_off, map_off, total; bool use_attr, compact; int rec_stride; };
@@ -329,7 +354,8 @@ static FwdLayout fwd_layout(const JrRenderArgs* a) {
   FwdLayout F{};
   int tw, th, nx, ny;
   choose_tiles(a->W, a->H, &tw, &th, &nx, &ny);
-  F.tiled = (nx * ny == 1) ? 0 : tiled_layout(a->B, a->W, a->H, a->T).total;
+  // binned path: records + bitmasks; single-tile path (k_vis3): the per-image spill list
+  F.tiled = (nx * ny == 1) ? (g_vis2 ? 0 : v3_workspace_bytes(a->B, a->T)) : tiled_layout(a->B, a->W, a->H, a->T).total;
   // per-triangle attribute records pay off when a triangle is shared by several pixels
   // Per-triangle attribute records, built for the VISIBLE triangles only.  More pixels than triangles: the
   // record of triangle t sits in slot t.  More triangles than pixels (32x32 Brax frames): at most W*H
@@ -363,15 +389,7 @@ int jr_render_forward(const JrRenderArgs* a, jr_stream_t stream_) {
   choose_tiles(a->W, a->H, &tw, &th, &nx, &ny);
   const long long ctas = (long long)a->B * nx * ny;
   if (ctas > 2147483647LL) return JR_ERR_DIMS;
-  static std::once_flag attr_once;
-  std::call_once(attr_once, [] {
-    cudaFuncSetAttribute(k_vis2<true, true, V2_K32_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(k_vis2<true, false, V2_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(k_vis2<false, false, V2_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(k_raster_tile<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    cudaFuncSetAttribute(k_raster_tile<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    cudaFuncSetAttribute(k_raster_tile<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-  });
+  set_kernel_attributes_once();
   const bool depth = a->shader == JR_DEPTH;
   if (nx * ny > 1 && !g_no_bins) {
     // two-level path: per-triangle records + per-tile bitmasks, then one CTA per (image, tile)
@@ -395,6 +413,22 @@ int jr_render_forward(const JrRenderArgs* a, jr_stream_t stream_) {
     if (k32t) k_raster_tile<true, true><<<(unsigned)ctas2, TL_THREADS, sm, stream>>>(*a, recs, masks, TLy);
     else if (depth) k_raster_tile<true, false><<<(unsigned)ctas2, TL_THREADS, sm, stream>>>(*a, recs, masks, TLy);
     else k_raster_tile<false, false><<<(unsigned)ctas2, TL_THREADS, sm, stream>>>(*a, recs, masks, TLy);
+  } else if (nx * ny == 1 && !g_vis2) {
+    // single-tile canvases: filtered two-phase kernel (jr_vis3.cuh); z-only 32-bit keys for the depth shader
+    // without a triangle-id output
+    const bool k32 = depth && !a->tri_id && !g_key64;
+    const V3Layout L = v3_layout(a->W, a->H, k32 ? 4 : 8);  // bytes: L.total
+    if (a->T > 0 && (!a->workspace || a->workspace_bytes < v3_workspace_bytes(a->B, a->T))) return JR_ERR_WORKSPACE;
+    const unsigned g = (unsigned)ctas;
+    if (a->stats) {
+      if (k32) k_vis3<true, true, true><<<g, V3_THREADS, L.total, stream>>>(*a);
+      else if (depth) k_vis3<true, false, true><<<g, V3_THREADS, L.total, stream>>>(*a);
+      else k_vis3<false, false, true><<<g, V3_THREADS, L.total, stream>>>(*a);
+    } else {
+      if (k32) k_vis3<true, true, false><<<g, V3_THREADS, L.total, stream>>>(*a);
+      else if (depth) k_vis3<true, false, false><<<g, V3_THREADS, L.total, stream>>>(*a);
+      else k_vis3<false, false, false><<<g, V3_THREADS, L.total, stream>>>(*a);
+    }
   } else {
     // depth shader without a triangle-id output: z-only 32-bit keys (half the shared memory, native atomic min)
     const bool k32 = depth && !a->tri_id && !g_key64;

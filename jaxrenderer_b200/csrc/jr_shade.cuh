@@ -52,6 +52,7 @@ struct Frag {
   bool lit;
   // S5 (Darboux) intermediates, kept for backward
   int dvtx[3];                 // vertices of the tangent-frame triangle (faces_indices[id_to_face[v0]])
+  int dvuv[3];                 // the same ids clamped to the uv rows
   Vec3 dP[3];                  // their world positions
   float dtr[3][3], dtw[3];     // their NDC positions and clip w
   float dAI[9];                // inverse of [tr1 - tr0; tr2 - tr0; n]
@@ -229,19 +230,23 @@ __device__ __forceinline__ void frag_pixel(const JrRenderArgs& a, int b, int x, 
       const float* __restrict__ uvp = a.uv.ptr + (long long)b * a.uv.batch_stride;
       const int32_t* __restrict__ i2f = a.id_to_face.ptr + (long long)b * a.id_to_face.batch_stride;
       const int32_t* __restrict__ fidx = a.faces_indices.ptr + (long long)b * a.faces_indices.batch_stride;
-      const int face = i2f[f.fi[0]];
+      // gathers wrap one negative and clamp, like the reference's jnp indexing (and never leave the arrays)
+      const int face = wrap_clamp(i2f[f.fi[0]], a.n_faces_indices);
       float tr[3][3], tuv[3][2];
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        const int vtx = fidx[3 * face + k];
+        const int vraw = fidx[3 * face + k];
+        const int vtx = wrap_clamp(vraw, a.n_pos);
+        const int vuv = wrap_clamp(vraw, a.n_uv);
         float tcq[4];
         to_clip(w2c, pos[3 * vtx], pos[3 * vtx + 1], pos[3 * vtx + 2], tcq);
         const bool w0 = tcq[3] == 0.0f;
         tr[k][0] = w0 ? tcq[0] : tcq[0] / tcq[3];
         tr[k][1] = w0 ? tcq[1] : tcq[1] / tcq[3];
         tr[k][2] = w0 ? tcq[2] : tcq[2] / tcq[3];
-        tuv[k][0] = uvp[2 * vtx]; tuv[k][1] = uvp[2 * vtx + 1];
+        tuv[k][0] = uvp[2 * vuv]; tuv[k][1] = uvp[2 * vuv + 1];
         f.dvtx[k] = vtx;
+        f.dvuv[k] = vuv;
         f.dP[k] = Vec3{pos[3 * vtx], pos[3 * vtx + 1], pos[3 * vtx + 2]};
         f.dtr[k][0] = tr[k][0]; f.dtr[k][1] = tr[k][1]; f.dtr[k][2] = tr[k][2];
         f.dtw[k] = tcq[3];

@@ -84,6 +84,7 @@ k_setup_bin(const __grid_constant__ JrRenderArgs a, TriRecord* __restrict__ recs
   const int32_t* __restrict__ faces = a.faces.ptr + (long long)b * a.faces.batch_stride;
   const int t = blockIdx.x * 256 + tid;
   bool surv = false;
+  bool wrote = false;  // this thread stored its record
   int x0 = 0, x1 = a.W - 1, y0 = 0, y1 = a.H - 1;
   if (t < a.T) {
     const int vmax = a.n_pos - 1;  // out-of-range indices are clamped, never read out of bounds
@@ -135,11 +136,14 @@ k_setup_bin(const __grid_constant__ JrRenderArgs a, TriRecord* __restrict__ recs
         float4* dst = reinterpret_cast<float4*>(recs + (size_t)b * a.T + t);
         const float4* src = reinterpret_cast<const float4*>(&r);
         dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+        wrote = true;
         if (fallback0) surv = false;  // not a candidate: never enters a bin
       }
     }
-    // record 0's flag is always defined (the raster kernel looks at it for the DepthShader quirk)
-    if (DEPTH && t == 0 && !(cand && !behind) && !(fallback0 && !behind)) recs[(size_t)b * a.T].flags = 0;
+    // record 0's flag is always defined (the raster kernel looks at it for the DepthShader quirk), also when
+    // triangle 0 is front-facing but its bbox was culled: the workspace is never cleared, a stale flag from an
+    // earlier call would switch the fallback on
+    if (DEPTH && t == 0 && !wrote) recs[(size_t)b * a.T].flags = 0;
   }
   // ---- publish tile bitmask words (one writer per (tile, word))
   int tx0 = x0 / TL_TILE, tx1 = x1 / TL_TILE, ty0 = y0 / TL_TILE, ty1 = y1 / TL_TILE;

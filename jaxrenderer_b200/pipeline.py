@@ -129,6 +129,32 @@ def _collect(shader: type, camera: Any, face_indices: Any, extra: Any) -> Dict[s
     return arr
 
 
+_STATS: Optional[Tensor] = None   # set by `visibility_stats()`: device uint64[8] the kernels add their counters to
+STAT_NAMES = ("triangles", "filter_passed", "exact_kept", "n_test", "fragments", "exact_rounds", "batches")
+
+
+class visibility_stats:
+    """Context manager: forward renders inside it run the COUNTING variant of the visibility kernel
+    (``JrRenderArgs.stats``, include/jr_b200.h) and accumulate ``n_test`` (edge-function evaluations; the
+    reference evaluates W*H*T of them, ``pipeline.py:163-279``), survivors of the filter / exact cull, ...
+    ``.read()`` synchronises and returns them as a dict.  Measurement aid only (single-tile canvases)."""
+
+    def __init__(self, device: Any = "cuda"):
+        self.buf = torch.zeros(8, dtype=torch.int64, device=device)
+
+    def __enter__(self) -> "visibility_stats":
+        global _STATS
+        self._prev, _STATS = _STATS, self.buf
+        return self
+
+    def __exit__(self, *exc: Any) -> None:
+        global _STATS
+        _STATS = self._prev
+
+    def read(self) -> Dict[str, int]:
+        return dict(zip(STAT_NAMES, (int(v) for v in self.buf.cpu().tolist())))
+
+
 class _Call:
     """Everything about one render call that is not a differentiable tensor."""
 
@@ -173,6 +199,7 @@ class _Call:
         a.canvas = canvas.data_ptr() if canvas is not None else None
         a.tri_id = tri_id.data_ptr() if tri_id is not None else None
         a.workspace, a.workspace_bytes = None, 0
+        a.stats = _STATS.data_ptr() if (_STATS is not None and _STATS.device == zbuffer.device) else None
         return a
 
 

@@ -53,6 +53,36 @@ def test_config2_full_batch_4096_depth_84():
                                    sc["faces"][idx].numpy(), np.ones((len(idx), W, H), np.float32))
     assert np.array_equal(t1[idx].cpu().numpy(), to)
     assert np.array_equal(z1[idx].cpu().numpy(), zo)
+    # the BENCH variant (no triangle-id output -> z-only 32-bit keys) directly against the C oracle, and
+    # against the 64-bit-key variant on all 4096 images
+    z3 = torch.full((B, W, H), 1.0, device=DEV)
+    jr.render(camd, DepthShader, jr.Buffers(z3, ()), faces, DepthExtraInput(position=pos), inplace=True)
+    assert np.array_equal(z3[idx].cpu().numpy(), zo), "z-only-key kernel differs from the C oracle"
+    assert torch.equal(z3, z1), "z-only-key kernel differs from the packed-key kernel"
+
+
+def test_config2_counters_and_filter_audit():
+    """The counting variant of the visibility kernel on the bench workload: N_test far below the reference's
+    W*H*T, every fragment accounted for, and results unchanged."""
+    from jaxrenderer_b200 import pipeline
+
+    B, W, H = 256, 84, 84
+    sc = synthetic.brax_like_batch(B, n_capsules=10, env0=5000)
+    cam = synthetic.brax_cameras(sc["eye"], sc["target"], W, H)
+    pos, faces, camd = sc["position"].to(DEV), sc["faces"].to(DEV), _cam_d(cam)
+    z_plain = torch.full((B, W, H), 1.0, device=DEV)
+    jr.render(camd, DepthShader, jr.Buffers(z_plain, ()), faces, DepthExtraInput(position=pos), inplace=True)
+    z_cnt = torch.full((B, W, H), 1.0, device=DEV)
+    with pipeline.visibility_stats(DEV) as st:
+        jr.render(camd, DepthShader, jr.Buffers(z_cnt, ()), faces, DepthExtraInput(position=pos), inplace=True)
+    c = st.read()
+    print("visibility counters:", c)
+    assert torch.equal(z_cnt, z_plain)
+    T = faces.shape[1]
+    assert c["triangles"] == B * T
+    assert 0 < c["exact_kept"] <= c["filter_passed"] < c["triangles"]
+    assert c["fragments"] <= c["n_test"] < B * W * H * T // 20     # reference: W*H*T tests per image
+    assert c["fragments"] > 0
 
 
 def test_config5_canvas_480x270_ant_3276_triangles():

@@ -24,7 +24,7 @@ def test_abi_library_exports_every_declared_symbol():
     assert declared == set(_native.EXPORTS), declared ^ set(_native.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.jr_abi_version() == 2
+    assert lib.jr_abi_version() == int(re.search(r'#define\s+JR_ABI_VERSION\s+(\d+)', header).group(1))
     assert lib.jr_strerror(-4).decode() == "workspace too small"
     # struct layout agreed between Python and C: a NULL args pointer is reported, not crashed on
     assert lib.jr_render_forward(None, None) == -1
@@ -160,6 +160,35 @@ def test_brax_pregen_loader_matches_committed_fixture():
     assert torch.equal(cam.position[frames], fix_cam.position)
     m = jr.merge_objects(objs)
     assert m.verts.shape == (30, 9816, 3) and m.faces.shape[-2:] == (3276, 3)
+
+
+def test_brax_unpickler_refuses_everything_but_the_exact_allow_list():
+    """the loader's unpickler must not expose builtins / numpy helpers that execute code."""
+    import io
+    import pickle
+
+    from jaxrenderer_b200 import brax_io
+
+    class Evil:
+        def __reduce__(self):
+            return (eval, ("__import__('os').getpid()",))
+
+    class EvilNumpy:
+        def __reduce__(self):
+            import numpy
+            return (numpy.load, ("/nonexistent",))
+
+    for payload in (Evil(), EvilNumpy(), getattr, print):
+        with pytest.raises(pickle.UnpicklingError, match="refusing"):
+            brax_io._Unpickler(io.BytesIO(pickle.dumps(payload))).load()
+    # an attacker-chosen constructor handed to the jax array hook is refused too
+    with pytest.raises(pickle.UnpicklingError):
+        brax_io._reconstruct_array(eval, ("1",), None, None)
+    # plain numpy arrays still load
+    import numpy as np
+    a = np.arange(6, dtype=np.float32).reshape(2, 3)
+    b = brax_io._Unpickler(io.BytesIO(pickle.dumps(a))).load()
+    assert np.array_equal(a, b)
 
 
 def test_graft_entry_check_matches_header():
