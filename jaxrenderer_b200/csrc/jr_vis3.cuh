@@ -42,9 +42,6 @@ constexpr int V3_NW = V3_THREADS / 32;
 #ifndef JR_V3_GRAIN2
 #define JR_V3_GRAIN2 32
 #endif
-#ifndef JR_V3_PREFETCH
-#define JR_V3_PREFETCH 1
-#endif
 #ifndef JR_V3_K64_CTAS
 #define JR_V3_K64_CTAS 3
 #endif
@@ -465,8 +462,9 @@ k_vis3(const __grid_constant__ JrRenderArgs a) {
 
   // ================================================================== phase A: filter, lane = triangle
   // (static interleaved assignment of 32-triangle groups to warps: the filter costs the same for every group).
-  // The face indices of a warp's NEXT group are loaded one iteration ahead and the lines of its vertices are
-  // prefetched, so a group waits for one global round trip at most instead of two dependent ones.
+  // The face indices of a warp's NEXT group are loaded one iteration ahead, so a group waits for one global
+  // round trip instead of two dependent ones.  (An L1 prefetch of the next group's vertex lines changed nothing:
+  // with ~45 KB of shared memory per CTA the L1 keeps too few lines.)
   int nf0 = 0, nf1 = 0, nf2 = 0;
   if (warp * 32 + lane < a.T) {
     const int tq = warp * 32 + lane;
@@ -488,9 +486,6 @@ k_vis3(const __grid_constant__ JrRenderArgs a) {
     const bool seq = !in || (i0 == vbase + 3 * lane && i1 == i0 + 1 && i2 == i0 + 2);
     if (__all_sync(0xffffffffu, seq) && vbase + 96 <= a.n_pos) {
       const float* __restrict__ src = pos + 3 * vbase + lane;
-      // corner-expanded meshes: this warp's next group most likely reads the vertices 3 * 256 further on
-      if (JR_V3_PREFETCH && lane < 9 && vbase + 3 * V3_THREADS + 96 <= a.n_pos)
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(pos + 3 * (vbase + 3 * V3_THREADS) + 32 * lane));
 #pragma unroll
       for (int k = 0; k < 9; ++k) stage[32 * k + lane] = src[32 * k];
       __syncwarp();
@@ -626,8 +621,9 @@ k_vis3(const __grid_constant__ JrRenderArgs a) {
     // bits.  Scalar products feeding packed sums are safe -- build.sh checks the SASS holds no FFMA2.)
     const int cx = lane & 7, gy = lane >> 3;
     const int nbx = (W + 7) >> 3, nby = (H + 4 * PX - 1) / (4 * PX);
+    const float rnby = 1.0f / (float)nby;
     for (int blk = warp; blk < nbx * nby; blk += V3_NW) {
-      const int bx = blk / nby, by = blk - bx * nby;
+      const int bx = (int)(((float)blk + 0.5f) * rnby), by = blk - bx * nby;  // exact quotient (blk < 2^16)
       const int x = bx * 8 + cx, y = by * (4 * PX) + gy * PX;
       const bool live = x < W && y < H;
       const int i = live ? (x * H + y) / PX : 0;

@@ -25,6 +25,11 @@ def load(build_if_missing: bool = True) -> C.CDLL:
             C.c_int, C.c_int, C.c_int, C.c_int,
             C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong,
             C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_int]
+        lib.jr_oracle_visibility.restype = C.c_int
+        lib.jr_oracle_visibility.argtypes = [
+            C.c_int, C.c_int, C.c_int, C.c_int,
+            C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong,
+            C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         lib.jr_oracle_max_threads.restype = C.c_int
         _lib = lib
     return _lib
@@ -60,3 +65,27 @@ def render_depth(world_to_clip, viewport, position, faces, zbuffer, num_threads:
     if rc != 0:
         raise MemoryError("jr_oracle_depth failed")
     return z, tri
+
+
+def visibility(world_to_clip, viewport, position, faces, W: int, H: int, num_threads: int = 0):
+    """The visibility stage for ONE image, any shader: ``(idx int64, has bool, keeps_chosen bool, gap f32)``
+    as torch tensors of shape (W, H) -- the tuple ``jr_oracle.visibility`` returns (bit-equal,
+    ``tests/test_oracle_c.py``), computed by the C brute force in seconds at 960x540 x 19 980 triangles."""
+    import torch
+
+    lib = load()
+    w2c, _ = _arr(world_to_clip, np.float32, 2)
+    vp, _ = _arr(viewport, np.float32, 2)
+    pos, _ = _arr(position, np.float32, 2)
+    f, _ = _arr(faces, np.int32, 2)
+    assert w2c.ndim == 2 and vp.ndim == 2 and pos.ndim == 2 and f.ndim == 2, "one image at a time"
+    f = np.clip(f, 0, max(pos.shape[0] - 1, 0)).astype(np.int32)   # out-of-range ids clamp (jnp gather)
+    idx = np.empty((W, H), np.int32); has = np.empty((W, H), np.uint8)
+    kc = np.empty((W, H), np.uint8); gap = np.empty((W, H), np.float32)
+    rc = lib.jr_oracle_visibility(1, W, H, f.shape[0], w2c.ctypes.data, 0, vp.ctypes.data, 0, pos.ctypes.data, 0,
+                                  f.ctypes.data, 0, idx.ctypes.data, has.ctypes.data, kc.ctypes.data,
+                                  gap.ctypes.data, int(num_threads))
+    if rc != 0:
+        raise MemoryError("jr_oracle_visibility failed")
+    return (torch.from_numpy(idx.astype(np.int64)), torch.from_numpy(has.astype(bool)),
+            torch.from_numpy(kc.astype(bool)), torch.from_numpy(gap))

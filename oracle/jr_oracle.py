@@ -84,7 +84,26 @@ def shader_name(shader: Any) -> str:
     return _CLASS_TO_NAME[shader.__name__]
 
 
-def _t(x: Any, dtype=F32) -> torch.Tensor:
+class precision:
+    """Context manager: run the oracle in another floating type (``torch.float64``): the same operations on the same
+    (exactly converted) inputs, i.e. the value fp32 arithmetic approximates.  Used by the gradient tests to tell
+    fp32 round-off of an ill-conditioned entry from an error."""
+
+    def __init__(self, dtype: torch.dtype):
+        self.dtype = dtype
+
+    def __enter__(self):
+        global F32
+        self.prev, F32 = F32, self.dtype
+        return self
+
+    def __exit__(self, *exc):
+        global F32
+        F32 = self.prev
+
+
+def _t(x: Any, dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    dtype = F32 if dtype is None else dtype
     if isinstance(x, torch.Tensor):
         return x.detach().cpu().to(dtype) if not x.requires_grad else x.cpu().to(dtype)
     return torch.as_tensor(x, dtype=dtype)
@@ -392,8 +411,12 @@ def _light(extra: Any) -> Tuple[torch.Tensor, torch.Tensor]:
 
 
 def render(camera: Any, shader: Any, zbuffer: Any, targets: Sequence[Any], face_indices: Any,
-           extra: Any) -> RenderOut:
-    """``pipeline.render`` for ONE image (no batch axes)."""
+           extra: Any, vis_fn: Any = None) -> RenderOut:
+    """``pipeline.render`` for ONE image (no batch axes).
+
+    ``vis_fn(world_to_clip, viewport, position, faces, W, H) -> (idx, has, keeps_chosen, gap)`` replaces the torch
+    brute force of the visibility stage (``oracle/c_oracle.py::visibility``: the same algorithm in C, bit-equal,
+    for the full-size configurations); everything after it -- the shading of the chosen fragments -- is unchanged."""
     name = shader_name(shader)
     w2c, vp = _t(camera.world_to_clip), _t(camera.viewport)
     zbuffer = _t(zbuffer)
@@ -408,7 +431,10 @@ def render(camera: Any, shader: Any, zbuffer: Any, targets: Sequence[Any], face_
     clip_v = mat4_apply(pos, w2c, w_one=True)
     with torch.no_grad():
         setup = primitive_setup(clip_v.detach(), faces)
-    idx, has, kc, gap = visibility(setup, vp, W, H)
+    if vis_fn is None:
+        idx, has, kc, gap = visibility(setup, vp, W, H)
+    else:
+        idx, has, kc, gap = vis_fn(w2c.detach(), vp.detach(), pos.detach(), faces, W, H)
     f_idx = faces[idx]                                   # (W,H,3) vertex ids of the chosen triangle
     fr = chosen_fragments(clip_v, f_idx, vp)
 
@@ -558,15 +584,16 @@ def shadow_camera(light_direction: Any, viewport: Any, centre: Any, up: Any,
                            world_to_eye_norm=torch.linalg.inv(view).T)
 
 
-def render_shadow_map(shadow_map: Any, verts: Any, faces: Any, camera: Any, offset: float) -> torch.Tensor:
+def render_shadow_map(shadow_map: Any, verts: Any, faces: Any, camera: Any, offset: float,
+                      vis_fn: Any = None) -> torch.Tensor:
     """Pass 1 of ``Shadow.render_shadow_map`` (``shadow.py:106-116``) given the
     light camera."""
-    out = render(camera, "depth", shadow_map, (), faces, SimpleNamespace(position=verts))
+    out = render(camera, "depth", shadow_map, (), faces, SimpleNamespace(position=verts), vis_fn=vis_fn)
     return out.zbuffer + offset
 
 
 def renderer_render(model: Any, light: Any, camera: Any, zbuffer: Any, canvas: Any,
-                    shadow_param: Any = None, shadow_cam: Any = None) -> Dict[str, Any]:
+                    shadow_param: Any = None, shadow_cam: Any = None, vis_fn: Any = None) -> Dict[str, Any]:
     """``Renderer.render`` (``renderer.py:254-385``) for one image.  ``model``
     has the ``MergedModel`` fields, ``light`` the ``LightParameters`` fields.
     ``shadow_cam`` overrides the light camera (tests pass the product's own so
@@ -589,16 +616,16 @@ def renderer_render(model: Any, light: Any, camera: Any, zbuffer: Any, canvas: A
         ambient=light.ambient, diffuse=light.diffuse, specular=light.specular)
     res: Dict[str, Any] = {}
     if shadow_param is None:
-        out = render(camera, "phong_reflection", zbuffer, (canvas,), face_indices, extra)
+        out = render(camera, "phong_reflection", zbuffer, (canvas,), face_indices, extra, vis_fn=vis_fn)
     else:
         if shadow_cam is None:
             shadow_cam = shadow_camera(light.direction, camera.viewport, shadow_param.centre,
                                        shadow_param.up)
         sm0 = torch.full_like(_t(zbuffer), torch.finfo(F32).max)
-        smap = render_shadow_map(sm0, model.verts, faces, shadow_cam, float(shadow_param.offset))
+        smap = render_shadow_map(sm0, model.verts, faces, shadow_cam, float(shadow_param.offset), vis_fn=vis_fn)
         extra.shadow = SimpleNamespace(shadow_map=smap, strength=shadow_param.strength, camera=shadow_cam)
         extra.camera = camera
-        out = render(camera, "phong_reflection_shadow", zbuffer, (canvas,), face_indices, extra)
+        out = render(camera, "phong_reflection_shadow", zbuffer, (canvas,), face_indices, extra, vis_fn=vis_fn)
         res["shadow_map"] = smap
     res["out"] = out
     return res

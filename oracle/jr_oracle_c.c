@@ -81,6 +81,12 @@ typedef struct RowJob {
   float* zb;
   int32_t* tb;
   int rc;
+  /* general visibility mode (jr_oracle_visibility): per-pixel argmin index, "some candidate", keep&inside of
+   * the chosen triangle, second-best minus best depth -- what oracle/jr_oracle.py::visibility returns */
+  int32_t* idx_out;
+  uint8_t* has_out;
+  uint8_t* kc_out;
+  float* gap_out;
 } RowJob;
 
 static void* row_worker(void* arg) {
@@ -119,6 +125,28 @@ static void* row_worker(void* arg) {
       /* first-index argmin (shader.py:217) */
       int idx = 0;
       float bestd = depth[0];
+      if (j->idx_out) {
+        /* general mode: also the runner-up depth (ties count: equal depths give gap 0) */
+        float second = inf;
+        for (int t = 1; t < T; ++t) {
+          const float d = depth[t];
+          if (d < bestd) { second = bestd; bestd = d; idx = t; }
+          else if (d < second) second = d;
+        }
+        const size_t p = (size_t)x * H + y;
+        j->idx_out[p] = idx;
+        j->has_out[p] = bestd < INFINITY;
+        uint8_t kc = 1;
+        if (!(bestd < INFINITY)) {
+          const float c0 = (xn * inv[0][0] + yn * inv[3][0]) + inv[6][0];
+          const float c1 = (xn * inv[1][0] + yn * inv[4][0]) + inv[7][0];
+          const float c2 = (xn * inv[2][0] + yn * inv[5][0]) + inv[8][0];
+          kc = j->keep0 && c0 >= 0.f && c1 >= 0.f && c2 >= 0.f;
+        }
+        j->kc_out[p] = kc;
+        j->gap_out[p] = (second < INFINITY) ? second - bestd : inf;
+        continue;
+      }
       for (int t = 1; t < T; ++t)
         if (depth[t] < bestd) { bestd = depth[t]; idx = t; }
       int written = -1;
@@ -153,10 +181,10 @@ int jr_oracle_max_threads(void) {
  * zbuffer (B,W,H) in/out, tri_id (B,W,H) out (-1 = pixel not written), may be NULL.
  * num_threads <= 0: all online cores.  Returns 0, or -1 on allocation failure.
  */
-int jr_oracle_depth(int B, int W, int H, int T, const float* w2c, long long w2c_bs,
-                    const float* viewport, long long vp_bs, const float* position, long long pos_bs,
-                    const int32_t* faces, long long faces_bs, float* zbuffer, int32_t* tri_id,
-                    int num_threads) {
+static int run_images(int B, int W, int H, int T, const float* w2c, long long w2c_bs,
+                      const float* viewport, long long vp_bs, const float* position, long long pos_bs,
+                      const int32_t* faces, long long faces_bs, float* zbuffer, int32_t* tri_id,
+                      int32_t* idx_out, uint8_t* has_out, uint8_t* kc_out, float* gap_out, int num_threads) {
   if (num_threads <= 0) num_threads = jr_oracle_max_threads();
   if (num_threads > W) num_threads = W;
   if (num_threads > 1024) num_threads = 1024;
@@ -195,8 +223,11 @@ int jr_oracle_depth(int B, int W, int H, int T, const float* w2c, long long w2c_
       candf[t] = 0.f;
     }
     for (int i = 0; i < num_threads; ++i) {
+      const size_t o = (size_t)b * W * H;
       RowJob j = {W, H, T, keep0, i, num_threads, Tp, vp, inv, zc, candf,
-                  zbuffer + (size_t)b * W * H, tri_id ? tri_id + (size_t)b * W * H : NULL, 0};
+                  zbuffer ? zbuffer + o : NULL, tri_id ? tri_id + o : NULL, 0,
+                  idx_out ? idx_out + o : NULL, has_out ? has_out + o : NULL, kc_out ? kc_out + o : NULL,
+                  gap_out ? gap_out + o : NULL};
       jobs[i] = j;
       if (i > 0 && pthread_create(&th[i], NULL, row_worker, &jobs[i]) != 0) {
         row_worker(&jobs[i]);       /* could not spawn: do the rows here */
@@ -212,4 +243,29 @@ int jr_oracle_depth(int B, int W, int H, int T, const float* w2c, long long w2c_
   }
   free(tab); free(th); free(jobs);
   return rc;
+}
+
+int jr_oracle_depth(int B, int W, int H, int T, const float* w2c, long long w2c_bs,
+                    const float* viewport, long long vp_bs, const float* position, long long pos_bs,
+                    const int32_t* faces, long long faces_bs, float* zbuffer, int32_t* tri_id,
+                    int num_threads) {
+  return run_images(B, W, H, T, w2c, w2c_bs, viewport, vp_bs, position, pos_bs, faces, faces_bs, zbuffer, tri_id,
+                    NULL, NULL, NULL, NULL, num_threads);
+}
+
+/*
+ * The visibility stage alone, for ANY built-in shader (pipeline.py:332-336 + shader.py:159-251): per pixel the
+ * first-index argmin over `keep & inside & front` depths (`idx`, 0 when there is no candidate), whether a candidate
+ * exists (`has`), `(keep & inside)[idx]` (`kc`) and the runner-up depth minus the best (`gap`, +inf when there is
+ * no runner-up) -- the tuple oracle/jr_oracle.py::visibility computes with torch, bit for bit
+ * (tests/test_oracle_c.py).  Lets the full-size configurations (960x540 x 19 980 triangles) be shaded by the torch
+ * oracle on the chosen fragments.  Outputs (B,W,H).
+ */
+int jr_oracle_visibility(int B, int W, int H, int T, const float* w2c, long long w2c_bs,
+                         const float* viewport, long long vp_bs, const float* position, long long pos_bs,
+                         const int32_t* faces, long long faces_bs, int32_t* idx, uint8_t* has, uint8_t* kc,
+                         float* gap, int num_threads) {
+  if (!idx || !has || !kc || !gap) return -1;
+  return run_images(B, W, H, T, w2c, w2c_bs, viewport, vp_bs, position, pos_bs, faces, faces_bs, NULL, NULL,
+                    idx, has, kc, gap, num_threads);
 }
