@@ -4,16 +4,21 @@
 Workload (BASELINE.json configs[1], the config the headline metric is quoted
 on): DepthShader, 84x84, batch 4096 synthetic Brax "ant-like" scenes
 (ground cube + 10 capsules = 1932 triangles / 5784 vertices each, full-view
-camera), PER GPU (weak scaling: the batch axis is sharded, no data-path
-collective).  One "step" = one `pipeline.render` of the whole per-GPU batch.
+camera; the robot's body is fixed, its pose differs per environment, as in
+Brax), PER GPU (weak scaling: the batch axis is sharded, no data-path
+collective; `--scaling strong` fixes the GLOBAL batch at 4096 instead).  One
+"step" = one `pipeline.render` of the whole per-GPU batch.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--scaling weak|strong]
 
-`value`   images/s with inputs resident in HBM (device-timed, max over ranks).
-`e2e`     images/s through the public API with HOST (pinned) geometry: H2D of
-          positions/faces/camera and D2H of the z-buffers inside the timed region.
-`roofline` HBM roofline of the dominant kernel (jr::k_vis2<true,true>) + `roofline.issue`, the issue-slot figure
-          that actually binds it.
+`value`   images/s with inputs resident in HBM: merged world-space positions (B, V, 3) + faces (B, T, 3), the
+          arrays the reference's `pipeline.render` takes (device-timed, max over ranks).
+`e2e`     images/s through the public API from HOST buffers holding what Brax produces per step -- the objects'
+          transforms and the camera parameters: H2D of those, `merge_objects` (kept factored: the kernels instance
+          the geometry), camera construction, `pipeline.render`, D2H of the z-buffers, all inside the timed region.
+`roofline` HBM roofline of the dominant kernel (jr::k_vis3<true,true,false>), its achieved FP32 rate from an
+          in-kernel N_test counter, and `roofline.issue`, the issue-slot figure.
+`secondary` configs[0], [2], [3], [4]-forward of BASELINE.json: ms per step and images/s (`--no-secondary` skips).
 `fwd_bwd` secondary lines: forward + backward images/s (phong_reflection_shadow, 84x84 x 4096 and 480x270 x 512).
 `cpu_baseline` / `--impl reference`: the reference's brute-force algorithm
           (C port, oracle/jr_oracle_c.c) on the host cores, bounded sample.
@@ -53,17 +58,26 @@ def _config(n_gpus: int, batch: int) -> dict:
 
 
 # ----------------------------------------------------------------------------- CPU arm
+def _scene_host(n_images: int, env0: int = 0):
+    """Merged world-space positions / faces / cameras of n_images bench scenes on the host."""
+    import jaxrenderer_b200 as jr
+    from jaxrenderer_b200 import synthetic
+
+    objs, eye, tgt = synthetic.brax_like_objects(n_images, n_capsules=N_CAPSULES, env0=env0)
+    m = jr.merge_objects(objs)
+    cam = synthetic.brax_cameras(eye, tgt, W, H)
+    return m.verts.contiguous(), m.faces, cam
+
+
 def _cpu_sample(n_images: int, threads: int = 0, env0: int = 0):
     """Time the C oracle (reference algorithm, brute force) on n_images scenes."""
     import numpy as np
 
-    from jaxrenderer_b200 import synthetic
     from oracle import c_oracle
 
-    sc = synthetic.brax_like_batch(n_images, n_capsules=N_CAPSULES, env0=env0)
-    cam = synthetic.brax_cameras(sc["eye"], sc["target"], W, H)
+    pos, faces, cam = _scene_host(n_images, env0)
     z0 = np.ones((n_images, W, H), np.float32)
-    args = (cam.world_to_clip.numpy(), cam.viewport.numpy(), sc["position"].numpy(), sc["faces"].numpy(), z0)
+    args = (cam.world_to_clip.numpy(), cam.viewport.numpy(), pos.numpy(), faces.numpy(), z0)
     t0 = time.perf_counter()
     c_oracle.render_depth(*args, num_threads=threads)
     return time.perf_counter() - t0
@@ -152,12 +166,24 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- GPU arm
+def _csrc_sha16() -> str:
+    """Hash of the kernel sources: ties `profiles/roofline_traffic.json` (an ncu capture) to the code it was taken on."""
+    import hashlib
+
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "jaxrenderer_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh")):
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
 def run_ours(args) -> None:
     import torch
     import torch.distributed as dist
 
     import jaxrenderer_b200 as jr
-    from jaxrenderer_b200 import _native, synthetic
+    from jaxrenderer_b200 import _native, pipeline, synthetic
     from jaxrenderer_b200.shaders import DepthExtraInput, DepthShader
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -169,16 +195,32 @@ def run_ours(args) -> None:
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _native.load()
-    B = args.batch
+    strong = args.scaling == "strong"
+    B = args.batch // world if strong else args.batch      # images on THIS GPU
+    assert B >= 1, "global batch smaller than the number of GPUs"
 
-    # ---- synthetic inputs (host, pinned), disjoint environments per rank
-    sc = synthetic.brax_like_batch(B, n_capsules=N_CAPSULES, env0=rank * B)
-    cam_h = synthetic.brax_cameras(sc["eye"], sc["target"], W, H)
-    pos_h = sc["position"].pin_memory()
-    faces_h = sc["faces"].pin_memory()
-    w2c_h, vp_h = cam_h.world_to_clip.contiguous().pin_memory(), cam_h.viewport.contiguous().pin_memory()
-    pos_d, faces_d = pos_h.to(dev), faces_h.to(dev)
-    cam_d = type(cam_h)(*[t.to(dev) for t in cam_h])
+    # ---- synthetic inputs: what Brax produces per step, on the host (pinned), disjoint environments per rank
+    objs_h, eye_h, tgt_h = synthetic.brax_like_objects(B, n_capsules=N_CAPSULES, env0=rank * B)
+    tf_h = torch.stack([o.transform for o in objs_h[1:]], dim=1).contiguous().pin_memory()   # (B, n_caps, 4, 4)
+    eye_h, tgt_h = eye_h.pin_memory(), tgt_h.pin_memory()
+    meshes_d = [type(o.model)(*[t.to(dev) for t in o.model]) for o in objs_h]            # the robot: resident
+    ground_scale = objs_h[0].local_scaling.to(dev)
+
+    def objects_on_device(tf):
+        out = [jr.ModelObject(model=meshes_d[0], local_scaling=ground_scale)]
+        for i in range(N_CAPSULES):
+            out.append(jr.ModelObject(model=meshes_d[i + 1], transform=tf[:, i]))
+        return out
+
+    def camera_on_device(eye, tgt):
+        return jr.Renderer.create_camera_from_parameters(jr.CameraParameters(
+            viewWidth=W, viewHeight=H, hfov=58.0, vfov=58.0 * H / W, position=eye, target=tgt), device=dev)
+
+    # resident arrays of the reference boundary: merged positions (B, V, 3), faces (B, T, 3), cameras
+    model_d = jr.merge_objects(objects_on_device(tf_h.to(dev)))
+    pos_d = model_d.verts.materialise().contiguous()
+    faces_d = model_d.faces.unsqueeze(0).expand(B, -1, -1).contiguous()
+    cam_d = camera_on_device(eye_h.to(dev), tgt_h.to(dev))
     z = torch.full((B, W, H), 1.0, device=dev)
     extra_d = DepthExtraInput(position=pos_d)
 
@@ -214,15 +256,18 @@ def run_ours(args) -> None:
     ms_per_step = float(t.item()) / args.steps
     value = B * world / (ms_per_step / 1e3)
 
-    # ---- end to end through the public API with host geometry: `e2e`
-    cam_e2e = cam_h._replace(world_to_clip=w2c_h, viewport=vp_h)
-    extra_h = DepthExtraInput(position=pos_h)
-    z_host = torch.empty((B, W, H), dtype=torch.float32).pin_memory()
+    # in-kernel counters of one extra (untimed) launch: N_test, survivors of the filter / exact cull
+    with pipeline.visibility_stats(dev) as st:
+        step_resident()
+    counters = st.read()
 
-    # The batch is streamed in chunks over two CUDA streams so the H2D copy of chunk i+1, the
-    # kernel of chunk i and the D2H copy of chunk i-1 overlap (PCIe is full duplex).  Every chunk
-    # is one call of the public API with host tensors.
-    n_chunks = 8 if B % 8 == 0 and B >= 64 else 1
+    # ---- end to end through the public API from the host buffers Brax produces: `e2e`
+    z_host = torch.empty((B, W, H), dtype=torch.float32).pin_memory()
+    # The batch is streamed in chunks over two CUDA streams so the H2D copy of chunk i+1, the kernels of
+    # chunk i and the D2H copy of chunk i-1 overlap (PCIe is full duplex).  Every chunk is the public API:
+    # merge_objects -> create_camera_from_parameters -> pipeline.render.
+    # (host cost of one public-API call chain is ~0.5 ms: few chunks)
+    n_chunks = int(os.environ.get("JR_E2E_CHUNKS", "0")) or (2 if B % 2 == 0 and B >= 64 else 1)
     Bc = B // n_chunks
     streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
 
@@ -233,10 +278,12 @@ def run_ours(args) -> None:
         for i in range(n_chunks):
             sl = slice(i * Bc, (i + 1) * Bc)
             with torch.cuda.stream(streams[i % 2]):
+                tf = tf_h[sl].to(dev, non_blocking=True)
+                cam_i = camera_on_device(eye_h[sl].to(dev, non_blocking=True), tgt_h[sl].to(dev, non_blocking=True))
+                m = jr.merge_objects(objects_on_device(tf))
                 bufs = jr.Renderer.create_buffers(W, H, batch=Bc, device=dev)
-                cam_i = cam_e2e._replace(world_to_clip=w2c_h[sl])
-                out = jr.render(cam_i, DepthShader, jr.Buffers(bufs.zbuffer, ()), faces_h[sl],
-                                DepthExtraInput(position=pos_h[sl]), inplace=True)
+                out = jr.render(cam_i, DepthShader, jr.Buffers(bufs.zbuffer, ()), m.faces,
+                                DepthExtraInput(position=m.verts), inplace=True)
                 z_host[sl].copy_(out.zbuffer, non_blocking=True)
         for s_ in streams:
             cur.wait_stream(s_)
@@ -257,9 +304,9 @@ def run_ours(args) -> None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item()) / e2e_steps
     clocks = sampler.stop() if rank == 0 else None   # sampled over both timed regions (resident + e2e)
-    h2d = pos_h.numel() * 4 + faces_h.numel() * 4 + w2c_h.numel() * 4 + vp_h.numel() * 4
+    h2d = (tf_h.numel() + eye_h.numel() + tgt_h.numel()) * 4
     d2h = z_host.numel() * 4
-    # parity guard: the e2e result equals the resident result
+    # parity guard: the e2e result (instanced geometry) equals the resident result (merged arrays) bit for bit
     assert torch.equal(z_host, z.cpu()), "e2e output differs from the device-resident output"
 
     fwd_bwd = None
@@ -267,6 +314,9 @@ def run_ours(args) -> None:
         # the metric's 84x84 scenes at the metric's batch, and configs[4] as named (480x270, T = 3276, B = 512)
         fwd_bwd = {"84x84": fwd_bwd_secondary(dev, rank, world, shape=(84, 84, 10, 4096)),
                    "480x270": fwd_bwd_secondary(dev, rank, world, shape=(480, 270, 17, 512))}
+    secondary = None
+    if not args.no_secondary and world == 1:
+        secondary = secondary_configs(dev)
     if rank == 0:
         nv, ntri = synthetic.scene_sizes(N_CAPSULES)
         alg_bytes = (12 * nv + 12 * ntri + 4 * W * H) * B       # geometry read once + z write
@@ -279,50 +329,161 @@ def run_ours(args) -> None:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         traffic = warp_inst = None
+        traffic_note = "no ncu capture on record"
         try:
             prof = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
-            traffic = prof.get("k_visibility_depth_bytes_per_launch")
-            warp_inst = prof.get("k_visibility_depth_warp_instructions_per_launch")
+            if prof.get("csrc_sha16") == _csrc_sha16():
+                traffic = prof.get("dram_bytes_per_launch")
+                warp_inst = prof.get("warp_instructions_per_launch")
+                traffic_note = prof.get("source", "")
+            else:
+                traffic_note = ("profiles/roofline_traffic.json was captured on other kernel sources (csrc hash "
+                                "differs): not reported")
         except (OSError, ValueError):
             pass
         achieved = alg_bytes / (avg_ms / 1e3) / 1e9
-        # The kernel is bound by instruction issue, not by HBM: next to the HBM figure
-        # the contract asks for, report the issue rate = warp instructions per launch (ncu, same workload)
-        # / live launch time, against 148 SMs x 4 schedulers x the SM clock sampled during this run.
+        sm_mhz = float(clocks["sm_mhz"]) if clocks and clocks.get("sm_mhz") else None
+        # FP32: SURVEY 8d's algorithmic flops 28 V + 90 T + 16 N_test per image, N_test from the kernel's own counter
+        n_test = counters["n_test"]
+        flops = (28.0 * nv + 90.0 * ntri) * B + 16.0 * n_test
+        fp32_peak = 148 * 128 * 2 * (sm_mhz or 1965.0) * 1e6
+        fp32 = {"bound": "fp32", "achieved": flops / (avg_ms / 1e3) / 1e12, "peak": fp32_peak / 1e12, "unit": "TFLOP/s",
+                "frac": flops / (avg_ms / 1e3) / fp32_peak, "n_test_per_launch": n_test,
+                "n_test_reference_per_launch": W * H * ntri * B, "counters": counters,
+                "peak_source": "148 SMs x 128 fp32 lanes x 2 x SM clock sampled in this run"}
         issue = None
-        if warp_inst and clocks and clocks.get("sm_mhz"):
-            peak_issue = 148 * 4 * float(clocks["sm_mhz"]) * 1e6
+        if warp_inst and sm_mhz:
+            peak_issue = 148 * 4 * sm_mhz * 1e6
             ach_issue = warp_inst * (B / BATCH) / (avg_ms / 1e3)
-            issue = {"bound": "fp32 issue slots", "achieved": ach_issue / 1e9, "peak": peak_issue / 1e9,
+            issue = {"bound": "issue slots", "achieved": ach_issue / 1e9, "peak": peak_issue / 1e9,
                      "unit": "G warp-instructions/s", "frac": ach_issue / peak_issue,
                      "warp_instructions_per_launch": warp_inst * (B / BATCH)}
+        cfg = _config(world, B)
+        if strong:
+            cfg["workload"] += f" (strong scaling: global batch {args.batch} split over {world} GPUs)"
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": _config(world, B),
+            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": cfg,
             "clocks": clocks,
             "e2e": {"value": B * world / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": e2e_steps},
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": e2e_steps,
+                    "inputs": "host: object transforms + camera parameters (what Brax produces); geometry instanced "
+                              "in-kernel from the resident robot meshes"},
             "gpu_launches": int(launches),
             "roofline": {
-                "kernel": "jr::k_vis2<true,true> (fused vertex transform + triangle setup + raster + depth resolve)",
+                "kernel": "jr::k_vis3<true,true,false> (filter + exact triangle setup + raster + depth resolve)",
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic,
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
+                "frac": achieved / peak, "traffic": traffic * (B / BATCH) if traffic else None,
+                "traffic_source": traffic_note,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "launch_ms_avg": avg_ms, "launch_ms_median": med_ms,
-                "issue": issue,
+                "fp32": fp32, "issue": issue,
             },
         }
         if fwd_bwd is not None:
             line["fwd_bwd"] = fwd_bwd
+            line["fwd_bwd_images_per_s"] = fwd_bwd["84x84"]["value"]
+            line["fwd_bwd_480x270_images_per_s"] = fwd_bwd["480x270"]["value"]
+        if secondary is not None:
+            line["secondary"] = secondary
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def _time_steps(fn, steps: int, warmup: int = 3) -> float:
+    import torch
+
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def secondary_configs(dev, steps: int = 5) -> dict:
+    """The other configurations BASELINE.json names, device-resident, one GPU (secondary lines):
+    configs[0] simple_cube 640x480 latency (B = 1, both shadow modes), configs[2] gouraud_texture 32x32 x 16384,
+    configs[3] phong_reflection_shadow 960x540 x 256 (19 980 triangles, shadow pass), configs[4] forward 480x270 x 512."""
+    import torch
+
+    import jaxrenderer_b200 as jr
+    from jaxrenderer_b200 import synthetic
+    from jaxrenderer_b200.shaders import GouraudTextureExtraInput, GouraudTextureShader
+
+    out = {}
+    light = jr.LightParameters(direction=(0.57735, -0.57735, 0.57735), ambient=(0.8,) * 3, diffuse=(0.8,) * 3,
+                               specular=(0.6,) * 3)
+    # ---- configs[0]: examples/simple_cube.py, one image, eager and CUDA-graph replay
+    cube = jr.create_cube(torch.ones(3), torch.ones(2), torch.zeros(2, 2, 3).index_fill_(2, torch.tensor([2]), 1.0),
+                          torch.ones(2, 2) * 2.0)
+    objs = [jr.ModelObject(model=type(cube)(*[t.to(dev) for t in cube]))]
+    camp = jr.CameraParameters(viewWidth=640, viewHeight=480, position=torch.tensor([2.0, 4.0, 1.0], device=dev))
+    for name, sp in (("no_shadow", None), ("shadow", jr.ShadowParameters())):
+        fn = lambda: jr.Renderer.get_camera_image(objs, jr.LightParameters(), camp, 640, 480, shadow_param=sp)  # noqa: E731
+        ms = _time_steps(fn, 20)
+        img, ms_g = fn(), None
+        try:    # the whole facade call replayed as ONE CUDA graph (allocation- and sync-free after warm-up)
+            g = torch.cuda.CUDAGraph()
+            s_ = torch.cuda.Stream(device=dev)
+            with torch.cuda.stream(s_):
+                fn(); fn()
+                with torch.cuda.graph(g, stream=s_):
+                    img = fn()
+            torch.cuda.synchronize()
+            ms_g = _time_steps(g.replay, 20)
+        except RuntimeError as e:   # pragma: no cover
+            ms_g = f"capture failed: {str(e)[:80]}"
+            torch.cuda.synchronize()
+        out[f"configs[0] simple_cube 640x480 B=1 {name}"] = {"ms_per_image_eager": ms, "ms_per_image_cuda_graph": ms_g,
+                                                             "covered_pixels": int((img != 1.0).any(-1).sum())}
+    # ---- configs[2]: gouraud_texture 32x32, 16384 images
+    B, Wd, Hd = 16384, 32, 32
+    sc = synthetic.brax_like_batch(B, n_capsules=10, env0=20_000_000, with_attributes=True)
+    cam = synthetic.brax_cameras(sc["eye"], sc["target"], Wd, Hd)
+    cam = type(cam)(*[t.to(dev) for t in cam])
+    ex = GouraudTextureExtraInput(sc["position"].to(dev), sc["normal"].to(dev), (sc["uv"] * 100).to(dev),
+                                  jr.LightSource(torch.tensor((0.57735, -0.57735, 0.57735), device=dev), torch.ones(3, device=dev)),
+                                  synthetic.checker_texture().to(dev))
+    faces = sc["faces"].to(dev)
+    z, c = torch.empty(B, Wd, Hd, device=dev), torch.empty(B, Wd, Hd, 3, device=dev)
+
+    def step3():
+        z.fill_(1.0); c.fill_(0.0)
+        jr.render(cam, GouraudTextureShader, jr.Buffers(z, (c,)), faces, ex, inplace=True)
+    ms = _time_steps(step3, steps)
+    out["configs[2] gouraud_texture 32x32 B=16384 T=1932"] = {"ms_per_step": ms, "images_per_s": B / ms * 1e3}
+    del sc, ex, faces, z, c
+    # ---- configs[3] (B = 256) and configs[4] forward (B = 512): Renderer.render with the shadow pass
+    for key, (Wd, Hd, n_caps, B) in (("configs[3] phong_reflection_shadow 960x540 B=256 T=19980", (960, 540, 104, 256)),
+                                     ("configs[4] forward phong_reflection_shadow 480x270 B=512 T=3276", (480, 270, 17, 512))):
+        sc = synthetic.brax_like_batch(B, n_capsules=n_caps, env0=30_000_000, with_attributes=True)
+        cam = synthetic.brax_cameras(sc["eye"], sc["target"], Wd, Hd)
+        cam = type(cam)(*[t.to(dev) for t in cam])
+        model = synthetic.merged_model_from_batch(sc, n_caps, dev)
+        sp = jr.ShadowParameters(centre=sc["target"].to(dev))
+        bufs = jr.Renderer.create_buffers(Wd, Hd, batch=B, device=dev)
+
+        def step():
+            bufs.zbuffer.fill_(1.0)
+            jr.Renderer.render(model, light, cam, bufs, shadow_param=sp, inplace=True)
+        ms = _time_steps(step, steps)
+        out[key] = {"ms_per_step": ms, "images_per_s": B / ms * 1e3,
+                    "pixels_per_s": B * Wd * Hd / ms * 1e3}
+        del sc, model, bufs
+        torch.cuda.empty_cache()
+    return out
 
 
 def fwd_bwd_secondary(dev, rank: int, world: int, steps: int = 5, shape=(480, 270, 17, 64)) -> dict:
@@ -390,9 +551,12 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=("ours", "reference"), default="ours")
-    ap.add_argument("--batch", type=int, default=BATCH, help="images per GPU")
+    ap.add_argument("--batch", type=int, default=BATCH, help="images per GPU (weak) / in total (strong)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-fwd-bwd", action="store_true", help="skip the secondary forward+backward measurement")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary configurations (configs[0], [2], [3], [4])")
+    ap.add_argument("--scaling", choices=("weak", "strong"), default="weak",
+                    help="weak: --batch images per GPU; strong: --batch images in total, split over the GPUs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

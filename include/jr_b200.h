@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define JR_ABI_VERSION 3
+#define JR_ABI_VERSION 5
 
 typedef void* jr_stream_t; /* cudaStream_t */
 
@@ -131,6 +131,33 @@ typedef struct JrRenderArgs {
   void* workspace;         /* >= jr_workspace_bytes(args) bytes, or NULL if that is 0 */
   size_t workspace_bytes;
 
+  /* Instanced geometry: the world-space merge of `merge_objects` (renderer/model.py:447-555)
+   * evaluated INSIDE the render kernels instead of being materialised per image.  Active when
+   * inst_transform.ptr != NULL; then
+   *   `position` holds the LOCAL-space vertices of all objects, concatenated (usually shared by the batch:
+   *   batch_stride 0), and vertex i of image b is
+   *        to_cartesian(to_homogeneous(position[i] * inst_scaling[o]) @ inst_transform[o]^T),  o = inst_vert_object[i]
+   *   (model.py:489-499) -- the arithmetic of jr_merge_objects, so results equal the merged path bit for bit;
+   *   `normal` holds the LOCAL normals and normal j is  ((normal[j] / f1) @ R^T) / f2  with R = inst_normal_matrix[o]
+   *   (= inverse(transform)^T, host-computed), o = inst_norm_object[j] and (f1, f2) = inst_norm_scale[o]: the two
+   *   whole-array (Frobenius) normalisations of model.py:517-530, produced by jr_instance_norm_scales.
+   * Forward only (jr_render_backward wants materialised arrays); not with JR_PHONG_DARBOUX. */
+  JrI32 inst_vert_object;    /* (n_pos) */
+  JrF32 inst_scaling;        /* (n_inst,3) */
+  JrF32 inst_transform;      /* (n_inst,4,4) */
+  JrI32 inst_norm_object;    /* (n_nrm)  non-depth shaders */
+  JrF32 inst_normal_matrix;  /* (n_inst,4,4) */
+  JrF32 inst_norm_scale;     /* (n_inst,2) */
+  int32_t n_inst;
+
+  /* Depth epilogue, JR_DEPTH only (the shadow-map pass, shadow.py:106-116, in ONE launch): every depth the
+   * kernel writes is `z + depth_offset` (one rounded fp32 add; 0 = off), and when depth_fill != 0 the pixels no
+   * triangle covers are written too, with `depth_fill_value + depth_offset` -- so the caller neither pre-fills the
+   * map (renderer.py:349-354 fills it with the largest float) nor adds the offset afterwards. */
+  float depth_offset;
+  int32_t depth_fill;
+  float depth_fill_value;
+
   /* Optional measurement counters (device, 8 x uint64, caller zero-fills; NULL = off, the normal case).
    * When set, the visibility kernels run their counting variant and ADD: [0] triangles visited,
    * [1] triangles passed by the filter phase, [2] triangles kept by the exact cull, [3] N_test = edge-function
@@ -224,6 +251,10 @@ typedef struct JrMergeArgs {
   float* out_norms;       /* (B,n_norms,3) */
 } JrMergeArgs;
 int jr_merge_objects(const JrMergeArgs* args, jr_stream_t stream);
+/* The two Frobenius normalisation constants (f1, f2) per (image, object) of the normal transform above, WITHOUT
+ * writing any normal: out_scales (B, n_objects, 2).  Same reductions, hence the same bits, as jr_merge_objects
+ * (out_verts / out_norms of `args` are ignored).  Feeds JrRenderArgs.inst_norm_scale. */
+int jr_instance_norm_scales(const JrMergeArgs* args, float* out_scales, jr_stream_t stream);
 
 /* Fused camera construction: all 8 matrices of `Camera` (geometry.py:205-278) per
  * batch element in ONE launch.

@@ -23,6 +23,7 @@ EXPORTS = (
     "jr_depth_forward", "jr_gouraud_forward", "jr_gouraud_texture_forward", "jr_phong_forward",
     "jr_phong_darboux_forward", "jr_phong_reflection_forward", "jr_phong_reflection_shadow_forward",
     "jr_add_scalar", "jr_canvas_to_uint8_display", "jr_launch_count", "jr_merge_objects", "jr_camera_build",
+    "jr_instance_norm_scales",
 )
 
 
@@ -53,6 +54,10 @@ class JrRenderArgs(C.Structure):
         ("shadow_strength", JrF32), ("shadow_world_to_clip", JrF32), ("shadow_viewport", JrF32),
         ("zbuffer", C.c_void_p), ("canvas", C.c_void_p), ("tri_id", C.c_void_p),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("inst_vert_object", JrI32), ("inst_scaling", JrF32), ("inst_transform", JrF32),
+        ("inst_norm_object", JrI32), ("inst_normal_matrix", JrF32), ("inst_norm_scale", JrF32),
+        ("n_inst", C.c_int32),
+        ("depth_offset", C.c_float), ("depth_fill", C.c_int32), ("depth_fill_value", C.c_float),
         ("stats", C.c_void_p),
     ]
 
@@ -123,6 +128,8 @@ def load() -> C.CDLL:
     lib.jr_launch_count.restype = C.c_longlong
     lib.jr_merge_objects.restype = C.c_int
     lib.jr_merge_objects.argtypes = [C.POINTER(JrMergeArgs), C.c_void_p]
+    lib.jr_instance_norm_scales.restype = C.c_int
+    lib.jr_instance_norm_scales.argtypes = [C.POINTER(JrMergeArgs), C.c_void_p, C.c_void_p]
     lib.jr_camera_build.restype = C.c_int
     lib.jr_camera_build.argtypes = [C.POINTER(JrCameraArgs), C.c_void_p]
     _lib = lib

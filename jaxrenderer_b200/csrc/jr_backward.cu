@@ -1087,6 +1087,7 @@ int jr_render_backward(const JrRenderArgs* a, const JrGradArgs* g, jr_stream_t s
   if (a->shader < 0 || a->shader >= JR_NUM_SHADERS) return JR_ERR_SHADER;
   if (a->B <= 0 || a->W <= 0 || a->H <= 0 || a->B > 65535) return JR_ERR_DIMS;  // grid.y = batch
   if (!a->tri_id || !a->world_to_clip.ptr || !a->viewport.ptr) return JR_ERR_NULL;
+  if (a->inst_transform.ptr) return JR_ERR_UNSUPPORTED;  // reverse mode wants the materialised world-space arrays
   cudaStream_t stream = (cudaStream_t)stream_;
   switch (a->shader) {
     case JR_DEPTH: return backward_impl<JR_DEPTH>(a, g, stream);

@@ -152,7 +152,9 @@ __device__ __forceinline__ float block_sum_256(float v, float* red) {
 // The first Frobenius norm depends only on the object's local normals: computed once per CTA when the
 // local mesh is shared by the batch (the usual case), and reused for the group's batch elements.
 constexpr int MN_GROUP = 8;
-__global__ void __launch_bounds__(256) k_merge_norms(const __grid_constant__ JrMergeArgs m) {
+// out_scales != nullptr: write only the two normalisation constants (f1, f2) of every (image, object) --
+// jr_instance_norm_scales, for geometry instanced inside the render kernels -- and no normal.
+__global__ void __launch_bounds__(256) k_merge_norms(const __grid_constant__ JrMergeArgs m, float* __restrict__ out_scales) {
   __shared__ float red[8];
   const int o = blockIdx.x;
   const bool shared_mesh = m.local_norms.batch_stride == 0 && m.norm_start.batch_stride == 0;
@@ -191,6 +193,13 @@ __global__ void __launch_bounds__(256) k_merge_norms(const __grid_constant__ JrM
       ss2 += dot3(tx, ty, tz, tx, ty, tz);
     }
     const float f2 = sqrtf(block_sum_256(ss2, red));
+    if (out_scales) {
+      if (threadIdx.x == 0) {
+        out_scales[((long long)b * m.n_objects + o) * 2] = f1;
+        out_scales[((long long)b * m.n_objects + o) * 2 + 1] = f2;
+      }
+      continue;
+    }
     float* out = m.out_norms + (long long)b * m.n_norms * 3;
 #pragma unroll
     for (int kk = 0; kk < KEEP; ++kk) {
@@ -286,6 +295,12 @@ static int check_common(const JrRenderArgs* a) {
         !a->shadow_viewport.ptr)
       return JR_ERR_NULL;
     if (a->shadow_w <= 0 || a->shadow_h <= 0) return JR_ERR_DIMS;
+  }
+  if (a->inst_transform.ptr) {  // instanced geometry
+    if (a->n_inst <= 0) return JR_ERR_DIMS;
+    if (!a->inst_vert_object.ptr || !a->inst_scaling.ptr) return JR_ERR_NULL;
+    if (s != JR_DEPTH && (!a->inst_norm_object.ptr || !a->inst_normal_matrix.ptr || !a->inst_norm_scale.ptr)) return JR_ERR_NULL;
+    if (s == JR_PHONG_DARBOUX) return JR_ERR_UNSUPPORTED;
   }
   return JR_OK;
 }
@@ -430,6 +445,8 @@ int jr_render_forward(const JrRenderArgs* a, jr_stream_t stream_) {
       else k_vis3<false, false, false><<<g, V3_THREADS, L.total, stream>>>(*a);
     }
   } else {
+    if (a->inst_transform.ptr) return JR_ERR_UNSUPPORTED;  // k_vis2 (A/B switch) reads merged arrays only
+    if (a->depth_fill || a->depth_offset != 0.f) return JR_ERR_UNSUPPORTED;
     // depth shader without a triangle-id output: z-only 32-bit keys (half the shared memory, native atomic min)
     const bool k32 = depth && !a->tri_id && !g_key64;
     const V2Layout L = v2_layout(tw, th, k32 ? 4 : 8);
@@ -517,9 +534,18 @@ int jr_merge_objects(const JrMergeArgs* m, jr_stream_t stream_) {
   }
   if (m->n_norms > 0) {
     if (!m->local_norms.ptr || !m->norm_start.ptr || !m->out_norms) return JR_ERR_NULL;
-    k_merge_norms<<<dim3(m->n_objects, (m->B + MN_GROUP - 1) / MN_GROUP), 256, 0, stream>>>(*m);
+    k_merge_norms<<<dim3(m->n_objects, (m->B + MN_GROUP - 1) / MN_GROUP), 256, 0, stream>>>(*m, nullptr);
     jr::g_launches++;
   }
+  return cudaGetLastError() == cudaSuccess ? JR_OK : JR_ERR_CUDA;
+}
+
+int jr_instance_norm_scales(const JrMergeArgs* m, float* out_scales, jr_stream_t stream_) {
+  if (!m || !out_scales) return JR_ERR_NULL;
+  if (m->B <= 0 || m->B > 65535 * MN_GROUP || m->n_objects <= 0 || m->n_norms <= 0) return JR_ERR_DIMS;
+  if (!m->local_norms.ptr || !m->norm_start.ptr || !m->normal_matrix.ptr) return JR_ERR_NULL;
+  k_merge_norms<<<dim3(m->n_objects, (m->B + MN_GROUP - 1) / MN_GROUP), 256, 0, (cudaStream_t)stream_>>>(*m, out_scales);
+  jr::g_launches++;
   return cudaGetLastError() == cudaSuccess ? JR_OK : JR_ERR_CUDA;
 }
 

@@ -5,6 +5,7 @@
 #pragma once
 #include "../../include/jr_b200.h"
 #include "jr_device.cuh"
+#include "jr_geometry.cuh"
 
 namespace jr {
 
@@ -70,7 +71,7 @@ __device__ __forceinline__ void frag_setup_tri(const JrRenderArgs& a, int b, int
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     f.fi[k] = min(max(faces[3 * tri + k], 0), a.n_pos - 1);  // clamped like the visibility kernels
-    f.P[k] = loadv3(pos, f.fi[k]);
+    f.P[k] = fetch_position(a, b, pos, f.fi[k]);
     to_clip(w2c, f.P[k].x, f.P[k].y, f.P[k].z, f.cl[k]);
   }
   float M[9];
@@ -118,7 +119,7 @@ __device__ __forceinline__ void frag_vertex(const JrRenderArgs& a, int b, int tr
   const float* __restrict__ nrm = a.normal.ptr + (long long)b * a.normal.batch_stride;
   load3(a.light_colour, b, f.lcol);
 #pragma unroll
-  for (int k = 0; k < 3; ++k) f.nraw[k] = loadv3(nrm, f.fn[k]);
+  for (int k = 0; k < 3; ++k) f.nraw[k] = fetch_normal(a, b, nrm, f.fn[k]);
   if (SHADER >= JR_GOURAUD_TEXTURE) {
     const float* __restrict__ uvp = a.uv.ptr + (long long)b * a.uv.batch_stride;
 #pragma unroll

@@ -13,6 +13,7 @@
 // Triangle setup therefore runs once per triangle instead of once per (triangle, tile).
 #pragma once
 #include "jr_device.cuh"
+#include "jr_geometry.cuh"
 #include "jr_visibility.cuh"
 
 namespace jr {
@@ -90,9 +91,10 @@ k_setup_bin(const __grid_constant__ JrRenderArgs a, TriRecord* __restrict__ recs
     const int vmax = a.n_pos - 1;  // out-of-range indices are clamped, never read out of bounds
     const int i0 = min(max(faces[3 * t + 0], 0), vmax), i1 = min(max(faces[3 * t + 1], 0), vmax),
               i2 = min(max(faces[3 * t + 2], 0), vmax);
-    const float p0x = pos[3 * i0], p0y = pos[3 * i0 + 1], p0z = pos[3 * i0 + 2];
-    const float p1x = pos[3 * i1], p1y = pos[3 * i1 + 1], p1z = pos[3 * i1 + 2];
-    const float p2x = pos[3 * i2], p2y = pos[3 * i2 + 1], p2z = pos[3 * i2 + 2];
+    const Vec3 q0 = fetch_position(a, b, pos, i0), q1 = fetch_position(a, b, pos, i1), q2 = fetch_position(a, b, pos, i2);
+    const float p0x = q0.x, p0y = q0.y, p0z = q0.z;
+    const float p1x = q1.x, p1y = q1.y, p1z = q1.z;
+    const float p2x = q2.x, p2y = q2.y, p2z = q2.z;
     float M[9];
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
@@ -388,17 +390,18 @@ k_raster_tile(const __grid_constant__ JrRenderArgs a, const TriRecord* __restric
     if (ly >= th) continue;
     const long long pix = (long long)(tx0 + lx) * a.H + (ty0 + ly);
     int tri = -1;
-    bool covered;
+    bool covered, wrote = false;
+    float zv = a.depth_fill_value;
     if (K32) {
       const uint32_t key = keys32[i];
       covered = key != ~0u;
-      if (covered) z_out[pix] = from_orderable(key);
+      if (covered) { zv = from_orderable(key); wrote = true; }
     } else {
       const unsigned long long key = keys[i];
       covered = key != ~0ull;
       if (covered) {
         tri = (int)(unsigned)(key & 0xFFFFFFFFull);
-        if (DEPTH) z_out[pix] = from_orderable((uint32_t)(key >> 32));
+        if (DEPTH) { zv = from_orderable((uint32_t)(key >> 32)); wrote = true; }
       }
     }
     if (covered) {
@@ -407,10 +410,12 @@ k_raster_tile(const __grid_constant__ JrRenderArgs a, const TriRecord* __restric
       clip_coef(tri0.inv, xs[lx], ys[ly], c);
       if (c[0] >= 0.f && c[1] >= 0.f && c[2] >= 0.f) {
         const float z = (c[0] * tri0.zc[0] + c[1] * tri0.zc[1]) + c[2] * tri0.zc[2];
-        z_out[pix] = z * vp22 + vp23;
+        zv = z * vp22 + vp23; wrote = true;
         tri = 0;
       }
     }
+    // depth epilogue (jr_b200.h): + offset on every written depth, optional fill of the uncovered pixels
+    if (DEPTH && (wrote || a.depth_fill != 0)) z_out[pix] = a.depth_offset != 0.f ? zv + a.depth_offset : zv;
     if (tri_out) tri_out[pix] = tri;
   }
 }

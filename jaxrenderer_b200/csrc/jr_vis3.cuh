@@ -27,6 +27,7 @@
 #pragma once
 #include <type_traits>
 #include "jr_device.cuh"
+#include "jr_geometry.cuh"
 #include "jr_visibility.cuh"
 
 namespace jr {
@@ -43,7 +44,7 @@ constexpr int V3_NW = V3_THREADS / 32;
 #define JR_V3_GRAIN2 32
 #endif
 #ifndef JR_V3_K64_CTAS
-#define JR_V3_K64_CTAS 3
+#define JR_V3_K64_CTAS 4
 #endif
 // survivor lists by bbox size (pixels): <= 4, <= 16, <= 64, larger (incl. "whole tile")
 constexpr int V3_A0 = 4, V3_A1 = 16, V3_A2 = 64;
@@ -202,7 +203,7 @@ template <bool DEPTH, bool K32>
 __device__ __noinline__ void v3_resolve_scalar(const unsigned long long* keys, const unsigned short* spans, const V3Big* bigq,
                                                const float* xs, const float* ys, int W, int H, int nbig, const TriSetup* tri0,
                                                float* __restrict__ z_out, int32_t* __restrict__ tri_out, float vp22,
-                                               float vp23, int tid) {
+                                               float vp23, int tid, float z_off, bool z_fill, float z_fillv) {
   typedef typename std::conditional<K32, uint32_t, unsigned long long>::type KeyT;
   const uint32_t* keys32 = reinterpret_cast<const uint32_t*>(keys);
   const int npix_img = W * H;
@@ -228,22 +229,25 @@ __device__ __noinline__ void v3_resolve_scalar(const unsigned long long* keys, c
     }
     int tri = -1;
     const bool covered = key != (KeyT)~(KeyT)0;
+    bool wrote = false;
+    float zv = z_fillv;
     if (covered) {
       if (K32) {
-        z_out[pix] = from_orderable((uint32_t)key);
+        zv = from_orderable((uint32_t)key); wrote = true;
       } else {
         tri = (int)(unsigned)((unsigned long long)key & 0xFFFFFFFFull);
-        if (DEPTH) z_out[pix] = from_orderable((uint32_t)((unsigned long long)key >> 32));
+        if (DEPTH) { zv = from_orderable((uint32_t)((unsigned long long)key >> 32)); wrote = true; }
       }
     } else if (tri0) {
       float c[3];
       clip_coef(tri0->inv, xs[lx], ys[ly], c);
       if (c[0] >= 0.f && c[1] >= 0.f && c[2] >= 0.f) {
         const float z = (c[0] * tri0->zc[0] + c[1] * tri0->zc[1]) + c[2] * tri0->zc[2];
-        z_out[pix] = z * vp22 + vp23;
+        zv = z * vp22 + vp23; wrote = true;
         tri = 0;
       }
     }
+    if (DEPTH && (wrote || z_fill)) z_out[pix] = z_off != 0.f ? zv + z_off : zv;   // depth epilogue (jr_b200.h)
     if (tri_out) tri_out[pix] = tri;
   }
 }
@@ -421,9 +425,10 @@ k_vis3(const __grid_constant__ JrRenderArgs a) {
   auto exact_setup = [&](int t, float* M, float* zc, unsigned& bb) -> bool {
     const int i0 = min(max(faces[3 * t + 0], 0), vmax), i1 = min(max(faces[3 * t + 1], 0), vmax),
               i2 = min(max(faces[3 * t + 2], 0), vmax);
-    const float p0x = pos[3 * i0], p0y = pos[3 * i0 + 1], p0z = pos[3 * i0 + 2];
-    const float p1x = pos[3 * i1], p1y = pos[3 * i1 + 1], p1z = pos[3 * i1 + 2];
-    const float p2x = pos[3 * i2], p2y = pos[3 * i2 + 1], p2z = pos[3 * i2 + 2];
+    const Vec3 q0 = fetch_position(a, b, pos, i0), q1 = fetch_position(a, b, pos, i1), q2 = fetch_position(a, b, pos, i2);
+    const float p0x = q0.x, p0y = q0.y, p0z = q0.z;
+    const float p1x = q1.x, p1y = q1.y, p1z = q1.z;
+    const float p2x = q2.x, p2y = q2.y, p2z = q2.z;
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
       const int rr = (r == 2) ? 3 : r;
@@ -496,6 +501,12 @@ k_vis3(const __grid_constant__ JrRenderArgs a) {
       p[0] = pos[3 * i0]; p[1] = pos[3 * i0 + 1]; p[2] = pos[3 * i0 + 2];
       p[3] = pos[3 * i1]; p[4] = pos[3 * i1 + 1]; p[5] = pos[3 * i1 + 2];
       p[6] = pos[3 * i2]; p[7] = pos[3 * i2 + 1]; p[8] = pos[3 * i2 + 2];
+    }
+    if (instanced(a) && in) {
+      // instanced geometry: local -> world (the merge's own arithmetic; the filter needs no more than that)
+      instance_vertex(a, b, i0, p[0], p[1], p[2], p[0], p[1], p[2]);
+      instance_vertex(a, b, i1, p[3], p[4], p[5], p[3], p[4], p[5]);
+      instance_vertex(a, b, i2, p[6], p[7], p[8], p[6], p[7], p[8]);
     }
     int cls = -1;
     if (in) cls = v3_filter(s_w2c, s_aux, vp00, vp03, vp11, vp13, p, tw, th);
@@ -611,6 +622,11 @@ k_vis3(const __grid_constant__ JrRenderArgs a) {
   const bool aligned = ((DEPTH ? (reinterpret_cast<uintptr_t>(z_out) & (K32 ? 15 : 7)) : 0) == 0) &&
                        ((tri_out ? (reinterpret_cast<uintptr_t>(tri_out) & 7) : 0) == 0);
   const bool fused = !use0 && (H % PX) == 0 && aligned;
+  // depth epilogue (jr_b200.h): + offset on every written depth, optional fill of the uncovered pixels
+  const float z_off = DEPTH ? a.depth_offset : 0.f;
+  const bool z_fill = DEPTH && a.depth_fill != 0;
+  const float z_fillv = a.depth_fill_value;
+  auto zfin = [&](float v) { return z_off != 0.f ? v + z_off : v; };
   typedef typename std::conditional<K32, uint32_t, unsigned long long>::type KeyT;
   if (fused) {
     // A warp resolves blocks of 8 columns x (4 * PX) rows: lane = (column, group of PX consecutive rows), one
@@ -678,25 +694,27 @@ k_vis3(const __grid_constant__ JrRenderArgs a) {
       if (!live) continue;
       if (K32) {
         const uint32_t k0 = (uint32_t)k[0], k1 = (uint32_t)k[1], k2 = (uint32_t)k[2 % PX], k3 = (uint32_t)k[3 % PX];
-        if (k0 != ~0u && k1 != ~0u && k2 != ~0u && k3 != ~0u) {
+        if (z_fill || (k0 != ~0u && k1 != ~0u && k2 != ~0u && k3 != ~0u)) {
           reinterpret_cast<float4*>(z_out)[i] =
-              make_float4(from_orderable(k0), from_orderable(k1), from_orderable(k2), from_orderable(k3));
+              make_float4(zfin(k0 != ~0u ? from_orderable(k0) : z_fillv), zfin(k1 != ~0u ? from_orderable(k1) : z_fillv),
+                          zfin(k2 != ~0u ? from_orderable(k2) : z_fillv), zfin(k3 != ~0u ? from_orderable(k3) : z_fillv));
         } else {
-          if (k0 != ~0u) z_out[4 * i] = from_orderable(k0);
-          if (k1 != ~0u) z_out[4 * i + 1] = from_orderable(k1);
-          if (k2 != ~0u) z_out[4 * i + 2] = from_orderable(k2);
-          if (k3 != ~0u) z_out[4 * i + 3] = from_orderable(k3);
+          if (k0 != ~0u) z_out[4 * i] = zfin(from_orderable(k0));
+          if (k1 != ~0u) z_out[4 * i + 1] = zfin(from_orderable(k1));
+          if (k2 != ~0u) z_out[4 * i + 2] = zfin(from_orderable(k2));
+          if (k3 != ~0u) z_out[4 * i + 3] = zfin(from_orderable(k3));
         }
       } else {
         const unsigned long long q0 = k[0], q1 = k[1];
         const bool e0 = q0 == ~0ull, e1 = q1 == ~0ull;
         if (DEPTH) {
-          if (!e0 && !e1) {
+          if (z_fill || (!e0 && !e1)) {
             reinterpret_cast<float2*>(z_out)[i] =
-                make_float2(from_orderable((uint32_t)(q0 >> 32)), from_orderable((uint32_t)(q1 >> 32)));
+                make_float2(zfin(e0 ? z_fillv : from_orderable((uint32_t)(q0 >> 32))),
+                            zfin(e1 ? z_fillv : from_orderable((uint32_t)(q1 >> 32))));
           } else {
-            if (!e0) z_out[2 * i] = from_orderable((uint32_t)(q0 >> 32));
-            if (!e1) z_out[2 * i + 1] = from_orderable((uint32_t)(q1 >> 32));
+            if (!e0) z_out[2 * i] = zfin(from_orderable((uint32_t)(q0 >> 32)));
+            if (!e1) z_out[2 * i + 1] = zfin(from_orderable((uint32_t)(q1 >> 32)));
           }
         }
         if (tri_out)
@@ -704,7 +722,8 @@ k_vis3(const __grid_constant__ JrRenderArgs a) {
       }
     }
   } else {
-    v3_resolve_scalar<DEPTH, K32>(keys, spans, bigq, xs, ys, W, H, nbig, use0 ? &tri0 : nullptr, z_out, tri_out, vp22, vp23, tid);
+    v3_resolve_scalar<DEPTH, K32>(keys, spans, bigq, xs, ys, W, H, nbig, use0 ? &tri0 : nullptr, z_out, tri_out, vp22, vp23, tid,
+                                  z_off, z_fill, z_fillv);
   }
 
   if (STATS && a.stats) {

@@ -221,6 +221,8 @@ def _merge_static(models: Sequence[Model], dev: torch.device) -> dict:
         "vert_object": torch.repeat_interleave(torch.arange(n_obj, dtype=torch.int32),
                                                torch.tensor(counts_v)).to(dev),
         "norm_start": torch.tensor(starts(counts_n), dtype=torch.int32).to(dev),
+        "norm_object": torch.repeat_interleave(torch.arange(n_obj, dtype=torch.int32),
+                                               torch.tensor(counts_n)).to(dev),
         "local_verts": cat_attr([m.verts for m in models]),
         "local_norms": cat_attr([m.norms for m in models]),
         "uvs": cat_attr([m.uvs for m in models]),
@@ -239,52 +241,181 @@ def _merge_static(models: Sequence[Model], dev: torch.device) -> dict:
     return st
 
 
+class InstancedGeometry:
+    """The geometry half of ``merge_objects`` kept in FACTORED form: shared local meshes
+    (``st``, memoised) + per-image object ``scaling`` / ``transform`` / ``normal_matrix``.  The render kernels
+    evaluate the world-space merge on the fly from these (``JrRenderArgs.inst_*``), so a batch of B images moves
+    ``B * n_objects * 35`` floats instead of ``B * (Nv + Nn) * 3``; ``materialise()`` runs the fused
+    ``jr_merge_objects`` kernels (the same arithmetic, bit-identical results) for everything else."""
+
+    def __init__(self, objects: Sequence["ModelObject"], dev: torch.device, st: dict):
+        self.st, self.dev = st, dev
+        self.n_obj = len(objects)
+
+        def stack(vals, base_rank, shape):
+            ts = [_f32(v, dev) for v in vals]
+            if any(t.ndim > base_rank for t in ts):
+                batch = torch.broadcast_shapes(*[t.shape[: t.ndim - base_rank] for t in ts])
+                ts = [t.expand(*batch, *shape) for t in ts]
+            return torch.stack(ts, dim=-(base_rank + 1)).contiguous()
+
+        self.scaling = stack([o.local_scaling for o in objects], 1, (3,))
+        self.transform = stack([o.transform for o in objects], 2, (4, 4))
+        self._nmat: Optional[Tensor] = None   # inverse-transpose of the transforms: only normals need it
+        lv, ln = st["local_verts"], st["local_norms"]
+        B = None
+        for t, r in ((lv, 2), (ln, 2), (self.scaling, 2), (self.transform, 3)):
+            if t.ndim == r + 1:
+                B = t.shape[0]
+        self.batch = B                      # None = un-batched
+        self._verts: Optional[Tensor] = None
+        self._norms: Optional[Tensor] = None
+        self._scales: Optional[Tensor] = None
+
+    @property
+    def nmat(self) -> Tensor:
+        if self._nmat is None:
+            # inv_ex: no host synchronisation on the singularity check (a singular transform gives inf / nan
+            # normals, as in the reference)
+            self._nmat = torch.linalg.inv_ex(self.transform, check_errors=False).inverse.transpose(-1, -2).contiguous()
+        return self._nmat
+
+    # ---- C-ABI plumbing
+    def _merge_args(self):
+        from ._native import JrF32, JrI32, JrMergeArgs
+
+        st = self.st
+        lv, ln = st["local_verts"], st["local_norms"]
+
+        def f32(t, r):
+            return JrF32(t.data_ptr(), int(t[0].numel()) if t.ndim == r + 1 else 0)
+
+        a = JrMergeArgs()
+        a.B, a.n_objects = (1 if self.batch is None else self.batch), self.n_obj
+        a.n_verts, a.n_norms = lv.shape[-2], ln.shape[-2]
+        a.local_verts, a.local_norms = f32(lv, 2), f32(ln, 2)
+        a.vert_object = JrI32(st["vert_object"].data_ptr(), 0)
+        a.norm_start = JrI32(st["norm_start"].data_ptr(), 0)
+        a.scaling, a.transform, a.normal_matrix = f32(self.scaling, 2), f32(self.transform, 3), f32(self.nmat, 3)
+        return a
+
+    def materialise(self) -> Tuple[Tensor, Tensor]:
+        """World-space ``(verts, norms)``: two launches of ``jr_merge_objects`` (cached)."""
+        if self._verts is None:
+            import ctypes as C
+
+            from . import _native
+
+            a = self._merge_args()
+            out_v = torch.empty((a.B, a.n_verts, 3), dtype=torch.float32, device=self.dev)
+            out_n = torch.empty((a.B, a.n_norms, 3), dtype=torch.float32, device=self.dev)
+            a.out_verts, a.out_norms = out_v.data_ptr(), out_n.data_ptr()
+            lib = _native.load()
+            with torch.cuda.device(self.dev):
+                _native.check(lib.jr_merge_objects(C.byref(a), _native.stream_ptr(self.dev)))
+            self._verts, self._norms = (out_v[0], out_n[0]) if self.batch is None else (out_v, out_n)
+        return self._verts, self._norms
+
+    def norm_scales(self) -> Tensor:
+        """``(B?, n_objects, 2)``: the two Frobenius normalisation constants of the normal transform
+        (``model.py:517-530``) per (image, object): one launch of ``jr_instance_norm_scales`` (cached)."""
+        if self._scales is None:
+            import ctypes as C
+
+            from . import _native
+
+            a = self._merge_args()
+            out = torch.empty((a.B, self.n_obj, 2), dtype=torch.float32, device=self.dev)
+            lib = _native.load()
+            with torch.cuda.device(self.dev):
+                _native.check(lib.jr_instance_norm_scales(C.byref(a), out.data_ptr(), _native.stream_ptr(self.dev)))
+            self._scales = out[0] if self.batch is None else out
+        return self._scales
+
+
+class InstancedArray:
+    """``MergedModel.verts`` / ``.norms`` of a CUDA ``merge_objects`` call, not yet materialised.  Passed on to
+    ``Renderer.render`` / ``pipeline.render`` / the shadow pass it makes the kernels instance the geometry
+    themselves; touched in any other way (indexing, arithmetic, ``.cpu()``, any ``torch.*`` function) it turns
+    into the ordinary world-space tensor, computed once by the fused merge kernels."""
+
+    def __init__(self, kind: str, geom: InstancedGeometry):
+        assert kind in ("verts", "norms")
+        self.kind, self.geom = kind, geom
+
+    # ---- what the host code asks without needing values
+    @property
+    def shape(self) -> torch.Size:
+        n = self.geom.st["local_verts" if self.kind == "verts" else "local_norms"].shape[-2]
+        return torch.Size(((self.geom.batch,) if self.geom.batch is not None else ()) + (n, 3))
+
+    @property
+    def ndim(self) -> int:
+        return len(self.shape)
+
+    def dim(self) -> int:
+        return self.ndim
+
+    @property
+    def device(self) -> torch.device:
+        return self.geom.dev
+
+    dtype = torch.float32
+    requires_grad = False
+    is_cuda = True
+
+    def detach(self) -> "InstancedArray":
+        return self
+
+    # ---- everything else: the materialised tensor
+    def materialise(self) -> Tensor:
+        v, n = self.geom.materialise()
+        return v if self.kind == "verts" else n
+
+    def __getattr__(self, name: str):       # .cpu(), .to(), .abs(), ... (only reached for names not defined above)
+        if name.startswith("__"):
+            raise AttributeError(name)
+        return getattr(self.materialise(), name)
+
+    def __getitem__(self, idx):
+        return self.materialise()[idx]
+
+    def __len__(self) -> int:
+        return self.shape[0]
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        conv = lambda x: x.materialise() if isinstance(x, InstancedArray) else x  # noqa: E731
+        args = tuple(conv(a) if not isinstance(a, (list, tuple)) else type(a)(conv(b) for b in a) for a in args)
+        kwargs = {k: conv(v) for k, v in (kwargs or {}).items()}
+        return func(*args, **kwargs)
+
+    def _binary(name):  # noqa: N805
+        def op(self, other):
+            other = other.materialise() if isinstance(other, InstancedArray) else other
+            return getattr(self.materialise(), name)(other)
+        return op
+
+    __add__, __radd__, __sub__, __rsub__ = _binary("__add__"), _binary("__radd__"), _binary("__sub__"), _binary("__rsub__")
+    __mul__, __rmul__, __truediv__, __matmul__ = _binary("__mul__"), _binary("__rmul__"), _binary("__truediv__"), _binary("__matmul__")
+    __eq__, __ne__ = _binary("__eq__"), _binary("__ne__")
+    __hash__ = object.__hash__
+    del _binary
+
+    def __neg__(self):
+        return -self.materialise()
+
+    def __repr__(self) -> str:
+        return f"InstancedArray({self.kind}, shape={tuple(self.shape)}, device={self.device})"
+
+
 def _merge_geometry_fused(objects: Sequence[ModelObject], dev: torch.device, st: dict):
     """CUDA fast path of the vertex / normal part of ``merge_objects``: two launches of
     ``jr_merge_objects`` (``csrc/jr_forward.cu``) instead of ~15 framework ops per object."""
-    import ctypes as C
+    return InstancedGeometry(objects, dev, st).materialise()
 
-    from . import _native
-    from ._native import JrF32, JrI32, JrMergeArgs
 
-    n_obj = len(objects)
-    lv, ln = st["local_verts"], st["local_norms"]
-
-    def stack(vals, base_rank, shape):
-        ts = [_f32(v, dev) for v in vals]
-        if any(t.ndim > base_rank for t in ts):
-            batch = torch.broadcast_shapes(*[t.shape[: t.ndim - base_rank] for t in ts])
-            ts = [t.expand(*batch, *shape) for t in ts]
-        return torch.stack(ts, dim=-(base_rank + 1)).contiguous()
-
-    scaling = stack([o.local_scaling for o in objects], 1, (3,))
-    transform = stack([o.transform for o in objects], 2, (4, 4))
-    # inv_ex: no host synchronisation on the singularity check (a singular transform gives inf / nan
-    # normals, as in the reference)
-    nmat = torch.linalg.inv_ex(transform, check_errors=False).inverse.transpose(-1, -2).contiguous()
-    B = None
-    for t, r in ((lv, 2), (ln, 2), (scaling, 2), (transform, 3)):
-        if t.ndim == r + 1:
-            B = t.shape[0]
-    squeeze = B is None
-    B = 1 if B is None else B
-    V, Nn = lv.shape[-2], ln.shape[-2]
-    out_v = torch.empty((B, V, 3), dtype=torch.float32, device=dev)
-    out_n = torch.empty((B, Nn, 3), dtype=torch.float32, device=dev)
-
-    def f32(t, r):
-        return JrF32(t.data_ptr(), int(t[0].numel()) if t.ndim == r + 1 else 0)
-
-    a = JrMergeArgs()
-    a.B, a.n_objects, a.n_verts, a.n_norms = B, n_obj, V, Nn
-    a.local_verts, a.local_norms = f32(lv, 2), f32(ln, 2)
-    a.vert_object, a.norm_start = JrI32(st["vert_object"].data_ptr(), 0), JrI32(st["norm_start"].data_ptr(), 0)
-    a.scaling, a.transform, a.normal_matrix = f32(scaling, 2), f32(transform, 3), f32(nmat, 3)
-    a.out_verts, a.out_norms = out_v.data_ptr(), out_n.data_ptr()
-    lib = _native.load()
-    with torch.cuda.device(dev):
-        _native.check(lib.jr_merge_objects(C.byref(a), _native.stream_ptr(dev)))
-    return (out_v[0], out_n[0]) if squeeze else (out_v, out_n)
+_DOUBLE_SIDED_CACHE: dict = {}
 
 
 def _double_sided_per_vertex(objects: Sequence[ModelObject], st: dict, dev: torch.device) -> Tensor:
@@ -297,8 +428,17 @@ def _double_sided_per_vertex(objects: Sequence[ModelObject], st: dict, dev: torc
         else:
             per_obj = torch.stack([torch.as_tensor(f, device=dev).reshape(-1)[0].to(torch.bool) for f in flags])
         return per_obj[st["vert_object"].long()]
-    return MergedModel.generate_object_vert_info(
-        st["counts"], [bool(torch.as_tensor(f).reshape(-1)[0]) for f in flags]).to(dev)
+    # host flags (Python bools / host tensors): memoised by value on the device (no per-call host->device copy,
+    # which would also break CUDA-graph capture of the facade)
+    vals = tuple(bool(torch.as_tensor(f).reshape(-1)[0]) for f in flags)
+    key = (str(dev), tuple(st["counts"]), vals)
+    hit = _DOUBLE_SIDED_CACHE.get(key)
+    if hit is None:
+        hit = MergedModel.generate_object_vert_info(st["counts"], list(vals)).to(dev)
+        if len(_DOUBLE_SIDED_CACHE) > 64:
+            _DOUBLE_SIDED_CACHE.clear()
+        _DOUBLE_SIDED_CACHE[key] = hit
+    return hit
 
 
 def merge_objects(objects: Sequence[ModelObject]) -> MergedModel:
@@ -328,7 +468,10 @@ def merge_objects(objects: Sequence[ModelObject]) -> MergedModel:
         isinstance(t, torch.Tensor) and t.requires_grad
         for o in objects for t in (o.model.verts, o.model.norms, o.local_scaling, o.transform))
     if dev.type == "cuda" and not needs_grad:
-        verts, norms = _merge_geometry_fused(objects, dev, st)
+        # factored form: the render kernels instance the geometry themselves; any other use of .verts / .norms
+        # materialises them with the fused merge kernels (InstancedArray)
+        geom = InstancedGeometry(objects, dev, st)
+        verts, norms = InstancedArray("verts", geom), InstancedArray("norms", geom)
     else:
         verts, _ = MergedModel.merge_verts(
             [transform_vert(o.model.verts, o.local_scaling, o.transform) for o in objects],

@@ -31,6 +31,7 @@ import torch
 from . import _native
 from ._native import JrF32, JrGradArgs, JrI32, JrRenderArgs
 from .geometry import Camera
+from .model import InstancedArray
 from .shader import Shader, UnsupportedShaderError
 from .shaders import BUILTIN_SHADERS
 from .types import Buffers, Tensor, _f32, _i32
@@ -164,10 +165,29 @@ class _Call:
         self.texture_offset = texture_offset
         self.batched = batched
         self.tri_id: Optional[Tensor] = None
+        self.depth_epilogue: Optional[Tuple[float, Optional[float]]] = None
 
     def stride(self, name: str) -> int:
         t = self.arrays[name]
         return int(t[0].numel()) if self.batched[name] else 0
+
+    def _fill_instanced(self, a: JrRenderArgs) -> None:
+        """``JrRenderArgs.inst_*``: local meshes + per-image object transforms."""
+        g = self.arrays["position"].geom
+        st = g.st
+
+        def f32(t, r):
+            return JrF32(t.data_ptr(), int(t[0].numel()) if t.ndim == r + 1 else 0)
+
+        a.position = f32(st["local_verts"], 2)
+        a.inst_vert_object = JrI32(st["vert_object"].data_ptr(), 0)
+        a.inst_scaling, a.inst_transform = f32(g.scaling, 2), f32(g.transform, 3)
+        a.n_inst = g.n_obj
+        if "normal" in self.arrays:
+            a.normal = f32(st["local_norms"], 2)
+            a.inst_norm_object = JrI32(st["norm_object"].data_ptr(), 0)
+            a.inst_normal_matrix = f32(g.nmat, 3)
+            a.inst_norm_scale = f32(g.norm_scales(), 2)
 
     def fill(self, zbuffer: Tensor, canvas: Optional[Tensor], tri_id: Tensor) -> JrRenderArgs:
         a = JrRenderArgs()
@@ -178,8 +198,9 @@ class _Call:
         a.n_pos = A["position"].shape[-2]
         a.n_nrm = A["normal"].shape[-2] if "normal" in A else 0
         a.n_uv = A["uv"].shape[-2] if "uv" in A else 0
+        inst = isinstance(A["position"], InstancedArray)
         for name, t in A.items():
-            if name in ("zbuffer", "canvas"):
+            if name in ("zbuffer", "canvas") or isinstance(t, InstancedArray):
                 continue
             is_float = _SPEC[name][1]
             setattr(a, name, (JrF32 if is_float else JrI32)(t.data_ptr(), self.stride(name)))
@@ -198,6 +219,12 @@ class _Call:
         a.zbuffer = zbuffer.data_ptr()
         a.canvas = canvas.data_ptr() if canvas is not None else None
         a.tri_id = tri_id.data_ptr() if tri_id is not None else None
+        if inst:
+            self._fill_instanced(a)
+        if self.depth_epilogue is not None and self.sid == _native.JR_DEPTH:
+            off, fill = self.depth_epilogue
+            a.depth_offset = off
+            a.depth_fill, a.depth_fill_value = (0, 0.0) if fill is None else (1, fill)
         a.workspace, a.workspace_bytes = None, 0
         a.stats = _STATS.data_ptr() if (_STATS is not None and _STATS.device == zbuffer.device) else None
         return a
@@ -303,7 +330,8 @@ class _RenderFn(torch.autograd.Function):
 
 
 def _render_arrays(sid: int, arrays: Dict[str, Any], zbuffer: Any, canvas: Optional[Any],
-                   inplace: bool = False, return_tri_id: bool = False):
+                   inplace: bool = False, return_tri_id: bool = False,
+                   depth_epilogue: Optional[Tuple[float, Optional[float]]] = None):
     """Internal entry: flat C-ABI array names -> (zbuffer, canvas, tri_id)."""
     _native.load()  # fail loudly before anything else when the extension is missing
     arrays = dict(arrays)
@@ -313,8 +341,19 @@ def _render_arrays(sid: int, arrays: Dict[str, Any], zbuffer: Any, canvas: Optio
     for name, v in list(arrays.items()) + [("zbuffer", zbuffer), ("canvas", canvas)]:
         if v is None:
             continue
-        raw[name] = v if isinstance(v, torch.Tensor) else torch.as_tensor(
+        raw[name] = v if isinstance(v, (torch.Tensor, InstancedArray)) else torch.as_tensor(
             v, dtype=torch.float32 if _SPEC[name][1] else torch.int32)
+    # Instanced geometry (merge_objects on CUDA) stays factored only where the kernels can instance it themselves:
+    # forward, no gradient anywhere, position AND normal from the same merge, not the Darboux shader.
+    inst = [n for n in ("position", "normal") if isinstance(raw.get(n), InstancedArray)]
+    if inst:
+        same = len({id(raw[n].geom) for n in inst}) == 1 and isinstance(raw["position"], InstancedArray) and (
+            "normal" not in raw or isinstance(raw["normal"], InstancedArray))
+        grads = torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in raw.values())
+        on_dev = isinstance(zbuffer, torch.Tensor) and zbuffer.is_cuda and zbuffer.device == raw[inst[0]].device
+        if not same or grads or not on_dev or sid == _native.JR_PHONG_DARBOUX:
+            for n in inst:
+                raw[n] = raw[n].materialise()
     B = None
     batched: Dict[str, bool] = {}
     for name, t in raw.items():
@@ -351,7 +390,8 @@ def _render_arrays(sid: int, arrays: Dict[str, Any], zbuffer: Any, canvas: Optio
         dev = torch.device("cuda", torch.cuda.current_device())
     else:
         dev = zbuffer.device
-    tens: Dict[str, Tensor] = {n: _as(t, _SPEC[n][1], dev) for n, t in raw.items() if n not in ("zbuffer", "canvas")}
+    tens: Dict[str, Tensor] = {n: (t if isinstance(t, InstancedArray) else _as(t, _SPEC[n][1], dev))
+                               for n, t in raw.items() if n not in ("zbuffer", "canvas")}
     z = _as(raw["zbuffer"], True, dev, written=True)
     c = _as(raw["canvas"], True, dev, written=True) if canvas is not None else None
     squeeze = B is None
@@ -362,6 +402,7 @@ def _render_arrays(sid: int, arrays: Dict[str, Any], zbuffer: Any, canvas: Optio
     if c is not None and not batched["canvas"]:
         c = c.unsqueeze(0).expand(B, W, H, 3)
     call = _Call(sid, tens, B, W, H, texture_offset, batched)
+    call.depth_epilogue = depth_epilogue     # (offset, fill value or None): JrRenderArgs.depth_*, depth shader only
     needs_grad = torch.is_grad_enabled() and any(
         t.requires_grad for t in list(tens.values()) + [z] + ([c] if c is not None else []))
     if needs_grad:

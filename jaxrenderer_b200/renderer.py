@@ -20,7 +20,7 @@ from . import _native
 from .geometry import Camera, _deg_tan_half, _normalise_last, camera_build_native
 from .model import MergedModel, ModelObject, merge_objects
 from .pipeline import _render_arrays
-from .shadow import Shadow
+from .shadow import ConstantFill, Shadow
 from .types import Buffers, DtypeInfo, Tensor, _f32
 
 
@@ -134,8 +134,10 @@ class Renderer:
             z, c, _ = _render_arrays(_native.JR_PHONG_REFLECTION, arrays, buffers.zbuffer, canvas,
                                      inplace=inplace)
             return Buffers(zbuffer=z, targets=(c,))
+        zb = buffers.zbuffer
+        fill = DtypeInfo.create(zb.dtype).max
         shadow = Shadow.render_shadow_map(
-            shadow_map=torch.full_like(buffers.zbuffer, DtypeInfo.create(buffers.zbuffer.dtype).max),
+            shadow_map=(ConstantFill(tuple(zb.shape), fill, zb.device) if zb.is_cuda else torch.full_like(zb, fill)),
             # no gradient reaches the shadow map (it is only compared against, shadow.py:129-153)
             verts=model.verts.detach(), faces=model.faces, light_direction=ldir_raw.detach(),
             viewport_matrix=camera.viewport.detach(), centre=shadow_param.centre, up=shadow_param.up,

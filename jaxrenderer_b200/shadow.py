@@ -17,6 +17,15 @@ from .geometry import Camera, camera_build_native
 from .types import Tensor, _f32
 
 
+class ConstantFill(NamedTuple):
+    """A shadow map that is still a constant (what ``Renderer.render`` passes: the largest float everywhere), not
+    materialised: lets the depth kernel write the fill itself."""
+
+    shape: Any
+    value: float
+    device: Any
+
+
 class Shadow(NamedTuple):
     """``shadow.py:27-38``."""
 
@@ -31,7 +40,9 @@ class Shadow(NamedTuple):
                           loop_unroll: int = 1) -> "Shadow":
         """``shadow.py:49-125``.  NB the light direction is used as given
         (un-normalised), exactly like the reference (``renderer.py:357``)."""
-        dev = shadow_map.device if isinstance(shadow_map, torch.Tensor) else None
+        dev = shadow_map.device if isinstance(shadow_map, (torch.Tensor, ConstantFill)) else None
+        if dev is not None and not isinstance(dev, torch.device):
+            dev = torch.device(dev)
         centre = _f32(centre, dev)
         ld = _f32(light_direction, dev)
         up = _f32(up, dev)
@@ -59,9 +70,17 @@ class Shadow(NamedTuple):
                              view_inv=Camera.view_matrix_inv(eye=eye, centre=centre, up=up))
 
     @staticmethod
-    def _finish(cam: Camera, arrays: dict, shadow_map: Tensor, strength: Any, offset: float) -> "Shadow":
+    def _finish(cam: Camera, arrays: dict, shadow_map: Any, strength: Any, offset: float) -> "Shadow":
         from .pipeline import _render_arrays  # local: pipeline imports this module's users
 
+        if isinstance(shadow_map, ConstantFill):
+            # `Renderer.render`'s map (renderer.py:349-354: filled with the largest float): ONE launch -- the depth
+            # kernel writes `z + offset` where a triangle covers the pixel and `fill + offset` elsewhere
+            # (JrRenderArgs.depth_offset / depth_fill), no fill pass before, no `+ offset` pass after.
+            z = torch.empty(shadow_map.shape, dtype=torch.float32, device=shadow_map.device)
+            z, _, _ = _render_arrays(_native.JR_DEPTH, arrays, z, None, inplace=True,
+                                     depth_epilogue=(float(offset), float(shadow_map.value)))
+            return Shadow(shadow_map=z, strength=strength, camera=cam)
         z, _, _ = _render_arrays(_native.JR_DEPTH, arrays, shadow_map, None, inplace=False)
         if z.is_cuda:
             lib = _native.load()

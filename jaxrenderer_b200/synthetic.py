@@ -95,6 +95,47 @@ def brax_like_batch(B: int, n_capsules: int = 10, env0: int = 0,
     return out
 
 
+def brax_like_objects(B: int, n_capsules: int = 10, env0: int = 0, body_seed: int = 0, device=None):
+    """The same kind of scene in FACTORED form, the way Brax hands it to the renderer (``notebooks/Generate
+    Data.ipynb``: one ``ModelObject`` per body, the mesh fixed, the transform per environment): a ground cube
+    (``local_scaling`` = half extents) + ``n_capsules`` capsules whose sizes (the robot's BODY, seeded by
+    ``body_seed``) are shared by all environments and whose POSES (rotation + position, seeded per environment like
+    ``brax_like_batch``) carry the batch axis.  Returns ``(objects, eye (B,3), target (B,3))``; host tensors unless
+    ``device`` is given.  ``merge_objects(objects)`` has 24 + 576 n vertices and 12 + 192 n triangles."""
+    from .model import ModelObject
+    from .shapes.capsule import UpAxis, create_capsule
+    from .shapes.cube import create_cube
+
+    body = np.random.default_rng(SEED0 - 1 - body_seed)
+    radius = body.uniform(0.04, 0.1, size=n_capsules).astype(np.float32)
+    hh = body.uniform(0.05, 0.3, size=n_capsules).astype(np.float32)
+    T = np.zeros((n_capsules, B, 4, 4), dtype=np.float32)
+    T[..., 3, 3] = 1.0
+    eye = np.empty((B, 3), dtype=np.float32)
+    tgt = np.empty((B, 3), dtype=np.float32)
+    for b in range(B):
+        rng = np.random.default_rng(SEED0 + env0 + b)
+        q = rng.normal(size=(n_capsules, 4)); q /= np.linalg.norm(q, axis=-1, keepdims=True)
+        d = rng.normal(size=(n_capsules, 3)); d /= np.linalg.norm(d, axis=-1, keepdims=True)
+        centre = d * rng.uniform(0.0, 1.0, size=(n_capsules, 1)) ** (1 / 3) * 0.6
+        centre[:, 2] = np.abs(centre[:, 2]) * 0.5 + 0.45
+        T[:, b, :3, :3] = _quat_to_mat(q)
+        T[:, b, :3, 3] = centre
+        root = np.array([rng.uniform(-0.1, 0.1), rng.uniform(-0.1, 0.1), 0.0])
+        dist = rng.uniform(1.15, 1.45)
+        eye[b] = root + np.array([2.0 * dist, -2.0 * dist, 1.5 * dist])
+        tgt[b] = root
+    dev = torch.device(device) if device is not None else torch.device("cpu")
+    g = torch.Generator().manual_seed(1)
+    ground = create_cube(torch.ones(3), torch.tensor((GROUND_TEXTURE_SCALING,) * 2), checker_texture(), torch.full((100, 100), 2.0))
+    objects = [ModelObject(model=type(ground)(*[t.to(dev) for t in ground]),
+                           local_scaling=torch.tensor((1000.0, 1000.0, 1e-4), device=dev))]
+    for i in range(n_capsules):
+        m = create_capsule(float(radius[i]), float(hh[i]), UpAxis.Z, torch.rand(1, 1, 3, generator=g), torch.full((1, 1), 2.0))
+        objects.append(ModelObject(model=type(m)(*[t.to(dev) for t in m]), transform=torch.from_numpy(T[i]).to(dev)))
+    return objects, torch.from_numpy(eye), torch.from_numpy(tgt)
+
+
 def brax_cameras(eye: torch.Tensor, target: torch.Tensor, width: int, height: int,
                  hfov: float = 58.0, vfov: Optional[float] = None):
     """Full-view cameras (``viewWidth=width, viewHeight=height``, SURVEY 6 note 3)."""

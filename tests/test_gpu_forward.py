@@ -292,3 +292,77 @@ def test_fused_merge_objects_matches_host_merge():
     g1 = jr.merge_objects(one)
     assert g1.verts.shape == (9816, 3)
     assert float((g1.verts - got.verts[1]).abs().max()) == 0.0 and float((g1.norms - got.norms[1]).abs().max()) == 0.0
+
+
+def test_instanced_geometry_equals_merged_path_bit_for_bit():
+    """SURVEY 8f-1 in full: `merge_objects` on CUDA hands the render kernels the FACTORED geometry (shared local
+    meshes + per-image object transforms); they instance it on the fly.  Results must equal the materialised
+    (merged world-space arrays) path bit for bit: depth via `pipeline.render`, phong_reflection and
+    phong_reflection_shadow (with its shadow pass) via `Renderer.render`, on the real Brax ant fixture (18 objects,
+    batched transforms), single-tile (84x84) and binned (200x150) canvases."""
+    from jaxrenderer_b200 import _native
+    from jaxrenderer_b200.model import InstancedArray
+
+    objs, camp = load_brax_fixture()
+    objs_d = [jr.ModelObject(model=_cuda(o.model), local_scaling=o.local_scaling.to(DEV),
+                             transform=o.transform.to(DEV), double_sided=o.double_sided) for o in objs]
+    B = objs[0].transform.shape[0]
+    light = jr.LightParameters(direction=(0.57735, -0.57735, 0.57735), ambient=(0.8,) * 3,
+                               diffuse=(0.8,) * 3, specular=(0.6,) * 3)
+    for (W, H) in ((84, 84), (200, 150)):
+        cp = jr.CameraParameters(**{k: v.to(DEV) for k, v in camp._asdict().items()})._replace(
+            viewWidth=W, viewHeight=H, vfov=58.0 * H / W)
+        cam = jr.Renderer.create_camera_from_parameters(cp)
+        sp = jr.ShadowParameters(centre=cp.target)
+        lazy = jr.merge_objects(objs_d)
+        assert isinstance(lazy.verts, InstancedArray) and isinstance(lazy.norms, InstancedArray)
+        assert lazy.verts.shape == (B, 9816, 3)
+        merged = lazy._replace(verts=lazy.verts.materialise(), norms=lazy.norms.materialise())
+        n0 = _native.launch_count()
+        for shadow in (None, sp):
+            a = jr.Renderer.render(lazy, light, cam, jr.Renderer.create_buffers(W, H, batch=B, device=DEV), shadow_param=shadow)
+            m = jr.Renderer.render(merged, light, cam, jr.Renderer.create_buffers(W, H, batch=B, device=DEV), shadow_param=shadow)
+            assert torch.equal(a.zbuffer, m.zbuffer), (W, H, shadow is not None)
+            assert torch.equal(a.targets[0], m.targets[0]), (W, H, shadow is not None)
+            assert int((a.zbuffer != 1.0).sum()) > 0.5 * a.zbuffer.numel()
+        # depth shader through the generic boundary, lazy positions handed over as they are
+        za, ta = jr.render(cam, DepthShader, jr.Buffers(torch.full((B, W, H), 1.0, device=DEV), ()), lazy.faces,
+                           DepthExtraInput(position=lazy.verts), return_tri_id=True)
+        zm, tm = jr.render(cam, DepthShader, jr.Buffers(torch.full((B, W, H), 1.0, device=DEV), ()), merged.faces,
+                           DepthExtraInput(position=merged.verts), return_tri_id=True)
+        assert torch.equal(za.zbuffer, zm.zbuffer) and torch.equal(ta, tm)
+        # z-only-key variant
+        zk = jr.render(cam, DepthShader, jr.Buffers(torch.full((B, W, H), 1.0, device=DEV), ()), lazy.faces,
+                       DepthExtraInput(position=lazy.verts))
+        assert torch.equal(zk.zbuffer, zm.zbuffer)
+    # gradients requested -> the materialised path is used transparently
+    atlas = lazy.diffuse_map.clone().requires_grad_(True)
+    out = jr.Renderer.render(lazy._replace(diffuse_map=atlas), light, cam,
+                             jr.Renderer.create_buffers(W, H, batch=B, device=DEV))
+    out.targets[0].sum().backward()
+    assert atlas.grad is not None and float(atlas.grad.abs().sum()) > 0
+
+
+@pytest.mark.parametrize("wh", [(84, 84), (50, 37), (200, 150)])
+def test_shadow_pass_in_one_launch_equals_fill_render_add(wh):
+    """The depth epilogue (JrRenderArgs.depth_offset / depth_fill): `Renderer.render`'s shadow map -- fill with the
+    largest float, depth render from the light, `+ offset` (renderer.py:349-354, shadow.py:106-116) -- in ONE launch,
+    bit-equal to the three-pass form, on single-tile (vector and scalar resolve) and binned canvases."""
+    from jaxrenderer_b200 import _native
+    from jaxrenderer_b200.shadow import ConstantFill
+
+    W, H = wh
+    B = 3
+    sc = synthetic.brax_like_batch(B, n_capsules=3, env0=77)
+    cam = synthetic.brax_cameras(sc["eye"], sc["target"], W, H)
+    fill = torch.finfo(torch.float32).max
+    args = (sc["position"].to(DEV), sc["faces"].to(DEV), torch.tensor((0.57735, -0.57735, 0.57735)),
+            cam.viewport.to(DEV), sc["target"].to(DEV), (0.0, 0.0, 1.0), (0.6, 0.6, 0.6))
+    three = jr.Shadow.render_shadow_map(torch.full((B, W, H), fill, device=DEV), *args, offset=0.05)
+    n0 = _native.launch_count()
+    one = jr.Shadow.render_shadow_map(ConstantFill((B, W, H), fill, torch.device(DEV)), *args, offset=0.05)
+    n1 = _native.launch_count()
+    assert torch.equal(one.shadow_map, three.shadow_map)
+    assert int((one.shadow_map < 1e30).sum()) > 0 and bool((one.shadow_map[one.shadow_map > 1e30] == fill).all())
+    # light camera (1) + depth kernel(s): no fill pass, no add pass
+    assert n1 - n0 <= (2 if W * H * 8 <= 96 * 1024 else 3), n1 - n0

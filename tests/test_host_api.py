@@ -24,6 +24,8 @@ def test_abi_library_exports_every_declared_symbol():
     assert declared == set(_native.EXPORTS), declared ^ set(_native.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name
+        # every entry point has its ctypes signature declared (an undeclared one would truncate 64-bit pointers)
+        assert getattr(lib, name).argtypes is not None or name in ("jr_abi_version", "jr_launch_count"), name
     assert lib.jr_abi_version() == int(re.search(r'#define\s+JR_ABI_VERSION\s+(\d+)', header).group(1))
     assert lib.jr_strerror(-4).decode() == "workspace too small"
     # struct layout agreed between Python and C: a NULL args pointer is reported, not crashed on
