@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define JR_ABI_VERSION 5
+#define JR_ABI_VERSION 6
 
 typedef void* jr_stream_t; /* cudaStream_t */
 
@@ -149,6 +149,15 @@ typedef struct JrRenderArgs {
   JrF32 inst_normal_matrix;  /* (n_inst,4,4) */
   JrF32 inst_norm_scale;     /* (n_inst,2) */
   int32_t n_inst;
+
+  /* Display epilogue fused into the shading store (utils.py:79-98 + the uint8 cast of every published
+   * benchmark, notebooks/32x32/A100.ipynb:326-337): when canvas_u8 != NULL the shading kernels (all shaders but
+   * JR_DEPTH and JR_PHONG_DARBOUX) write  uint8(clamp(colour, 0, 1) * 255)  for EVERY pixel into canvas_u8 (B,H,W,3),
+   * transposed and vertically flipped (row H-1-y, column x), instead of the fp32 canvas: pixels the render does not
+   * write show the incoming `canvas` value if canvas != NULL, else canvas_u8_background.  z-buffer and tri_id are
+   * written as usual; the fp32 canvas is then only read. */
+  uint8_t* canvas_u8;
+  float canvas_u8_background[3];
 
   /* Depth epilogue, JR_DEPTH only (the shadow-map pass, shadow.py:106-116, in ONE launch): every depth the
    * kernel writes is `z + depth_offset` (one rounded fp32 add; 0 = off), and when depth_fill != 0 the pixels no

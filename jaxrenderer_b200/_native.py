@@ -57,6 +57,7 @@ class JrRenderArgs(C.Structure):
         ("inst_vert_object", JrI32), ("inst_scaling", JrF32), ("inst_transform", JrF32),
         ("inst_norm_object", JrI32), ("inst_normal_matrix", JrF32), ("inst_norm_scale", JrF32),
         ("n_inst", C.c_int32),
+        ("canvas_u8", C.c_void_p), ("canvas_u8_background", C.c_float * 3),
         ("depth_offset", C.c_float), ("depth_fill", C.c_int32), ("depth_fill_value", C.c_float),
         ("stats", C.c_void_p),
     ]

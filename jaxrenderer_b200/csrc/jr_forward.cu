@@ -115,6 +115,52 @@ __global__ void __launch_bounds__(256, JR_SHADE_CTAS) k_shade_rec(const __grid_c
   }
 }
 
+// Shading with the display epilogue fused into the store (JrRenderArgs.canvas_u8): one CTA per
+// 32 x 32 pixel tile of one image.  Threads read the G-buffer along y (coalesced), shade, write z, park the uint8
+// colour of EVERY pixel of the tile in shared memory, and the tile is then written out along x -- the display
+// layout (B, H, W, 3), flipped vertically -- with coalesced byte stores.  The fp32 canvas is never written.
+template <int SHADER>
+__global__ void __launch_bounds__(256, JR_SHADE_CTAS) k_shade_rec_u8(const __grid_constant__ JrRenderArgs a,
+                                                      const float* __restrict__ attrs, int rec_stride,
+                                                      const int* __restrict__ slot_map, int tiles_x, int tiles_y) {
+  __shared__ uint8_t tile[32][32 * 3 + 4];   // [y][x * 3 + c]
+  const int b = blockIdx.y;
+  const int tx = blockIdx.x / tiles_y, ty = blockIdx.x - tx * tiles_y;
+  const int x0 = tx * 32, y0 = ty * 32;
+  const int ly = threadIdx.x & 31;
+  const long long img = (long long)b * a.W * a.H;
+#pragma unroll 1
+  for (int lx = threadIdx.x >> 5; lx < 32; lx += 8) {
+    const int x = x0 + lx, y = y0 + ly;
+    if (x >= a.W || y >= a.H) continue;
+    const long long gi = img + (long long)x * a.H + y;
+    const int tri = a.tri_id[gi];
+    float col[3] = {a.canvas_u8_background[0], a.canvas_u8_background[1], a.canvas_u8_background[2]};
+    if (a.canvas) { col[0] = a.canvas[gi * 3]; col[1] = a.canvas[gi * 3 + 1]; col[2] = a.canvas[gi * 3 + 2]; }
+    if (tri >= 0) {
+      Frag f;
+      const int slot = slot_map ? slot_map[(long long)b * a.T + tri] : tri;
+      attr_load<SHADER>(a, b, attrs + ((size_t)b * rec_stride + slot) * TA_FLOATS, f);
+      frag_pixel<SHADER>(a, b, x, y, f);
+      if (f.keep) {
+        a.zbuffer[gi] = f.zw;
+        col[0] = f.col[0]; col[1] = f.col[1]; col[2] = f.col[2];
+      } else {
+        a.tri_id[gi] = -1;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) tile[ly][lx * 3 + c] = (uint8_t)(fminf(fmaxf(col[c], 0.f), 1.f) * 255.f);
+  }
+  __syncthreads();
+  const int tw = min(32, a.W - x0), th = min(32, a.H - y0);
+  uint8_t* __restrict__ out = a.canvas_u8 + (long long)b * a.W * a.H * 3;
+  for (int j = threadIdx.x; j < th * tw * 3; j += 256) {
+    const int r = j / (tw * 3), q = j - r * (tw * 3);
+    out[((long long)(a.H - 1 - (y0 + r)) * a.W + x0) * 3 + q] = tile[r][q];
+  }
+}
+
 // ---------------------------------------------------------------- merge_objects (model.py:447-555)
 __global__ void __launch_bounds__(256) k_merge_verts(const __grid_constant__ JrMergeArgs m) {
   // (staging the block's 3 KB in shared memory for 128-bit stores was measured slower: 292 vs 231 us)
@@ -261,6 +307,8 @@ __global__ void k_to_uint8_display(const float* __restrict__ canvas, uint8_t* __
 // ===================================================================== C ABI
 using namespace jr;
 
+static bool g_no_attr_early() { static const bool v = getenv("JR_NO_ATTR") != nullptr; return v; }
+
 static int check_common(const JrRenderArgs* a) {
   if (!a) return JR_ERR_NULL;
   if (a->shader < 0 || a->shader >= JR_NUM_SHADERS) return JR_ERR_SHADER;
@@ -272,7 +320,8 @@ static int check_common(const JrRenderArgs* a) {
   if (a->T > 0 && a->n_pos <= 0) return JR_ERR_DIMS;
   const int s = a->shader;
   if (s != JR_DEPTH) {
-    if (!a->canvas || !a->normal.ptr || !a->light_colour.ptr) return JR_ERR_NULL;
+    if ((!a->canvas && !a->canvas_u8) || !a->normal.ptr || !a->light_colour.ptr) return JR_ERR_NULL;
+    if (a->canvas_u8 && (s == JR_PHONG_DARBOUX || g_no_attr_early() || a->T <= 0)) return JR_ERR_UNSUPPORTED;
     if (a->T > 0 && a->n_nrm <= 0) return JR_ERR_DIMS;
   }
   if (s == JR_GOURAUD && (!a->colour.ptr || !a->light_direction.ptr)) return JR_ERR_NULL;
@@ -477,10 +526,13 @@ int jr_render_forward(const JrRenderArgs* a, jr_stream_t stream_) {
       const int rec_stride = F.rec_stride;
       const bool compact = F.compact;
       dim3 g1((a->T + 127) / 128, a->B);
+      const int tiles_x = (a->W + 31) / 32, tiles_y = (a->H + 31) / 32;
+      const dim3 gu8(tiles_x * tiles_y, a->B);
 #define JR_ATTR_CASE(S)                                                          \
   case S:                                                                        \
     k_tri_attr<S><<<g1, 128, 0, stream>>>(*a, attrs, list, count, rec_stride, compact); \
-    k_shade_rec<S><<<blocks, threads, 0, stream>>>(*a, attrs, rec_stride, slot_map); \
+    if (a->canvas_u8) k_shade_rec_u8<S><<<gu8, 256, 0, stream>>>(*a, attrs, rec_stride, slot_map, tiles_x, tiles_y); \
+    else k_shade_rec<S><<<blocks, threads, 0, stream>>>(*a, attrs, rec_stride, slot_map); \
     break;
       switch (a->shader) {
         JR_ATTR_CASE(JR_GOURAUD)

@@ -18,7 +18,7 @@ import numpy as np
 
 import torch
 
-from .types import Tensor, _device_constant, _f32
+from .types import Tensor, _device_constant, _f32, _is_vmapped
 
 View = Tensor
 Projection = Tensor
@@ -294,6 +294,8 @@ def camera_build_native(mode: int, fields: Sequence[Tuple[Any, int]], dev: torch
     batch: Optional[int] = None
     tensors = [v for v, _ in fields] + [viewport]
     if torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors):
+        return None
+    if _is_vmapped(*tensors):
         return None
     off = 0
     for v, w in fields:

@@ -16,7 +16,7 @@ from typing import Any, List, NamedTuple, Optional, Sequence, Tuple
 import torch
 
 from .geometry import to_cartesian, to_homogeneous, transform_matrix_from_rotation
-from .types import Tensor, _f32, _i32
+from .types import Tensor, _f32, _i32, _is_vmapped
 
 
 class Model(NamedTuple):
@@ -186,7 +186,7 @@ def _merge_static(models: Sequence[Model], dev: torch.device) -> dict:
     gradient-carrying mesh tensors bypass the cache."""
     tensors = [getattr(m, f) for m in models for f in _STATIC_FIELDS]
     cacheable = all(isinstance(t, torch.Tensor) and not t.requires_grad and t.ndim == r
-                    for t, r in zip(tensors, _STATIC_RANK * len(models)))
+                    for t, r in zip(tensors, _STATIC_RANK * len(models))) and not _is_vmapped(*tensors)
     key = (dev, tuple((id(t), t._version) for t in tensors)) if cacheable else None
     if key is not None:
         hit = _STATIC_CACHE.get(key)
@@ -467,7 +467,8 @@ def merge_objects(objects: Sequence[ModelObject]) -> MergedModel:
     needs_grad = torch.is_grad_enabled() and any(
         isinstance(t, torch.Tensor) and t.requires_grad
         for o in objects for t in (o.model.verts, o.model.norms, o.local_scaling, o.transform))
-    if dev.type == "cuda" and not needs_grad:
+    vmapped = _is_vmapped(*[t for o in objects for t in (o.model.verts, o.model.norms, o.local_scaling, o.transform)])
+    if dev.type == "cuda" and not needs_grad and not vmapped:
         # factored form: the render kernels instance the geometry themselves; any other use of .verts / .norms
         # materialises them with the fused merge kernels (InstancedArray)
         geom = InstancedGeometry(objects, dev, st)

@@ -34,7 +34,7 @@ from .geometry import Camera
 from .model import InstancedArray
 from .shader import Shader, UnsupportedShaderError
 from .shaders import BUILTIN_SHADERS
-from .types import Buffers, Tensor, _f32, _i32
+from .types import Buffers, Tensor, _f32, _i32, _is_vmapped
 
 # name -> (un-batched rank, is_float)
 _SPEC: Dict[str, Tuple[int, bool]] = {
@@ -166,6 +166,8 @@ class _Call:
         self.batched = batched
         self.tri_id: Optional[Tensor] = None
         self.depth_epilogue: Optional[Tuple[float, Optional[float]]] = None
+        self.u8_out: Optional[Tensor] = None
+        self.u8_background: Tuple[float, float, float] = (1.0, 1.0, 1.0)
 
     def stride(self, name: str) -> int:
         t = self.arrays[name]
@@ -221,6 +223,9 @@ class _Call:
         a.tri_id = tri_id.data_ptr() if tri_id is not None else None
         if inst:
             self._fill_instanced(a)
+        if self.u8_out is not None:
+            a.canvas_u8 = self.u8_out.data_ptr()
+            a.canvas_u8_background = (C.c_float * 3)(*self.u8_background)
         if self.depth_epilogue is not None and self.sid == _native.JR_DEPTH:
             off, fill = self.depth_epilogue
             a.depth_offset = off
@@ -253,20 +258,37 @@ class _RenderFn(torch.autograd.Function):
     """custom_vjp: forward = visibility + shading kernels, backward = the
     gradient kernels through the saved triangle-id G-buffer."""
 
+    # forward / setup_context are separate (the form torch.func transforms require: the renderer may be called
+    # inside torch.func.vmap, see _render_arrays_vmapped)
     @staticmethod
-    def forward(ctx: Any, call: _Call, *diff: Optional[Tensor]):  # type: ignore[override]
+    def forward(call: _Call, *diff: Optional[Tensor]):  # type: ignore[override]
         named = dict(zip(_DIFF, diff))
         zbuffer = named["zbuffer"].clone()
         canvas = named["canvas"].clone() if named["canvas"] is not None else None
         tri_id = _forward_native(call, zbuffer, canvas)
+        if canvas is None:
+            return zbuffer, tri_id
+        return zbuffer, canvas, tri_id
+
+    @staticmethod
+    def vmap(info: Any, in_dims: Any, call: _Call, *diff: Optional[Tensor]):
+        """torch.func.vmap rule.  The public entry points re-batch natively BEFORE reaching this Function
+        (_render_arrays_vmapped: every mapped input, differentiable or not, becomes a batched array of ONE
+        kernel call), so its operands are never mapped at the enclosing level and functorch lowers the call
+        without consulting this rule; it exists because functorch insists on one, and to fail clearly if the
+        Function is ever applied to mapped tensors directly."""
+        raise NotImplementedError("_RenderFn applied to vmapped tensors: call jaxrenderer_b200.render / "
+                                  "Renderer.render inside torch.func.vmap instead (they batch natively)")
+
+    @staticmethod
+    def setup_context(ctx: Any, inputs: Any, output: Any) -> None:
+        call, *diff = inputs
+        named = dict(zip(_DIFF, diff))
         ctx.call = call
         ctx.present = [t is not None for t in diff]
         ctx.save_for_backward(*[t for t in diff if t is not None and t is not named["zbuffer"]
                                 and t is not named["canvas"]])
-        ctx.mark_non_differentiable(tri_id)
-        if canvas is None:
-            return zbuffer, tri_id
-        return zbuffer, canvas, tri_id
+        ctx.mark_non_differentiable(output[-1])
 
     @staticmethod
     def backward(ctx: Any, *grads: Optional[Tensor]):  # type: ignore[override]
@@ -331,10 +353,20 @@ class _RenderFn(torch.autograd.Function):
 
 def _render_arrays(sid: int, arrays: Dict[str, Any], zbuffer: Any, canvas: Optional[Any],
                    inplace: bool = False, return_tri_id: bool = False,
-                   depth_epilogue: Optional[Tuple[float, Optional[float]]] = None):
-    """Internal entry: flat C-ABI array names -> (zbuffer, canvas, tri_id)."""
+                   depth_epilogue: Optional[Tuple[float, Optional[float]]] = None,
+                   display_u8: Optional[Sequence[float]] = None):
+    """Internal entry: flat C-ABI array names -> (zbuffer, canvas, tri_id).
+
+    ``display_u8`` (a background colour): the shading kernels write the display image -- ``(B?, H, W, 3)`` uint8,
+    clamped, transposed, flipped (``utils.py:79-98``) -- instead of the fp32 canvas, which is returned in its
+    place; ``canvas`` may then be ``None`` (pixels nothing covers show the background colour) or the incoming
+    canvas (read only).  Forward only."""
     _native.load()  # fail loudly before anything else when the extension is missing
     arrays = dict(arrays)
+    if _is_vmapped(zbuffer, canvas, *arrays.values()):
+        if display_u8 is not None:
+            raise NotImplementedError("display_uint8 inside torch.func.vmap")
+        return _render_arrays_vmapped(sid, arrays, zbuffer, canvas, return_tri_id, depth_epilogue)
     texture_offset = int(arrays.pop("texture_offset", 0))
     # ---- validate shapes first (host side, before any transfer or launch)
     raw: Dict[str, Tensor] = {}
@@ -403,6 +435,12 @@ def _render_arrays(sid: int, arrays: Dict[str, Any], zbuffer: Any, canvas: Optio
         c = c.unsqueeze(0).expand(B, W, H, 3)
     call = _Call(sid, tens, B, W, H, texture_offset, batched)
     call.depth_epilogue = depth_epilogue     # (offset, fill value or None): JrRenderArgs.depth_*, depth shader only
+    if display_u8 is not None:
+        if needs_grad_any(tens, z, c) or sid in (_native.JR_DEPTH, _native.JR_PHONG_DARBOUX) or host_in:
+            raise NotImplementedError("display_uint8 needs CUDA buffers, a canvas shader other than the Darboux "
+                                      "shader, and no gradient")
+        call.u8_background = tuple(float(v) for v in display_u8)
+        call.u8_out = torch.empty((B, H, W, 3), dtype=torch.uint8, device=dev)
     needs_grad = torch.is_grad_enabled() and any(
         t.requires_grad for t in list(tens.values()) + [z] + ([c] if c is not None else []))
     if needs_grad:
@@ -428,8 +466,13 @@ def _render_arrays(sid: int, arrays: Dict[str, Any], zbuffer: Any, canvas: Optio
             return tc if (fresh or inplace) else tc.clone()
 
         z_out = _own(z, zbuffer)
-        c_out = _own(c, canvas) if c is not None else None
-        tri = _forward_native(call, z_out, c_out, need_tri=return_tri_id)
+        if call.u8_out is not None:
+            c_in = c.contiguous() if c is not None else None      # read only: the background
+            tri = _forward_native(call, z_out, c_in, need_tri=return_tri_id)
+            c_out = call.u8_out
+        else:
+            c_out = _own(c, canvas) if c is not None else None
+            tri = _forward_native(call, z_out, c_out, need_tri=return_tri_id)
     if squeeze:
         z_out = z_out[0]
         c_out = c_out[0] if c_out is not None else None
@@ -439,6 +482,49 @@ def _render_arrays(sid: int, arrays: Dict[str, Any], zbuffer: Any, canvas: Optio
         c_out = c_out.cpu() if c_out is not None else None
         tri = tri.cpu() if (return_tri_id and tri is not None) else tri
     return z_out, c_out, tri
+
+
+def needs_grad_any(tens: Dict[str, Any], z: Tensor, c: Optional[Tensor]) -> bool:
+    return torch.is_grad_enabled() and any(
+        getattr(t, "requires_grad", False) for t in list(tens.values()) + [z] + ([c] if c is not None else []))
+
+
+def _render_arrays_vmapped(sid: int, arrays: Dict[str, Any], zbuffer: Any, canvas: Optional[Any],
+                           return_tri_id: bool, depth_epilogue: Any):
+    """``torch.func.vmap`` support (the reference's batching idiom: ``jax.vmap(lambda m, b: Renderer.render(...))``,
+    ``examples/batch_rendering.py:87-95``).  Inside a vmap every mapped input is a functorch BatchedTensor; the
+    kernels batch NATIVELY, so the mapped axis of each input is moved to the front and handed to the ordinary
+    (batched) call -- mapped inputs become batched arrays, un-mapped ones stay shared (``in_axes=None`` = batch
+    stride 0) -- and the outputs are re-wrapped for the enclosing vmap.  One vmap level; gradients taken OUTSIDE the
+    vmap flow through the underlying tensors as usual."""
+    f = torch._C._functorch
+    level = None
+
+    def unwrap(name: str, v: Any) -> Any:
+        nonlocal level
+        if not (isinstance(v, torch.Tensor) and f.is_batchedtensor(v)):
+            if isinstance(v, torch.Tensor) and v.ndim == _SPEC[name][0] + 1:
+                raise NotImplementedError(f"`{name}` carries its own batch axis inside torch.func.vmap: nested "
+                                          "batching is not supported (map that axis with the vmap instead)")
+            return v
+        lvl, bdim = f.maybe_get_level(v), f.maybe_get_bdim(v)
+        raw = f.get_unwrapped(v)
+        if f.is_batchedtensor(raw):
+            raise NotImplementedError("nested torch.func.vmap around the renderer is not supported")
+        if level not in (None, lvl):
+            raise NotImplementedError("inputs mapped by different vmap levels")
+        level = lvl
+        if raw.ndim - 1 != _SPEC[name][0]:
+            raise ValueError(f"`{name}` has rank {raw.ndim - 1} inside vmap, expected {_SPEC[name][0]}")
+        return raw.movedim(bdim, 0)
+
+    raw_arrays = {k: (unwrap(k, v) if k in _SPEC else v) for k, v in arrays.items()}
+    z = unwrap("zbuffer", zbuffer)
+    c = unwrap("canvas", canvas) if canvas is not None else None
+    z_out, c_out, tri = _render_arrays(sid, raw_arrays, z, c, inplace=False, return_tri_id=return_tri_id,
+                                       depth_epilogue=depth_epilogue)
+    wrap = lambda t: None if t is None else f._add_batch_dim(t, 0, level)  # noqa: E731
+    return wrap(z_out), wrap(c_out), wrap(tri)
 
 
 def render(camera: Camera, shader: type, buffers: Buffers, face_indices: Any, extra: Any,

@@ -104,9 +104,15 @@ class Renderer:
     @classmethod
     def render(cls, model: MergedModel, light: "LightParameters", camera: Camera, buffers: Buffers,
                shadow_param: Optional[ShadowParameters] = None, loop_unroll: int = 1,
-               *, inplace: bool = False) -> Buffers:
+               *, inplace: bool = False, display_uint8: Optional[Sequence[float]] = None) -> Buffers:
         """``renderer.py:254-385``: phong_reflection, or shadow-map pass +
-        phong_reflection_shadow when ``shadow_param`` is given."""
+        phong_reflection_shadow when ``shadow_param`` is given.
+
+        ``display_uint8=(r, g, b)`` (extension): the target returned is the display image
+        ``(B?, H, W, 3) uint8`` -- ``transpose_for_display((clip(canvas, 0, 1) * 255).astype(uint8))``, what every
+        published benchmark of the reference computes next (``notebooks/32x32/A100.ipynb:326-337``) -- written by
+        the shading kernel itself; the fp32 canvas is never materialised and ``buffers.targets`` may be ``()``
+        (background = the given colour) or hold the incoming canvas (read only)."""
         del loop_unroll
         dev = buffers.zbuffer.device
         ldir_raw = _f32(light.direction, dev)
@@ -129,10 +135,12 @@ class Renderer:
             "texture": model.diffuse_map, "specular_map": model.specular_map,
             "texture_shape": model.texture_shape, "texture_offset": int(model.offset),
         }
-        (canvas,) = buffers.targets
+        canvas = buffers.targets[0] if len(buffers.targets) else None
+        if canvas is None and display_uint8 is None:
+            raise ValueError("Renderer.render needs a canvas in buffers.targets (or display_uint8=background)")
         if shadow_param is None:
             z, c, _ = _render_arrays(_native.JR_PHONG_REFLECTION, arrays, buffers.zbuffer, canvas,
-                                     inplace=inplace)
+                                     inplace=inplace, display_u8=display_uint8)
             return Buffers(zbuffer=z, targets=(c,))
         zb = buffers.zbuffer
         fill = DtypeInfo.create(zb.dtype).max
@@ -148,16 +156,20 @@ class Renderer:
             "shadow_viewport": shadow.camera.viewport,
         })
         z, c, _ = _render_arrays(_native.JR_PHONG_REFLECTION_SHADOW, arrays, buffers.zbuffer, canvas,
-                                 inplace=inplace)
+                                 inplace=inplace, display_u8=display_uint8)
         return Buffers(zbuffer=z, targets=(c,))
 
     @classmethod
     def get_camera_image(cls, objects: Sequence[ModelObject], light: "LightParameters",
                          camera: Union[Camera, CameraParameters], width: int, height: int,
                          colour_default: Any = (1.0, 1.0, 1.0), zbuffer_default: Any = 1.0,
-                         shadow_param: Optional[ShadowParameters] = None, loop_unroll: int = 1) -> Tensor:
+                         shadow_param: Optional[ShadowParameters] = None, loop_unroll: int = 1,
+                         *, display_uint8: bool = False) -> Tensor:
         """``renderer.py:395-476``.  Batched inputs (leading axis on object
-        transforms / camera parameters) give a batched canvas ``(B, W, H, 3)``."""
+        transforms / camera parameters) give a batched canvas ``(B, W, H, 3)``.
+
+        ``display_uint8=True`` (extension, CUDA): returns the display image ``(B?, H, W, 3) uint8`` instead
+        (see ``render``); no fp32 canvas is allocated, filled or written."""
         model = merge_objects(objects)
         dev = model.verts.device
         cam = cls.create_camera_from_parameters(camera, dev) if isinstance(camera, CameraParameters) else camera
@@ -166,6 +178,14 @@ class Renderer:
             base = 2 if t is not model.diffuse_map else 3
             if t.ndim == base + 1:
                 batch = t.shape[0]
+        if display_uint8:
+            b = (batch,) if batch is not None else ()
+            z = torch.full((*b, width, height), float(zbuffer_default), dtype=torch.float32, device=dev)
+            bg = [float(v) for v in (colour_default.reshape(-1).tolist() if isinstance(colour_default, torch.Tensor)
+                                     else colour_default)]
+            out = cls.render(model=model, light=light, camera=cam, buffers=Buffers(z, ()), shadow_param=shadow_param,
+                             inplace=True, display_uint8=bg)
+            return out.targets[0]
         buffers = cls.create_buffers(width, height, batch, colour_default, zbuffer_default, device=dev)
         out = cls.render(model=model, light=light, camera=cam, buffers=buffers,
                          shadow_param=shadow_param, loop_unroll=loop_unroll, inplace=dev.type == "cuda")

@@ -65,6 +65,13 @@ def _as_dtype(x: Any, dtype: torch.dtype, np_dtype: Any, device: Any) -> Tensor:
     return torch.as_tensor(x, dtype=dtype, device=dev)
 
 
+def _is_vmapped(*values: Any) -> bool:
+    """True when any value is a ``torch.func.vmap`` batched tensor (the native fast paths take raw device pointers:
+    inside a vmap they step aside for the torch builders, and ``pipeline._render_arrays`` re-batches natively)."""
+    f = torch._C._functorch
+    return any(isinstance(v, torch.Tensor) and f.is_batchedtensor(v) for v in values)
+
+
 def _f32(x: Any, device: Any = None) -> Tensor:
     """``jnp.asarray(x, dtype=float32)`` equivalent."""
     return _as_dtype(x, torch.float32, np.float32, device)

@@ -366,3 +366,83 @@ def test_shadow_pass_in_one_launch_equals_fill_render_add(wh):
     assert int((one.shadow_map < 1e30).sum()) > 0 and bool((one.shadow_map[one.shadow_map > 1e30] == fill).all())
     # light camera (1) + depth kernel(s): no fill pass, no add pass
     assert n1 - n0 <= (2 if W * H * 8 <= 96 * 1024 else 3), n1 - n0
+
+
+def test_torch_func_vmap_is_the_native_batch():
+    """Batch rendering "via vmap" (BASELINE north_star; examples/batch_rendering.py:87-95:
+    `jax.vmap(lambda m, b: Renderer.render(m, light, camera, b))`): `torch.func.vmap` around `Renderer.render` /
+    `pipeline.render` gives exactly the natively batched result (mapped inputs -> batched arrays, un-mapped ones ->
+    shared), and a gradient taken outside the vmap equals the native one."""
+    from torch.func import vmap
+
+    W, H, B = 84, 84, 5
+    sc = synthetic.brax_like_batch(B, n_capsules=3, env0=555, with_attributes=True)
+    cam1 = synthetic.brax_cameras(sc["eye"][0], sc["target"][0], W, H)          # one shared camera
+    cam = _cuda(cam1)
+    model = synthetic.merged_model_from_batch(sc, 3, DEV)                        # verts / norms batched, rest shared
+    light = jr.LightParameters(direction=(0.57735, -0.57735, 0.57735), ambient=(0.8,) * 3, diffuse=(0.8,) * 3,
+                               specular=(0.6,) * 3)
+    sp = jr.ShadowParameters(centre=sc["target"][0].to(DEV))
+    native = jr.Renderer.render(model, light, cam, jr.Renderer.create_buffers(W, H, batch=B, device=DEV), shadow_param=sp)
+    one = jr.Renderer.create_buffers(W, H, device=DEV)
+
+    def per_image(v, n, z, c):
+        out = jr.Renderer.render(model._replace(verts=v, norms=n), light, cam, jr.Buffers(z, (c,)), shadow_param=sp)
+        return out.zbuffer, out.targets[0]
+    # model mapped, buffers shared (in_axes None) ...
+    z1, c1 = vmap(per_image, in_dims=(0, 0, None, None))(model.verts, model.norms, one.zbuffer, one.targets[0])
+    assert torch.equal(z1, native.zbuffer) and torch.equal(c1, native.targets[0])
+    # ... and both mapped, as in the reference's example
+    bufs = jr.Renderer.create_buffers(W, H, batch=B, device=DEV)
+    z2, c2 = vmap(per_image)(model.verts, model.norms, bufs.zbuffer, bufs.targets[0])
+    assert torch.equal(z2, native.zbuffer) and torch.equal(c2, native.targets[0])
+    # the generic boundary, position mapped along axis 1
+    pos_t = model.verts.transpose(0, 1).contiguous()                              # (Nv, B, 3)
+    zd = vmap(lambda p: jr.render(cam, DepthShader, jr.Buffers(torch.full((W, H), 1.0, device=DEV), ()), model.faces,
+                                  DepthExtraInput(position=p)).zbuffer, in_dims=1)(pos_t)
+    want = jr.render(cam, DepthShader, jr.Buffers(torch.full((B, W, H), 1.0, device=DEV), ()), model.faces,
+                     DepthExtraInput(position=model.verts)).zbuffer
+    assert torch.equal(zd, want)
+    # gradient outside the vmap (shared atlas)
+    atlas = model.diffuse_map.clone().requires_grad_(True)
+    cv = vmap(lambda v, n: jr.Renderer.render(model._replace(verts=v, norms=n, diffuse_map=atlas), light, cam,
+                                              jr.Buffers(one.zbuffer, one.targets)).targets[0])(model.verts, model.norms)
+    cv.sum().backward()
+    atlas_n = model.diffuse_map.clone().requires_grad_(True)
+    jr.Renderer.render(model._replace(diffuse_map=atlas_n), light, cam,
+                       jr.Renderer.create_buffers(W, H, batch=B, device=DEV)).targets[0].sum().backward()
+    assert torch.equal(atlas.grad, atlas_n.grad)
+    # nested batching is refused with a clear message
+    with pytest.raises(NotImplementedError, match="nested"):
+        vmap(lambda z: jr.render(cam, DepthShader, jr.Buffers(z, ()), model.faces,
+                                 DepthExtraInput(position=model.verts)).zbuffer)(bufs.zbuffer)
+
+
+@pytest.mark.parametrize("wh", [(84, 84), (50, 37), (200, 150)])
+def test_display_uint8_fused_into_the_shading_store(wh):
+    """`get_camera_image(..., display_uint8=True)` -- the uint8 / transposed / flipped display image
+    written by the shading kernel itself -- equals the fp32 render followed by the reference's epilogue
+    (`transpose_for_display((clip(c, 0, 1) * 255).astype(uint8))`, utils.py:79-98), with and without the shadow
+    pass, constant background and incoming canvas."""
+    W, H = wh
+    B = 3
+    objs, eye, tgt = synthetic.brax_like_objects(B, n_capsules=3, env0=99, device=DEV)
+    cam = _cuda(synthetic.brax_cameras(eye, tgt, W, H))
+    light = jr.LightParameters(direction=(0.57735, -0.57735, 0.57735), ambient=(0.8,) * 3, diffuse=(0.9,) * 3,
+                               specular=(0.9,) * 3)          # bright enough to exercise the clamp
+    for sp in (None, jr.ShadowParameters(centre=tgt.to(DEV))):
+        ref = jr.Renderer.get_camera_image(objs, light, cam, W, H, colour_default=(0.2, 0.5, 1.3), shadow_param=sp)
+        want = (ref.clamp(0, 1) * 255).to(torch.uint8).transpose(1, 2).flip(1)
+        got = jr.Renderer.get_camera_image(objs, light, cam, W, H, colour_default=(0.2, 0.5, 1.3), shadow_param=sp,
+                                           display_uint8=True)
+        assert got.dtype == torch.uint8 and got.shape == (B, H, W, 3)
+        assert torch.equal(got, want), (wh, sp is not None)
+        assert torch.equal(got, jr.canvas_to_uint8_display(ref))
+    # incoming canvas as background, through Renderer.render
+    model = jr.merge_objects(objs)
+    g = torch.Generator(device="cpu").manual_seed(1)
+    bg = torch.rand(B, W, H, 3, generator=g).to(DEV)
+    a = jr.Renderer.render(model, light, cam, jr.Buffers(torch.ones(B, W, H, device=DEV), (bg.clone(),)))
+    u = jr.Renderer.render(model, light, cam, jr.Buffers(torch.ones(B, W, H, device=DEV), (bg.clone(),)),
+                           display_uint8=(0.0, 0.0, 0.0))
+    assert torch.equal(u.targets[0], jr.canvas_to_uint8_display(a.targets[0])) and torch.equal(u.zbuffer, a.zbuffer)

@@ -6,7 +6,7 @@ timeout 2400 python -m pytest tests -m gpu -q -s > gpurun_out/r2i_pytest.log 2>&
 echo "pytest rc=$?" >> gpurun_out/r2i_pytest.log
 tail -5 gpurun_out/r2i_pytest.log
 grep -n "FAILED\|Error" gpurun_out/r2i_pytest.log | head -20
-timeout 900 python bench.py --steps 30 > gpurun_out/r2i_bench.json 2> gpurun_out/r2i_bench.err; tail -3 gpurun_out/r2i_bench.err
+timeout 900 python bench.py --steps 30 --no-secondary --no-fwd-bwd --no-cpu > gpurun_out/r2i_bench.json 2> gpurun_out/r2i_bench.err; tail -3 gpurun_out/r2i_bench.err
 python - <<'PY'
 import json
 d=json.load(open('gpurun_out/r2i_bench.json'))
