@@ -289,6 +289,11 @@ typedef struct JrCameraArgs {
   float* out;       /* (8,B,4,4) */
 } JrCameraArgs;
 int jr_camera_build(const JrCameraArgs* args, jr_stream_t stream);
+/* Reverse mode of jr_camera_build (the reference differentiates its jnp builders, renderer.py:141-196,
+ * shadow.py:84-103): d_out (8,B,4,4) = cotangents of the 8 matrices -> d_params (B,16) and, JR_CAMERA_LIGHT with
+ * d_viewport != NULL, d_viewport (B,4,4).  `args->out` is ignored.  Exact derivative of the kernel's own formulas
+ * (the same code evaluated on dual numbers), not a finite difference. */
+int jr_camera_vjp(const JrCameraArgs* args, const float* d_out, float* d_params, float* d_viewport, jr_stream_t stream);
 
 /* Introspection for benchmarks: number of kernel launches issued by this
  * library since load (monotonic). */

@@ -283,8 +283,8 @@ def camera_build_native(mode: int, fields: Sequence[Tuple[Any, int]], dev: torch
     """All 8 ``Camera`` matrices in ONE launch of ``jr_camera_build`` (``csrc/jr_camera.cu``) instead of
     ~120 framework ops.  ``fields`` are the (value, width) pairs of the 16-float parameter row described
     in ``include/jr_b200.h``; every value is un-batched or carries ONE leading batch axis.  Returns
-    ``None`` when the fast path does not apply (gradients requested, deeper batch nesting): the caller
-    then uses the differentiable torch builders above."""
+    ``None`` when the fast path does not apply (deeper batch nesting, inside ``torch.func.vmap``): the caller
+    then uses the torch builders above.  Differentiable: gradients flow through ``jr_camera_vjp``."""
     import ctypes as C
 
     from . import _native
@@ -293,17 +293,16 @@ def camera_build_native(mode: int, fields: Sequence[Tuple[Any, int]], dev: torch
     dev_parts = []
     batch: Optional[int] = None
     tensors = [v for v, _ in fields] + [viewport]
-    if torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors):
-        return None
     if _is_vmapped(*tensors):
         return None
+    needs_grad = torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors)
     off = 0
     for v, w in fields:
         base = 1 if w > 1 else 0
         nd = v.ndim if isinstance(v, torch.Tensor) else np.ndim(v)
         if nd > base + 1:
             return None
-        if nd == base + 1 or (isinstance(v, torch.Tensor) and v.is_cuda):
+        if nd == base + 1 or (isinstance(v, torch.Tensor) and (v.is_cuda or v.requires_grad)):
             t = _f32(v, dev).reshape(-1, w)
             if t.shape[0] > 1:
                 if batch not in (None, t.shape[0]):
@@ -319,6 +318,8 @@ def camera_build_native(mode: int, fields: Sequence[Tuple[Any, int]], dev: torch
         vp = _f32(viewport, dev).contiguous()
         if vp.ndim > 3:
             return None
+        if tuple(vp.shape[-2:]) != (4, 4):
+            raise ValueError(f"viewport matrix must be (..., 4, 4), got {tuple(vp.shape)}")
         if vp.ndim == 3 and vp.shape[0] > 1:
             if batch not in (None, vp.shape[0]):
                 raise ValueError(f"inconsistent batch sizes {batch} and {vp.shape[0]}")
@@ -329,20 +330,81 @@ def camera_build_native(mode: int, fields: Sequence[Tuple[Any, int]], dev: torch
         rows = rows.expand(B, 16).clone()
         for o, w, t in dev_parts:
             rows[:, o:o + w] = t
-    out = torch.empty((8, B, 4, 4), dtype=torch.float32, device=dev)
+    if needs_grad:
+        # differentiable: the same launch, with jr_camera_vjp (the kernel's own formulas on dual numbers) as its
+        # reverse mode -- gradients w.r.t. CameraParameters / the light camera's inputs without the ~120 torch ops
+        out = _CameraFn.apply(rows if rows.ndim == 2 else rows.expand(B, 16), vp, mode, B)
+    else:
+        out = _camera_launch(rows, vp, mode, B, dev)
+    mats = out.unbind(0)
+    if batch is None:
+        mats = tuple(m[0] for m in mats)
+    return Camera(*mats)
+
+
+def _camera_args(rows: Tensor, vp: Optional[Tensor], mode: int, B: int):
+    from . import _native
+
     a = _native.JrCameraArgs()
     a.B, a.mode = B, mode
     a.params = _native.JrF32(rows.data_ptr(), 16 if rows.ndim == 2 else 0)
     if vp is not None:
         a.viewport = _native.JrF32(vp.data_ptr(), 16 if (vp.ndim == 3 and vp.shape[0] > 1) else 0)
+    return a
+
+
+def _camera_launch(rows: Tensor, vp: Optional[Tensor], mode: int, B: int, dev: torch.device) -> Tensor:
+    import ctypes as C
+
+    from . import _native
+
+    out = torch.empty((8, B, 4, 4), dtype=torch.float32, device=dev)
+    a = _camera_args(rows, vp, mode, B)
     a.out = out.data_ptr()
     lib = _native.load()
     with torch.cuda.device(dev):
         _native.check(lib.jr_camera_build(C.byref(a), _native.stream_ptr(dev)))
-    mats = out.unbind(0)
-    if batch is None:
-        mats = tuple(m[0] for m in mats)
-    return Camera(*mats)
+    return out
+
+
+class _CameraFn(torch.autograd.Function):
+    """``jr_camera_build`` with ``jr_camera_vjp`` as its reverse mode."""
+
+    @staticmethod
+    def forward(rows: Tensor, vp: Optional[Tensor], mode: int, B: int):  # type: ignore[override]
+        return _camera_launch(rows.contiguous(), vp, mode, B, rows.device)
+
+    @staticmethod
+    def setup_context(ctx: Any, inputs: Any, output: Any) -> None:
+        rows, vp, mode, B = inputs
+        ctx.mode, ctx.B = mode, B
+        ctx.save_for_backward(rows, vp)
+
+    @staticmethod
+    def backward(ctx: Any, d_out: Tensor):  # type: ignore[override]
+        import ctypes as C
+
+        from . import _native
+
+        rows, vp = ctx.saved_tensors
+        rows = rows.contiguous()
+        dev = rows.device
+        d_out = d_out.contiguous()
+        d_rows = torch.empty((ctx.B, 16), dtype=torch.float32, device=dev)
+        want_vp = vp is not None and ctx.needs_input_grad[1] and ctx.mode == _native.JR_CAMERA_LIGHT
+        d_vp = torch.empty((ctx.B, 4, 4), dtype=torch.float32, device=dev) if want_vp else None
+        a = _camera_args(rows, vp, ctx.mode, ctx.B)
+        lib = _native.load()
+        with torch.cuda.device(dev):
+            _native.check(lib.jr_camera_vjp(C.byref(a), d_out.data_ptr(), d_rows.data_ptr(),
+                                            d_vp.data_ptr() if d_vp is not None else None, _native.stream_ptr(dev)))
+        if d_vp is not None and not (vp.ndim == 3 and vp.shape[0] > 1):
+            d_vp = d_vp.sum(0).reshape(vp.shape)          # shared viewport: the batch sum
+        return d_rows, d_vp, None, None
+
+    @staticmethod
+    def vmap(info: Any, in_dims: Any, *args: Any):
+        raise NotImplementedError("camera construction inside torch.func.vmap uses the torch builders")
 
 
 def compute_normal(triangle_verts: Tensor) -> Tensor:
