@@ -295,6 +295,14 @@ int jr_camera_build(const JrCameraArgs* args, jr_stream_t stream);
  * (the same code evaluated on dual numbers), not a finite difference. */
 int jr_camera_vjp(const JrCameraArgs* args, const float* d_out, float* d_params, float* d_viewport, jr_stream_t stream);
 
+/* Test aid: audit of the conservative culls (the phase-A filter of the single-tile kernel and the bbox margin of
+ * the exact phase / binned setup).  One warp per triangle brute-forces every pixel with the exact edge functions
+ * (cost T*W*H per image: small scenes only) and ADDS to counters (device, 5 x uint64, caller zero-fills):
+ * [0] triangles the filter drops although the exact cull keeps them, [1] pixels a kept triangle covers outside its
+ * rasterised bbox, [2] pixels covered by triangles the bbox cull rejects, [3] triangles kept, [4] inside pixels.
+ * [0], [1], [2] must be 0 (tests/test_gpu_fuzz.py, tests/test_gpu_full_size.py). */
+int jr_debug_audit_cull(const JrRenderArgs* args, unsigned long long* counters, jr_stream_t stream);
+
 /* Introspection for benchmarks: number of kernel launches issued by this
  * library since load (monotonic). */
 long long jr_launch_count(void);

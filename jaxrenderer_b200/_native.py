@@ -23,7 +23,7 @@ EXPORTS = (
     "jr_depth_forward", "jr_gouraud_forward", "jr_gouraud_texture_forward", "jr_phong_forward",
     "jr_phong_darboux_forward", "jr_phong_reflection_forward", "jr_phong_reflection_shadow_forward",
     "jr_add_scalar", "jr_canvas_to_uint8_display", "jr_launch_count", "jr_merge_objects", "jr_camera_build",
-    "jr_instance_norm_scales", "jr_camera_vjp",
+    "jr_instance_norm_scales", "jr_camera_vjp", "jr_debug_audit_cull",
 )
 
 
@@ -133,6 +133,8 @@ def load() -> C.CDLL:
     lib.jr_instance_norm_scales.argtypes = [C.POINTER(JrMergeArgs), C.c_void_p, C.c_void_p]
     lib.jr_camera_build.restype = C.c_int
     lib.jr_camera_build.argtypes = [C.POINTER(JrCameraArgs), C.c_void_p]
+    lib.jr_debug_audit_cull.restype = C.c_int
+    lib.jr_debug_audit_cull.argtypes = [C.POINTER(JrRenderArgs), C.c_void_p, C.c_void_p]
     lib.jr_camera_vjp.restype = C.c_int
     lib.jr_camera_vjp.argtypes = [C.POINTER(JrCameraArgs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     _lib = lib

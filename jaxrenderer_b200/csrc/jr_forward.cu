@@ -601,6 +601,18 @@ int jr_instance_norm_scales(const JrMergeArgs* m, float* out_scales, jr_stream_t
   return cudaGetLastError() == cudaSuccess ? JR_OK : JR_ERR_CUDA;
 }
 
+int jr_debug_audit_cull(const JrRenderArgs* a, unsigned long long* counters, jr_stream_t stream) {
+  int st = check_common(a);
+  if (st != JR_OK) return st;
+  if (!counters) return JR_ERR_NULL;
+  if (a->B > 65535) return JR_ERR_DIMS;
+  if (a->T > 0) {
+    k_audit_cull<<<dim3((a->T + 7) / 8, a->B), 256, 0, (cudaStream_t)stream>>>(*a, counters);
+    jr::g_launches++;
+  }
+  return cudaGetLastError() == cudaSuccess ? JR_OK : JR_ERR_CUDA;
+}
+
 int jr_add_scalar(float* data, long long n, float value, jr_stream_t stream) {
   if (!data) return JR_ERR_NULL;
   if (n <= 0) return JR_OK;

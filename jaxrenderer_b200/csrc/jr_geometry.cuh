@@ -47,4 +47,43 @@ __device__ __forceinline__ Vec3 fetch_normal(const JrRenderArgs& a, int b, const
   return n;
 }
 
+// Exact (reference-order, no-FMA) per-triangle cull and conservative pixel bbox, shared by k_vis3's exact phase,
+// the binned setup and the audit kernel: clip x / y / w of the three vertices (rows 0, 1, 3 of world_to_clip) into
+// M, `keep & front-facing` (det > 1e-6, pipeline.py:98-100, :232), "all w <= 0" (behind the camera), and -- when all
+// w > 0 -- the screen bbox grown by bbox_margin (jr_device.cuh); any w <= 0: the whole canvas.  Returns false when
+// the triangle cannot cover a sample.  Bbox inclusive, in pixels of a W x H canvas.
+__device__ __forceinline__ bool exact_cull_bbox(const float* __restrict__ w2c, float vp00, float vp03, float vp11,
+                                                float vp13, int W, int H, Vec3 q0, Vec3 q1, Vec3 q2, float M[9],
+                                                int& x0, int& x1, int& y0, int& y1) {
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int rr = (r == 2) ? 3 : r;
+    const float m0 = w2c[4 * rr], m1 = w2c[4 * rr + 1], m2 = w2c[4 * rr + 2], m3 = w2c[4 * rr + 3];
+    M[0 + r] = ((q0.x * m0 + q0.y * m1) + q0.z * m2) + m3;
+    M[3 + r] = ((q1.x * m0 + q1.y * m1) + q1.z * m2) + m3;
+    M[6 + r] = ((q2.x * m0 + q2.y * m1) + q2.z * m2) + m3;
+  }
+  const float det = det3(M);
+  const bool cand = det > 1e-6f;
+  const float w0 = M[2], w1 = M[5], w2 = M[8];
+  const bool behind = (w0 <= 0.f && w1 <= 0.f && w2 <= 0.f);
+  if (!cand || behind) return false;
+  x0 = 0; x1 = W - 1; y0 = 0; y1 = H - 1;
+  if (w0 > 0.f && w1 > 0.f && w2 > 0.f) {
+    const float r0 = __fdividef(1.f, w0), r1 = __fdividef(1.f, w1), r2 = __fdividef(1.f, w2);
+    const float sx0 = (M[0] * r0) * vp00 + vp03, sx1 = (M[3] * r1) * vp00 + vp03, sx2 = (M[6] * r2) * vp00 + vp03;
+    const float sy0 = (M[1] * r0) * vp11 + vp13, sy1 = (M[4] * r1) * vp11 + vp13, sy2 = (M[7] * r2) * vp11 + vp13;
+    const float mg = bbox_margin(sx0, sy0, sx1, sy1, sx2, sy2, 2.f * fmaxf(vp00, vp11));
+    const float mnx = fmaxf(fminf(fminf(sx0, sx1), sx2) - mg, 0.f);
+    const float mxx = fminf(fmaxf(fmaxf(sx0, sx1), sx2) + mg, (float)(W - 1));
+    const float mny = fmaxf(fminf(fminf(sy0, sy1), sy2) - mg, 0.f);
+    const float mxy = fminf(fmaxf(fmaxf(sy0, sy1), sy2) + mg, (float)(H - 1));
+    if (!(mnx <= mxx) || !(mny <= mxy)) return false;
+    x0 = (int)ceilf(mnx); x1 = (int)floorf(mxx);
+    y0 = (int)ceilf(mny); y1 = (int)floorf(mxy);
+    if (x0 > x1 || y0 > y1) return false;
+  }
+  return true;
+}
+
 }  // namespace jr

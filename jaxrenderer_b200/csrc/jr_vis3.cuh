@@ -426,37 +426,11 @@ k_vis3(const __grid_constant__ JrRenderArgs a) {
     const int i0 = min(max(faces[3 * t + 0], 0), vmax), i1 = min(max(faces[3 * t + 1], 0), vmax),
               i2 = min(max(faces[3 * t + 2], 0), vmax);
     const Vec3 q0 = fetch_position(a, b, pos, i0), q1 = fetch_position(a, b, pos, i1), q2 = fetch_position(a, b, pos, i2);
+    int x0, x1, y0, y1;
+    if (!exact_cull_bbox(s_w2c, vp00, vp03, vp11, vp13, tw, th, q0, q1, q2, M, x0, x1, y0, y1)) return false;
     const float p0x = q0.x, p0y = q0.y, p0z = q0.z;
     const float p1x = q1.x, p1y = q1.y, p1z = q1.z;
     const float p2x = q2.x, p2y = q2.y, p2z = q2.z;
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      const int rr = (r == 2) ? 3 : r;
-      const float m0 = s_w2c[4 * rr], m1 = s_w2c[4 * rr + 1], m2 = s_w2c[4 * rr + 2], m3 = s_w2c[4 * rr + 3];
-      M[0 + r] = ((p0x * m0 + p0y * m1) + p0z * m2) + m3;
-      M[3 + r] = ((p1x * m0 + p1y * m1) + p1z * m2) + m3;
-      M[6 + r] = ((p2x * m0 + p2y * m1) + p2z * m2) + m3;
-    }
-    const float det = det3(M);
-    const bool cand = det > 1e-6f;  // keep & front (pipeline.py:98-100, :232)
-    const float w0 = M[2], w1 = M[5], w2 = M[8];
-    const bool behind = (w0 <= 0.f && w1 <= 0.f && w2 <= 0.f);
-    if (!cand || behind) return false;
-    int x0 = 0, x1 = tw - 1, y0 = 0, y1 = th - 1;
-    if (w0 > 0.f && w1 > 0.f && w2 > 0.f) {
-      const float r0 = __fdividef(1.f, w0), r1 = __fdividef(1.f, w1), r2 = __fdividef(1.f, w2);
-      const float sx0 = (M[0] * r0) * vp00 + vp03, sx1 = (M[3] * r1) * vp00 + vp03, sx2 = (M[6] * r2) * vp00 + vp03;
-      const float sy0 = (M[1] * r0) * vp11 + vp13, sy1 = (M[4] * r1) * vp11 + vp13, sy2 = (M[7] * r2) * vp11 + vp13;
-      const float mg = bbox_margin(sx0, sy0, sx1, sy1, sx2, sy2, 2.f * fmaxf(vp00, vp11));
-      const float mnx = fmaxf(fminf(fminf(sx0, sx1), sx2) - mg, 0.f);
-      const float mxx = fminf(fmaxf(fmaxf(sx0, sx1), sx2) + mg, (float)(tw - 1));
-      const float mny = fmaxf(fminf(fminf(sy0, sy1), sy2) - mg, 0.f);
-      const float mxy = fminf(fmaxf(fmaxf(sy0, sy1), sy2) + mg, (float)(th - 1));
-      if (!(mnx <= mxx) || !(mny <= mxy)) return false;
-      x0 = (int)ceilf(mnx); x1 = (int)floorf(mxx);
-      y0 = (int)ceilf(mny); y1 = (int)floorf(mxy);
-      if (x0 > x1 || y0 > y1) return false;
-    }
     const float m0 = s_w2c[8], m1 = s_w2c[9], m2 = s_w2c[10], m3 = s_w2c[11];
     zc[0] = ((p0x * m0 + p0y * m1) + p0z * m2) + m3;
     zc[1] = ((p1x * m0 + p1y * m1) + p1z * m2) + m3;
@@ -740,6 +714,81 @@ k_vis3(const __grid_constant__ JrRenderArgs a) {
       atomicAdd(a.stats + V3S_FRAGS, v[3]); atomicAdd(a.stats + V3S_ROUNDS, v[4]);
       if (warp == 0) { atomicAdd(a.stats + V3S_BATCHES, 1ull); atomicAdd(a.stats + V3S_TRIS, (unsigned long long)a.T); }
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Audit of the two conservative culls (tests only, jr_debug_audit_cull): one warp per triangle
+// brute-forces EVERY pixel of the canvas with the exact edge functions -- the reference's own test, pipeline.py:190 --
+// and counts what the fast paths would have lost:
+//   counters[0]  triangles the phase-A filter of k_vis3 drops although the exact cull keeps them
+//   counters[1]  pixels an exactly-kept triangle covers OUTSIDE the bbox the exact phase rasterises (bbox_margin)
+//   counters[2]  pixels covered by triangles the exact bbox cull rejects altogether
+//   counters[3]  triangles audited that the exact cull keeps,   counters[4]  inside pixels seen in total
+// All of [0..2] must read 0.
+__global__ void __launch_bounds__(256) k_audit_cull(const __grid_constant__ JrRenderArgs a, unsigned long long* __restrict__ counters) {
+  __shared__ float s_w2c[16], s_vp[16];
+  __shared__ V3Aux s_aux;
+  const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x < 16) {
+    s_w2c[threadIdx.x] = a.world_to_clip.ptr[(long long)b * a.world_to_clip.batch_stride + threadIdx.x];
+    s_vp[threadIdx.x] = a.viewport.ptr[(long long)b * a.viewport.batch_stride + threadIdx.x];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const float* m = s_w2c;
+    const float rx = fmaxf(fmaxf(fabsf(m[0]), fabsf(m[1])), fabsf(m[2]));
+    const float ry = fmaxf(fmaxf(fabsf(m[4]), fabsf(m[5])), fabsf(m[6]));
+    const float rw = fmaxf(fmaxf(fabsf(m[12]), fabsf(m[13])), fabsf(m[14]));
+    s_aux.wa = 1e-6f * rw; s_aux.wb = 1e-6f * fabsf(m[15]);
+    s_aux.qa = (rx + ry) + rw; s_aux.qb = (fabsf(m[3]) + fabsf(m[7])) + fabsf(m[15]);
+    s_aux.mg_c = 3.8e-6f * (2.f * fmaxf(s_vp[0], s_vp[5]));
+  }
+  __syncthreads();
+  const int t = blockIdx.x * 8 + warp;
+  if (t >= a.T) return;
+  const float vp00 = s_vp[0], vp03 = s_vp[3], vp11 = s_vp[5], vp13 = s_vp[7];
+  const float* __restrict__ pos = a.position.ptr + (long long)b * a.position.batch_stride;
+  const int32_t* __restrict__ faces = a.faces.ptr + (long long)b * a.faces.batch_stride;
+  const int vmax = a.n_pos - 1;
+  const int i0 = min(max(faces[3 * t], 0), vmax), i1 = min(max(faces[3 * t + 1], 0), vmax), i2 = min(max(faces[3 * t + 2], 0), vmax);
+  const Vec3 q0 = fetch_position(a, b, pos, i0), q1 = fetch_position(a, b, pos, i1), q2 = fetch_position(a, b, pos, i2);
+  const float p[9] = {q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, q2.x, q2.y, q2.z};
+  // single-tile canvases only: the filter's bbox lives on the whole canvas there
+  const bool single = a.W <= 255 && a.H <= 255;
+  const int cls = single ? v3_filter(s_w2c, s_aux, vp00, vp03, vp11, vp13, p, a.W, a.H) : 0;
+  float M[9];
+  int x0 = 0, x1 = -1, y0 = 0, y1 = -1;
+  const bool kept = exact_cull_bbox(s_w2c, vp00, vp03, vp11, vp13, a.W, a.H, q0, q1, q2, M, x0, x1, y0, y1);
+  // the reference's own predicate for this triangle, without any bbox
+  const bool cand = det3(M) > 1e-6f;   // (exact_cull_bbox filled M before any early return)
+  unsigned long long in_total = 0, out_of_box = 0;
+  if (cand) {
+    float inv[9];
+    lu_inverse3(M, inv);
+    for (int pix = lane; pix < a.W * a.H; pix += 32) {
+      const int x = pix / a.H, y = pix - x * a.H;
+      const float xn = ((float)x - vp03) / vp00, yn = ((float)y - vp13) / vp11;
+      const float c0 = (xn * inv[0] + yn * inv[3]) + inv[6];
+      const float c1 = (xn * inv[1] + yn * inv[4]) + inv[7];
+      const float c2 = (xn * inv[2] + yn * inv[5]) + inv[8];
+      if (c0 >= 0.f && c1 >= 0.f && c2 >= 0.f) {
+        ++in_total;
+        if (!kept || x < x0 || x > x1 || y < y0 || y > y1) ++out_of_box;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    in_total += __shfl_xor_sync(0xffffffffu, in_total, o);
+    out_of_box += __shfl_xor_sync(0xffffffffu, out_of_box, o);
+  }
+  if (lane == 0) {
+    if (kept && cls < 0) atomicAdd(counters + 0, 1ull);
+    if (kept && out_of_box) atomicAdd(counters + 1, out_of_box);
+    if (!kept && out_of_box) atomicAdd(counters + 2, out_of_box);
+    if (kept) atomicAdd(counters + 3, 1ull);
+    atomicAdd(counters + 4, in_total);
   }
 }
 

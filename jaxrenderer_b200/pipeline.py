@@ -156,6 +156,30 @@ class visibility_stats:
         return dict(zip(STAT_NAMES, (int(v) for v in self.buf.cpu().tolist())))
 
 
+def audit_cull(camera: Any, face_indices: Any, position: Any) -> Dict[str, int]:
+    """Test aid (``jr_debug_audit_cull``, include/jr_b200.h): brute-force every pixel of every triangle with the exact
+    edge functions and count what the conservative culls -- the filter phase of the single-tile kernel, the bbox
+    margin of the exact phase / binned setup -- would have lost.  ``filter_lost_triangles``, ``pixels_outside_bbox``
+    and ``pixels_of_rejected_triangles`` must be 0.  Costs T*W*H per image."""
+    lib = _native.load()
+    dev = position.device if isinstance(position, (torch.Tensor, InstancedArray)) else torch.device("cuda")
+    W = int(round(float(torch.as_tensor(camera.viewport).reshape(-1, 16)[0, 0]) * 2))
+    H = int(round(float(torch.as_tensor(camera.viewport).reshape(-1, 16)[0, 5]) * 2))
+    arrays = {"world_to_clip": camera.world_to_clip, "viewport": camera.viewport, "position": position, "faces": face_indices}
+    raw = {k: (v if isinstance(v, InstancedArray) else _as(torch.as_tensor(v), _SPEC[k][1], dev)) for k, v in arrays.items()}
+    batched = {k: v.ndim == _SPEC[k][0] + 1 for k, v in raw.items()}
+    B = max([v.shape[0] for k, v in raw.items() if batched[k]] + [1])
+    call = _Call(_native.JR_DEPTH, raw, B, W, H, 0, batched)
+    z = torch.empty((B, W, H), device=dev)
+    args = call.fill(z, None, None)
+    counters = torch.zeros(8, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        _native.check(lib.jr_debug_audit_cull(C.byref(args), counters.data_ptr(), _native.stream_ptr(dev)))
+    c = counters.cpu().tolist()
+    return {"filter_lost_triangles": c[0], "pixels_outside_bbox": c[1], "pixels_of_rejected_triangles": c[2],
+            "triangles_kept": c[3], "inside_pixels": c[4]}
+
+
 class _Call:
     """Everything about one render call that is not a differentiable tensor."""
 

@@ -62,3 +62,36 @@ def test_fuzz_small_and_needle_triangles(case):
     assert covered > 0.02 * B * W * H
     assert mism == 0
     assert np.array_equal(out.zbuffer.cpu().numpy(), zo)
+    # the guard of the conservative culls: every triangle brute-forced over the whole canvas
+    if W * H * n_tri * B <= 3_000_000_000:
+        from jaxrenderer_b200 import pipeline
+        audit = pipeline.audit_cull(camd, faces.to(DEV), pos.to(DEV))
+        print("  cull audit:", audit)
+        assert audit["filter_lost_triangles"] == 0 and audit["pixels_outside_bbox"] == 0
+        assert audit["pixels_of_rejected_triangles"] == 0 and audit["triangles_kept"] > 0
+
+
+def test_cull_audit_reads_zero_on_brax_scenes():
+    """The same guard on the scene families of the benchmark: synthetic ant-like scenes at 84x84 and 32x32, the real
+    Brax ant fixture (instanced geometry), and a 480x270 binned-path scene."""
+    from jaxrenderer_b200 import pipeline, synthetic
+    from tests.helpers import load_brax_fixture
+
+    for (W, H, B, n_caps) in ((84, 84, 16, 10), (32, 32, 16, 10), (480, 270, 1, 17)):
+        objs, eye, tgt = synthetic.brax_like_objects(B, n_capsules=n_caps, env0=123, device=DEV)
+        cam = synthetic.brax_cameras(eye, tgt, W, H)
+        camd = type(cam)(*[t.to(DEV) for t in cam])
+        m = jr.merge_objects(objs)
+        audit = pipeline.audit_cull(camd, m.faces, m.verts)          # factored geometry, instanced in the kernel
+        print(f"  {W}x{H} B={B}: {audit}")
+        assert audit["filter_lost_triangles"] == 0 and audit["pixels_outside_bbox"] == 0
+        assert audit["pixels_of_rejected_triangles"] == 0 and audit["inside_pixels"] > W * H * B
+    objs, camp = load_brax_fixture()
+    objs_d = [jr.ModelObject(model=type(o.model)(*[t.to(DEV) for t in o.model]), local_scaling=o.local_scaling.to(DEV),
+                             transform=o.transform.to(DEV), double_sided=o.double_sided) for o in objs]
+    cp = jr.CameraParameters(**{k: v.to(DEV) for k, v in camp._asdict().items()})._replace(viewWidth=84, viewHeight=84, vfov=58.0)
+    cam = jr.Renderer.create_camera_from_parameters(cp)
+    m = jr.merge_objects(objs_d)
+    audit = pipeline.audit_cull(cam, m.faces, m.verts)
+    print("  brax ant fixture 84x84:", audit)
+    assert audit["filter_lost_triangles"] == 0 and audit["pixels_outside_bbox"] == 0 and audit["pixels_of_rejected_triangles"] == 0
