@@ -81,7 +81,11 @@ __device__ __forceinline__ void lu_inverse3(const float A[9], float inv[9]) {
   float u11 = a11, u12 = a12;
   float l21 = a21 * (1.0f / u11);
   float u22 = a22 - l21 * u12;
+#ifdef JR_LU_ROLLED
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
   for (int j = 0; j < 3; ++j) {
     float y0 = r0[3 + j];
     float y1 = r1[3 + j] - y0 * l10;

@@ -377,12 +377,15 @@ static void set_kernel_attributes_once() {
     smem_attr(k_vis2<true, true, V2_K32_THREADS>, 200 * 1024);
     smem_attr(k_vis2<true, false, V2_THREADS>, 200 * 1024);
     smem_attr(k_vis2<false, false, V2_THREADS>, 200 * 1024);
-    smem_attr(k_vis3<true, true, false>, 200 * 1024);
-    smem_attr(k_vis3<true, false, false>, 200 * 1024);
-    smem_attr(k_vis3<false, false, false>, 200 * 1024);
-    smem_attr(k_vis3<true, true, true>, 200 * 1024);
-    smem_attr(k_vis3<true, false, true>, 200 * 1024);
-    smem_attr(k_vis3<false, false, true>, 200 * 1024);
+    smem_attr(k_vis3<true, true, false, false>, 200 * 1024);
+    smem_attr(k_vis3<true, false, false, false>, 200 * 1024);
+    smem_attr(k_vis3<false, false, false, false>, 200 * 1024);
+    smem_attr(k_vis3<true, true, false, true>, 200 * 1024);
+    smem_attr(k_vis3<true, false, false, true>, 200 * 1024);
+    smem_attr(k_vis3<false, false, false, true>, 200 * 1024);
+    smem_attr(k_vis3<true, true, true, true>, 200 * 1024);
+    smem_attr(k_vis3<true, false, true, true>, 200 * 1024);
+    smem_attr(k_vis3<false, false, true, true>, 200 * 1024);
     smem_attr(k_raster_tile<true, true>, 64 * 1024);
     smem_attr(k_raster_tile<true, false>, 64 * 1024);
     smem_attr(k_raster_tile<false, false>, 64 * 1024);
@@ -484,14 +487,19 @@ int jr_render_forward(const JrRenderArgs* a, jr_stream_t stream_) {
     const V3Layout L = v3_layout(a->W, a->H, k32 ? 4 : 8);  // bytes: L.total
     if (a->T > 0 && (!a->workspace || a->workspace_bytes < v3_workspace_bytes(a->B, a->T))) return JR_ERR_WORKSPACE;
     const unsigned g = (unsigned)ctas;
-    if (a->stats) {
-      if (k32) k_vis3<true, true, true><<<g, V3_THREADS, L.total, stream>>>(*a);
-      else if (depth) k_vis3<true, false, true><<<g, V3_THREADS, L.total, stream>>>(*a);
-      else k_vis3<false, false, true><<<g, V3_THREADS, L.total, stream>>>(*a);
+    const bool inst = a->inst_transform.ptr != nullptr;
+    if (a->stats) {  // counting variant (measurement aid): always the instancing-capable build
+      if (k32) k_vis3<true, true, true, true><<<g, V3_THREADS, L.total, stream>>>(*a);
+      else if (depth) k_vis3<true, false, true, true><<<g, V3_THREADS, L.total, stream>>>(*a);
+      else k_vis3<false, false, true, true><<<g, V3_THREADS, L.total, stream>>>(*a);
+    } else if (inst) {
+      if (k32) k_vis3<true, true, false, true><<<g, V3_THREADS, L.total, stream>>>(*a);
+      else if (depth) k_vis3<true, false, false, true><<<g, V3_THREADS, L.total, stream>>>(*a);
+      else k_vis3<false, false, false, true><<<g, V3_THREADS, L.total, stream>>>(*a);
     } else {
-      if (k32) k_vis3<true, true, false><<<g, V3_THREADS, L.total, stream>>>(*a);
-      else if (depth) k_vis3<true, false, false><<<g, V3_THREADS, L.total, stream>>>(*a);
-      else k_vis3<false, false, false><<<g, V3_THREADS, L.total, stream>>>(*a);
+      if (k32) k_vis3<true, true, false, false><<<g, V3_THREADS, L.total, stream>>>(*a);
+      else if (depth) k_vis3<true, false, false, false><<<g, V3_THREADS, L.total, stream>>>(*a);
+      else k_vis3<false, false, false, false><<<g, V3_THREADS, L.total, stream>>>(*a);
     }
   } else {
     if (a->inst_transform.ptr) return JR_ERR_UNSUPPORTED;  // k_vis2 (A/B switch) reads merged arrays only

@@ -43,6 +43,12 @@ constexpr int V3_NW = V3_THREADS / 32;
 #ifndef JR_V3_GRAIN2
 #define JR_V3_GRAIN2 32
 #endif
+#ifndef JR_V3_RESOLVE_UNROLL
+#define JR_V3_RESOLVE_UNROLL 4
+#endif
+#ifndef JR_V3_NV
+#define JR_V3_NV 1
+#endif
 #ifndef JR_V3_K64_CTAS
 #define JR_V3_K64_CTAS 4
 #endif
@@ -264,7 +270,9 @@ __device__ __noinline__ void v3_raster_hier(float i0, float i1, float i2, float 
                         xs, ys, keys_saddr, key_stride, vp22, vp23);
 }
 
-template <bool DEPTH, bool K32, bool STATS>
+// INST: geometry instanced at the fetch (JrRenderArgs.inst_*); a template parameter so that the merged-array kernel
+// does not carry the instancing code (the instruction footprint of this kernel is worth several percent).
+template <bool DEPTH, bool K32, bool STATS, bool INST>
 __global__ void __launch_bounds__(V3_THREADS, K32 ? JR_V3_K32_CTAS : JR_V3_K64_CTAS)
 k_vis3(const __grid_constant__ JrRenderArgs a) {
   static_assert(DEPTH || !K32, "z-only keys are for the depth shader");
@@ -425,7 +433,13 @@ k_vis3(const __grid_constant__ JrRenderArgs a) {
   auto exact_setup = [&](int t, float* M, float* zc, unsigned& bb) -> bool {
     const int i0 = min(max(faces[3 * t + 0], 0), vmax), i1 = min(max(faces[3 * t + 1], 0), vmax),
               i2 = min(max(faces[3 * t + 2], 0), vmax);
-    const Vec3 q0 = fetch_position(a, b, pos, i0), q1 = fetch_position(a, b, pos, i1), q2 = fetch_position(a, b, pos, i2);
+    Vec3 q0{pos[3 * i0], pos[3 * i0 + 1], pos[3 * i0 + 2]}, q1{pos[3 * i1], pos[3 * i1 + 1], pos[3 * i1 + 2]},
+        q2{pos[3 * i2], pos[3 * i2 + 1], pos[3 * i2 + 2]};
+    if (INST && instanced(a)) {
+      instance_vertex(a, b, i0, q0.x, q0.y, q0.z, q0.x, q0.y, q0.z);
+      instance_vertex(a, b, i1, q1.x, q1.y, q1.z, q1.x, q1.y, q1.z);
+      instance_vertex(a, b, i2, q2.x, q2.y, q2.z, q2.x, q2.y, q2.z);
+    }
     int x0, x1, y0, y1;
     if (!exact_cull_bbox(s_w2c, vp00, vp03, vp11, vp13, tw, th, q0, q1, q2, M, x0, x1, y0, y1)) return false;
     const float p0x = q0.x, p0y = q0.y, p0z = q0.z;
@@ -476,7 +490,7 @@ k_vis3(const __grid_constant__ JrRenderArgs a) {
       p[3] = pos[3 * i1]; p[4] = pos[3 * i1 + 1]; p[5] = pos[3 * i1 + 2];
       p[6] = pos[3 * i2]; p[7] = pos[3 * i2 + 1]; p[8] = pos[3 * i2 + 2];
     }
-    if (instanced(a) && in) {
+    if (INST && instanced(a) && in) {
       // instanced geometry: local -> world (the merge's own arithmetic; the filter needs no more than that)
       instance_vertex(a, b, i0, p[0], p[1], p[2], p[0], p[1], p[2]);
       instance_vertex(a, b, i1, p[3], p[4], p[5], p[3], p[4], p[5]);
@@ -499,11 +513,13 @@ k_vis3(const __grid_constant__ JrRenderArgs a) {
       base01 = __shfl_sync(0xffffffffu, base01, 0);
       base23 = __shfl_sync(0xffffffffu, base23, 0);
       if (cls >= 0) {
-        const unsigned mine = cls == 0 ? m0 : (cls == 1 ? m1 : (cls == 2 ? m2 : m3));
-        const int off = cls == 0 ? V3_OFF0 : (cls == 1 ? V3_OFF1 : (cls == 2 ? V3_OFF2 : V3_OFF3));
-        const int cap = cls == 0 ? V3_CAP0 : V3_CAP1;  // CAP1 == CAP2 == CAP3
-        const unsigned bs = cls < 2 ? base01 : base23;
-        const int slot = (int)((bs >> (16 * (cls & 1))) & 0xffffu) + __popc(mine & lt_mask);
+        // (arithmetic instead of per-lane selects: the lists are 1024 + 3 x 512 entries)
+        static_assert(V3_CAP0 == 1024 && V3_CAP1 == 512 && V3_CAP2 == 512 && V3_CAP3 == 512, "list offsets below");
+        const unsigned mine = ms & ((cls & 1) ? b0 : ~b0) & ((cls & 2) ? b1 : ~b1);
+        const int off = (cls + (cls != 0)) << 9;                  // 0, 1024, 1536, 2048
+        const int cap = 512 << (cls == 0);
+        const unsigned bs = (cls & 2) ? base23 : base01;
+        const int slot = (int)((bs >> ((cls & 1) << 4)) & 0xffffu) + __popc(mine & lt_mask);
         // list full (or a triangle index beyond 16 bits): the triangle goes to the image's spill list in the
         // workspace (global memory) and is set up after the lists
         if (slot < cap && t < V3_TMAX16) lists[off + slot] = (unsigned short)t;
@@ -609,40 +625,49 @@ k_vis3(const __grid_constant__ JrRenderArgs a) {
     // large triangle is evaluated once per block, not once per triangle.  (Packed FMUL2 feeding FADD2 is not
     // used: ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under -fmad=false, which changes
     // bits.  Scalar products feeding packed sums are safe -- build.sh checks the SASS holds no FFMA2.)
+    // Each thread owns NV vectors = PXT consecutive rows of one column (per-thread overheads -- span fetch, triangle
+    // coefficients, index arithmetic -- are paid once per PXT pixels).
+    constexpr int NV = JR_V3_NV, PXT = PX * NV, RU = JR_V3_RESOLVE_UNROLL;
     const int cx = lane & 7, gy = lane >> 3;
-    const int nbx = (W + 7) >> 3, nby = (H + 4 * PX - 1) / (4 * PX);
+    const int nbx = (W + 7) >> 3, nby = (H + 4 * PXT - 1) / (4 * PXT);
     const float rnby = 1.0f / (float)nby;
     for (int blk = warp; blk < nbx * nby; blk += V3_NW) {
       const int bx = (int)(((float)blk + 0.5f) * rnby), by = blk - bx * nby;  // exact quotient (blk < 2^16)
-      const int x = bx * 8 + cx, y = by * (4 * PX) + gy * PX;
+      const int x = bx * 8 + cx, y = by * (4 * PXT) + gy * PXT;
       const bool live = x < W && y < H;
-      const int i = live ? (x * H + y) / PX : 0;
-      KeyT k[PX];
-      if (K32) {
-        const uint4 kk = reinterpret_cast<const uint4*>(keys32)[i];
-        k[0] = kk.x; k[1] = kk.y; k[2 % PX] = kk.z; k[3 % PX] = kk.w;
-      } else {
-        const ulonglong2 kk = reinterpret_cast<const ulonglong2*>(keys)[i];
-        k[0] = (KeyT)kk.x; k[1] = (KeyT)kk.y;
+      const int nrow = live ? min(PXT, H - y) : 0;     // rows of this thread inside the canvas (a multiple of PX)
+      const int i = live ? (x * H + y) / PX : 0;      // index of the first vector
+      KeyT k[PXT];
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const int iv = (v * PX < nrow) ? i + v : i;
+        if (K32) {
+          const uint4 kk = reinterpret_cast<const uint4*>(keys32)[iv];
+          k[v * PX + 0] = kk.x; k[v * PX + 1] = kk.y; k[v * PX + 2 % PX] = kk.z; k[v * PX + 3 % PX] = kk.w;
+        } else {
+          const ulonglong2 kk = reinterpret_cast<const ulonglong2*>(keys)[iv];
+          k[v * PX + 0] = (KeyT)kk.x; k[v * PX + 1] = (KeyT)kk.y;
+        }
       }
       if (nbig) {
         const int xc = live ? x : 0, yc = live ? y : 0;
         const float xn = xs[xc];
-        float yn[PX];
+        float yn[PXT];
 #pragma unroll
-        for (int p = 0; p < PX; ++p) yn[p] = ys[yc + p];
+        for (int p = 0; p < PXT; ++p) yn[p] = ys[min(yc + p, H - 1)];
         for (int e = 0; e < nbig; ++e) {
           const unsigned sp = spans[e * W + xc];
           const int lo = (int)(sp & 0xffu), hi = (int)(sp >> 8);
-          const bool overlap = live && hi >= yc && lo <= yc + PX - 1;
+          const bool overlap = live && hi >= yc && lo <= yc + nrow - 1;
           if (!__any_sync(0xffffffffu, overlap)) continue;
           const V3Big& q = bigq[e];
           const float i3 = q.inv[3].x, i4 = q.inv[4].x, i5 = q.inv[5].x, i6 = q.inv[6].x, i7 = q.inv[7].x, i8 = q.inv[8].x;
           const float px0 = xn * q.inv[0].x, px1 = xn * q.inv[1].x, px2 = xn * q.inv[2].x;
           const float z0 = q.zc[0].x, z1 = q.zc[1].x, z2 = q.zc[2].x;
           const unsigned tri = (unsigned)q.tri;
-#pragma unroll
-          for (int h = 0; h < PX / 2; ++h) {
+          const int rlo = overlap ? lo - yc : PXT, rhi = overlap ? hi - yc : -1;   // span in this thread's rows
+#pragma unroll RU
+          for (int h = 0; h < PXT / 2; ++h) {
             // Two rows at a time: scalar FMUL products, packed FADD2 sums (sm_100; each half is rounded like the
             // scalar FADD: the rasterisers' expressions, same bits).  Branch-free: evaluate, then select by the span.
             const float ya = yn[2 * h], yb = yn[2 * h + 1];
@@ -654,45 +679,50 @@ k_vis3(const __grid_constant__ JrRenderArgs a) {
             const float2 zw = add2(make_float2(z.x * vp22, z.y * vp22), make_float2(vp23, vp23));
             const float zwp[2] = {zw.x, zw.y};
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              const int p = 2 * h + j;
-              const bool inside = overlap && (yc + p >= lo) && (yc + p <= hi);
-              KeyT key = K32 ? (KeyT)min(orderable(zwp[j]), 0xFFFFFFFEu)
-                             : (KeyT)(((unsigned long long)orderable(zwp[j]) << 32) | tri);
+            for (int jj = 0; jj < 2; ++jj) {
+              const int p = 2 * h + jj;
+              const bool inside = (p >= rlo) && (p <= rhi);
+              KeyT key = K32 ? (KeyT)min(orderable(zwp[jj]), 0xFFFFFFFEu)
+                             : (KeyT)(((unsigned long long)orderable(zwp[jj]) << 32) | tri);
               key = inside ? key : (KeyT)~(KeyT)0;
               k[p] = key < k[p] ? key : k[p];
             }
           }
         }
       }
-      if (!live) continue;
-      if (K32) {
-        const uint32_t k0 = (uint32_t)k[0], k1 = (uint32_t)k[1], k2 = (uint32_t)k[2 % PX], k3 = (uint32_t)k[3 % PX];
-        if (z_fill || (k0 != ~0u && k1 != ~0u && k2 != ~0u && k3 != ~0u)) {
-          reinterpret_cast<float4*>(z_out)[i] =
-              make_float4(zfin(k0 != ~0u ? from_orderable(k0) : z_fillv), zfin(k1 != ~0u ? from_orderable(k1) : z_fillv),
-                          zfin(k2 != ~0u ? from_orderable(k2) : z_fillv), zfin(k3 != ~0u ? from_orderable(k3) : z_fillv));
-        } else {
-          if (k0 != ~0u) z_out[4 * i] = zfin(from_orderable(k0));
-          if (k1 != ~0u) z_out[4 * i + 1] = zfin(from_orderable(k1));
-          if (k2 != ~0u) z_out[4 * i + 2] = zfin(from_orderable(k2));
-          if (k3 != ~0u) z_out[4 * i + 3] = zfin(from_orderable(k3));
-        }
-      } else {
-        const unsigned long long q0 = k[0], q1 = k[1];
-        const bool e0 = q0 == ~0ull, e1 = q1 == ~0ull;
-        if (DEPTH) {
-          if (z_fill || (!e0 && !e1)) {
-            reinterpret_cast<float2*>(z_out)[i] =
-                make_float2(zfin(e0 ? z_fillv : from_orderable((uint32_t)(q0 >> 32))),
-                            zfin(e1 ? z_fillv : from_orderable((uint32_t)(q1 >> 32))));
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        if (v * PX >= nrow) continue;
+        const int iv = i + v;
+        if (K32) {
+          const uint32_t k0 = (uint32_t)k[v * PX], k1 = (uint32_t)k[v * PX + 1], k2 = (uint32_t)k[v * PX + 2 % PX],
+                         k3 = (uint32_t)k[v * PX + 3 % PX];
+          if (z_fill || (k0 != ~0u && k1 != ~0u && k2 != ~0u && k3 != ~0u)) {
+            reinterpret_cast<float4*>(z_out)[iv] =
+                make_float4(zfin(k0 != ~0u ? from_orderable(k0) : z_fillv), zfin(k1 != ~0u ? from_orderable(k1) : z_fillv),
+                            zfin(k2 != ~0u ? from_orderable(k2) : z_fillv), zfin(k3 != ~0u ? from_orderable(k3) : z_fillv));
           } else {
-            if (!e0) z_out[2 * i] = zfin(from_orderable((uint32_t)(q0 >> 32)));
-            if (!e1) z_out[2 * i + 1] = zfin(from_orderable((uint32_t)(q1 >> 32)));
+            if (k0 != ~0u) z_out[4 * iv] = zfin(from_orderable(k0));
+            if (k1 != ~0u) z_out[4 * iv + 1] = zfin(from_orderable(k1));
+            if (k2 != ~0u) z_out[4 * iv + 2] = zfin(from_orderable(k2));
+            if (k3 != ~0u) z_out[4 * iv + 3] = zfin(from_orderable(k3));
           }
+        } else {
+          const unsigned long long q0 = k[v * PX], q1 = k[v * PX + 1];
+          const bool e0 = q0 == ~0ull, e1 = q1 == ~0ull;
+          if (DEPTH) {
+            if (z_fill || (!e0 && !e1)) {
+              reinterpret_cast<float2*>(z_out)[iv] =
+                  make_float2(zfin(e0 ? z_fillv : from_orderable((uint32_t)(q0 >> 32))),
+                              zfin(e1 ? z_fillv : from_orderable((uint32_t)(q1 >> 32))));
+            } else {
+              if (!e0) z_out[2 * iv] = zfin(from_orderable((uint32_t)(q0 >> 32)));
+              if (!e1) z_out[2 * iv + 1] = zfin(from_orderable((uint32_t)(q1 >> 32)));
+            }
+          }
+          if (tri_out)
+            reinterpret_cast<int2*>(tri_out)[iv] = make_int2(e0 ? -1 : (int)(unsigned)q0, e1 ? -1 : (int)(unsigned)q1);
         }
-        if (tri_out)
-          reinterpret_cast<int2*>(tri_out)[i] = make_int2(e0 ? -1 : (int)(unsigned)q0, e1 ? -1 : (int)(unsigned)q1);
       }
     }
   } else {
