@@ -266,12 +266,15 @@ def run_ours(args) -> None:
     # The batch is streamed in chunks over two CUDA streams so the H2D copy of chunk i+1, the kernels of
     # chunk i and the D2H copy of chunk i-1 overlap (PCIe is full duplex).  Every chunk is the public API:
     # merge_objects -> create_camera_from_parameters -> pipeline.render.
-    # (host cost of one public-API call chain is ~0.5 ms: few chunks)
-    n_chunks = int(os.environ.get("JR_E2E_CHUNKS", "0")) or (2 if B % 2 == 0 and B >= 64 else 1)
-    Bc = B // n_chunks
+    # Two ways of issuing the same calls, both timed:
+    #   eager  every step calls the API chunk by chunk (host cost of one chain ~0.7 ms: few chunks, host-bound);
+    #   graph  the same chunked call sequence captured ONCE into a CUDA graph (what `jax.jit` gives the reference's
+    #          users; the facade is allocation- and sync-free) and replayed per step: the copies read
+    #          the pinned host buffers Brax refills and write the pinned result buffer, inside the timed region.
     streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
 
-    def step_e2e():
+    def enqueue_e2e(n_chunks):
+        Bc = B // n_chunks
         cur = torch.cuda.current_stream(dev)
         for s_ in streams:
             s_.wait_stream(cur)
@@ -287,22 +290,59 @@ def run_ours(args) -> None:
                 z_host[sl].copy_(out.zbuffer, non_blocking=True)
         for s_ in streams:
             cur.wait_stream(s_)
-        cur.synchronize()
 
-    for _ in range(3):
-        step_e2e()
-    barrier()
-    e2e_steps = max(3, min(args.steps, 20))
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(e2e_steps):
-        step_e2e()
-    e1.record()
-    barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item()) / e2e_steps
+    def pick_chunks(want):
+        n = max(1, min(want, B))
+        while B % n:
+            n -= 1
+        return n
+
+    def time_e2e(step):
+        for _ in range(3):
+            step()
+        barrier()
+        steps = max(3, min(args.steps, 20))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        barrier()
+        tt = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item()) / steps, steps
+
+    eager_chunks = pick_chunks(int(os.environ.get("JR_E2E_CHUNKS", "0")) or (2 if B >= 64 else 1))
+
+    def step_eager():
+        enqueue_e2e(eager_chunks)
+        torch.cuda.current_stream(dev).synchronize()
+
+    eager_ms, e2e_steps = time_e2e(step_eager)
+    e2e_ms, e2e_mode, e2e_chunks = eager_ms, "eager", eager_chunks
+    graph_note = None
+    if args.e2e != "eager":
+        graph_chunks = pick_chunks(int(os.environ.get("JR_E2E_GRAPH_CHUNKS", "0")) or (8 if B >= 1024 else 2))
+        try:
+            enqueue_e2e(graph_chunks)                       # warm-up: workspaces, memoised constants
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                enqueue_e2e(graph_chunks)
+
+            def step_graph():
+                graph.replay()
+                torch.cuda.current_stream(dev).synchronize()
+
+            z_host.zero_()
+            step_graph()
+            assert torch.equal(z_host, z.cpu()), "graph-replayed e2e output differs from the device-resident output"
+            graph_ms, e2e_steps = time_e2e(step_graph)
+            e2e_ms, e2e_mode, e2e_chunks = graph_ms, "graph", graph_chunks
+        except Exception as exc:  # capture not possible: the eager figure stands, and the line says why
+            graph_note = f"{type(exc).__name__}: {exc}"[:200]
+            torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None   # sampled over both timed regions (resident + e2e)
     h2d = (tf_h.numel() + eye_h.numel() + tgt_h.numel()) * 4
     d2h = z_host.numel() * 4
@@ -369,6 +409,9 @@ def run_ours(args) -> None:
             "clocks": clocks,
             "e2e": {"value": B * world / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": e2e_steps,
+                    "mode": e2e_mode, "chunks": e2e_chunks,
+                    "eager": {"value": B * world / (eager_ms / 1e3), "ms_per_step": eager_ms, "chunks": eager_chunks},
+                    "graph_error": graph_note,
                     "inputs": "host: object transforms + camera parameters (what Brax produces); geometry instanced "
                               "in-kernel from the resident robot meshes"},
             "gpu_launches": int(launches),
@@ -555,6 +598,9 @@ def main() -> None:
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-fwd-bwd", action="store_true", help="skip the secondary forward+backward measurement")
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary configurations (configs[0], [2], [3], [4])")
+    ap.add_argument("--e2e", choices=("graph", "eager"), default="graph",
+                    help="how the e2e step issues the public-API calls: captured once into a CUDA graph and replayed "
+                         "(default; the eager figure is reported beside it) or eagerly every step")
     ap.add_argument("--scaling", choices=("weak", "strong"), default="weak",
                     help="weak: --batch images per GPU; strong: --batch images in total, split over the GPUs")
     args = ap.parse_args()

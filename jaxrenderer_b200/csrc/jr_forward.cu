@@ -58,12 +58,14 @@ __global__ void __launch_bounds__(256, JR_SHADE_CTAS) k_shade(const __grid_const
 template <int SHADER>
 __global__ void __launch_bounds__(128) k_tri_attr(const __grid_constant__ JrRenderArgs a, float* __restrict__ attrs,
                                                   const int* __restrict__ list, const int* __restrict__ count,
-                                                  int rec_stride, bool compact) {
+                                                  int rec_stride, bool compact, PixConst* __restrict__ pcs) {
   // records are staged in shared memory and written out as coalesced float4 (a thread writing its
   // own 176 B record with scalar stores made this kernel 4x slower)
   __shared__ __align__(16) float stage[128 * TA_FLOATS];
   __shared__ int s_tri[128];
   const int b = blockIdx.y;
+  // the image's pixel-stage constants (read by k_shade_rec*), by the first warp of the image's first block
+  if (blockIdx.x == 0 && threadIdx.x < 32) pix_const_write<SHADER>(a, b, pcs + b);
   const int n_vis = count[b];
   const int i0 = blockIdx.x * 128;
   if (i0 >= n_vis) return;
@@ -91,27 +93,31 @@ __global__ void __launch_bounds__(128) k_tri_attr(const __grid_constant__ JrRend
 template <int SHADER>
 __global__ void __launch_bounds__(256, JR_SHADE_CTAS) k_shade_rec(const __grid_constant__ JrRenderArgs a,
                                                    const float* __restrict__ attrs, int rec_stride,
-                                                   const int* __restrict__ slot_map) {
-  // grid = (blocks per image, images): all index arithmetic stays 32-bit (a 64-bit division per
-  // pixel cost ~100 instructions)
+                                                   const int* __restrict__ slot_map, const PixConst* __restrict__ pcs) {
+  // One pixel per thread, no loops: grid = (ceil(W * H / 256), min(B, 65535), ceil(B / 65535)); all index arithmetic
+  // stays 32-bit (a 64-bit division per pixel cost ~100 instructions); per-image constants through `pcs`
+  // (PixConst, written by k_tri_attr); pix -> (x, y) by a multiply-high with the stored reciprocal of H (the integer
+  // division was 3 % of the kernel).
   const int npix = a.W * a.H;
-  for (int b = blockIdx.y; b < a.B; b += gridDim.y)
-  for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += gridDim.x * blockDim.x) {
-    const long long gi = (long long)b * npix + pix;
-    const int tri = a.tri_id[gi];
-    if (tri < 0) continue;
-    const int x = pix / a.H, y = pix - x * a.H;
-    Frag f;
-    const int slot = slot_map ? slot_map[(long long)b * a.T + tri] : tri;
-    attr_load<SHADER>(a, b, attrs + ((size_t)b * rec_stride + slot) * TA_FLOATS, f);
-    frag_pixel<SHADER>(a, b, x, y, f);
-    if (f.keep) {
-      a.zbuffer[gi] = f.zw;
-      float* o = a.canvas + gi * 3;
-      o[0] = f.col[0]; o[1] = f.col[1]; o[2] = f.col[2];
-    } else {
-      a.tri_id[gi] = -1;
-    }
+  const int b = blockIdx.z * 65535 + blockIdx.y;
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= a.B || pix >= npix) return;
+  const long long gi = (long long)b * npix + pix;
+  const int tri = a.tri_id[gi];
+  if (tri < 0) return;
+  const PixConst* __restrict__ pc = pcs + b;
+  const unsigned hm = pc->h_magic;
+  const int x = hm ? (int)__umulhi((unsigned)pix, hm) : pix / a.H, y = pix - x * a.H;
+  Frag f;
+  const int slot = slot_map ? slot_map[(long long)b * a.T + tri] : tri;
+  attr_load<SHADER, true>(a, b, attrs + ((size_t)b * rec_stride + slot) * TA_FLOATS, f);
+  frag_pixel<SHADER, true>(a, b, x, y, f, pc);
+  if (f.keep) {
+    a.zbuffer[gi] = f.zw;
+    float* o = a.canvas + gi * 3;
+    o[0] = f.col[0]; o[1] = f.col[1]; o[2] = f.col[2];
+  } else {
+    a.tri_id[gi] = -1;
   }
 }
 
@@ -122,9 +128,11 @@ __global__ void __launch_bounds__(256, JR_SHADE_CTAS) k_shade_rec(const __grid_c
 template <int SHADER>
 __global__ void __launch_bounds__(256, JR_SHADE_CTAS) k_shade_rec_u8(const __grid_constant__ JrRenderArgs a,
                                                       const float* __restrict__ attrs, int rec_stride,
-                                                      const int* __restrict__ slot_map, int tiles_x, int tiles_y) {
+                                                      const int* __restrict__ slot_map, int tiles_x, int tiles_y,
+                                                      const PixConst* __restrict__ pcs) {
   __shared__ uint8_t tile[32][32 * 3 + 4];   // [y][x * 3 + c]
   const int b = blockIdx.y;
+  const PixConst* __restrict__ pc = pcs + b;
   const int tx = blockIdx.x / tiles_y, ty = blockIdx.x - tx * tiles_y;
   const int x0 = tx * 32, y0 = ty * 32;
   const int ly = threadIdx.x & 31;
@@ -140,8 +148,8 @@ __global__ void __launch_bounds__(256, JR_SHADE_CTAS) k_shade_rec_u8(const __gri
     if (tri >= 0) {
       Frag f;
       const int slot = slot_map ? slot_map[(long long)b * a.T + tri] : tri;
-      attr_load<SHADER>(a, b, attrs + ((size_t)b * rec_stride + slot) * TA_FLOATS, f);
-      frag_pixel<SHADER>(a, b, x, y, f);
+      attr_load<SHADER, true>(a, b, attrs + ((size_t)b * rec_stride + slot) * TA_FLOATS, f);
+      frag_pixel<SHADER, true>(a, b, x, y, f, pc);
       if (f.keep) {
         a.zbuffer[gi] = f.zw;
         col[0] = f.col[0]; col[1] = f.col[1]; col[2] = f.col[2];
@@ -175,10 +183,7 @@ __global__ void __launch_bounds__(256) k_merge_verts(const __grid_constant__ JrM
   float h[4];
   to_clip(T, x, y, z, h);  // to_homogeneous(p) @ T^T
   float* out = m.out_verts + ((long long)b * m.n_verts + v) * 3;
-  const bool w0 = h[3] == 0.0f;  // to_cartesian (geometry.py:183-202)
-  out[0] = w0 ? h[0] : h[0] / h[3];
-  out[1] = w0 ? h[1] : h[1] / h[3];
-  out[2] = w0 ? h[2] : h[2] / h[3];
+  to_cartesian3(h, out[0], out[1], out[2]);  // geometry.py:183-202
 }
 
 __device__ __forceinline__ float block_sum_256(float v, float* red) {
@@ -416,7 +421,7 @@ static const bool g_key64 = getenv("JR_KEY64") != nullptr;      // depth shader:
 static const bool g_vis2 = getenv("JR_VIS2") != nullptr;        // single-tile canvases: the one-phase kernel k_vis2
 
 // Forward scratch: [binned visibility: triangle records + tile bitmasks][shading attribute records]
-struct FwdLayout { size_t tiled, attr_off, flags_off, list_off, map_off, total; bool use_attr, compact; int rec_stride; };
+struct FwdLayout { size_t tiled, attr_off, flags_off, list_off, map_off, pc_off, total; bool use_attr, compact; int rec_stride; };
 static FwdLayout fwd_layout(const JrRenderArgs* a) {
   FwdLayout F{};
   int tw, th, nx, ny;
@@ -437,7 +442,9 @@ static FwdLayout fwd_layout(const JrRenderArgs* a) {
   const size_t flag_bytes = ((((size_t)a->B * a->T + 31) / 32) * 4 + (size_t)a->B * 4 + 255) & ~(size_t)255;
   F.list_off = F.flags_off + flag_bytes;
   F.map_off = F.list_off + (((size_t)a->B * a->T * 4 + 255) & ~(size_t)255);
-  F.total = F.use_attr ? F.map_off + (F.compact ? (size_t)a->B * a->T * 4 : 0) : F.tiled;
+  // per-image pixel-stage constants (PixConst) behind the slot map
+  F.pc_off = (F.map_off + (F.compact ? (size_t)a->B * a->T * 4 : 0) + 255) & ~(size_t)255;
+  F.total = F.use_attr ? F.pc_off + (size_t)a->B * sizeof(PixConst) : F.tiled;
   return F;
 }
 
@@ -533,14 +540,16 @@ int jr_render_forward(const JrRenderArgs* a, jr_stream_t stream_) {
                                                                            a->T, a->B, slot_map);
       const int rec_stride = F.rec_stride;
       const bool compact = F.compact;
+      PixConst* pcs = (PixConst*)((char*)a->workspace + F.pc_off);
       dim3 g1((a->T + 127) / 128, a->B);
       const int tiles_x = (a->W + 31) / 32, tiles_y = (a->H + 31) / 32;
       const dim3 gu8(tiles_x * tiles_y, a->B);
+      const dim3 grec((npix + threads - 1) / threads, a->B > 65535 ? 65535 : a->B, (a->B + 65534) / 65535);
 #define JR_ATTR_CASE(S)                                                          \
   case S:                                                                        \
-    k_tri_attr<S><<<g1, 128, 0, stream>>>(*a, attrs, list, count, rec_stride, compact); \
-    if (a->canvas_u8) k_shade_rec_u8<S><<<gu8, 256, 0, stream>>>(*a, attrs, rec_stride, slot_map, tiles_x, tiles_y); \
-    else k_shade_rec<S><<<blocks, threads, 0, stream>>>(*a, attrs, rec_stride, slot_map); \
+    k_tri_attr<S><<<g1, 128, 0, stream>>>(*a, attrs, list, count, rec_stride, compact, pcs); \
+    if (a->canvas_u8) k_shade_rec_u8<S><<<gu8, 256, 0, stream>>>(*a, attrs, rec_stride, slot_map, tiles_x, tiles_y, pcs); \
+    else k_shade_rec<S><<<grec, threads, 0, stream>>>(*a, attrs, rec_stride, slot_map, pcs); \
     break;
       switch (a->shader) {
         JR_ATTR_CASE(JR_GOURAUD)

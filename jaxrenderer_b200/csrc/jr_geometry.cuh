@@ -10,6 +10,15 @@ namespace jr {
 
 __device__ __forceinline__ bool instanced(const JrRenderArgs& a) { return a.inst_transform.ptr != nullptr; }
 
+// to_cartesian (geometry.py:183-202) of a homogeneous point: h / h.w unless w == 0.  w == 1 -- every affine object
+// transform -- skips the three IEEE divisions: x / 1 == x bit for bit.
+__device__ __forceinline__ void to_cartesian3(const float h[4], float& x, float& y, float& z) {
+  const bool keep = h[3] == 0.0f || h[3] == 1.0f;
+  x = keep ? h[0] : h[0] / h[3];
+  y = keep ? h[1] : h[1] / h[3];
+  z = keep ? h[2] : h[2] / h[3];
+}
+
 // local vertex (lx, ly, lz) with index i of image b -> world space (model.py:489-499; geometry.py:183-202)
 __device__ __forceinline__ void instance_vertex(const JrRenderArgs& a, int b, int i, float lx, float ly, float lz,
                                                 float& x, float& y, float& z) {
@@ -18,10 +27,33 @@ __device__ __forceinline__ void instance_vertex(const JrRenderArgs& a, int b, in
   const float* __restrict__ T = a.inst_transform.ptr + (long long)b * a.inst_transform.batch_stride + 16 * o;
   float h[4];
   to_clip(T, lx * s[0], ly * s[1], lz * s[2], h);  // to_homogeneous(p * scaling) @ T^T
-  const bool w0 = h[3] == 0.0f;                      // to_cartesian
-  x = w0 ? h[0] : h[0] / h[3];
-  y = w0 ? h[1] : h[1] / h[3];
-  z = w0 ? h[2] : h[2] / h[3];
+  to_cartesian3(h, x, y, z);
+}
+
+// The three vertices of one triangle (p = x0 y0 z0 x1 y1 z1 x2 y2 z2, local -> world in place).  A triangle's
+// vertices normally belong to ONE object: its scaling and transform are then fetched once (19 loads instead of 57;
+// the visibility kernels do this for every triangle of every image).  Same arithmetic as instance_vertex.
+__device__ __forceinline__ void instance_triangle(const JrRenderArgs& a, int b, int i0, int i1, int i2, float p[9]) {
+  const int32_t* __restrict__ vo = a.inst_vert_object.ptr + (long long)b * a.inst_vert_object.batch_stride;
+  const int o0 = min(max(vo[i0], 0), a.n_inst - 1), o1 = min(max(vo[i1], 0), a.n_inst - 1), o2 = min(max(vo[i2], 0), a.n_inst - 1);
+  if (o0 == o1 && o0 == o2) {
+    const float* __restrict__ s = a.inst_scaling.ptr + (long long)b * a.inst_scaling.batch_stride + 3 * o0;
+    const float* __restrict__ T = a.inst_transform.ptr + (long long)b * a.inst_transform.batch_stride + 16 * o0;
+    const float s0 = s[0], s1 = s[1], s2 = s[2];
+    float m[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) m[k] = T[k];
+#pragma unroll
+    for (int v = 0; v < 3; ++v) {
+      float h[4];
+      to_clip(m, p[3 * v] * s0, p[3 * v + 1] * s1, p[3 * v + 2] * s2, h);
+      to_cartesian3(h, p[3 * v], p[3 * v + 1], p[3 * v + 2]);
+    }
+  } else {
+    instance_vertex(a, b, i0, p[0], p[1], p[2], p[0], p[1], p[2]);
+    instance_vertex(a, b, i1, p[3], p[4], p[5], p[3], p[4], p[5]);
+    instance_vertex(a, b, i2, p[6], p[7], p[8], p[6], p[7], p[8]);
+  }
 }
 
 // world-space position of vertex i (pos_b = a.position.ptr + b * batch_stride)

@@ -79,16 +79,70 @@ __device__ __forceinline__ void frag_setup_tri(const JrRenderArgs& a, int b, int
   lu_inverse3(M, f.inv);
 }
 
+// Per-IMAGE constants of the pixel stage.  The record-based forward path writes them ONCE per image into the
+// workspace (k_tri_attr's first block, pix_const_write) -- light / material parameters, the NORMALISED light
+// direction (the reference normalises it per fragment: the same operations on the same inputs, done once), the
+// viewport entries, the shadow viewport, the reciprocal of H -- and the pixel kernels read them through one
+// pointer: a pixel then needs no 64-bit address arithmetic per parameter and skips a sqrt and three IEEE divisions.
+// Values are bit-identical to what frag_pixel computes on its own (PC == false).  (Staging them in shared memory
+// per CTA was measured slower: two barriers and a dependent load -> sqrt -> divide chain in front of 256 pixels.)
+struct __align__(16) PixConst {
+  float vp0, vp3, vp5, vp7, vp10, vp11;
+  float lcol[3], nl[3], amb[3], dif[3], spe[3], str[3];
+  float svp[16];
+  unsigned h_magic;   // ceil(2^32 / H) when floor(pix / H) == umulhi(pix, h_magic) for every pixel index, else 0
+  float pad[7];
+};
+static_assert(sizeof(PixConst) == 192, "PixConst is 192 bytes");
+// Executed by ONE warp (no barrier: every entry is written by the lane that loads it).
+template <int SHADER>
+__device__ __forceinline__ void pix_const_write(const JrRenderArgs& a, int b, PixConst* __restrict__ c) {
+  const int t = threadIdx.x & 31;
+  if (t < 6) {
+    const int k = t == 0 ? 0 : (t == 1 ? 3 : (t == 2 ? 5 : (t == 3 ? 7 : (t == 4 ? 10 : 11))));
+    reinterpret_cast<float*>(c)[t] = (a.viewport.ptr + (long long)b * a.viewport.batch_stride)[k];
+  } else if (t < 9) {
+    if (SHADER != JR_DEPTH) c->lcol[t - 6] = (a.light_colour.ptr + (long long)b * a.light_colour.batch_stride)[t - 6];
+  } else if (t == 9) {
+    if (SHADER >= JR_PHONG) {
+      const JrF32& ld = SHADER >= JR_PHONG_REFLECTION ? a.light_dir_eye : a.light_direction;
+      float l[3];
+      load3(ld, b, l);
+      const Vec3 n = normalise3(Vec3{l[0], l[1], l[2]});
+      c->nl[0] = n.x; c->nl[1] = n.y; c->nl[2] = n.z;
+    }
+  } else if (t == 10) {
+    // m = floor(2^32 / H) + 1 = (2^32 + e) / H with 0 < e <= H: umulhi(p, m) == floor(p / H) while p * e < 2^32,
+    // guaranteed for p < W * H when W * H * H < 2^32 (H >= 2: for H == 1 the magic number does not fit 32 bits)
+    const unsigned long long whh = (unsigned long long)a.W * a.H * a.H;
+    c->h_magic = (a.H >= 2 && whh < (1ull << 32)) ? (0xFFFFFFFFu / (unsigned)a.H + 1u) : 0u;
+  } else if (t >= 12 && t < 15) {
+    if (SHADER >= JR_PHONG_REFLECTION) {
+      c->amb[t - 12] = (a.ambient.ptr + (long long)b * a.ambient.batch_stride)[t - 12];
+      c->dif[t - 12] = (a.diffuse.ptr + (long long)b * a.diffuse.batch_stride)[t - 12];
+      c->spe[t - 12] = (a.specular.ptr + (long long)b * a.specular.batch_stride)[t - 12];
+    }
+    if (SHADER == JR_PHONG_REFLECTION_SHADOW)
+      c->str[t - 12] = (a.shadow_strength.ptr + (long long)b * a.shadow_strength.batch_stride)[t - 12];
+  } else if (t >= 16) {
+    if (SHADER == JR_PHONG_REFLECTION_SHADOW)
+      c->svp[t - 16] = (a.shadow_viewport.ptr + (long long)b * a.shadow_viewport.batch_stride)[t - 16];
+  }
+}
+
 // Per-PIXEL part: NDC position, edge functions, 1/w, depth, perspective-correct weights.
 // Needs f.inv and f.cl[k][2].
-__device__ __forceinline__ void frag_setup_pix(const JrRenderArgs& a, int b, int x, int y, Frag& f) {
+template <bool PC = false>
+__device__ __forceinline__ void frag_setup_pix(const JrRenderArgs& a, int b, int x, int y, Frag& f,
+                                               const PixConst* __restrict__ pc = nullptr) {
   const float* __restrict__ vp = a.viewport.ptr + (long long)b * a.viewport.batch_stride;
-  f.xn = ((float)x - vp[3]) / vp[0];
-  f.yn = ((float)y - vp[7]) / vp[5];
+  const float vp0 = PC ? pc->vp0 : vp[0], vp3 = PC ? pc->vp3 : vp[3], vp5 = PC ? pc->vp5 : vp[5], vp7 = PC ? pc->vp7 : vp[7];
+  f.xn = fdiv_z((float)x - vp3, vp0);   // (zero at the centre column / row of the canvas)
+  f.yn = fdiv_z((float)y - vp7, vp5);
   clip_coef(f.inv, f.xn, f.yn, f.cc);
   f.w_rec = (f.cc[0] + f.cc[1]) + f.cc[2];
   f.z = (f.cc[0] * f.cl[0][2] + f.cc[1] * f.cl[1][2]) + f.cc[2] * f.cl[2][2];
-  f.zw = f.z * vp[10] + vp[11];
+  f.zw = f.z * (PC ? pc->vp10 : vp[10]) + (PC ? pc->vp11 : vp[11]);
 #pragma unroll
   for (int k = 0; k < 3; ++k) f.tc[k] = f.cc[k] / f.w_rec;
 }
@@ -179,9 +233,11 @@ __device__ __forceinline__ void frag_vertex(const JrRenderArgs& a, int b, int tr
 // Interpolate + fragment + mix for pixel (x, y) given the triangle's vertex-stage outputs in `f`
 // (either just computed by frag_vertex or loaded from a TriAttr record).  `tri` is only used by
 // the Darboux shader.
-template <int SHADER>
-__device__ __forceinline__ void frag_pixel(const JrRenderArgs& a, int b, int x, int y, Frag& f) {
-  frag_setup_pix(a, b, x, y, f);
+template <int SHADER, bool PC = false>
+__device__ __forceinline__ void frag_pixel(const JrRenderArgs& a, int b, int x, int y, Frag& f,
+                                           const PixConst* __restrict__ pc = nullptr) {
+  frag_setup_pix<PC>(a, b, x, y, f, pc);
+  if (PC && SHADER != JR_DEPTH) { f.lcol[0] = pc->lcol[0]; f.lcol[1] = pc->lcol[1]; f.lcol[2] = pc->lcol[2]; }
   const float* tc = f.tc;
   f.col[0] = f.col[1] = f.col[2] = 0.f;
   f.keep = true;
@@ -219,8 +275,12 @@ __device__ __forceinline__ void frag_pixel(const JrRenderArgs& a, int b, int x, 
   f.nn = normalise3(f.normal);
 
   if (SHADER == JR_PHONG || SHADER == JR_PHONG_DARBOUX) {
-    load3(a.light_direction, b, f.lraw);
-    f.nl = normalise3(Vec3{f.lraw[0], f.lraw[1], f.lraw[2]});
+    if (PC) {
+      f.nl = Vec3{pc->nl[0], pc->nl[1], pc->nl[2]};
+    } else {
+      load3(a.light_direction, b, f.lraw);
+      f.nl = normalise3(Vec3{f.lraw[0], f.lraw[1], f.lraw[2]});
+    }
     const int ui = pymod((int)floorf(u), a.tex_w), vi = pymod((int)floorf(v), a.tex_h);
     f.texel = (long long)ui * a.tex_h + vi;
     Vec3 nn = f.nn;
@@ -299,11 +359,17 @@ __device__ __forceinline__ void frag_pixel(const JrRenderArgs& a, int b, int x, 
   const int U = (int)floorf(ur), V = (int)floorf(vr);
   f.texel = (long long)wrap_clamp(U, a.tex_w) * a.tex_h + wrap_clamp(V, a.tex_h);
   f.spec_idx = (long long)wrap_clamp(U, a.spec_w) * a.spec_h + wrap_clamp(V, a.spec_h);
-  load3(a.light_dir_eye, b, f.lraw);
-  load3(a.ambient, b, f.amb);
-  load3(a.diffuse, b, f.dif);
-  load3(a.specular, b, f.spe);
-  f.nl = normalise3(Vec3{f.lraw[0], f.lraw[1], f.lraw[2]});
+  if (PC) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { f.amb[c] = pc->amb[c]; f.dif[c] = pc->dif[c]; f.spe[c] = pc->spe[c]; }
+    f.nl = Vec3{pc->nl[0], pc->nl[1], pc->nl[2]};
+  } else {
+    load3(a.light_dir_eye, b, f.lraw);
+    load3(a.ambient, b, f.amb);
+    load3(a.diffuse, b, f.dif);
+    load3(a.specular, b, f.spe);
+    f.nl = normalise3(Vec3{f.lraw[0], f.lraw[1], f.lraw[2]});
+  }
   const Vec3 nn = f.nn, ld = f.nl;
   f.ndl = dot3(nn.x, nn.y, nn.z, ld.x, ld.y, ld.z);
   f.diffuse = fmaxf(f.ndl, 0.f);
@@ -316,7 +382,7 @@ __device__ __forceinline__ void frag_pixel(const JrRenderArgs& a, int b, int x, 
   f.shadow[0] = f.shadow[1] = f.shadow[2] = 1.f;
   f.lit = true;
   if (SHADER == JR_PHONG_REFLECTION_SHADOW) {
-    const float* __restrict__ svp = a.shadow_viewport.ptr + (long long)b * a.shadow_viewport.batch_stride;
+    const float* __restrict__ svp = PC ? pc->svp : a.shadow_viewport.ptr + (long long)b * a.shadow_viewport.batch_stride;
     float sc[4], ss[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) sc[j] = interp3(tc, f.scv[0][j], f.scv[1][j], f.scv[2][j]);
@@ -336,7 +402,8 @@ __device__ __forceinline__ void frag_pixel(const JrRenderArgs& a, int b, int x, 
     if (finite && px >= 0 && px < a.shadow_w && py >= 0 && py < a.shadow_h)
       sval = (a.shadow_map.ptr + (long long)b * a.shadow_map.batch_stride)[(long long)px * a.shadow_h + py];
     f.lit = sz <= sval;
-    load3(a.shadow_strength, b, f.str);
+    if (PC) { f.str[0] = pc->str[0]; f.str[1] = pc->str[1]; f.str[2] = pc->str[2]; }
+    else load3(a.shadow_strength, b, f.str);
 #pragma unroll
     for (int c = 0; c < 3; ++c) f.shadow[c] = f.lit ? 1.f : 1.f - f.str[c];
   }
@@ -393,13 +460,13 @@ __device__ __forceinline__ void attr_store(const Frag& f, float* __restrict__ r)
   if (SHADER == JR_GOURAUD_TEXTURE) { r[40] = f.inten[0]; r[41] = f.inten[1]; r[42] = f.inten[2]; }
 }
 
-template <int SHADER>
+template <int SHADER, bool PC = false>
 __device__ __forceinline__ void attr_load(const JrRenderArgs& a, int b, const float* __restrict__ r, Frag& f) {
 #pragma unroll
   for (int k = 0; k < 9; ++k) f.inv[k] = r[k];
   f.cl[0][2] = r[9]; f.cl[1][2] = r[10]; f.cl[2][2] = r[11];
   if (SHADER == JR_DEPTH) return;
-  load3(a.light_colour, b, f.lcol);
+  if (!PC) load3(a.light_colour, b, f.lcol);   // (PC: frag_pixel takes it from the staged constants)
   if (SHADER == JR_GOURAUD) {
 #pragma unroll
     for (int k = 0; k < 3; ++k)

@@ -436,9 +436,9 @@ k_vis3(const __grid_constant__ JrRenderArgs a) {
     Vec3 q0{pos[3 * i0], pos[3 * i0 + 1], pos[3 * i0 + 2]}, q1{pos[3 * i1], pos[3 * i1 + 1], pos[3 * i1 + 2]},
         q2{pos[3 * i2], pos[3 * i2 + 1], pos[3 * i2 + 2]};
     if (INST && instanced(a)) {
-      instance_vertex(a, b, i0, q0.x, q0.y, q0.z, q0.x, q0.y, q0.z);
-      instance_vertex(a, b, i1, q1.x, q1.y, q1.z, q1.x, q1.y, q1.z);
-      instance_vertex(a, b, i2, q2.x, q2.y, q2.z, q2.x, q2.y, q2.z);
+      float pl[9] = {q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, q2.x, q2.y, q2.z};
+      instance_triangle(a, b, i0, i1, i2, pl);
+      q0 = Vec3{pl[0], pl[1], pl[2]}; q1 = Vec3{pl[3], pl[4], pl[5]}; q2 = Vec3{pl[6], pl[7], pl[8]};
     }
     int x0, x1, y0, y1;
     if (!exact_cull_bbox(s_w2c, vp00, vp03, vp11, vp13, tw, th, q0, q1, q2, M, x0, x1, y0, y1)) return false;
@@ -492,13 +492,17 @@ k_vis3(const __grid_constant__ JrRenderArgs a) {
     }
     if (INST && instanced(a) && in) {
       // instanced geometry: local -> world (the merge's own arithmetic; the filter needs no more than that)
-      instance_vertex(a, b, i0, p[0], p[1], p[2], p[0], p[1], p[2]);
-      instance_vertex(a, b, i1, p[3], p[4], p[5], p[3], p[4], p[5]);
-      instance_vertex(a, b, i2, p[6], p[7], p[8], p[6], p[7], p[8]);
+      instance_triangle(a, b, i0, i1, i2, p);
     }
     int cls = -1;
     if (in) cls = v3_filter(s_w2c, s_aux, vp00, vp03, vp11, vp13, p, tw, th);
-    if (DEPTH && t == 0) v3_tri0_setup(s_w2c, p, &tri0, &tri0_flag);
+    if (DEPTH && t == 0) {
+      // (a copy: passing `p` itself to the out-of-line call would pin the array to local memory for every group)
+      float p0[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) p0[k] = p[k];
+      v3_tri0_setup(s_w2c, p0, &tri0, &tri0_flag);
+    }
     // ---- push survivors: two native shared atomics reserve slots in the four lists
     const unsigned ms = __ballot_sync(0xffffffffu, cls >= 0);
     if (ms) {
