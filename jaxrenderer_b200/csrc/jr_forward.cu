@@ -202,7 +202,7 @@ __device__ __forceinline__ float block_sum_256(float v, float* red) {
 // one CTA per (object, group of MN_GROUP batch elements): Camera.apply_vec with whole-array normalisation.
 // The first Frobenius norm depends only on the object's local normals: computed once per CTA when the
 // local mesh is shared by the batch (the usual case), and reused for the group's batch elements.
-constexpr int MN_GROUP = 8;
+constexpr int MN_GROUP = 16;
 // out_scales != nullptr: write only the two normalisation constants (f1, f2) of every (image, object) --
 // jr_instance_norm_scales, for geometry instanced inside the render kernels -- and no normal.
 __global__ void __launch_bounds__(256) k_merge_norms(const __grid_constant__ JrMergeArgs m, float* __restrict__ out_scales) {
@@ -210,6 +210,49 @@ __global__ void __launch_bounds__(256) k_merge_norms(const __grid_constant__ JrM
   const int o = blockIdx.x;
   const bool shared_mesh = m.local_norms.batch_stride == 0 && m.norm_start.batch_stride == 0;
   float f1 = 0.f;
+  if (out_scales && shared_mesh) {
+    // Scales only, shared local mesh (instanced rendering: the per-step call of the Brax facade).  The once-normalised
+    // normals n / f1 do not depend on the image: they are computed ONCE per CTA and kept in registers (3 IEEE
+    // divisions per normal and image saved); only the rotation and the second norm run per image.
+    const int n0 = m.norm_start.ptr[o], n1 = m.norm_start.ptr[o + 1];
+    const float* __restrict__ ln = m.local_norms.ptr;
+    float ss = 0.f;
+    for (int i = n0 + threadIdx.x; i < n1; i += 256)
+      ss += dot3(ln[3 * i], ln[3 * i + 1], ln[3 * i + 2], ln[3 * i], ln[3 * i + 1], ln[3 * i + 2]);
+    f1 = sqrtf(block_sum_256(ss, red));
+    constexpr int KEEP = 4;
+    float nx[KEEP], ny[KEEP], nz[KEEP];
+#pragma unroll
+    for (int kk = 0; kk < KEEP; ++kk) {
+      const int i = n0 + threadIdx.x + 256 * kk;
+      nx[kk] = ny[kk] = nz[kk] = 0.f;
+      if (i < n1) { nx[kk] = ln[3 * i] / f1; ny[kk] = ln[3 * i + 1] / f1; nz[kk] = ln[3 * i + 2] / f1; }
+    }
+    for (int b = blockIdx.y * MN_GROUP; b < min(m.B, (blockIdx.y + 1) * MN_GROUP); ++b) {
+      const float* __restrict__ R = m.normal_matrix.ptr + (long long)b * m.normal_matrix.batch_stride + 16 * o;
+      const float r0 = R[0], r1 = R[1], r2 = R[2], r4 = R[4], r5 = R[5], r6 = R[6], r8 = R[8], r9 = R[9], r10 = R[10];
+      float ss2 = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < KEEP; ++kk) {
+        if (n0 + threadIdx.x + 256 * kk < n1) {   // same accumulation order as the general path below
+          const float tx = (nx[kk] * r0 + ny[kk] * r1) + nz[kk] * r2, ty = (nx[kk] * r4 + ny[kk] * r5) + nz[kk] * r6,
+                      tz = (nx[kk] * r8 + ny[kk] * r9) + nz[kk] * r10;
+          ss2 += dot3(tx, ty, tz, tx, ty, tz);
+        }
+      }
+      for (int i = n0 + threadIdx.x + 256 * KEEP; i < n1; i += 256) {
+        const float x = ln[3 * i] / f1, y = ln[3 * i + 1] / f1, z = ln[3 * i + 2] / f1;
+        const float tx = (x * r0 + y * r1) + z * r2, ty = (x * r4 + y * r5) + z * r6, tz = (x * r8 + y * r9) + z * r10;
+        ss2 += dot3(tx, ty, tz, tx, ty, tz);
+      }
+      const float f2 = sqrtf(block_sum_256(ss2, red));
+      if (threadIdx.x == 0) {
+        out_scales[((long long)b * m.n_objects + o) * 2] = f1;
+        out_scales[((long long)b * m.n_objects + o) * 2 + 1] = f2;
+      }
+    }
+    return;
+  }
   for (int b = blockIdx.y * MN_GROUP; b < min(m.B, (blockIdx.y + 1) * MN_GROUP); ++b) {
     const int32_t* ns = m.norm_start.ptr + (long long)b * m.norm_start.batch_stride;
     const int n0 = ns[o], n1 = ns[o + 1];
@@ -419,6 +462,7 @@ static const bool g_no_attr = getenv("JR_NO_ATTR") != nullptr;  // shade without
 static const bool g_no_bins = getenv("JR_NO_BINS") != nullptr;  // every tile CTA scans all triangles
 static const bool g_key64 = getenv("JR_KEY64") != nullptr;      // depth shader: keep packed 64-bit keys
 static const bool g_vis2 = getenv("JR_VIS2") != nullptr;        // single-tile canvases: the one-phase kernel k_vis2
+static const bool g_no_fused_mark = getenv("JR_NO_FUSED_MARK") != nullptr;  // visible-triangle lists by k_mark_visible
 
 // Forward scratch: [binned visibility: triangle records + tile bitmasks][shading attribute records]
 struct FwdLayout { size_t tiled, attr_off, flags_off, list_off, map_off, pc_off, total; bool use_attr, compact; int rec_stride; };
@@ -465,6 +509,7 @@ int jr_render_forward(const JrRenderArgs* a, jr_stream_t stream_) {
   if (ctas > 2147483647LL) return JR_ERR_DIMS;
   set_kernel_attributes_once();
   const bool depth = a->shader == JR_DEPTH;
+  bool fused_mark = false;   // the visibility kernel built the visible-triangle lists itself
   if (nx * ny > 1 && !g_no_bins) {
     // two-level path: per-triangle records + per-tile bitmasks, then one CTA per (image, tile)
     const TiledLayout TLy = tiled_layout(a->B, a->W, a->H, a->T);
@@ -495,18 +540,31 @@ int jr_render_forward(const JrRenderArgs* a, jr_stream_t stream_) {
     if (a->T > 0 && (!a->workspace || a->workspace_bytes < v3_workspace_bytes(a->B, a->T))) return JR_ERR_WORKSPACE;
     const unsigned g = (unsigned)ctas;
     const bool inst = a->inst_transform.ptr != nullptr;
+    // shaders that go through attribute records: the resolve also emits the visible-triangle lists (V3Vis)
+    V3Vis vis{nullptr, nullptr, nullptr};
+    if (!depth) {
+      const FwdLayout F = fwd_layout(a);
+      if (F.use_attr && a->T <= V3_VIS_MAXT && !g_no_fused_mark) {
+        if (!a->workspace || a->workspace_bytes < F.total) return JR_ERR_WORKSPACE;
+        const size_t n_words = ((size_t)a->B * a->T + 31) / 32;
+        vis.count = (int*)((unsigned*)((char*)a->workspace + F.flags_off) + n_words);
+        vis.list = (int*)((char*)a->workspace + F.list_off);
+        vis.slot_map = F.compact ? (int*)((char*)a->workspace + F.map_off) : nullptr;
+        fused_mark = true;
+      }
+    }
     if (a->stats) {  // counting variant (measurement aid): always the instancing-capable build
-      if (k32) k_vis3<true, true, true, true><<<g, V3_THREADS, L.total, stream>>>(*a);
-      else if (depth) k_vis3<true, false, true, true><<<g, V3_THREADS, L.total, stream>>>(*a);
-      else k_vis3<false, false, true, true><<<g, V3_THREADS, L.total, stream>>>(*a);
+      if (k32) k_vis3<true, true, true, true><<<g, V3_THREADS, L.total, stream>>>(*a, vis);
+      else if (depth) k_vis3<true, false, true, true><<<g, V3_THREADS, L.total, stream>>>(*a, vis);
+      else k_vis3<false, false, true, true><<<g, V3_THREADS, L.total, stream>>>(*a, vis);
     } else if (inst) {
-      if (k32) k_vis3<true, true, false, true><<<g, V3_THREADS, L.total, stream>>>(*a);
-      else if (depth) k_vis3<true, false, false, true><<<g, V3_THREADS, L.total, stream>>>(*a);
-      else k_vis3<false, false, false, true><<<g, V3_THREADS, L.total, stream>>>(*a);
+      if (k32) k_vis3<true, true, false, true><<<g, V3_THREADS, L.total, stream>>>(*a, vis);
+      else if (depth) k_vis3<true, false, false, true><<<g, V3_THREADS, L.total, stream>>>(*a, vis);
+      else k_vis3<false, false, false, true><<<g, V3_THREADS, L.total, stream>>>(*a, vis);
     } else {
-      if (k32) k_vis3<true, true, false, false><<<g, V3_THREADS, L.total, stream>>>(*a);
-      else if (depth) k_vis3<true, false, false, false><<<g, V3_THREADS, L.total, stream>>>(*a);
-      else k_vis3<false, false, false, false><<<g, V3_THREADS, L.total, stream>>>(*a);
+      if (k32) k_vis3<true, true, false, false><<<g, V3_THREADS, L.total, stream>>>(*a, vis);
+      else if (depth) k_vis3<true, false, false, false><<<g, V3_THREADS, L.total, stream>>>(*a, vis);
+      else k_vis3<false, false, false, false><<<g, V3_THREADS, L.total, stream>>>(*a, vis);
     }
   } else {
     if (a->inst_transform.ptr) return JR_ERR_UNSUPPORTED;  // k_vis2 (A/B switch) reads merged arrays only
@@ -534,10 +592,13 @@ int jr_render_forward(const JrRenderArgs* a, jr_stream_t stream_) {
       const size_t n_words = ((size_t)a->B * a->T + 31) / 32;
       int* count = (int*)(flag_words + n_words);
       int* list = (int*)((char*)a->workspace + F.list_off);
-      cudaMemsetAsync(flag_words, 0, n_words * 4 + (size_t)a->B * 4, stream);
       int* slot_map = F.compact ? (int*)((char*)a->workspace + F.map_off) : nullptr;
-      k_mark_visible<0><<<dim3(bx > 64 ? 64 : bx, blocks.y), 256, 0, stream>>>(a->tri_id, flag_words, list, count, npix,
-                                                                           a->T, a->B, slot_map);
+      if (!fused_mark) {
+        cudaMemsetAsync(flag_words, 0, n_words * 4 + (size_t)a->B * 4, stream);
+        k_mark_visible<0><<<dim3(bx > 64 ? 64 : bx, blocks.y), 256, 0, stream>>>(a->tri_id, flag_words, list, count, npix,
+                                                                             a->T, a->B, slot_map);
+        jr::g_launches++;
+      }
       const int rec_stride = F.rec_stride;
       const bool compact = F.compact;
       PixConst* pcs = (PixConst*)((char*)a->workspace + F.pc_off);
@@ -559,7 +620,7 @@ int jr_render_forward(const JrRenderArgs* a, jr_stream_t stream_) {
         JR_ATTR_CASE(JR_PHONG_REFLECTION_SHADOW)
         default: return JR_ERR_SHADER;
       }
-      jr::g_launches += 3;
+      jr::g_launches += 2;
     } else {
       switch (a->shader) {
         case JR_GOURAUD: k_shade<JR_GOURAUD><<<blocks, threads, 0, stream>>>(*a); break;

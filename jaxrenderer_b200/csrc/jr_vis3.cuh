@@ -69,6 +69,11 @@ constexpr int V3_SM_LISTS = V3_SM_BIGQ + V3_BIGCAP * 128;
 constexpr int V3_SM_STAGE = V3_SM_LISTS + V3_LIST_ENTRIES * 2;
 constexpr int V3_SM_KEYS = V3_SM_STAGE + V3_NW * V3_STAGE_WORDS * 4;
 constexpr int V3_SM_SPAN_BYTES = V3_SM_KEYS - V3_SM_LISTS;  // 14336: 16 triangles x up to 448 columns x 2 bytes
+// Visible-triangle flags of the fused G-buffer scan (non-depth shaders, see V3Vis): one bit per triangle, behind the
+// span table (<= 16 x 255 x 2 bytes) in the lists + stage area, which is dead during the resolve.
+constexpr int V3_SM_VISFLAGS = V3_SM_LISTS + 8192;
+constexpr int V3_VIS_MAXT = (V3_SM_KEYS - V3_SM_VISFLAGS) * 8;   // 49152 triangles
+static_assert(V3_BIGCAP * 255 * 2 <= 8192, "span table overlaps the visibility flags");
 static_assert(V3_SM_KEYS % 16 == 0, "key tile must be 16-byte aligned");
 static_assert(V3_BIGCAP * 255 * 2 <= V3_SM_SPAN_BYTES, "span table does not fit");
 struct V3Layout { int keys, xs, ys, total; };
@@ -91,6 +96,12 @@ struct __align__(16) V3Big {  // 128 bytes
   int pad[5];
 };
 static_assert(sizeof(V3Big) == 128, "V3Big must be 128 bytes");
+
+// Fused scan of the G-buffer (what k_mark_visible does in a launch of its own, re-reading tri_id): the resolve of a
+// non-depth pass flags every triangle it writes, and the CTA then emits the image's list of VISIBLE triangles
+// (list[b][0..count[b])), their number and -- compact attribute records -- the triangle -> record slot map, for
+// k_tri_attr / k_shade_rec.  All three NULL: no scan.
+struct V3Vis { int* list; int* count; int* slot_map; };
 
 // workspace of the single-tile kernel: one int32 spill slot per (image, triangle)
 __host__ inline size_t v3_workspace_bytes(int B, int T) { return (size_t)B * (size_t)(T > 0 ? T : 0) * 4; }
@@ -209,7 +220,8 @@ template <bool DEPTH, bool K32>
 __device__ __noinline__ void v3_resolve_scalar(const unsigned long long* keys, const unsigned short* spans, const V3Big* bigq,
                                                const float* xs, const float* ys, int W, int H, int nbig, const TriSetup* tri0,
                                                float* __restrict__ z_out, int32_t* __restrict__ tri_out, float vp22,
-                                               float vp23, int tid, float z_off, bool z_fill, float z_fillv) {
+                                               float vp23, int tid, float z_off, bool z_fill, float z_fillv,
+                                               unsigned* vis_flags) {
   typedef typename std::conditional<K32, uint32_t, unsigned long long>::type KeyT;
   const uint32_t* keys32 = reinterpret_cast<const uint32_t*>(keys);
   const int npix_img = W * H;
@@ -255,6 +267,11 @@ __device__ __noinline__ void v3_resolve_scalar(const unsigned long long* keys, c
     }
     if (DEPTH && (wrote || z_fill)) z_out[pix] = z_off != 0.f ? zv + z_off : zv;   // depth epilogue (jr_b200.h)
     if (tri_out) tri_out[pix] = tri;
+    if (vis_flags && tri >= 0) {
+      unsigned* w = vis_flags + (tri >> 5);
+      const unsigned m = 1u << (tri & 31);
+      if (!(*w & m)) atomicOr(w, m);
+    }
   }
 }
 
@@ -274,7 +291,7 @@ __device__ __noinline__ void v3_raster_hier(float i0, float i1, float i2, float 
 // does not carry the instancing code (the instruction footprint of this kernel is worth several percent).
 template <bool DEPTH, bool K32, bool STATS, bool INST>
 __global__ void __launch_bounds__(V3_THREADS, K32 ? JR_V3_K32_CTAS : JR_V3_K64_CTAS)
-k_vis3(const __grid_constant__ JrRenderArgs a) {
+k_vis3(const __grid_constant__ JrRenderArgs a, const V3Vis vis) {
   static_assert(DEPTH || !K32, "z-only keys are for the depth shader");
   extern __shared__ __align__(16) unsigned char smem[];
   const int W = a.W, H = a.H;
@@ -288,7 +305,7 @@ k_vis3(const __grid_constant__ JrRenderArgs a) {
   unsigned short* spans = reinterpret_cast<unsigned short*>(smem + V3_SM_LISTS);  // resolve only
   __shared__ unsigned s_cnt01, s_cnt23;  // packed 16-bit push counters of lists (0, 1) and (2, 3)
   __shared__ unsigned s_head[5];  // consumption cursors of the four lists + the spill list
-  __shared__ int bigq_n, tri0_flag, spill_n;
+  __shared__ int bigq_n, tri0_flag, spill_n, s_vis_n;
   __shared__ TriSetup tri0;
   __shared__ float s_w2c[16];
   __shared__ float s_vp[16];
@@ -309,7 +326,7 @@ k_vis3(const __grid_constant__ JrRenderArgs a) {
     s_vp[tid] = a.viewport.ptr[(long long)b * a.viewport.batch_stride + tid];
   }
   if (tid == 0) {
-    bigq_n = 0; tri0_flag = 0; spill_n = 0; s_cnt01 = 0u; s_cnt23 = 0u;
+    bigq_n = 0; tri0_flag = 0; spill_n = 0; s_vis_n = 0; s_cnt01 = 0u; s_cnt23 = 0u;
     s_head[0] = s_head[1] = s_head[2] = s_head[3] = s_head[4] = 0u;
   }
   {
@@ -573,6 +590,13 @@ k_vis3(const __grid_constant__ JrRenderArgs a) {
   const bool use0 = DEPTH && tri0_flag;
   const int npix_img = W * H;
   const int nbig = min(bigq_n, V3_BIGCAP);
+  // fused G-buffer scan (V3Vis): flag bits of the triangles this image's resolve writes
+  const bool mark = !DEPTH && vis.list != nullptr;
+  unsigned* vis_flags = reinterpret_cast<unsigned*>(smem + V3_SM_VISFLAGS);
+  if (mark) {
+    for (int i = tid; i < (a.T + 31) >> 5; i += V3_THREADS) vis_flags[i] = 0u;
+    if (!nbig) __syncthreads();   // (with large triangles the barrier behind the span table does it)
+  }
   // ---- span table of the large triangles (the ground plane of a Brax scene).  For a fixed column x every
   // edge function  fl(fl(pk + fl(yn * i)) + c)  is monotone in yn (each rounded op is), and yn = ys[y] is
   // monotone in y: the rows where edge k is >= 0 form a prefix or a suffix of the column, the rows inside
@@ -726,12 +750,46 @@ k_vis3(const __grid_constant__ JrRenderArgs a) {
           }
           if (tri_out)
             reinterpret_cast<int2*>(tri_out)[iv] = make_int2(e0 ? -1 : (int)(unsigned)q0, e1 ? -1 : (int)(unsigned)q1);
+          if (!DEPTH && mark) {
+            // neighbouring rows mostly share their triangle; a plain load first: most pixels stop there
+            const unsigned t0 = (unsigned)q0, t1 = (unsigned)q1;
+            if (!e0) {
+              unsigned* w = vis_flags + (t0 >> 5);
+              const unsigned m = 1u << (t0 & 31);
+              if (!(*w & m)) atomicOr(w, m);
+            }
+            if (!e1 && (e0 || t1 != t0)) {
+              unsigned* w = vis_flags + (t1 >> 5);
+              const unsigned m = 1u << (t1 & 31);
+              if (!(*w & m)) atomicOr(w, m);
+            }
+          }
         }
       }
     }
   } else {
     v3_resolve_scalar<DEPTH, K32>(keys, spans, bigq, xs, ys, W, H, nbig, use0 ? &tri0 : nullptr, z_out, tri_out, vp22, vp23, tid,
-                                  z_off, z_fill, z_fillv);
+                                  z_off, z_fill, z_fillv, mark ? vis_flags : nullptr);
+  }
+  if (!DEPTH && mark) {
+    // flags -> the image's visible-triangle list (any order: every record goes to its own slot), count, slot map
+    __syncthreads();
+    int* __restrict__ list = vis.list + (long long)b * a.T;
+    int* __restrict__ smap = vis.slot_map ? vis.slot_map + (long long)b * a.T : nullptr;
+    for (int i = tid; i < (a.T + 31) >> 5; i += V3_THREADS) {
+      unsigned bits = vis_flags[i];
+      if (!bits) continue;
+      int slot = atomicAdd(&s_vis_n, __popc(bits));
+      while (bits) {
+        const int tri = 32 * i + __ffs(bits) - 1;
+        bits &= bits - 1;
+        list[slot] = tri;
+        if (smap) smap[tri] = slot;
+        ++slot;
+      }
+    }
+    __syncthreads();
+    if (tid == 0) vis.count[b] = s_vis_n;
   }
 
   if (STATS && a.stats) {
