@@ -120,6 +120,25 @@ def test_simple_shaders_random_soup(seed):
         assert rep["pixels"] - int((ref.tri_id < 0).sum()) > 50
 
 
+def test_visible_triangle_lists_fused_resolve_equals_separate_scan():
+    """Non-depth shaders on single-tile canvases: the visibility kernel's resolve builds the visible-triangle lists
+    itself (V3Vis, jr_vis3.cuh) while meshes of more than 49 152 triangles -- beyond its shared-memory flag array --
+    still go through `k_mark_visible`.  Padding the index buffer with degenerate triangles switches between the two
+    without changing the image: both must agree bit for bit (z, colours, triangle ids), compact records (T > W*H)
+    and slot-per-triangle records alike."""
+    for (n_tri, W, H) in ((60, 48, 40), (3000, 48, 40)):
+        s = random_mesh_scene(7, n_tri=n_tri, W=W, H=H)
+        z0, c0 = torch.full((W, H), 1.0), torch.full((W, H, 3), 0.25)
+        pad = torch.zeros((49160 - n_tri, 3), dtype=torch.int32)          # degenerate: never rasterised
+        for name, shader, extra in _shader_cases(s):
+            if name == "phong_darboux":
+                continue                                                    # no attribute records for this shader
+            z, c, tri = _run(s.cam, shader, z0, c0, s.faces, extra)
+            zp, cp, trip = _run(s.cam, shader, z0, c0, torch.cat((s.faces, pad)), extra)
+            assert int((tri >= 0).sum()) > 50
+            assert torch.equal(z, zp) and torch.equal(c, cp) and torch.equal(tri, trip), (name, n_tri)
+
+
 def _atlas_inputs(s, n_obj=3):
     g = s.gen
     tw, th = 8, 6

@@ -54,6 +54,7 @@ def main():
     ap.add_argument("--height", type=int, default=84)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--profile", action="store_true")
+    ap.add_argument("--merged", action="store_true", help="also time merge + materialise and the render of merged arrays")
     ap.add_argument("--graph", action="store_true",
                     help="also capture the whole facade call in a CUDA graph and time its replay")
     args = ap.parse_args()
@@ -85,7 +86,19 @@ def main():
     def render():
         return jr.Renderer.render(model, light, camera_obj, bufs, shadow_param=sp)
 
+    def materialise():
+        m = jr.merge_objects(objs)
+        return m._replace(verts=m.verts.materialise(), norms=m.norms.materialise())
+
+    model_merged = materialise()
+
+    def render_merged():
+        return jr.Renderer.render(model_merged, light, camera_obj, bufs, shadow_param=sp)
+
     out = {"workload": f"get_camera_image brax-ant fixture B={B} {W}x{H}", "T": int(model.faces.shape[-2])}
+    if args.merged:   # A/B: world-space arrays written by the merge kernels, render kernels without instancing
+        for name, fn in (("materialise", materialise), ("render_merged", render_merged)):
+            out[f"ms_{name}"], out[f"ms_{name}_host"] = (round(v, 4) for v in timeit(fn, args.steps))
     l0 = _native.launch_count()
     full()
     out["launches"] = _native.launch_count() - l0
