@@ -65,7 +65,8 @@ __global__ void __launch_bounds__(128) k_tri_attr(const __grid_constant__ JrRend
   __shared__ int s_tri[128];
   const int b = blockIdx.y;
   // the image's pixel-stage constants (read by k_shade_rec*), by the first warp of the image's first block
-  if (blockIdx.x == 0 && threadIdx.x < 32) pix_const_write<SHADER>(a, b, pcs + b);
+  if (blockIdx.x == 0 && threadIdx.x < 32)
+    pix_const_write<SHADER>(a, b, pcs + b, reinterpret_cast<float*>(pcs + a.B) + (size_t)b * (a.W + a.H));
   const int n_vis = count[b];
   const int i0 = blockIdx.x * 128;
   if (i0 >= n_vis) return;
@@ -489,9 +490,9 @@ static FwdLayout fwd_layout(const JrRenderArgs* a) {
   const size_t flag_bytes = ((((size_t)a->B * a->T + 31) / 32) * 4 + (size_t)a->B * 4 + 255) & ~(size_t)255;
   F.list_off = F.flags_off + flag_bytes;
   F.map_off = F.list_off + (((size_t)a->B * a->T * 4 + 255) & ~(size_t)255);
-  // per-image pixel-stage constants (PixConst) behind the slot map
+  // per-image pixel-stage constants (PixConst), then the per-image pixel -> NDC tables (W + H floats), behind the slot map
   F.pc_off = (F.map_off + (F.compact ? (size_t)a->B * a->T * 4 : 0) + 255) & ~(size_t)255;
-  F.total = F.use_attr ? F.pc_off + (size_t)a->B * sizeof(PixConst) : F.tiled;
+  F.total = F.use_attr ? F.pc_off + (size_t)a->B * (sizeof(PixConst) + (size_t)(a->W + a->H) * 4) : F.tiled;
   return F;
 }
 

@@ -91,13 +91,25 @@ struct __align__(16) PixConst {
   float lcol[3], nl[3], amb[3], dif[3], spe[3], str[3];
   float svp[16];
   unsigned h_magic;   // ceil(2^32 / H) when floor(pix / H) == umulhi(pix, h_magic) for every pixel index, else 0
-  float pad[7];
+  unsigned pad0;
+  const float* xs;    // the image's pixel -> NDC tables (W and H entries): frag_setup_pix's two divisions, done once
+  const float* ys;    // per column / row instead of once per pixel
+  float pad[2];
 };
 static_assert(sizeof(PixConst) == 192, "PixConst is 192 bytes");
-// Executed by ONE warp (no barrier: every entry is written by the lane that loads it).
+// Executed by ONE warp (no barrier: every entry is written by the lane that loads it).  `tabs`: the image's W + H
+// table entries.
 template <int SHADER>
-__device__ __forceinline__ void pix_const_write(const JrRenderArgs& a, int b, PixConst* __restrict__ c) {
+__device__ __forceinline__ void pix_const_write(const JrRenderArgs& a, int b, PixConst* __restrict__ c,
+                                                float* __restrict__ tabs) {
   const int t = threadIdx.x & 31;
+  {
+    const float* __restrict__ vp = a.viewport.ptr + (long long)b * a.viewport.batch_stride;
+    const float vp0 = vp[0], vp3 = vp[3], vp5 = vp[5], vp7 = vp[7];
+    for (int i = t; i < a.W; i += 32) tabs[i] = fdiv_z((float)i - vp3, vp0);          // frag_setup_pix's expressions
+    for (int i = t; i < a.H; i += 32) tabs[a.W + i] = fdiv_z((float)i - vp7, vp5);
+    if (t == 11) { c->xs = tabs; c->ys = tabs + a.W; }
+  }
   if (t < 6) {
     const int k = t == 0 ? 0 : (t == 1 ? 3 : (t == 2 ? 5 : (t == 3 ? 7 : (t == 4 ? 10 : 11))));
     reinterpret_cast<float*>(c)[t] = (a.viewport.ptr + (long long)b * a.viewport.batch_stride)[k];
@@ -137,8 +149,12 @@ __device__ __forceinline__ void frag_setup_pix(const JrRenderArgs& a, int b, int
                                                const PixConst* __restrict__ pc = nullptr) {
   const float* __restrict__ vp = a.viewport.ptr + (long long)b * a.viewport.batch_stride;
   const float vp0 = PC ? pc->vp0 : vp[0], vp3 = PC ? pc->vp3 : vp[3], vp5 = PC ? pc->vp5 : vp[5], vp7 = PC ? pc->vp7 : vp[7];
-  f.xn = fdiv_z((float)x - vp3, vp0);   // (zero at the centre column / row of the canvas)
-  f.yn = fdiv_z((float)y - vp7, vp5);
+  if (PC) {
+    f.xn = pc->xs[x]; f.yn = pc->ys[y];
+  } else {
+    f.xn = fdiv_z((float)x - vp3, vp0);   // (zero at the centre column / row of the canvas)
+    f.yn = fdiv_z((float)y - vp7, vp5);
+  }
   clip_coef(f.inv, f.xn, f.yn, f.cc);
   f.w_rec = (f.cc[0] + f.cc[1]) + f.cc[2];
   f.z = (f.cc[0] * f.cl[0][2] + f.cc[1] * f.cl[1][2]) + f.cc[2] * f.cl[2][2];
