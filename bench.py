@@ -233,6 +233,21 @@ def run_ours(args) -> None:
         torch.cuda.synchronize()
 
     # ---- device-resident throughput: `value`
+    # Small per-GPU batches (strong scaling: 512 images = one 55-microsecond kernel per step) are launch-bound from
+    # Python, eight ranks sharing the host cores: there the step is captured once into a CUDA graph and replayed
+    # (`--launch graph`; `auto` does that below 2048 images per GPU).  One replay == one `pipeline.render` call.
+    launch_mode = args.launch if args.launch != "auto" else ("graph" if B < 2048 else "eager")
+    step_eager = step_resident
+    if launch_mode == "graph":
+        for _ in range(3):
+            step_eager()
+        torch.cuda.synchronize()
+        step_graph_obj = torch.cuda.CUDAGraph()
+        l0 = _native.launch_count()
+        with torch.cuda.graph(step_graph_obj):
+            step_eager()
+        graph_launches_per_step = _native.launch_count() - l0    # kernels the library enqueued into the graph
+        step_resident = step_graph_obj.replay
     for _ in range(max(args.warmup, 3)):
         step_resident()
     barrier()
@@ -248,6 +263,8 @@ def run_ours(args) -> None:
         ev[k + 1].record()
     barrier()
     launches = _native.launch_count() - launches0
+    if launch_mode == "graph":
+        launches = graph_launches_per_step * args.steps          # replays do not pass through the host counter
     total_ms = ev[0].elapsed_time(ev[-1])
     per_launch_ms = sorted(ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps))
     t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
@@ -258,7 +275,7 @@ def run_ours(args) -> None:
 
     # in-kernel counters of one extra (untimed) launch: N_test, survivors of the filter / exact cull
     with pipeline.visibility_stats(dev) as st:
-        step_resident()
+        step_eager()
     counters = st.read()
 
     # ---- end to end through the public API from the host buffers Brax produces: `e2e`
@@ -399,6 +416,8 @@ def run_ours(args) -> None:
                      "unit": "G warp-instructions/s", "frac": ach_issue / peak_issue,
                      "warp_instructions_per_launch": warp_inst * (B / BATCH)}
         cfg = _config(world, B)
+        cfg["launch"] = ("one CUDA-graph replay per step (the render call captured once)" if launch_mode == "graph"
+                         else "eager (one pipeline.render call per step)")
         if strong:
             cfg["workload"] += f" (strong scaling: global batch {args.batch} split over {world} GPUs)"
         line = {
@@ -598,6 +617,9 @@ def main() -> None:
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-fwd-bwd", action="store_true", help="skip the secondary forward+backward measurement")
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary configurations (configs[0], [2], [3], [4])")
+    ap.add_argument("--launch", choices=("auto", "graph", "eager"), default="auto",
+                    help="how the device-resident step is issued: eagerly, as one CUDA-graph replay, or auto "
+                         "(graph below 2048 images per GPU, where the Python launch path is the bottleneck)")
     ap.add_argument("--e2e", choices=("graph", "eager"), default="graph",
                     help="how the e2e step issues the public-API calls: captured once into a CUDA graph and replayed "
                          "(default; the eager figure is reported beside it) or eagerly every step")
