@@ -435,6 +435,8 @@ static void set_kernel_attributes_once() {
     smem_attr(k_vis3<true, true, false, true>, 200 * 1024);
     smem_attr(k_vis3<true, false, false, true>, 200 * 1024);
     smem_attr(k_vis3<false, false, false, true>, 200 * 1024);
+    smem_attr(k_vis3<true, true, false, false, true>, 200 * 1024);
+    smem_attr(k_vis3<true, true, false, true, true>, 200 * 1024);
     smem_attr(k_vis3<true, true, true, true>, 200 * 1024);
     smem_attr(k_vis3<true, false, true, true>, 200 * 1024);
     smem_attr(k_vis3<false, false, true, true>, 200 * 1024);
@@ -467,6 +469,7 @@ static const bool g_no_bins = getenv("JR_NO_BINS") != nullptr;  // every tile CT
 static const bool g_key64 = getenv("JR_KEY64") != nullptr;      // depth shader: keep packed 64-bit keys
 static const bool g_vis2 = getenv("JR_VIS2") != nullptr;        // single-tile canvases: the one-phase kernel k_vis2
 static const bool g_no_fused_mark = getenv("JR_NO_FUSED_MARK") != nullptr;  // visible-triangle lists by k_mark_visible
+static const bool g_no_cluster = getenv("JR_NO_CLUSTER") != nullptr;        // small batches: one CTA per image as well
 
 // Forward scratch: [binned visibility: triangle records + tile bitmasks][shading attribute records]
 struct FwdLayout { size_t tiled, attr_off, flags_off, list_off, map_off, pc_off, total; bool use_attr, compact; int rec_stride; };
@@ -557,7 +560,34 @@ int jr_render_forward(const JrRenderArgs* a, jr_stream_t stream_) {
         fused_mark = true;
       }
     }
-    if (a->stats) {  // counting variant (measurement aid): always the instancing-capable build
+    // Batches that leave SMs idle: z-only-key depth passes split every image over a 2-CTA cluster
+    // (k_vis3<..., CLUSTER>) while ALL half-image CTAs are still resident at once (2 B <= 4 per SM).  Measured on the
+    // bench scene (84x84, 1932 triangles): B = 1..64 0.033 -> 0.027 ms, B = 192 0.039 -> 0.035, B = 256 equal; beyond
+    // one resident wave the split LOSES (B = 512: 0.054 -> 0.067 ms: a half-image CTA takes ~0.62 of a whole one --
+    // prologue, span table and barriers do not halve -- and two waves of those are slower than one wave of 512).
+    int n_sm = 148;
+    {
+      static int sm_cache[64] = {0};
+      int dev = 0;
+      cudaGetDevice(&dev);
+      if (!sm_cache[dev & 63]) cudaDeviceGetAttribute(&sm_cache[dev & 63], cudaDevAttrMultiProcessorCount, dev);
+      if (sm_cache[dev & 63] > 0) n_sm = sm_cache[dev & 63];
+    }
+    if (k32 && !a->stats && !g_no_cluster && a->T > 0 && 2 * ctas <= (long long)n_sm * JR_V3_K32_CTAS) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(2u * g, 1, 1);
+      cfg.blockDim = dim3(V3_THREADS, 1, 1);
+      cfg.dynamicSmemBytes = (size_t)L.total;
+      cfg.stream = stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      const cudaError_t e = inst ? cudaLaunchKernelEx(&cfg, k_vis3<true, true, false, true, true>, *a, vis)
+                                 : cudaLaunchKernelEx(&cfg, k_vis3<true, true, false, false, true>, *a, vis);
+      if (e != cudaSuccess) return JR_ERR_CUDA;
+    } else if (a->stats) {  // counting variant (measurement aid): always the instancing-capable build
       if (k32) k_vis3<true, true, true, true><<<g, V3_THREADS, L.total, stream>>>(*a, vis);
       else if (depth) k_vis3<true, false, true, true><<<g, V3_THREADS, L.total, stream>>>(*a, vis);
       else k_vis3<false, false, true, true><<<g, V3_THREADS, L.total, stream>>>(*a, vis);

@@ -104,7 +104,29 @@ static_assert(sizeof(V3Big) == 128, "V3Big must be 128 bytes");
 struct V3Vis { int* list; int* count; int* slot_map; };
 
 // workspace of the single-tile kernel: one int32 spill slot per (image, triangle)
-__host__ inline size_t v3_workspace_bytes(int B, int T) { return (size_t)B * (size_t)(T > 0 ? T : 0) * 4; }
+// (+ 512 slots so that the two CTAs of a clustered image -- V3_CLUSTER -- each own half of the image's row)
+constexpr int V3_SPILL_PAD = 512;
+__host__ inline size_t v3_workspace_bytes(int B, int T) { return (size_t)B * (size_t)((T > 0 ? T : 0) + V3_SPILL_PAD) * 4; }
+
+// ---- thread-block cluster helpers (CLUSTER builds: one image split over the two CTAs of a cluster, small batches)
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_map(uint32_t saddr, unsigned rank) {   // own shared address -> peer's
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ uint32_t ld_cluster_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint4 ld_cluster_u32x4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared::cluster.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
 
 __device__ __forceinline__ unsigned atoms_add(uint32_t saddr, unsigned v) {
   unsigned old;  // one native shared-memory atomic (the CUDA intrinsic adds a warp-aggregation prologue)
@@ -221,15 +243,17 @@ __device__ __noinline__ void v3_resolve_scalar(const unsigned long long* keys, c
                                                const float* xs, const float* ys, int W, int H, int nbig, const TriSetup* tri0,
                                                float* __restrict__ z_out, int32_t* __restrict__ tri_out, float vp22,
                                                float vp23, int tid, float z_off, bool z_fill, float z_fillv,
-                                               unsigned* vis_flags) {
+                                               unsigned* vis_flags, uint32_t peer_keys_saddr = 0u, int part = 0,
+                                               int nparts = 1) {
   typedef typename std::conditional<K32, uint32_t, unsigned long long>::type KeyT;
   const uint32_t* keys32 = reinterpret_cast<const uint32_t*>(keys);
   const int npix_img = W * H;
   const float rH = 1.0f / (float)H;
 #pragma unroll 1
-  for (int pix = tid; pix < npix_img; pix += V3_THREADS) {
+  for (int pix = tid + part * V3_THREADS; pix < npix_img; pix += V3_THREADS * nparts) {
     const int lx = (int)(((float)pix + 0.5f) * rH), ly = pix - lx * H;  // exact for pix < 2^16
     KeyT key = K32 ? (KeyT)keys32[pix] : (KeyT)keys[pix];
+    if (K32 && peer_keys_saddr) key = (KeyT)min((uint32_t)key, ld_cluster_u32(peer_keys_saddr + 4u * pix));
 #pragma unroll 1
     for (int e = 0; e < nbig; ++e) {
       const unsigned sp = spans[e * W + lx];
@@ -289,10 +313,18 @@ __device__ __noinline__ void v3_raster_hier(float i0, float i1, float i2, float 
 
 // INST: geometry instanced at the fetch (JrRenderArgs.inst_*); a template parameter so that the merged-array kernel
 // does not carry the instancing code (the instruction footprint of this kernel is worth several percent).
-template <bool DEPTH, bool K32, bool STATS, bool INST>
+// CLUSTER: the image is split over the TWO CTAs of a thread-block cluster (launch with cluster dimension 2, grid 2 B;
+// z-only-key depth passes of batches too small to occupy the machine -- latency of one render, shadow passes of small
+// batches).  Each CTA filters and rasterises every second group of 32 triangles into its OWN key tile; after a cluster
+// barrier each resolves half of the pixel blocks from the minimum of both tiles (the peer's through distributed
+// shared memory) and from the large triangles of both queues.  Same keys, same minima: bit-identical output.
+template <bool DEPTH, bool K32, bool STATS, bool INST, bool CLUSTER = false>
 __global__ void __launch_bounds__(V3_THREADS, K32 ? JR_V3_K32_CTAS : JR_V3_K64_CTAS)
 k_vis3(const __grid_constant__ JrRenderArgs a, const V3Vis vis) {
   static_assert(DEPTH || !K32, "z-only keys are for the depth shader");
+  static_assert(!CLUSTER || (K32 && !STATS), "the clustered build serves z-only-key depth passes");
+  constexpr int NPART = CLUSTER ? 2 : 1;                 // CTAs per image
+  constexpr int BIGCAP = CLUSTER ? V3_BIGCAP / 2 : V3_BIGCAP;   // per-CTA queue: the merged queue holds V3_BIGCAP
   extern __shared__ __align__(16) unsigned char smem[];
   const int W = a.W, H = a.H;
   const V3Layout L = v3_layout(W, H, K32 ? 4 : 8);
@@ -313,7 +345,8 @@ k_vis3(const __grid_constant__ JrRenderArgs a, const V3Vis vis) {
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float* stage = reinterpret_cast<float*>(smem + V3_SM_STAGE) + warp * V3_STAGE_WORDS;
-  const int b = blockIdx.x;
+  const int b = CLUSTER ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int crank = CLUSTER ? (int)(blockIdx.x & 1u) : 0;      // rank inside the cluster (cluster dimension (2, 1, 1))
   const uint32_t keys_saddr = (uint32_t)__cvta_generic_to_shared(keys);
   const uint32_t cnt01_saddr = (uint32_t)__cvta_generic_to_shared(&s_cnt01);
   const uint32_t cnt23_saddr = (uint32_t)__cvta_generic_to_shared(&s_cnt23);
@@ -359,7 +392,9 @@ k_vis3(const __grid_constant__ JrRenderArgs a, const V3Vis vis) {
   const float* __restrict__ pos = a.position.ptr + (long long)b * a.position.batch_stride;
   const int32_t* __restrict__ faces = a.faces.ptr + (long long)b * a.faces.batch_stride;
   const int vmax = a.n_pos - 1;
-  int* __restrict__ spill = reinterpret_cast<int*>(a.workspace) + (long long)b * a.T;  // (B, T) int32, see v3_workspace_bytes
+  // (B, T + V3_SPILL_PAD) int32, see v3_workspace_bytes; a clustered image's two CTAs take half a row each
+  int* __restrict__ spill = reinterpret_cast<int*>(a.workspace) + (long long)b * (a.T + V3_SPILL_PAD) +
+                            (CLUSTER ? crank * ((a.T + V3_SPILL_PAD) >> 1) : 0);
   const unsigned lt_mask = (1u << lane) - 1u;
 
   // ------------------------------------------------------------------ exact rasterisers (k_vis2's)
@@ -411,7 +446,7 @@ k_vis3(const __grid_constant__ JrRenderArgs a, const V3Vis vis) {
     bool is_medium = area > small_limit && area <= V2_MEDIUM_AREA;
     if (area > V2_MEDIUM_AREA) {
       const int slot = atomicAdd(&bigq_n, 1);
-      if (slot < V3_BIGCAP) {
+      if (slot < BIGCAP) {
         V3Big& q = bigq[slot];
 #pragma unroll
         for (int k = 0; k < 9; ++k) q.inv[k] = make_float2(inv[k], inv[k]);
@@ -475,18 +510,20 @@ k_vis3(const __grid_constant__ JrRenderArgs a, const V3Vis vis) {
   // The face indices of a warp's NEXT group are loaded one iteration ahead, so a group waits for one global
   // round trip instead of two dependent ones.  (An L1 prefetch of the next group's vertex lines changed nothing:
   // with ~45 KB of shared memory per CTA the L1 keeps too few lines.)
+  constexpr int GSTRIDE = V3_THREADS * NPART;   // triangles between a warp's consecutive groups
+  const int g_first = (warp + V3_NW * crank) * 32;
   int nf0 = 0, nf1 = 0, nf2 = 0;
-  if (warp * 32 + lane < a.T) {
-    const int tq = warp * 32 + lane;
+  if (g_first + lane < a.T) {
+    const int tq = g_first + lane;
     nf0 = faces[3 * tq]; nf1 = faces[3 * tq + 1]; nf2 = faces[3 * tq + 2];
   }
-  for (int t0 = warp * 32; t0 < a.T; t0 += V3_THREADS) {
+  for (int t0 = g_first; t0 < a.T; t0 += GSTRIDE) {
     const int t = t0 + lane;
     const bool in = t < a.T;
     // out-of-range indices are clamped (the reference's gathers clamp too) -- never read out of bounds
     const int i0 = min(max(nf0, 0), vmax), i1 = min(max(nf1, 0), vmax), i2 = min(max(nf2, 0), vmax);
-    if (t + V3_THREADS < a.T) {
-      const int tq = t + V3_THREADS;
+    if (t + GSTRIDE < a.T) {
+      const int tq = t + GSTRIDE;
       nf0 = faces[3 * tq]; nf1 = faces[3 * tq + 1]; nf2 = faces[3 * tq + 2];
     }
     float p[9];
@@ -584,12 +621,36 @@ k_vis3(const __grid_constant__ JrRenderArgs a, const V3Vis vis) {
       }
     }
   }
-  __syncthreads();
+  uint32_t peer_keys_saddr = 0u;
+  int nbig_merged = 0;
+  if (CLUSTER) {
+    // both key tiles and both queues are complete: merge the peer's large triangles (and the triangle-0 record, which
+    // lives in rank 0) into this CTA's shared memory; the peer's KEYS are read in place by the resolve
+    cluster_sync_all();
+    const unsigned peer = (unsigned)(crank ^ 1);
+    peer_keys_saddr = cluster_map(keys_saddr, peer);
+    const int n_own = min(bigq_n, BIGCAP);
+    const int n_peer = min((int)ld_cluster_u32(cluster_map((uint32_t)__cvta_generic_to_shared(&bigq_n), peer)), BIGCAP);
+    const uint32_t peer_bigq = cluster_map((uint32_t)__cvta_generic_to_shared(bigq), peer);
+    uint32_t* own_words = reinterpret_cast<uint32_t*>(bigq + n_own);
+    for (int i = tid; i < n_peer * 32; i += V3_THREADS) own_words[i] = ld_cluster_u32(peer_bigq + 4u * i);
+    if (crank == 1) {
+      const uint32_t p_flag = cluster_map((uint32_t)__cvta_generic_to_shared(&tri0_flag), 0u);
+      const uint32_t p_tri0 = cluster_map((uint32_t)__cvta_generic_to_shared(&tri0), 0u);
+      uint32_t* t0w = reinterpret_cast<uint32_t*>(&tri0);
+      for (int i = tid; i < (int)(sizeof(TriSetup) / 4); i += V3_THREADS) t0w[i] = ld_cluster_u32(p_tri0 + 4u * i);
+      if (tid == 0) tri0_flag = (int)ld_cluster_u32(p_flag);
+    }
+    nbig_merged = n_own + n_peer;   // (bigq_n itself stays as it is: the peer reads it)
+    __syncthreads();
+  } else {
+    __syncthreads();
+  }
 
   // ================================================================== resolve
   const bool use0 = DEPTH && tri0_flag;
   const int npix_img = W * H;
-  const int nbig = min(bigq_n, V3_BIGCAP);
+  const int nbig = CLUSTER ? nbig_merged : min(bigq_n, V3_BIGCAP);
   // fused G-buffer scan (V3Vis): flag bits of the triangles this image's resolve writes
   const bool mark = !DEPTH && vis.list != nullptr;
   unsigned* vis_flags = reinterpret_cast<unsigned*>(smem + V3_SM_VISFLAGS);
@@ -659,7 +720,7 @@ k_vis3(const __grid_constant__ JrRenderArgs a, const V3Vis vis) {
     const int cx = lane & 7, gy = lane >> 3;
     const int nbx = (W + 7) >> 3, nby = (H + 4 * PXT - 1) / (4 * PXT);
     const float rnby = 1.0f / (float)nby;
-    for (int blk = warp; blk < nbx * nby; blk += V3_NW) {
+    for (int blk = warp + V3_NW * crank; blk < nbx * nby; blk += V3_NW * NPART) {
       const int bx = (int)(((float)blk + 0.5f) * rnby), by = blk - bx * nby;  // exact quotient (blk < 2^16)
       const int x = bx * 8 + cx, y = by * (4 * PXT) + gy * PXT;
       const bool live = x < W && y < H;
@@ -670,7 +731,11 @@ k_vis3(const __grid_constant__ JrRenderArgs a, const V3Vis vis) {
       for (int v = 0; v < NV; ++v) {
         const int iv = (v * PX < nrow) ? i + v : i;
         if (K32) {
-          const uint4 kk = reinterpret_cast<const uint4*>(keys32)[iv];
+          uint4 kk = reinterpret_cast<const uint4*>(keys32)[iv];
+          if (CLUSTER) {
+            const uint4 pk = ld_cluster_u32x4(peer_keys_saddr + 16u * (unsigned)iv);
+            kk.x = min(kk.x, pk.x); kk.y = min(kk.y, pk.y); kk.z = min(kk.z, pk.z); kk.w = min(kk.w, pk.w);
+          }
           k[v * PX + 0] = kk.x; k[v * PX + 1] = kk.y; k[v * PX + 2 % PX] = kk.z; k[v * PX + 3 % PX] = kk.w;
         } else {
           const ulonglong2 kk = reinterpret_cast<const ulonglong2*>(keys)[iv];
@@ -769,8 +834,9 @@ k_vis3(const __grid_constant__ JrRenderArgs a, const V3Vis vis) {
     }
   } else {
     v3_resolve_scalar<DEPTH, K32>(keys, spans, bigq, xs, ys, W, H, nbig, use0 ? &tri0 : nullptr, z_out, tri_out, vp22, vp23, tid,
-                                  z_off, z_fill, z_fillv, mark ? vis_flags : nullptr);
+                                  z_off, z_fill, z_fillv, mark ? vis_flags : nullptr, peer_keys_saddr, crank, NPART);
   }
+  if (CLUSTER) cluster_sync_all();   // the peer may still be reading this CTA's key tile
   if (!DEPTH && mark) {
     // flags -> the image's visible-triangle list (any order: every record goes to its own slot), count, slot map
     __syncthreads();

@@ -120,6 +120,27 @@ def test_simple_shaders_random_soup(seed):
         assert rep["pixels"] - int((ref.tri_id < 0).sum()) > 50
 
 
+@pytest.mark.parametrize("wh", [(84, 84), (50, 37)])
+def test_clustered_small_batch_equals_one_cta_per_image(wh):
+    """Depth passes with z-only keys of batches that leave SMs idle split every image over a 2-CTA thread-block cluster
+    (`k_vis3<..., CLUSTER>`: two key tiles merged through distributed shared memory); larger batches run one CTA per
+    image.  The same images rendered both ways must be bit-identical (vector resolve at 84x84, scalar resolve at 50x37)."""
+    W, H = wh
+    B = 640                                   # 2 * 640 CTAs > 4 per SM on 148 SMs: one CTA per image
+    sc = synthetic.brax_like_batch(B, n_capsules=3, env0=901)
+    cam = synthetic.brax_cameras(sc["eye"], sc["target"], W, H)
+    camd = _cuda(cam)
+    pos, faces = sc["position"].to(DEV), sc["faces"].to(DEV)
+    z_all = jr.render(camd, DepthShader, jr.Buffers(torch.full((B, W, H), 1.0, device=DEV), ()), faces,
+                      DepthExtraInput(position=pos)).zbuffer
+    n = 12                                    # clustered
+    cam_n = type(camd)(*[(v[:n] if v.ndim == 3 and v.shape[0] == B else v) for v in camd])
+    z_few = jr.render(cam_n, DepthShader, jr.Buffers(torch.full((n, W, H), 1.0, device=DEV), ()), faces[:n],
+                      DepthExtraInput(position=pos[:n])).zbuffer
+    assert int((z_few != 1.0).sum()) > 0.2 * z_few.numel()
+    assert torch.equal(z_few, z_all[:n])
+
+
 def test_visible_triangle_lists_fused_resolve_equals_separate_scan():
     """Non-depth shaders on single-tile canvases: the visibility kernel's resolve builds the visible-triangle lists
     itself (V3Vis, jr_vis3.cuh) while meshes of more than 49 152 triangles -- beyond its shared-memory flag array --
