@@ -20,9 +20,15 @@ __device__ __forceinline__ float dot3(float a0, float a1, float a2, float b0, fl
 // IEEE a / b, bit for bit.  A ZERO dividend sends the compiler's division through its out-of-line slow path (FCHK
 // flags it: ~35 extra instructions per warp that holds one -- axis-aligned normals, the centre row / column of the
 // canvas); +-0 / b is +-0 for every finite non-zero b, so that case is answered directly and the division sees 1 / b.
+// (The substituted dividend goes through an empty asm: otherwise the compiler sees that the quotient is only used
+// when the dividend was not replaced, divides the original value after all, and the zero reaches FCHK again.)
+__device__ __forceinline__ float opaque(float x) {
+  asm volatile("" : "+f"(x));
+  return x;
+}
 __device__ __forceinline__ float fdiv_z(float a, float b) {
   const bool z = a == 0.f && fabsf(b) > 0.f && fabsf(b) <= 3.4028234664e38f;
-  const float q = (z ? 1.f : a) / b;
+  const float q = opaque(z ? 1.f : a) / b;
   return z ? __uint_as_float((__float_as_uint(a) ^ __float_as_uint(b)) & 0x80000000u) : q;
 }
 __device__ __forceinline__ Vec3 normalise3(Vec3 v) {
@@ -30,7 +36,7 @@ __device__ __forceinline__ Vec3 normalise3(Vec3 v) {
   // v / n with the zero components answered directly (see fdiv_z; n >= 0 here, so +-0 / n keeps its sign)
   const bool ok = n > 0.f && n <= 3.4028234664e38f;
   const bool zx = ok && v.x == 0.f, zy = ok && v.y == 0.f, zz = ok && v.z == 0.f;
-  const float qx = (zx ? 1.f : v.x) / n, qy = (zy ? 1.f : v.y) / n, qz = (zz ? 1.f : v.z) / n;
+  const float qx = opaque(zx ? 1.f : v.x) / n, qy = opaque(zy ? 1.f : v.y) / n, qz = opaque(zz ? 1.f : v.z) / n;
   return Vec3{zx ? v.x : qx, zy ? v.y : qy, zz ? v.z : qz};
 }
 

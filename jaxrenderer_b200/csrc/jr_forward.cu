@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(256) k_merge_norms(const __grid_constant__ JrM
     for (int kk = 0; kk < KEEP; ++kk) {
       const int i = n0 + threadIdx.x + 256 * kk;
       nx[kk] = ny[kk] = nz[kk] = 0.f;
-      if (i < n1) { nx[kk] = ln[3 * i] / f1; ny[kk] = ln[3 * i + 1] / f1; nz[kk] = ln[3 * i + 2] / f1; }
+      if (i < n1) { nx[kk] = fdiv_z(ln[3 * i], f1); ny[kk] = fdiv_z(ln[3 * i + 1], f1); nz[kk] = fdiv_z(ln[3 * i + 2], f1); }
     }
     for (int b = blockIdx.y * MN_GROUP; b < min(m.B, (blockIdx.y + 1) * MN_GROUP); ++b) {
       const float* __restrict__ R = m.normal_matrix.ptr + (long long)b * m.normal_matrix.batch_stride + 16 * o;
@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(256) k_merge_norms(const __grid_constant__ JrM
         }
       }
       for (int i = n0 + threadIdx.x + 256 * KEEP; i < n1; i += 256) {
-        const float x = ln[3 * i] / f1, y = ln[3 * i + 1] / f1, z = ln[3 * i + 2] / f1;
+        const float x = fdiv_z(ln[3 * i], f1), y = fdiv_z(ln[3 * i + 1], f1), z = fdiv_z(ln[3 * i + 2], f1);
         const float tx = (x * r0 + y * r1) + z * r2, ty = (x * r4 + y * r5) + z * r6, tz = (x * r8 + y * r9) + z * r10;
         ss2 += dot3(tx, ty, tz, tx, ty, tz);
       }
@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(256) k_merge_norms(const __grid_constant__ JrM
     for (int kk = 0; kk < KEEP; ++kk) {
       const int i = n0 + threadIdx.x + 256 * kk;
       if (i < n1) {
-        const float x = ln[3 * i] / f1, y = ln[3 * i + 1] / f1, z = ln[3 * i + 2] / f1;
+        const float x = fdiv_z(ln[3 * i], f1), y = fdiv_z(ln[3 * i + 1], f1), z = fdiv_z(ln[3 * i + 2], f1);
         const float tx = (x * R[0] + y * R[1]) + z * R[2], ty = (x * R[4] + y * R[5]) + z * R[6],
                     tz = (x * R[8] + y * R[9]) + z * R[10];
         ss2 += dot3(tx, ty, tz, tx, ty, tz);
@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(256) k_merge_norms(const __grid_constant__ JrM
       }
     }
     for (int i = n0 + threadIdx.x + 256 * KEEP; i < n1; i += 256) {
-      const float x = ln[3 * i] / f1, y = ln[3 * i + 1] / f1, z = ln[3 * i + 2] / f1;
+      const float x = fdiv_z(ln[3 * i], f1), y = fdiv_z(ln[3 * i + 1], f1), z = fdiv_z(ln[3 * i + 2], f1);
       const float tx = (x * R[0] + y * R[1]) + z * R[2], ty = (x * R[4] + y * R[5]) + z * R[6],
                   tz = (x * R[8] + y * R[9]) + z * R[10];
       ss2 += dot3(tx, ty, tz, tx, ty, tz);
@@ -303,16 +303,16 @@ __global__ void __launch_bounds__(256) k_merge_norms(const __grid_constant__ JrM
     for (int kk = 0; kk < KEEP; ++kk) {
       const int i = n0 + threadIdx.x + 256 * kk;
       if (i < n1) {
-        out[3 * i] = keep[kk][0] / f2;
-        out[3 * i + 1] = keep[kk][1] / f2;
-        out[3 * i + 2] = keep[kk][2] / f2;
+        out[3 * i] = fdiv_z(keep[kk][0], f2);
+        out[3 * i + 1] = fdiv_z(keep[kk][1], f2);
+        out[3 * i + 2] = fdiv_z(keep[kk][2], f2);
       }
     }
     for (int i = n0 + threadIdx.x + 256 * KEEP; i < n1; i += 256) {
-      const float x = ln[3 * i] / f1, y = ln[3 * i + 1] / f1, z = ln[3 * i + 2] / f1;
-      out[3 * i] = ((x * R[0] + y * R[1]) + z * R[2]) / f2;
-      out[3 * i + 1] = ((x * R[4] + y * R[5]) + z * R[6]) / f2;
-      out[3 * i + 2] = ((x * R[8] + y * R[9]) + z * R[10]) / f2;
+      const float x = fdiv_z(ln[3 * i], f1), y = fdiv_z(ln[3 * i + 1], f1), z = fdiv_z(ln[3 * i + 2], f1);
+      out[3 * i] = fdiv_z((x * R[0] + y * R[1]) + z * R[2], f2);
+      out[3 * i + 1] = fdiv_z((x * R[4] + y * R[5]) + z * R[6], f2);
+      out[3 * i + 2] = fdiv_z((x * R[8] + y * R[9]) + z * R[10], f2);
     }
   }
 }

@@ -71,10 +71,11 @@ __device__ __forceinline__ Vec3 fetch_normal(const JrRenderArgs& a, int b, const
     const float* __restrict__ R = a.inst_normal_matrix.ptr + (long long)b * a.inst_normal_matrix.batch_stride + 16 * o;
     const float* __restrict__ f = a.inst_norm_scale.ptr + (long long)b * a.inst_norm_scale.batch_stride + 2 * o;
     const float f1 = f[0], f2 = f[1];
-    const float x = n.x / f1, y = n.y / f1, z = n.z / f1;
-    n.x = ((x * R[0] + y * R[1]) + z * R[2]) / f2;
-    n.y = ((x * R[4] + y * R[5]) + z * R[6]) / f2;
-    n.z = ((x * R[8] + y * R[9]) + z * R[10]) / f2;
+    // (fdiv_z: local normals are full of exact zeros -- cube faces, capsule poles)
+    const float x = fdiv_z(n.x, f1), y = fdiv_z(n.y, f1), z = fdiv_z(n.z, f1);
+    n.x = fdiv_z((x * R[0] + y * R[1]) + z * R[2], f2);
+    n.y = fdiv_z((x * R[4] + y * R[5]) + z * R[6], f2);
+    n.z = fdiv_z((x * R[8] + y * R[9]) + z * R[10], f2);
   }
   return n;
 }
