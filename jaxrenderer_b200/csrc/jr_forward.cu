@@ -517,6 +517,14 @@ int jr_render_forward(const JrRenderArgs* a, jr_stream_t stream_) {
   set_kernel_attributes_once();
   const bool depth = a->shader == JR_DEPTH;
   bool fused_mark = false;   // the visibility kernel built the visible-triangle lists itself
+  if (!depth) {
+    // everything the shading stage will need is validated BEFORE the first launch: a failing call enqueues nothing
+    const FwdLayout F0 = fwd_layout(a);
+    if (F0.use_attr) {
+      if (!a->workspace || a->workspace_bytes < F0.total) return JR_ERR_WORKSPACE;
+      if (a->B > 65535) return JR_ERR_DIMS;
+    }
+  }
   if (nx * ny > 1 && !g_no_bins) {
     // two-level path: per-triangle records + per-tile bitmasks, then one CTA per (image, tile)
     const TiledLayout TLy = tiled_layout(a->B, a->W, a->H, a->T);
