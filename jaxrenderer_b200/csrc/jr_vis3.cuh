@@ -337,7 +337,7 @@ k_vis3(const __grid_constant__ JrRenderArgs a, const V3Vis vis) {
   unsigned short* spans = reinterpret_cast<unsigned short*>(smem + V3_SM_LISTS);  // resolve only
   __shared__ unsigned s_cnt01, s_cnt23;  // packed 16-bit push counters of lists (0, 1) and (2, 3)
   __shared__ unsigned s_head[5];  // consumption cursors of the four lists + the spill list
-  __shared__ int bigq_n, tri0_flag, spill_n, s_vis_n;
+  __shared__ int bigq_n, tri0_flag, spill_n;
   __shared__ TriSetup tri0;
   __shared__ float s_w2c[16];
   __shared__ float s_vp[16];
@@ -359,7 +359,7 @@ k_vis3(const __grid_constant__ JrRenderArgs a, const V3Vis vis) {
     s_vp[tid] = a.viewport.ptr[(long long)b * a.viewport.batch_stride + tid];
   }
   if (tid == 0) {
-    bigq_n = 0; tri0_flag = 0; spill_n = 0; s_vis_n = 0; s_cnt01 = 0u; s_cnt23 = 0u;
+    bigq_n = 0; tri0_flag = 0; spill_n = 0; s_cnt01 = 0u; s_cnt23 = 0u;
     s_head[0] = s_head[1] = s_head[2] = s_head[3] = s_head[4] = 0u;
   }
   {
@@ -838,14 +838,31 @@ k_vis3(const __grid_constant__ JrRenderArgs a, const V3Vis vis) {
   }
   if (CLUSTER) cluster_sync_all();   // the peer may still be reading this CTA's key tile
   if (!DEPTH && mark) {
-    // flags -> the image's visible-triangle list (any order: every record goes to its own slot), count, slot map
+    // flags -> the image's visible-triangle list in ASCENDING triangle order (deterministic slots; the attribute
+    // kernel then walks the index buffer forwards), count, slot map: every thread owns a contiguous run of flag words,
+    // a block-wide exclusive scan of the per-thread counts gives its first slot
     __syncthreads();
     int* __restrict__ list = vis.list + (long long)b * a.T;
     int* __restrict__ smap = vis.slot_map ? vis.slot_map + (long long)b * a.T : nullptr;
-    for (int i = tid; i < (a.T + 31) >> 5; i += V3_THREADS) {
+    const int n_words = (a.T + 31) >> 5;
+    const int per = (n_words + V3_THREADS - 1) / V3_THREADS;
+    const int w0 = min(tid * per, n_words), w1 = min(w0 + per, n_words);
+    int cnt = 0;
+    for (int i = w0; i < w1; ++i) cnt += __popc(vis_flags[i]);
+    int incl = cnt;   // inclusive scan inside the warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    __shared__ int s_scan[V3_NW];
+    if (lane == 31) s_scan[warp] = incl;
+    __syncthreads();
+    int base = incl - cnt;
+    for (int w = 0; w < warp; ++w) base += s_scan[w];
+    int slot = base;
+    for (int i = w0; i < w1; ++i) {
       unsigned bits = vis_flags[i];
-      if (!bits) continue;
-      int slot = atomicAdd(&s_vis_n, __popc(bits));
       while (bits) {
         const int tri = 32 * i + __ffs(bits) - 1;
         bits &= bits - 1;
@@ -854,8 +871,7 @@ k_vis3(const __grid_constant__ JrRenderArgs a, const V3Vis vis) {
         ++slot;
       }
     }
-    __syncthreads();
-    if (tid == 0) vis.count[b] = s_vis_n;
+    if (tid == V3_THREADS - 1) vis.count[b] = slot;   // the last thread's end == the total
   }
 
   if (STATS && a.stats) {
