@@ -297,7 +297,9 @@ __device__ __forceinline__ void frag_pixel(const JrRenderArgs& a, int b, int x, 
   f.normal = Vec3{interp3(tc, f.nvert[0].x, f.nvert[1].x, f.nvert[2].x),
                   interp3(tc, f.nvert[0].y, f.nvert[1].y, f.nvert[2].y),
                   interp3(tc, f.nvert[0].z, f.nvert[1].z, f.nvert[2].z)};
-  f.nn = normalise3(f.normal);
+  // continuous lighting only -- except for the Darboux shader, whose tangent frame inverts a matrix built on this
+  // normal (ill-conditioned: a last-bit change of nn showed up as 4e-5 in the colour): exact there
+  f.nn = SHADER == JR_PHONG_DARBOUX ? normalise3(f.normal) : normalise3_fast(f.normal);
 
   if (SHADER == JR_PHONG || SHADER == JR_PHONG_DARBOUX) {
     if (PC) {
@@ -400,7 +402,7 @@ __device__ __forceinline__ void frag_pixel(const JrRenderArgs& a, int b, int x, 
   f.diffuse = fmaxf(f.ndl, 0.f);
   const float two_ndl = 2.f * f.ndl;
   f.rv = Vec3{two_ndl * nn.x - ld.x, two_ndl * nn.y - ld.y, two_ndl * nn.z - ld.z};
-  const Vec3 refl = normalise3(f.rv);
+  const Vec3 refl = normalise3_fast(f.rv);
   f.sexp = (a.specular_map.ptr + (long long)b * a.specular_map.batch_stride)[f.spec_idx];
   f.base = fmaxf(refl.z, 0.f);
   f.specular = pow_unit(f.base, f.sexp);
