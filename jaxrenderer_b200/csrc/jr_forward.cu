@@ -67,27 +67,31 @@ __global__ void __launch_bounds__(128) k_tri_attr(const __grid_constant__ JrRend
   // the image's pixel-stage constants (read by k_shade_rec*), by the first warp of the image's first block
   if (blockIdx.x == 0 && threadIdx.x < 32)
     pix_const_write<SHADER>(a, b, pcs + b, reinterpret_cast<float*>(pcs + a.B) + (size_t)b * (a.W + a.H));
+  // The number of visible triangles is only known on the device (a few hundred of thousands, typically): a small
+  // grid of blocks per image walks the list in strides instead of ceil(T / 128) blocks of which most would find
+  // nothing to do (106 k launched for 16 k with work on the facade workload).
   const int n_vis = count[b];
-  const int i0 = blockIdx.x * 128;
-  if (i0 >= n_vis) return;
-  const int i = i0 + threadIdx.x;
-  int t = -1;
-  if (i < n_vis) {
-    t = list[(long long)b * a.T + i];
-    Frag f;
-    frag_vertex<SHADER>(a, b, t, f);
-    attr_store<SHADER>(f, stage + threadIdx.x * TA_FLOATS);
-  }
-  // record slot: the triangle id, or (compact layout, more triangles than pixels) the list position
-  s_tri[threadIdx.x] = compact ? i : t;
-  __syncthreads();
   constexpr int Q = TA_FLOATS / 4;
-  const int n = min(128, n_vis - i0) * Q;
   const float4* src = reinterpret_cast<const float4*>(stage);
   float4* base = reinterpret_cast<float4*>(attrs + (size_t)b * rec_stride * TA_FLOATS);
-  for (int j = threadIdx.x; j < n; j += 128) {
-    const int r = j / Q;
-    base[(size_t)s_tri[r] * Q + (j - r * Q)] = src[j];
+  for (int i0 = blockIdx.x * 128; i0 < n_vis; i0 += gridDim.x * 128) {
+    const int i = i0 + threadIdx.x;
+    int t = -1;
+    if (i < n_vis) {
+      t = list[(long long)b * a.T + i];
+      Frag f;
+      frag_vertex<SHADER>(a, b, t, f);
+      attr_store<SHADER>(f, stage + threadIdx.x * TA_FLOATS);
+    }
+    // record slot: the triangle id, or (compact layout, more triangles than pixels) the list position
+    s_tri[threadIdx.x] = compact ? i : t;
+    __syncthreads();
+    const int n = min(128, n_vis - i0) * Q;
+    for (int j = threadIdx.x; j < n; j += 128) {
+      const int r = j / Q;
+      base[(size_t)s_tri[r] * Q + (j - r * Q)] = src[j];
+    }
+    __syncthreads();   // the stage is reused by the next stride
   }
 }
 
@@ -644,7 +648,8 @@ int jr_render_forward(const JrRenderArgs* a, jr_stream_t stream_) {
       const int rec_stride = F.rec_stride;
       const bool compact = F.compact;
       PixConst* pcs = (PixConst*)((char*)a->workspace + F.pc_off);
-      dim3 g1((a->T + 127) / 128, a->B);
+      const int g1x = (a->T + 127) / 128;
+      dim3 g1(g1x < 8 ? g1x : 8, a->B);   // the kernel strides over the visible list
       const int tiles_x = (a->W + 31) / 32, tiles_y = (a->H + 31) / 32;
       const dim3 gu8(tiles_x * tiles_y, a->B);
       const dim3 grec((npix + threads - 1) / threads, a->B > 65535 ? 65535 : a->B, (a->B + 65534) / 65535);
