@@ -20,8 +20,10 @@
  *  - calls are asynchronous on `stream`, never allocate, never synchronise,
  *    never throw; they return 0 or a negative JrStatus;
  *  - re-entrant: no global state (a launch counter for benchmarks aside);
- *  - limits: W, H <= 32767; B <= 65535 for canvases larger than one shared-memory tile and for
- *    jr_render_backward (the batch is a grid dimension there); B * W * H < 2^30 for backward.
+ *  - limits: W, H <= 32767; B <= 65535 for canvases larger than one shared-memory tile, for every
+ *    non-depth shader (attribute-record stage) and for jr_render_backward (the batch is a grid
+ *    dimension there); B * W * H < 2^30 for backward.  Everything a call needs (workspace size,
+ *    limits) is validated before its first launch: a failing call enqueues nothing.
  */
 #ifndef JR_B200_H_
 #define JR_B200_H_

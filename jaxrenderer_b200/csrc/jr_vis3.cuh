@@ -21,9 +21,12 @@
 //            decides anything that reaches a pixel; the results are bit-identical to k_vis2.
 //   resolve  keys -> z (+ triangle id), large triangles folded in (k_vis2's resolve).
 //
-// At 84x84 a Brax ant frame has 1932 triangles of which ~340 survive phase A (~930 are front-facing,
-// ~590 of those hold no sample): the exact set-up (LU inverse: 9 IEEE divisions) runs in ~12 full warps
-// per image instead of 61 half-empty ones, and the per-lane raster loops are grouped by box size.
+// At 84x84 a bench image (ground cube + 10 capsules) has 1932 triangles of which ~480 survive phase A (~930 are
+// front-facing), ~410 the exact cull and ~150 cover a sample: the exact set-up (LU inverse: 9 IEEE divisions) runs in
+// ~18 well-filled warp rounds per image instead of 61 half-empty ones, and the per-lane raster loops are grouped by
+// box size.  Variants: INST (geometry instanced at the fetch), CLUSTER (one image split over a 2-CTA cluster, small
+// batches), STATS (counters); non-depth builds also emit the visible-triangle lists (V3Vis).  What was measured and
+// rejected (TMA / register prefetch of phase A, a per-sample coverage test in the filter, 5 CTAs/SM): profiles/README.md.
 #pragma once
 #include <type_traits>
 #include "jr_device.cuh"
