@@ -59,9 +59,15 @@ struct PixGrad {
   float d_pos2[3][3];
 };
 
+// 1 / |v| for the reverse pass (continuous arithmetic: reciprocal square root + one Newton step, < 1 ulp)
+__device__ __forceinline__ float inv_norm3(Vec3 v) {
+  const float d = fmaf(v.x, v.x, fmaf(v.y, v.y, v.z * v.z));
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+  return r * fmaf(-0.5f * d, r * r, 1.5f);
+}
 __device__ __forceinline__ Vec3 normalise_bwd(Vec3 v, Vec3 dy) {
-  const float n = sqrtf(v.x * v.x + v.y * v.y + v.z * v.z);
-  const float inv_n = 1.0f / n;
+  const float inv_n = inv_norm3(v);
   const Vec3 y = {v.x * inv_n, v.y * inv_n, v.z * inv_n};
   const float d = y.x * dy.x + y.y * dy.y + y.z * dy.z;
   return Vec3{(dy.x - y.x * d) * inv_n, (dy.y - y.y * d) * inv_n, (dy.z - y.z * d) * inv_n};
@@ -266,8 +272,7 @@ __device__ __forceinline__ void backprop_pixel(const JrRenderArgs& a, int b, con
       if (f.sexp != 0.f) d_base = d_s * f.sexp * (f.base > 0.f ? f.specular * (1.0f / f.base) : powf(f.base, f.sexp - 1.f));
       if (WT) o.d_sexp = (f.base > 0.f) ? d_s * f.specular * logf(f.base) : 0.f;
       const Vec3 rv = f.rv;
-      const float rn = sqrtf(rv.x * rv.x + rv.y * rv.y + rv.z * rv.z);
-      const float refl_z = rv.z / rn;
+      const float refl_z = rv.z * inv_norm3(rv);
       const float d_refl_z = (refl_z > 0.f) ? d_base : 0.f;
       const Vec3 d_rv = normalise_bwd(rv, Vec3{0.f, 0.f, d_refl_z});
       const Vec3 nn = f.nn, ld = f.nl;
