@@ -341,17 +341,23 @@ __device__ __forceinline__ void backprop_pixel(const JrRenderArgs& a, int b, con
       o.g[G_VP13] += -gv[1] * r_vp5;
       o.g[G_VP11] += -gv[1] * f.yn * r_vp5;
     }
+    if (WG) {
+      // d world_to_clip = sum_k (d gl_Position_k) (x) [P_k, 1] with d gl_Position_k = cc_k * (-gv0, -gv1, d_z, -gv2):
+      // the outer product factors into g (x) q, q = sum_k cc_k [P_k, 1] -- 16 accumulator updates instead of 48
+      const float g4[4] = {-gv[0], -gv[1], d_z, -gv[2]};
+      const float q4[4] = {f.cc[0] * f.P[0].x + f.cc[1] * f.P[1].x + f.cc[2] * f.P[2].x,
+                           f.cc[0] * f.P[0].y + f.cc[1] * f.P[1].y + f.cc[2] * f.P[2].y,
+                           f.cc[0] * f.P[0].z + f.cc[1] * f.P[1].z + f.cc[2] * f.P[2].z,
+                           f.cc[0] + f.cc[1] + f.cc[2]};
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) o.g[G_W2C + 4 * r + c] += g4[r] * q4[c];
+    }
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       // d gl_Position of vertex k: (x, y, z, w)
       const float dc[4] = {-f.cc[k] * gv[0], -f.cc[k] * gv[1], d_zc[k], -f.cc[k] * gv[2]};
-      const float ph[4] = {f.P[k].x, f.P[k].y, f.P[k].z, 1.f};
-      if (WG) {
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-#pragma unroll
-          for (int c = 0; c < 4; ++c) o.g[G_W2C + 4 * r + c] += dc[r] * ph[c];
-      }
       if (WV) {
 #pragma unroll
         for (int c = 0; c < 3; ++c)
