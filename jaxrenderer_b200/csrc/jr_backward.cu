@@ -288,6 +288,7 @@ __device__ __forceinline__ void backprop_pixel(const JrRenderArgs& a, int b, con
     if (active) {
       const Vec3 d_normal = normalise_bwd(f.normal, d_nn);
       const float* __restrict__ wen = a.world_to_eye_norm.ptr + (long long)b * a.world_to_eye_norm.batch_stride;
+      float wen_acc[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // summed over the corners first: 9 updates, not 27
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
         d_tc[k] += d_normal.x * f.nvert[k].x + d_normal.y * f.nvert[k].y + d_normal.z * f.nvert[k].z;
@@ -296,9 +297,9 @@ __device__ __forceinline__ void backprop_pixel(const JrRenderArgs& a, int b, con
           const Vec3 d_t = normalise_bwd(f.tvert[k], d_nv);
           const Vec3 m = f.mvert[k];
           if (WG) {
-            o.g[G_WEN + 0] += d_t.x * m.x; o.g[G_WEN + 1] += d_t.x * m.y; o.g[G_WEN + 2] += d_t.x * m.z;
-            o.g[G_WEN + 3] += d_t.y * m.x; o.g[G_WEN + 4] += d_t.y * m.y; o.g[G_WEN + 5] += d_t.y * m.z;
-            o.g[G_WEN + 6] += d_t.z * m.x; o.g[G_WEN + 7] += d_t.z * m.y; o.g[G_WEN + 8] += d_t.z * m.z;
+            wen_acc[0] += d_t.x * m.x; wen_acc[1] += d_t.x * m.y; wen_acc[2] += d_t.x * m.z;
+            wen_acc[3] += d_t.y * m.x; wen_acc[4] += d_t.y * m.y; wen_acc[5] += d_t.y * m.z;
+            wen_acc[6] += d_t.z * m.x; wen_acc[7] += d_t.z * m.y; wen_acc[8] += d_t.z * m.z;
           }
           if (WV) {
             const Vec3 d_m = {wen[0] * d_t.x + wen[4] * d_t.y + wen[8] * d_t.z,
@@ -310,6 +311,10 @@ __device__ __forceinline__ void backprop_pixel(const JrRenderArgs& a, int b, con
             o.d_nrm[k][0] = dn.x; o.d_nrm[k][1] = dn.y; o.d_nrm[k][2] = dn.z;
           }
         }
+      }
+      if (WG) {
+#pragma unroll
+        for (int j = 0; j < 9; ++j) o.g[G_WEN + j] += wen_acc[j];
       }
     }
   }
