@@ -4,11 +4,13 @@ The five stage names (``vertex``, ``primitive_chooser``, ``interpolate``,
 ``fragment``, ``mix``) and the carrier tuples ``PerVertex`` / ``PerFragment`` /
 ``MixerOutput`` are kept so code written against the reference imports
 unchanged.  In this implementation the stages of the seven built-in shaders
-are FUSED into hand-written CUDA kernels (``csrc/jr_forward.cu``); they are
-never executed as Python.  ``pipeline.render`` therefore accepts only the
+are FUSED into hand-written CUDA kernels (``csrc/jr_forward.cu``); rendering
+never executes them as Python.  ``pipeline.render`` therefore accepts only the
 built-in shader classes themselves; a user subclass (e.g. the custom shader of
 the reference's ``tests/smoke_test.py:155-232``) is rejected with
-``UnsupportedShaderError`` -- there is no Python/CPU fallback.
+``UnsupportedShaderError`` -- there is no Python/CPU fallback.  The stage
+methods themselves stay callable with the reference's signatures (host-side
+tensor code in ``stages.py``, checked against the oracle stage by stage).
 """
 from __future__ import annotations
 
@@ -44,42 +46,55 @@ class MixerOutput(NamedTuple):
     zbuffer: Any
 
 
-_FUSED = (
-    "stage `{}` of `{}` is fused into the CUDA kernels of jaxrenderer_b200 and is "
-    "not callable from Python; call `jaxrenderer_b200.pipeline.render` with the "
-    "built-in shader class instead."
-)
-
-
 class Shader:
-    """Base class (``shader.py:91-396``).  Subclass-and-override is the
-    reference's extension mechanism; here only the built-ins run (see module
-    docstring).  ``_jr_shader`` is the C-ABI shader id of a built-in."""
+    """Base class (``shader.py:91-396``).  Subclass-and-override is the reference's extension mechanism; here only the
+    built-ins RENDER (see module docstring): ``_jr_shader`` is the C-ABI shader id of a built-in.  The five stage methods
+    keep the reference's signatures and semantics as host-side tensor code (``stages.py``) so that code which calls,
+    composes or introspects them keeps working; ``pipeline.render`` never calls them."""
 
     _jr_shader: int = -1
 
-    @classmethod
-    def _fused(cls, stage: str) -> "UnsupportedShaderError":
-        return UnsupportedShaderError(_FUSED.format(stage, cls.__name__))
+    @staticmethod
+    def vertex(gl_VertexID: ID, gl_InstanceID: ID, camera: Any, extra: Any) -> Tuple[PerVertex, Any]:
+        """Abstract in the reference as well (``shader.py:103-157``)."""
+        raise NotImplementedError("vertex shader not implemented")
 
-    @classmethod
-    def vertex(cls, gl_VertexID: ID, gl_InstanceID: ID, camera: Any, extra: Any) -> Tuple[PerVertex, Any]:
-        raise cls._fused("vertex")
-
-    @classmethod
-    def primitive_chooser(cls, gl_FragCoord: Any, gl_FrontFacing: Any, gl_PointCoord: Any, keeps: Any,
+    @staticmethod
+    def primitive_chooser(gl_FragCoord: Any, gl_FrontFacing: Any, gl_PointCoord: Any, keeps: Any,
                           values: Any, barycentric_screen: Any, barycentric_clip: Any) -> Tuple[Any, ...]:
-        raise cls._fused("primitive_chooser")
+        from . import stages
 
-    @classmethod
-    def interpolate(cls, values: Any, barycentric_screen: Any, barycentric_clip: Any) -> Any:
-        raise cls._fused("interpolate")
+        return stages.base_primitive_chooser(gl_FragCoord, gl_FrontFacing, gl_PointCoord, keeps, values,
+                                             barycentric_screen, barycentric_clip)
 
-    @classmethod
-    def fragment(cls, gl_FragCoord: Any, gl_FrontFacing: Any, gl_PointCoord: Any, varying: Any,
+    @staticmethod
+    def interpolate(values: Any, barycentric_screen: Any, barycentric_clip: Any) -> Any:
+        from . import stages
+
+        return stages.base_interpolate(values, barycentric_screen, barycentric_clip)
+
+    @staticmethod
+    def fragment(gl_FragCoord: Any, gl_FrontFacing: Any, gl_PointCoord: Any, varying: Any,
                  extra: Any) -> Tuple[PerFragment, Any]:
-        raise cls._fused("fragment")
+        from . import stages
 
-    @classmethod
-    def mix(cls, gl_FragDepth: Any, keeps: Any, extra: Any) -> Tuple[MixerOutput, Any]:
-        raise cls._fused("mix")
+        return stages.base_fragment(gl_FragCoord, gl_FrontFacing, gl_PointCoord, varying, extra)
+
+    @staticmethod
+    def mix(gl_FragDepth: Any, keeps: Any, extra: Any) -> Tuple[MixerOutput, Any]:
+        from . import stages
+
+        return stages.base_mix(gl_FragDepth, keeps, extra)
+
+
+def _stage(name: str) -> staticmethod:
+    """A static method that forwards to ``stages.<name>`` (imported lazily: ``stages`` imports this module)."""
+
+    def call(*args: Any, **kwargs: Any) -> Any:
+        from . import stages
+
+        return getattr(stages, name)(*args, **kwargs)
+
+    call.__name__ = name.split("_")[-1]
+    call.__doc__ = f"Host-side evaluator of this stage: ``jaxrenderer_b200.stages.{name}`` (never called by ``render``)."
+    return staticmethod(call)

@@ -2,7 +2,7 @@
 from typing import Any, NamedTuple
 
 from .. import _native
-from ..shader import Shader
+from ..shader import Shader, _stage
 
 
 class DepthExtraInput(NamedTuple):
@@ -21,3 +21,4 @@ class DepthShader(Shader):
     """Writes the z-buffer only; fused into ``k_visibility<true>``."""
 
     _jr_shader = _native.JR_DEPTH
+    vertex = _stage("depth_vertex")

@@ -2,7 +2,7 @@
 from typing import Any, NamedTuple
 
 from .. import _native
-from ..shader import Shader
+from ..shader import Shader, _stage
 from ..types import LightSource
 
 
@@ -23,3 +23,6 @@ class GouraudExtraMixerOutput(NamedTuple):
 
 class GouraudShader(Shader):
     _jr_shader = _native.JR_GOURAUD
+    vertex = _stage("gouraud_vertex")
+    fragment = _stage("gouraud_fragment")
+    mix = _stage("gouraud_mix")

@@ -2,7 +2,7 @@
 from typing import Any, NamedTuple
 
 from .. import _native
-from ..shader import Shader
+from ..shader import Shader, _stage
 from ..types import LightSource
 
 
@@ -25,3 +25,6 @@ class GouraudTextureExtraMixerOutput(NamedTuple):
 
 class GouraudTextureShader(Shader):
     _jr_shader = _native.JR_GOURAUD_TEXTURE
+    vertex = _stage("gouraud_texture_vertex")
+    fragment = _stage("gouraud_texture_fragment")
+    mix = _stage("gouraud_texture_mix")

@@ -2,7 +2,7 @@
 from typing import Any, NamedTuple
 
 from .. import _native
-from ..shader import Shader
+from ..shader import Shader, _stage
 from ..types import LightSource
 
 
@@ -26,3 +26,6 @@ class PhongTextureExtraMixerOutput(NamedTuple):
 
 class PhongTextureShader(Shader):
     _jr_shader = _native.JR_PHONG
+    vertex = _stage("phong_vertex")
+    fragment = _stage("phong_fragment")
+    mix = _stage("phong_mix")

@@ -2,7 +2,7 @@
 from typing import Any, NamedTuple
 
 from .. import _native
-from ..shader import Shader
+from ..shader import Shader, _stage
 from ..types import LightSource
 
 
@@ -31,3 +31,7 @@ class PhongTextureDarbouxExtraMixerOutput(NamedTuple):
 
 class PhongTextureDarbouxShader(Shader):
     _jr_shader = _native.JR_PHONG_DARBOUX
+    vertex = _stage("phong_darboux_vertex")
+    interpolate = _stage("phong_darboux_interpolate")
+    fragment = _stage("phong_darboux_fragment")
+    mix = _stage("phong_darboux_mix")

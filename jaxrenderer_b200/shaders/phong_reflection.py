@@ -2,7 +2,7 @@
 from typing import Any, NamedTuple
 
 from .. import _native
-from ..shader import Shader
+from ..shader import Shader, _stage
 from ..types import LightSource
 
 
@@ -35,3 +35,7 @@ class PhongReflectionTextureExtraMixerOutput(NamedTuple):
 
 class PhongReflectionTextureShader(Shader):
     _jr_shader = _native.JR_PHONG_REFLECTION
+    vertex = _stage("phong_reflection_vertex")
+    interpolate = _stage("phong_reflection_interpolate")
+    fragment = _stage("phong_reflection_fragment")
+    mix = _stage("phong_reflection_mix")

@@ -2,7 +2,7 @@
 from typing import Any, NamedTuple
 
 from .. import _native
-from ..shader import Shader
+from ..shader import Shader, _stage
 from ..types import LightSource
 
 
@@ -38,3 +38,7 @@ class PhongReflectionShadowTextureExtraMixerOutput(NamedTuple):
 
 class PhongReflectionShadowTextureShader(Shader):
     _jr_shader = _native.JR_PHONG_REFLECTION_SHADOW
+    vertex = _stage("phong_reflection_shadow_vertex")
+    interpolate = _stage("phong_reflection_interpolate")
+    fragment = _stage("phong_reflection_shadow_fragment")
+    mix = _stage("phong_reflection_shadow_mix")

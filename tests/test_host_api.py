@@ -48,9 +48,10 @@ def test_custom_shader_is_rejected_without_fallback():
         jr.render(None, MyShader, bufs, torch.zeros(1, 3, dtype=torch.int32), (torch.zeros(3, 3),))
     with pytest.raises(jr.UnsupportedShaderError):
         jr.render(None, jr.Shader, bufs, torch.zeros(1, 3, dtype=torch.int32), (torch.zeros(3, 3),))
-    for s in BUILTIN_SHADERS:  # stage methods exist but are fused
-        with pytest.raises(jr.UnsupportedShaderError, match="fused"):
-            s.vertex(0, 0, None, None)
+    for s in BUILTIN_SHADERS:  # the stage methods stay callable (host-side tensor code, tests/test_stage_methods.py) ...
+        for stage in ("vertex", "primitive_chooser", "interpolate", "fragment", "mix"):
+            assert callable(getattr(s, stage))
+    # ... but rendering never goes through them: a subclass overriding one is rejected above, not executed
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU error path")
