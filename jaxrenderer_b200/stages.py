@@ -173,7 +173,7 @@ def phong_vertex(gl_VertexID: Any, gl_InstanceID: Any, camera: Camera, extra: An
 
     return (PerVertex(gl_Position=_clip_position(camera, extra.position, gl_VertexID)),
             PhongTextureExtraFragmentData(normal=_eye_normal(camera, extra.normal, gl_VertexID),
-                                          uv=_t(extra.uv)[gl_VertexID], colour=torch.zeros(3)))
+                                          uv=_t(extra.uv)[gl_VertexID], colour=torch.zeros(3, device=_t(extra.position).device)))
 
 
 def _phong_colour(normal: Tensor, uv: Tensor, extra: Any) -> Tensor:
@@ -210,7 +210,7 @@ def phong_darboux_vertex(gl_VertexID: Any, gl_InstanceID: Any, camera: Camera, e
     return (PerVertex(gl_Position=_clip_position(camera, extra.position, gl_VertexID)),
             PhongTextureDarbouxExtraFragmentData(normal=_eye_normal(camera, extra.normal, gl_VertexID),
                                                  uv=_t(extra.uv)[gl_VertexID], triangle=to_cartesian(tri_clip),
-                                                 triangle_uv=_t(extra.uv)[face], colour=torch.zeros(3)))
+                                                 triangle_uv=_t(extra.uv)[face], colour=torch.zeros(3, device=_t(extra.position).device)))
 
 
 def phong_darboux_interpolate(values: Any, barycentric_screen: Tensor, barycentric_clip: Tensor) -> Any:
@@ -258,7 +258,7 @@ def phong_reflection_vertex(gl_VertexID: Any, gl_InstanceID: Any, camera: Camera
     return (PerVertex(gl_Position=_clip_position(camera, extra.position, gl_VertexID)),
             PhongReflectionTextureExtraFragmentData(
                 normal=_eye_normal(camera, extra.normal, gl_VertexID), uv=_t(extra.uv)[gl_VertexID],
-                texture_index=_t(extra.texture_index, dtype=torch.int64)[gl_VertexID], colour=torch.zeros(3)))
+                texture_index=_t(extra.texture_index, dtype=torch.int64)[gl_VertexID], colour=torch.zeros(3, device=_t(extra.position).device)))
 
 
 def phong_reflection_interpolate(values: Any, barycentric_screen: Tensor, barycentric_clip: Tensor) -> Any:
@@ -319,7 +319,7 @@ def phong_reflection_shadow_vertex(gl_VertexID: Any, gl_InstanceID: Any, camera:
             PhongReflectionShadowTextureExtraFragmentData(
                 normal=_eye_normal(camera, extra.normal, gl_VertexID), uv=_t(extra.uv)[gl_VertexID],
                 texture_index=_t(extra.texture_index, dtype=torch.int64)[gl_VertexID],
-                shadow_coord=normalise_homogeneous(extra.shadow.camera.to_clip(world)), colour=torch.zeros(3)))
+                shadow_coord=normalise_homogeneous(extra.shadow.camera.to_clip(world)), colour=torch.zeros(3, device=_t(extra.position).device)))
 
 
 def phong_reflection_shadow_fragment(gl_FragCoord: Tensor, gl_FrontFacing: Tensor, gl_PointCoord: Tensor,

@@ -37,20 +37,31 @@ def _lead(tree):
     return None if tree is None else torch.as_tensor(tree)[None]
 
 
-def _compose(shader, cam, faces, extra, z0, c0):
-    """``pipeline.render`` out of the stage methods, for the triangle the visibility stage chose at each pixel."""
+def _to(tree, dev):
+    if isinstance(tree, torch.Tensor):
+        return tree.to(dev)
+    if isinstance(tree, tuple):
+        fields = [_to(t, dev) for t in tree]
+        return type(tree)(*fields) if hasattr(tree, "_fields") else tuple(fields)
+    return tree
+
+
+def _compose(shader, cam, faces, extra, z0, c0, dev="cpu", max_pixels=None):
+    """``pipeline.render`` out of the stage methods, for the triangle the visibility stage chose at each pixel.  The
+    visibility stage itself (not a shader stage) is the oracle's, on the CPU; the stage methods run on ``dev``."""
     W, H = z0.shape
     pos = extra.position
     clip_v = O.mat4_apply(pos, cam.world_to_clip, w_one=True)
     setup = O.primitive_setup(clip_v, faces.long())
     idx, has, kc, _ = O.visibility(setup, cam.viewport, W, H)
     f_idx = faces.long()[idx]
-    fr = O.chosen_fragments(clip_v, f_idx, cam.viewport)
-    z, canvas = z0.clone(), (None if c0 is None else c0.clone())
+    fr = _to(O.chosen_fragments(clip_v, f_idx, cam.viewport), dev)
+    cam, extra, clip_v, kc = _to(cam, dev), _to(extra, dev), clip_v.to(dev), kc.to(dev)
+    z, canvas = z0.clone().to(dev), (None if c0 is None else c0.clone().to(dev))
     n_checked = 0
     for x in range(W):
         for y in range(H):
-            if not bool(kc[x, y]):
+            if not bool(kc[x, y]) or (max_pixels is not None and n_checked >= max_pixels):
                 continue
             vids = [int(v) for v in f_idx[x, y]]
             per_vertex, varyings = zip(*[shader.vertex(v, 0, cam, extra) for v in vids])
@@ -58,8 +69,9 @@ def _compose(shader, cam, faces, extra, z0, c0):
                 assert torch.allclose(pv.gl_Position, clip_v[vids[k]], rtol=0, atol=1e-6)
             bc = fr.tc[x, y]
             varying = shader.interpolate(_stack(list(varyings)), bc, bc)
-            frag_coord = torch.stack((torch.tensor(float(x)), torch.tensor(float(y)), fr.zw[x, y], fr.w_rec[x, y]))
-            per_frag, varying = shader.fragment(frag_coord, fr.front[x, y], torch.zeros(2), varying, extra)
+            frag_coord = torch.stack((torch.tensor(float(x), device=dev), torch.tensor(float(y), device=dev), fr.zw[x, y],
+                                      fr.w_rec[x, y]))
+            per_frag, varying = shader.fragment(frag_coord, fr.front[x, y], torch.zeros(2, device=dev), varying, extra)
             depth = frag_coord[2] if bool(per_frag.use_default_depth) else per_frag.gl_FragDepth
             keeps = torch.as_tensor(per_frag.keeps) & kc[x, y]
             out, mixed = shader.mix(depth[None], keeps[None], _lead(varying))
@@ -68,7 +80,7 @@ def _compose(shader, cam, faces, extra, z0, c0):
                 if canvas is not None:
                     canvas[x, y] = mixed.canvas
             n_checked += 1
-    return z, canvas, n_checked
+    return z.cpu(), (None if canvas is None else canvas.cpu()), n_checked
 
 
 def _scene(seed):
@@ -146,3 +158,19 @@ def test_primitive_chooser_and_mix_semantics():
     assert not bool(mo.keep) and float(mo.zbuffer) == float("inf")
     with pytest.raises(NotImplementedError):
         jr.Shader.vertex(0, 0, None, None)
+
+
+@pytest.mark.gpu
+def test_stage_methods_are_device_agnostic():
+    """The same composition with every tensor on the GPU (a handful of pixels: the stage methods are per-element host
+    code, not a rendering path)."""
+    s, refl = _scene(0)
+    for name, shader, extra, oracle_extra in _cases(s, refl):
+        if name not in ("gouraud_texture", "phong_darboux", "phong_reflection_shadow"):
+            continue
+        z0, c0 = torch.full((s.W, s.H), 1.0), torch.full((s.W, s.H, 3), 0.25)
+        z, c, n = _compose(shader, s.cam, s.faces, extra, z0, c0, dev="cuda", max_pixels=12)
+        ref = O.render(s.cam, name, z0, (c0,), s.faces, oracle_extra or extra)
+        written = (c != c0).any(-1)
+        assert n == 12 and int(written.sum()) > 0
+        assert float((c - ref.targets[0])[written].abs().max()) <= 1e-5, name
