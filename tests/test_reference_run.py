@@ -3,7 +3,9 @@
 `tests/golden/reference_run.npz` holds inputs and outputs of the unmodified reference (`/root/reference/renderer`)
 executed on small scenes through a NumPy stand-in for jax (`tools/jax_numpy_shim`, generator
 `tools/gen_reference_fixtures.py`): all seven built-in shaders through `pipeline.render`, the shadow pass,
-`merge_objects`, `create_camera_from_parameters` and `Renderer.get_camera_image`.  The CPU tests pin the oracle and
+`merge_objects`, `create_camera_from_parameters` and `Renderer.get_camera_image`; `reference_run_large.npz` the same
+seven shaders on a 64x48 canvas covered to 86 % (`tools/gen_reference_fixtures_large.py`), `reference_run_brax84.npz`
+the facade on the real Brax ant frame at 84x84 (BASELINE.json configs[1]'s canvas).  The CPU tests pin the oracle and
 the host-side glue of the package against it; the GPU tests pin the CUDA path.
 
 Tolerances: colours 1e-5 relative to the largest channel value (BASELINE.json), z 5e-6 absolute (~80 ulp of a window depth near 1:
@@ -21,8 +23,11 @@ import jaxrenderer_b200 as jr
 from jaxrenderer_b200 import shaders as S
 from oracle import jr_oracle as O
 
-D = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_run.npz"))
-SOUPS = sorted({k.split("/")[0] for k in D.files if k.startswith("soup")})
+_GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+D = dict(np.load(os.path.join(_GOLDEN, "reference_run.npz")))
+# soup5: 64x48, 48 triangles 2.6 x larger, 86 % of the canvas covered (tools/gen_reference_fixtures_large.py)
+D.update(np.load(os.path.join(_GOLDEN, "reference_run_large.npz")))
+SOUPS = sorted({k.split("/")[0] for k in D if k.startswith("soup")})
 SHADERS = ("depth", "gouraud", "gouraud_texture", "phong", "phong_darboux", "phong_reflection",
            "phong_reflection_shadow")
 Z_ATOL, C_RTOL, MAX_COVERAGE_FLIPS = 5e-6, 1e-5, 0   # no coverage flip is excused

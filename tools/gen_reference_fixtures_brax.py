@@ -1,9 +1,12 @@
 #!/usr/bin/env python
 """Frame 0 of the reference's pre-generated Brax ant scene (`tests/golden/brax_ant_frames.npz`, 18 objects, 3276
-triangles) rendered by the UNMODIFIED reference's `Renderer.get_camera_image` (with the shadow pass) at 20x20 through the
-NumPy stand-in for jax -> `tests/golden/reference_run_brax.npz`.  About 10-15 minutes (vmap is a Python loop).
+triangles) rendered by the UNMODIFIED reference's `Renderer.get_camera_image` (with the shadow pass) through the NumPy
+stand-in for jax: at 20x20 -> `tests/golden/reference_run_brax.npz` (10-15 minutes, vmap is a Python loop), and at the
+size BASELINE.json's configs[1] names, 84x84 -> `tests/golden/reference_run_brax84.npz` (46 M fragment evaluations:
+about 40 minutes with the stand-in's outermost vmap split over 8 forked workers, JAX_SHIM_PROCS=8).
 
   python tools/gen_reference_fixtures_brax.py [/root/reference]
+  JAX_SHIM_PROCS=8 python tools/gen_reference_fixtures_brax.py /root/reference 84
 """
 from __future__ import annotations
 
@@ -13,6 +16,7 @@ import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
+SIZE = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 sys.path.insert(0, os.path.join(ROOT, "tools", "jax_numpy_shim"))
 sys.path.insert(0, REF)
 
@@ -20,7 +24,7 @@ import numpy as np  # noqa: E402
 import jax.numpy as jnp  # noqa: E402
 import renderer as R  # noqa: E402
 
-W = H = 20
+W = H = SIZE
 FRAME = 0
 
 
@@ -45,7 +49,7 @@ def main():
     t = time.time()
     img = R.Renderer.get_camera_image(objs, light, cp, W, H, shadow_param=sp)
     print(f"rendered in {time.time() - t:.0f}s; background fraction {(np.asarray(img) == 1).all(-1).mean():.2f}")
-    dst = os.path.join(ROOT, "tests", "golden", "reference_run_brax.npz")
+    dst = os.path.join(ROOT, "tests", "golden", "reference_run_brax.npz" if SIZE == 20 else f"reference_run_brax{SIZE}.npz")
     np.savez_compressed(dst, canvas=np.asarray(img), W=W, H=H, frame=FRAME, vfov=np.float32(float(c["hfov"]) * H / W),
                         light_direction=np.asarray(light.direction), ambient=np.asarray(light.ambient),
                         diffuse=np.asarray(light.diffuse), specular=np.asarray(light.specular))

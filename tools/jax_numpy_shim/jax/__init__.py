@@ -3,6 +3,7 @@ from __future__ import annotations
 
 import contextlib
 import functools
+import os as _os
 
 import numpy as _np
 
@@ -46,6 +47,48 @@ def named_scope(name):
     yield
 
 
+_VMAP_DEPTH = 0
+
+
+def _forked_map(one, size, procs):
+    """`[one(i) for i in range(size)]` over `procs` forked workers (JAX_SHIM_PROCS): the stand-in's `vmap` is a Python
+    loop, and a render of the real Brax frame at 84x84 is hours of it.  Same calls, same order of the results, same
+    arithmetic -- the workers are forks of this very process (closures and all), each takes every procs-th index and
+    pickles its results back through a pipe."""
+    import pickle
+
+    global _VMAP_DEPTH
+    pipes = []
+    for w in range(procs):
+        r, wfd = _os.pipe()
+        pid = _os.fork()
+        if pid == 0:                      # worker
+            _os.close(r)
+            code = 0
+            try:
+                _VMAP_DEPTH = 1           # nested vmaps inside a worker stay plain loops
+                res = [(i, one(i)) for i in range(w, size, procs)]
+                with _os.fdopen(wfd, "wb") as fh:
+                    pickle.dump(res, fh, protocol=pickle.HIGHEST_PROTOCOL)
+            except BaseException:         # noqa: BLE001  (report and die: never return into the parent's stack)
+                import traceback
+                traceback.print_exc()
+                code = 1
+            _os._exit(code)
+        _os.close(wfd)
+        pipes.append((pid, r))
+    outs = [None] * size
+    for pid, r in pipes:
+        with _os.fdopen(r, "rb") as fh:
+            data = fh.read()
+        _, status = _os.waitpid(pid, 0)
+        if status != 0 or not data:
+            raise RuntimeError("a forked vmap worker failed (see its traceback above)")
+        for i, v in pickle.loads(data):
+            outs[i] = v
+    return outs
+
+
 def vmap(f, in_axes=0, out_axes=0):
     """`jax.vmap` as a Python loop: slices every mapped leaf along its axis, calls `f`, stacks the results."""
 
@@ -68,14 +111,25 @@ def vmap(f, in_axes=0, out_axes=0):
             flat_args.append((leaves, treedef))
             flat_axes.append(ax_leaves)
         assert size is not None, "vmap needs at least one mapped argument"
-        outs = []
-        for i in range(size):
+
+        def one(i):
             call_args = []
             for (leaves, treedef), ax_leaves in zip(flat_args, flat_axes):
                 sl = [leaf if a is None else _wrap(_np.take(_np.asarray(leaf), i, axis=a))
                       for leaf, a in zip(leaves, ax_leaves)]
                 call_args.append(tree_unflatten(treedef, sl))
-            outs.append(f(*call_args))
+            return f(*call_args)
+
+        global _VMAP_DEPTH
+        procs = int(_os.environ.get("JAX_SHIM_PROCS", "1"))
+        if procs > 1 and _VMAP_DEPTH == 0 and size >= 2 * procs:
+            outs = _forked_map(one, size, procs)     # the OUTERMOST loop only, split over forked workers
+        else:
+            _VMAP_DEPTH += 1
+            try:
+                outs = [one(i) for i in range(size)]
+            finally:
+                _VMAP_DEPTH -= 1
         return tree_map(lambda *xs: _wrap(_np.stack([_np.asarray(x) for x in xs], axis=out_axes)), *outs)
 
     return mapped
