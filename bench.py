@@ -479,6 +479,75 @@ def _time_steps(fn, steps: int, warmup: int = 3) -> float:
     return e0.elapsed_time(e1) / steps
 
 
+_VIS_KERNELS = ("memset+k_setup_bin", "k_raster_tile", "k_vis3", "k_vis2")
+_SHADE_KERNELS = ("memset+k_mark_visible", "k_tri_attr", "k_shade_rec", "k_shade_rec_u8", "k_shade")
+
+
+def _hbm_peak() -> tuple:
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    except (OSError, ValueError, KeyError):
+        return 6650.0, "fallback 6650 GB/s"
+
+
+def _stage_rooflines(step, B: int, W: int, H: int, n_verts: int, n_tris: int, shade_bytes_per_pixel: int,
+                     reps: int = 3) -> dict:
+    """Per-stage rooflines of one secondary step from the library's own per-kernel event timing
+    (`jr_debug_kernel_timing`, include/jr_b200.h): the step runs `reps` more times with an event after every launch;
+    kernels are grouped per entry-point call into the visibility stage (binning + raster, or the single-tile kernel)
+    and the shading stage (visible-triangle lists + attribute records + pixel stage).  Algorithmic bytes
+    (SURVEY 8d / DESIGN 3): visibility = geometry once + one 4-byte plane out = B (12 Nv + 12 T + 4 W H); shading =
+    `shade_bytes_per_pixel` x B W H (G-buffer in, z + colour out, + the shadow-map sample) -- varyings and texels of
+    the visible triangles are left out, so the shading fraction is a lower bound."""
+    import torch
+
+    from jaxrenderer_b200 import _native
+
+    peak, peak_src = _hbm_peak()
+    torch.cuda.synchronize()
+    _native.kernel_timing(True)
+    try:
+        for _ in range(reps):
+            step()
+        torch.cuda.synchronize()
+        rows = _native.kernel_times()
+    finally:
+        _native.kernel_timing(False)
+    if not rows:
+        return {}
+    calls_per_step = (max(c for _, _, c in rows) + 1) // reps
+    stages, order = {}, []
+    for name, ms, call in rows:
+        c = call % calls_per_step
+        kind = "visibility" if name in _VIS_KERNELS else ("shading" if name in _SHADE_KERNELS else "other")
+        key = (c, kind)
+        if key not in stages:
+            stages[key] = {}
+            order.append(key)
+        stages[key][name] = stages[key].get(name, 0.0) + ms / reps
+    out, depth_pass_seen = [], False
+    n_vis = sum(1 for _, k in order if k == "visibility")
+    for c, kind in order:
+        ks = stages[(c, kind)]
+        ms = sum(ks.values())
+        row = {"stage": kind, "call": c, "kernels_ms": {k: round(v, 5) for k, v in ks.items()}, "ms": ms}
+        if kind == "visibility":
+            if n_vis > 1:
+                row["stage"] = "visibility (shadow pass)" if not depth_pass_seen else "visibility (main pass)"
+            depth_pass_seen = True
+            nbytes = B * (12 * n_verts + 12 * n_tris + 4 * W * H)
+        elif kind == "shading":
+            nbytes = B * W * H * shade_bytes_per_pixel
+        else:
+            nbytes = None
+        if nbytes:
+            row["roofline"] = {"bound": "hbm", "algorithmic_bytes": nbytes, "achieved": nbytes / (ms / 1e3) / 1e9,
+                               "peak": peak, "unit": "GB/s", "frac": nbytes / (ms / 1e3) / 1e9 / peak}
+        out.append(row)
+    return {"stages": out, "kernels_ms_total": sum(r["ms"] for r in out), "peak_source": peak_src,
+            "timing": f"CUDA events recorded by the library after each launch, mean of {reps} steps"}
+
+
 def secondary_configs(dev, steps: int = 5) -> dict:
     """The other configurations BASELINE.json names, device-resident, one GPU (secondary lines):
     configs[0] simple_cube 640x480 latency (B = 1, both shadow modes), configs[2] gouraud_texture 32x32 x 16384,
@@ -530,7 +599,9 @@ def secondary_configs(dev, steps: int = 5) -> dict:
         z.fill_(1.0); c.fill_(0.0)
         jr.render(cam, GouraudTextureShader, jr.Buffers(z, (c,)), faces, ex, inplace=True)
     ms = _time_steps(step3, steps)
-    out["configs[2] gouraud_texture 32x32 B=16384 T=1932"] = {"ms_per_step": ms, "images_per_s": B / ms * 1e3}
+    out["configs[2] gouraud_texture 32x32 B=16384 T=1932"] = {
+        "ms_per_step": ms, "images_per_s": B / ms * 1e3,
+        **_stage_rooflines(step3, B, Wd, Hd, sc["position"].shape[-2], faces.shape[-2], 24)}
     del sc, ex, faces, z, c
     # ---- configs[3] (B = 256) and configs[4] forward (B = 512): Renderer.render with the shadow pass
     for key, (Wd, Hd, n_caps, B) in (("configs[3] phong_reflection_shadow 960x540 B=256 T=19980", (960, 540, 104, 256)),
@@ -547,7 +618,8 @@ def secondary_configs(dev, steps: int = 5) -> dict:
             jr.Renderer.render(model, light, cam, bufs, shadow_param=sp, inplace=True)
         ms = _time_steps(step, steps)
         out[key] = {"ms_per_step": ms, "images_per_s": B / ms * 1e3,
-                    "pixels_per_s": B * Wd * Hd / ms * 1e3}
+                    "pixels_per_s": B * Wd * Hd / ms * 1e3,
+                    **_stage_rooflines(step, B, Wd, Hd, sc["position"].shape[-2], sc["faces"].shape[-2], 28)}
         del sc, model, bufs
         torch.cuda.empty_cache()
     return out
@@ -605,8 +677,20 @@ def fwd_bwd_secondary(dev, rank: int, world: int, steps: int = 5, shape=(480, 27
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item()) / steps
+    kernels_ms = None
+    if world == 1:   # where the step goes, kernel by kernel (the library's own event timing, one more step)
+        from jaxrenderer_b200 import _native
+        _native.kernel_timing(True)
+        try:
+            step()
+            torch.cuda.synchronize()
+            kernels_ms = {}
+            for name, k_ms, _ in _native.kernel_times():
+                kernels_ms[name] = round(kernels_ms.get(name, 0.0) + k_ms, 5)
+        finally:
+            _native.kernel_timing(False)
     return {"value": Bd * world / (ms / 1e3), "unit": "images/s (forward + backward)", "ms_per_step": ms,
-            "steps": steps,
+            "steps": steps, "kernels_ms": kernels_ms,
             "config": {"workload": f"phong_reflection_shadow {Wd}x{Hd}, {synthetic.scene_sizes(n_caps)[1]} triangles, "
                                    f"{Bd} images per GPU, grads w.r.t. light, world_to_clip, shared diffuse atlas",
                        "allreduce_floats": int(atlas.numel() + 6) if world > 1 else 0}}

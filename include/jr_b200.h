@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define JR_ABI_VERSION 6
+#define JR_ABI_VERSION 7
 
 typedef void* jr_stream_t; /* cudaStream_t */
 
@@ -308,6 +308,23 @@ int jr_debug_audit_cull(const JrRenderArgs* args, unsigned long long* counters, 
 /* Introspection for benchmarks: number of kernel launches issued by this
  * library since load (monotonic). */
 long long jr_launch_count(void);
+
+/* Measurement aid (ABI v7): per-kernel device times of the calls made through this library.  While switched on,
+ * every entry point records a CUDA event on its stream at its start and after each of its launches;
+ * jr_debug_kernel_times waits for those events, writes (kernel name, milliseconds since the event before it on the
+ * same call) in launch order into out[0 .. min(n, capacity)), forgets them and returns n (or a negative JrStatus).
+ * bench.py builds the per-kernel rooflines of its secondary lines from it.  Process-wide switch, at most
+ * JR_KERNEL_TIMES_MAX marks are kept between two reads; do NOT leave it on while capturing a CUDA graph (event
+ * records with timing cannot be captured) or while timing a step from outside (the events serialise nothing, but
+ * each costs a host call).  Switching (either way) forgets what was recorded. */
+#define JR_KERNEL_TIMES_MAX 4096
+typedef struct JrKernelTime {
+  char name[24];
+  float ms;
+  int32_t call; /* index of the entry-point call the launch belongs to (0, 1, ... since the switch-on / last read) */
+} JrKernelTime;
+int jr_debug_kernel_timing(int enable);
+int jr_debug_kernel_times(JrKernelTime* out, int capacity);
 
 #ifdef __cplusplus
 }

@@ -24,6 +24,7 @@ EXPORTS = (
     "jr_phong_darboux_forward", "jr_phong_reflection_forward", "jr_phong_reflection_shadow_forward",
     "jr_add_scalar", "jr_canvas_to_uint8_display", "jr_launch_count", "jr_merge_objects", "jr_camera_build",
     "jr_instance_norm_scales", "jr_camera_vjp", "jr_debug_audit_cull",
+    "jr_debug_kernel_timing", "jr_debug_kernel_times",
 )
 
 
@@ -92,6 +93,13 @@ class JrCameraArgs(C.Structure):
 
 JR_CAMERA_PERSPECTIVE, JR_CAMERA_LIGHT = 0, 1
 
+
+class JrKernelTime(C.Structure):
+    _fields_ = [("name", C.c_char * 24), ("ms", C.c_float), ("call", C.c_int32)]
+
+
+JR_KERNEL_TIMES_MAX = 4096
+
 _lib: Optional[C.CDLL] = None
 
 
@@ -137,6 +145,10 @@ def load() -> C.CDLL:
     lib.jr_debug_audit_cull.argtypes = [C.POINTER(JrRenderArgs), C.c_void_p, C.c_void_p]
     lib.jr_camera_vjp.restype = C.c_int
     lib.jr_camera_vjp.argtypes = [C.POINTER(JrCameraArgs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.jr_debug_kernel_timing.restype = C.c_int
+    lib.jr_debug_kernel_timing.argtypes = [C.c_int]
+    lib.jr_debug_kernel_times.restype = C.c_int
+    lib.jr_debug_kernel_times.argtypes = [C.POINTER(JrKernelTime), C.c_int]
     _lib = lib
     return lib
 
@@ -152,3 +164,18 @@ def stream_ptr(device: Any) -> int:
 
 def launch_count() -> int:
     return int(load().jr_launch_count())
+
+
+def kernel_timing(enable: bool) -> None:
+    """Switch the library's per-kernel event timing (measurement aid, ``jr_debug_kernel_timing``)."""
+    check(load().jr_debug_kernel_timing(1 if enable else 0))
+
+
+def kernel_times() -> list:
+    """``[(kernel name, ms, call index), ...]`` in launch order for every launch since the switch-on / the last
+    read (waits for them: ``jr_debug_kernel_times``)."""
+    buf = (JrKernelTime * JR_KERNEL_TIMES_MAX)()
+    n = load().jr_debug_kernel_times(buf, JR_KERNEL_TIMES_MAX)
+    if n < 0:
+        check(n)
+    return [(buf[i].name.decode(), float(buf[i].ms), int(buf[i].call)) for i in range(min(n, JR_KERNEL_TIMES_MAX))]

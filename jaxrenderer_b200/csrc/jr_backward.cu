@@ -878,16 +878,20 @@ static int run_keyed(const JrRenderArgs* a, const JrGradArgs* g, const BwdLayout
   } else {
     k_bwd_keys<S, MODE><<<dim3(bx, a->B > 65535 ? 65535 : a->B), 256, 0, stream>>>(*a, plan, keys_a, vals_a);
     g_launches++;
+    mark(stream, "k_bwd_keys");
   }
   size_t tmp = L.cub_bytes;
   const int end_bit = bit_length((unsigned long long)plan.invalid_key);
   cub::DeviceRadixSort::SortPairs(ws + L.cub_temp, tmp, keys_in, keys_b, vals_in, vals_b, (int)plan.n_entries, 0,
                                   end_bit, stream);
+  mark(stream, "cub::DeviceRadixSort");
   const long long nchunks = (plan.n_entries + 255) / 256;
   k_bwd_segreduce<S, MODE, C><<<(unsigned)nchunks, 256, 0, stream>>>(*a, *g, plan, keys_b, vals_b, carry);
   g_launches++;
+  mark(stream, "k_bwd_segreduce");
   k_bwd_segfix<MODE, C><<<(unsigned)((nchunks + 7) / 8), 256, 0, stream>>>(plan, carry, keys_b, (int)nchunks);
   g_launches++;
+  mark(stream, "k_bwd_segfix");
   return cudaGetLastError() == cudaSuccess ? JR_OK : JR_ERR_CUDA;
 }
 
@@ -900,6 +904,7 @@ static int backward_impl(const JrRenderArgs* a, const JrGradArgs* g, cudaStream_
   const long long total = npix * a->B;
   if (total * 4 > 0xFFFFFFFFLL) return JR_ERR_DIMS;  // payload packing (gi * 4 + corner) is 32-bit
   int rc = JR_OK;
+  mark(stream, nullptr);
   // ---- pixel pass: scene-global partial sums + keys / values of the one-entry-per-pixel targets
   const bool want_tex = S >= JR_GOURAUD_TEXTURE && g->d_texture.ptr;
   const bool want_spec = S >= JR_PHONG_REFLECTION && g->d_specular_map.ptr;
@@ -960,6 +965,7 @@ static int backward_impl(const JrRenderArgs* a, const JrGradArgs* g, cudaStream_
       k_bwd_records<CAN_REC ? S : JR_PHONG_REFLECTION><<<dim3((a->T + 127) / 128, a->B), 128, 0, stream>>>(
           *a, (float*)(ws + L.rec_off), list, count);
       g_launches += 2;
+      mark(stream, "k_mark_vis+k_bwd_recs");
       recs = (const float*)(ws + L.rec_off);
     }
     const size_t sm = NG * BWD_THREADS * 4;
@@ -975,6 +981,7 @@ static int backward_impl(const JrRenderArgs* a, const JrGradArgs* g, cudaStream_
     }
 #undef JR_PIXEL_PASS
     g_launches++;
+    mark(stream, "k_bwd_global");
   }
   if (wants_global(g)) {
     float* partials = (float*)(ws + L.partials);
@@ -999,6 +1006,7 @@ static int backward_impl(const JrRenderArgs* a, const JrGradArgs* g, cudaStream_
     set(G_STR, 3, g->d_shadow_strength, nullptr);
     k_bwd_global_final<<<NG, 128, 0, stream>>>(partials, a->B, L.nblk, out);
     g_launches++;
+    mark(stream, "k_bwd_global_final");
   }
   if (want_tex) {
     KeyedPlan p{};
@@ -1089,6 +1097,7 @@ static int backward_impl(const JrRenderArgs* a, const JrGradArgs* g, cudaStream_
     k_bwd_mask<<<(unsigned)blocks, 256, 0, stream>>>(a->tri_id, g->d_zbuffer, S != JR_DEPTH ? g->d_canvas : nullptr,
                                                      total);
     g_launches++;
+    mark(stream, "k_bwd_mask");
   }
   return cudaGetLastError() == cudaSuccess ? JR_OK : JR_ERR_CUDA;
 }

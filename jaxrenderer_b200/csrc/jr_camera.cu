@@ -213,8 +213,10 @@ extern "C" int jr_camera_build(const JrCameraArgs* a, jr_stream_t stream) {
   if (a->B <= 0) return JR_ERR_DIMS;
   if (a->mode != JR_CAMERA_PERSPECTIVE && a->mode != JR_CAMERA_LIGHT) return JR_ERR_UNSUPPORTED;
   if (a->mode == JR_CAMERA_LIGHT && !a->viewport.ptr) return JR_ERR_NULL;
+  jr::mark((cudaStream_t)stream, nullptr);
   jr::k_camera<<<(a->B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*a);
   jr::g_launches++;
+  jr::mark((cudaStream_t)stream, "k_camera");
   return cudaGetLastError() == cudaSuccess ? JR_OK : JR_ERR_CUDA;
 }
 
@@ -226,7 +228,9 @@ extern "C" int jr_camera_vjp(const JrCameraArgs* a, const float* d_out, float* d
   if (a->mode == JR_CAMERA_LIGHT && !a->viewport.ptr) return JR_ERR_NULL;
   const int n_in = (a->mode == JR_CAMERA_LIGHT && d_viewport) ? 32 : 16;
   const long long n = (long long)a->B * n_in;
+  jr::mark((cudaStream_t)stream, nullptr);
   jr::k_camera_vjp<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(*a, d_out, d_params, d_viewport);
   jr::g_launches++;
+  jr::mark((cudaStream_t)stream, "k_camera_vjp");
   return cudaGetLastError() == cudaSuccess ? JR_OK : JR_ERR_CUDA;
 }

@@ -520,6 +520,8 @@ int jr_render_forward(const JrRenderArgs* a, jr_stream_t stream_) {
   if (ctas > 2147483647LL) return JR_ERR_DIMS;
   set_kernel_attributes_once();
   const bool depth = a->shader == JR_DEPTH;
+  const char* vis_name = "k_vis3";
+  jr::mark(stream, nullptr);
   bool fused_mark = false;   // the visibility kernel built the visible-triangle lists itself
   if (!depth) {
     // everything the shading stage will need is validated BEFORE the first launch: a failing call enqueues nothing
@@ -543,7 +545,9 @@ int jr_render_forward(const JrRenderArgs* a, jr_stream_t stream_) {
       if (depth) k_setup_bin<true><<<g1, 256, 0, stream>>>(*a, recs, masks, TLy);
       else k_setup_bin<false><<<g1, 256, 0, stream>>>(*a, recs, masks, TLy);
       jr::g_launches++;
+      jr::mark(stream, "memset+k_setup_bin");
     }
+    vis_name = "k_raster_tile";
     const long long ctas2 = (long long)a->B * TLy.tiles;
     if (ctas2 > 2147483647LL) return JR_ERR_DIMS;
     const bool k32t = depth && !a->tri_id && !g_key64;
@@ -613,6 +617,7 @@ int jr_render_forward(const JrRenderArgs* a, jr_stream_t stream_) {
       else k_vis3<false, false, false, false><<<g, V3_THREADS, L.total, stream>>>(*a, vis);
     }
   } else {
+    vis_name = "k_vis2";
     if (a->inst_transform.ptr) return JR_ERR_UNSUPPORTED;  // k_vis2 (A/B switch) reads merged arrays only
     if (a->depth_fill || a->depth_offset != 0.f) return JR_ERR_UNSUPPORTED;
     // depth shader without a triangle-id output: z-only 32-bit keys (half the shared memory, native atomic min)
@@ -623,6 +628,7 @@ int jr_render_forward(const JrRenderArgs* a, jr_stream_t stream_) {
     else k_vis2<false, false, V2_THREADS><<<(unsigned)ctas, V2_THREADS, L.total, stream>>>(*a, tw, th, nx, ny);
   }
   jr::g_launches++;
+  jr::mark(stream, vis_name);
   if (!depth) {
     const int threads = 256;
     const int npix = a->W * a->H;
@@ -644,6 +650,7 @@ int jr_render_forward(const JrRenderArgs* a, jr_stream_t stream_) {
         k_mark_visible<0><<<dim3(bx > 64 ? 64 : bx, blocks.y), 256, 0, stream>>>(a->tri_id, flag_words, list, count, npix,
                                                                              a->T, a->B, slot_map);
         jr::g_launches++;
+        jr::mark(stream, "memset+k_mark_visible");
       }
       const int rec_stride = F.rec_stride;
       const bool compact = F.compact;
@@ -656,6 +663,7 @@ int jr_render_forward(const JrRenderArgs* a, jr_stream_t stream_) {
 #define JR_ATTR_CASE(S)                                                          \
   case S:                                                                        \
     k_tri_attr<S><<<g1, 128, 0, stream>>>(*a, attrs, list, count, rec_stride, compact, pcs); \
+    jr::mark(stream, "k_tri_attr");                                              \
     if (a->canvas_u8) k_shade_rec_u8<S><<<gu8, 256, 0, stream>>>(*a, attrs, rec_stride, slot_map, tiles_x, tiles_y, pcs); \
     else k_shade_rec<S><<<grec, threads, 0, stream>>>(*a, attrs, rec_stride, slot_map, pcs); \
     break;
@@ -668,6 +676,7 @@ int jr_render_forward(const JrRenderArgs* a, jr_stream_t stream_) {
         default: return JR_ERR_SHADER;
       }
       jr::g_launches += 2;
+      jr::mark(stream, a->canvas_u8 ? "k_shade_rec_u8" : "k_shade_rec");
     } else {
       switch (a->shader) {
         case JR_GOURAUD: k_shade<JR_GOURAUD><<<blocks, threads, 0, stream>>>(*a); break;
@@ -680,6 +689,7 @@ int jr_render_forward(const JrRenderArgs* a, jr_stream_t stream_) {
         default: return JR_ERR_SHADER;
       }
       jr::g_launches++;
+      jr::mark(stream, "k_shade");
     }
   }
   return cudaGetLastError() == cudaSuccess ? JR_OK : JR_ERR_CUDA;
@@ -704,15 +714,18 @@ int jr_merge_objects(const JrMergeArgs* m, jr_stream_t stream_) {
   if (m->B <= 0 || m->B > 65535 || m->n_objects <= 0 || m->n_verts < 0 || m->n_norms < 0) return JR_ERR_DIMS;
   if (!m->scaling.ptr || !m->transform.ptr || !m->normal_matrix.ptr) return JR_ERR_NULL;
   cudaStream_t stream = (cudaStream_t)stream_;
+  jr::mark(stream, nullptr);
   if (m->n_verts > 0) {
     if (!m->local_verts.ptr || !m->vert_object.ptr || !m->out_verts) return JR_ERR_NULL;
     k_merge_verts<<<dim3((m->n_verts + 255) / 256, m->B), 256, 0, stream>>>(*m);
     jr::g_launches++;
+    jr::mark(stream, "k_merge_verts");
   }
   if (m->n_norms > 0) {
     if (!m->local_norms.ptr || !m->norm_start.ptr || !m->out_norms) return JR_ERR_NULL;
     k_merge_norms<<<dim3(m->n_objects, (m->B + MN_GROUP - 1) / MN_GROUP), 256, 0, stream>>>(*m, nullptr);
     jr::g_launches++;
+    jr::mark(stream, "k_merge_norms");
   }
   return cudaGetLastError() == cudaSuccess ? JR_OK : JR_ERR_CUDA;
 }
@@ -721,8 +734,10 @@ int jr_instance_norm_scales(const JrMergeArgs* m, float* out_scales, jr_stream_t
   if (!m || !out_scales) return JR_ERR_NULL;
   if (m->B <= 0 || m->B > 65535 * MN_GROUP || m->n_objects <= 0 || m->n_norms <= 0) return JR_ERR_DIMS;
   if (!m->local_norms.ptr || !m->norm_start.ptr || !m->normal_matrix.ptr) return JR_ERR_NULL;
+  jr::mark((cudaStream_t)stream_, nullptr);
   k_merge_norms<<<dim3(m->n_objects, (m->B + MN_GROUP - 1) / MN_GROUP), 256, 0, (cudaStream_t)stream_>>>(*m, out_scales);
   jr::g_launches++;
+  jr::mark((cudaStream_t)stream_, "k_merge_norms(scales)");
   return cudaGetLastError() == cudaSuccess ? JR_OK : JR_ERR_CUDA;
 }
 
@@ -743,8 +758,10 @@ int jr_add_scalar(float* data, long long n, float value, jr_stream_t stream) {
   if (n <= 0) return JR_OK;
   long long blocks = (n + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
+  jr::mark((cudaStream_t)stream, nullptr);
   k_add_scalar<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(data, n, value);
   jr::g_launches++;
+  jr::mark((cudaStream_t)stream, "k_add_scalar");
   return cudaGetLastError() == cudaSuccess ? JR_OK : JR_ERR_CUDA;
 }
 
@@ -752,8 +769,10 @@ int jr_canvas_to_uint8_display(const float* canvas, uint8_t* out, int B, int W, 
   if (!canvas || !out) return JR_ERR_NULL;
   if (B <= 0 || W <= 0 || H <= 0 || B > 65535) return JR_ERR_DIMS;
   dim3 grid((W + 31) / 32, (H + 31) / 32, B), block(32, 8);
+  jr::mark((cudaStream_t)stream, nullptr);
   k_to_uint8_display<<<grid, block, 0, (cudaStream_t)stream>>>(canvas, out, B, W, H);
   jr::g_launches++;
+  jr::mark((cudaStream_t)stream, "k_to_uint8_display");
   return cudaGetLastError() == cudaSuccess ? JR_OK : JR_ERR_CUDA;
 }
 

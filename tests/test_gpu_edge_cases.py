@@ -229,3 +229,36 @@ def test_facade_captures_into_a_cuda_graph():
     moved = full()
     assert torch.equal(img, moved)
     assert img.shape == (4, 84, 84, 3) and bool(torch.isfinite(img).all())
+
+
+@pytest.mark.gpu
+def test_library_kernel_timing_lists_every_launch_of_a_call():
+    """`jr_debug_kernel_timing` / `jr_debug_kernel_times` (include/jr_b200.h): one event per launch, names in launch
+    order, grouped by entry-point call; nothing is recorded while the switch is off."""
+    from jaxrenderer_b200 import _native
+
+    s = random_mesh_scene(3, n_tri=30, W=48, H=40)
+    cam = _cam_d(s.cam)
+    faces, pos, nrm, col = (t.to(DEV) for t in (s.faces, s.pos, s.nrm, s.col))
+    light = jr.LightSource(torch.tensor((0.0, 0.3, -1.0), device=DEV), torch.ones(3, device=DEV))
+
+    def both():
+        z = jr.render(cam, DepthShader, jr.Buffers(torch.ones(48, 40, device=DEV), ()), faces, DepthExtraInput(pos))
+        g = jr.render(cam, GouraudShader, jr.Buffers(torch.ones(48, 40, device=DEV), (torch.zeros(48, 40, 3, device=DEV),)),
+                      faces, GouraudExtraInput(pos, col, nrm, light))
+        return z, g
+
+    plain = both()
+    _native.kernel_timing(True)
+    try:
+        timed = both()
+        rows = _native.kernel_times()
+        assert _native.kernel_times() == []          # a read forgets what it returned
+    finally:
+        _native.kernel_timing(False)
+    assert [(n, c) for n, _, c in rows] == [("k_vis3", 0), ("k_vis3", 1), ("k_tri_attr", 1), ("k_shade_rec", 1)], rows
+    assert all(0.0 < ms < 50.0 for _, ms, _ in rows), rows
+    for a, b in zip(plain, timed):                   # the marks change nothing
+        assert torch.equal(a.zbuffer, b.zbuffer)
+    both()
+    assert _native.kernel_times() == []              # switched off: nothing recorded

@@ -28,6 +28,9 @@ def test_abi_library_exports_every_declared_symbol():
         assert getattr(lib, name).argtypes is not None or name in ("jr_abi_version", "jr_launch_count"), name
     assert lib.jr_abi_version() == int(re.search(r'#define\s+JR_ABI_VERSION\s+(\d+)', header).group(1))
     assert lib.jr_strerror(-4).decode() == "workspace too small"
+    # the per-kernel timing switch needs no device: nothing was launched, nothing is reported
+    assert lib.jr_debug_kernel_timing(1) == 0 and lib.jr_debug_kernel_times(None, 0) == 0
+    assert lib.jr_debug_kernel_timing(0) == 0 and _native.kernel_times() == []
     # struct layout agreed between Python and C: a NULL args pointer is reported, not crashed on
     assert lib.jr_render_forward(None, None) == -1
     bad = _native.JrRenderArgs()
