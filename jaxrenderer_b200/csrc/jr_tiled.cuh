@@ -33,6 +33,12 @@ constexpr int TL_BIG_AREA = JR_TL_BIG_AREA;  // bbox (clipped to the tile) above
 #ifndef JR_TL_MASKCAP
 #define JR_TL_MASKCAP 1024
 #endif
+#ifndef JR_TL_SPAN
+#define JR_TL_SPAN 1      // warp-cooperative boxes of >= V2_HIER_AREA pixels: span raster (0: hierarchical block raster)
+#endif
+#ifndef JR_TL_BIG_FILL
+#define JR_TL_BIG_FILL 6  // of 16 samples: boxes above TL_BIG_AREA go to the CTA-wide sweep only when this full
+#endif
 #ifndef JR_TL_CTAS
 #define JR_TL_CTAS 4
 #endif
@@ -169,7 +175,11 @@ k_setup_bin(const __grid_constant__ JrRenderArgs a, TriRecord* __restrict__ recs
     }
 }
 
-struct TLSmem { size_t keys, xs, ys, ring, bigq, mask, total; };
+#ifndef JR_TL_MEDCAP
+#define JR_TL_MEDCAP 1024
+#endif
+constexpr int TL_MEDCAP = JR_TL_MEDCAP;  // warp-cooperative triangles queued per tile for phase 2 (overflow: rasterised in place)
+struct TLSmem { size_t keys, xs, ys, ring, bigq, mask, nz, medq, total; };
 __host__ __device__ inline TLSmem tl_smem(int key_bytes) {
   TLSmem S;
   S.keys = 0;
@@ -178,7 +188,9 @@ __host__ __device__ inline TLSmem tl_smem(int key_bytes) {
   S.ring = S.ys + TL_TILE * 4;
   S.bigq = S.ring + (TL_THREADS / 32) * 64 * 4;
   S.mask = S.bigq + (size_t)TL_BIGCAP * 64;
-  S.total = S.mask + (size_t)TL_MASKCAP * 4;
+  S.nz = S.mask + (size_t)TL_MASKCAP * 4;
+  S.medq = S.nz + (size_t)TL_MASKCAP * 2;
+  S.total = S.medq + (size_t)TL_MEDCAP * 4;
   return S;
 }
 
@@ -196,13 +208,15 @@ k_raster_tile(const __grid_constant__ JrRenderArgs a, const TriRecord* __restric
   float* ys = reinterpret_cast<float*>(smem + S.ys);
   V2Big* bigq = reinterpret_cast<V2Big*>(smem + S.bigq);
   unsigned* s_mask = reinterpret_cast<unsigned*>(smem + S.mask);
+  unsigned short* s_nz = reinterpret_cast<unsigned short*>(smem + S.nz);   // indices of the chunk's non-zero words
+  int* medq = reinterpret_cast<int*>(smem + S.medq);                       // warp-cooperative triangles (phase 2)
+  __shared__ int s_nzn, s_next, s_medn, s_mednext;
   __shared__ int bigq_n;
   __shared__ int tri0_flag;
   __shared__ TriSetup tri0;
   __shared__ float s_vp[16];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr int NW = TL_THREADS / 32;
   int* ring = reinterpret_cast<int*>(smem + S.ring) + warp * 64;
   const int b = blockIdx.x / L.tiles;
   const int tile = blockIdx.x - b * L.tiles;
@@ -217,6 +231,8 @@ k_raster_tile(const __grid_constant__ JrRenderArgs a, const TriRecord* __restric
   if (tid == 0) {
     bigq_n = 0;
     tri0_flag = 0;
+    s_medn = 0;
+    s_mednext = 0;
   }
   {
     uint4* k4 = reinterpret_cast<uint4*>(smem + S.keys);
@@ -237,6 +253,24 @@ k_raster_tile(const __grid_constant__ JrRenderArgs a, const TriRecord* __restric
       const float z = (c0 * zc[0] + c1 * zc[1]) + c2 * zc[2];
       const float zw = z * vp22 + vp23;
       put_key<K32>(keys_saddr, x * TL_TILE + y, zw, tri);
+    }
+  };
+
+  // one warp, one triangle (warp-uniform arguments, tile-local inclusive box of more than V2_SMALL_AREA pixels)
+  auto warp_raster = [&](const float* binv, const float* bzc, unsigned btri, int sx0, int sy0, int sx1, int sy1) {
+    const int sbh = sy1 - sy0 + 1;
+    const int n = (sx1 - sx0 + 1) * sbh;
+    if (n >= V2_HIER_AREA) {
+      if (JR_TL_SPAN)
+        raster_span_warp<K32>(binv, bzc, btri, sx0, sy0, sx1, sy1, lane, xs, ys, keys_saddr, TL_TILE, vp22, vp23);
+      else
+        raster_hier_warp<K32>(binv, bzc, btri, sx0, sy0, sx1, sy1, lane, xs, ys, keys_saddr, TL_TILE, vp22, vp23);
+    } else {
+      const float rbh = 1.0f / (float)sbh;
+      for (int i = lane; i < n; i += 32) {
+        const int dx = (int)(((float)i + 0.5f) * rbh);
+        put(sx0 + dx, sy0 + (i - dx * sbh), binv, bzc, btri);
+      }
     }
   };
 
@@ -261,7 +295,21 @@ k_raster_tile(const __grid_constant__ JrRenderArgs a, const TriRecord* __restric
     // frame hold nothing else) are queued for the whole CTA -- one warp sweeping 2 x 4096 pixels while
     // the other seven idle was the critical path of those tiles
     bool is_medium = area > V2_SMALL_AREA;
-    if (area > TL_BIG_AREA) {
+    bool is_big = area > TL_BIG_AREA;
+    if (JR_TL_SPAN && is_big) {
+      // the CTA-wide sweep visits every pixel of the box: it is for triangles that FILL theirs (the ground plane).
+      // A thin triangle with a large box (fill ~7 %) is left to the warp's span raster.  4 x 4 samples decide.
+      int inside = 0;
+#pragma unroll 1
+      for (int s = 0; s < 16; ++s) {
+        const int sx = x0 + ((2 * (s >> 2) + 1) * (bw - 1)) / 8, sy = y0 + ((2 * (s & 3) + 1) * (bh - 1)) / 8;
+        const float xn = xs[sx], yn = ys[sy];
+        inside += (((xn * inv[0] + yn * inv[3]) + inv[6]) >= 0.f && ((xn * inv[1] + yn * inv[4]) + inv[7]) >= 0.f &&
+                   ((xn * inv[2] + yn * inv[5]) + inv[8]) >= 0.f) ? 1 : 0;
+      }
+      is_big = inside >= JR_TL_BIG_FILL;
+    }
+    if (is_big) {
       const int slot = atomicAdd(&bigq_n, 1);
       if (slot < TL_BIGCAP) {
         V2Big& q = bigq[slot];
@@ -277,7 +325,18 @@ k_raster_tile(const __grid_constant__ JrRenderArgs a, const TriRecord* __restric
       for (int x = x0; x <= x1; ++x)
         for (int y = y0; y <= y1; ++y) put(x, y, inv, zc, (unsigned)t);
     }
+    const unsigned lt = (1u << lane) - 1u;
     unsigned mm = __ballot_sync(0xffffffffu, is_medium);
+    if (mm) {
+      // warp-cooperative boxes are not rasterised here: a warp whose 32 triangles hold a dozen of them kept the other
+      // seven waiting at the barrier (half of all stall samples).  They are queued; phase 2 hands them out one by one.
+      int base = 0;
+      if (lane == 0) base = atomicAdd(&s_medn, __popc(mm));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      const int slot = base + __popc(mm & lt);
+      if (is_medium && slot < TL_MEDCAP) { medq[slot] = t; is_medium = false; }
+      mm = __ballot_sync(0xffffffffu, is_medium);   // queue full: in place, as before
+    }
     while (mm) {
       const int src = __ffs(mm) - 1;
       mm &= mm - 1;
@@ -287,19 +346,8 @@ k_raster_tile(const __grid_constant__ JrRenderArgs a, const TriRecord* __restric
 #pragma unroll
       for (int k = 0; k < 3; ++k) bzc[k] = __shfl_sync(0xffffffffu, zc[k], src);
       const unsigned btri = (unsigned)__shfl_sync(0xffffffffu, t, src);
-      const int sx0 = __shfl_sync(0xffffffffu, x0, src), sy0 = __shfl_sync(0xffffffffu, y0, src);
-      const int sbh = __shfl_sync(0xffffffffu, bh, src);
-      const int n = __shfl_sync(0xffffffffu, area, src);
-      if (n >= V2_HIER_AREA) {
-        const int sx1 = __shfl_sync(0xffffffffu, x1, src), sy1 = __shfl_sync(0xffffffffu, y1, src);
-        raster_hier_warp<K32>(binv, bzc, btri, sx0, sy0, sx1, sy1, lane, xs, ys, keys_saddr, TL_TILE, vp22, vp23);
-      } else {
-        const float rbh = 1.0f / (float)sbh;
-        for (int i = lane; i < n; i += 32) {
-          const int dx = (int)(((float)i + 0.5f) * rbh);
-          put(sx0 + dx, sy0 + (i - dx * sbh), binv, bzc, btri);
-        }
-      }
+      warp_raster(binv, bzc, btri, __shfl_sync(0xffffffffu, x0, src), __shfl_sync(0xffffffffu, y0, src),
+                  __shfl_sync(0xffffffffu, x1, src), __shfl_sync(0xffffffffu, y1, src));
     }
   };
 
@@ -322,11 +370,32 @@ k_raster_tile(const __grid_constant__ JrRenderArgs a, const TriRecord* __restric
     // stage the tile's bitmask words in shared memory (coalesced; a per-word global load in the
     // scan loop below serialised ~80 dependent DRAM round trips per warp)
     const int n = min(TL_MASKCAP, L.words - chunk0);
-    for (int i = tid; i < n; i += TL_THREADS) s_mask[i] = mrow[chunk0 + i];
+    if (tid == 0) { s_nzn = 0; s_next = 0; }
     __syncthreads();
-    for (int i = warp; i < n; i += NW) {
+    // stage the words and list the non-zero ones (most tiles of a frame see two triangles of 20 000: stepping through
+    // 625 empty words per warp-eighth was 11-13 % of the kernel's instructions)
+    for (int i0 = 0; i0 < n; i0 += TL_THREADS) {
+      const int i = i0 + tid;
+      const unsigned w = i < n ? mrow[chunk0 + i] : 0u;
+      if (i < n) s_mask[i] = w;
+      const unsigned nzb = __ballot_sync(0xffffffffu, w != 0u);
+      if (nzb) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&s_nzn, __popc(nzb));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (w != 0u) s_nz[base + __popc(nzb & lt_mask)] = (unsigned short)i;
+      }
+    }
+    __syncthreads();
+    // warps claim non-zero words one at a time (the order is free: the key updates are minima)
+    const int nzn = s_nzn;
+    for (;;) {
+      int e = 0;
+      if (lane == 0) e = atomicAdd(&s_next, 1);
+      e = __shfl_sync(0xffffffffu, e, 0);
+      if (e >= nzn) break;
+      const int i = s_nz[e];
       const unsigned w = s_mask[i];
-      if (w == 0u) continue;
       if ((w >> lane) & 1u) ring[(head + pc + __popc(w & lt_mask)) & 63] = (chunk0 + i) * 32 + lane;
       pc += __popc(w);
       __syncwarp();
@@ -345,6 +414,26 @@ k_raster_tile(const __grid_constant__ JrRenderArgs a, const TriRecord* __restric
     fire(lane < pc, t);
   }
   __syncthreads();
+  // ---- phase 2: the queued warp-cooperative triangles, one per claim (every lane fetches the same record: one
+  // broadcast transaction per 16 bytes instead of 16 shuffles)
+  {
+    const int nmed = min(s_medn, TL_MEDCAP);
+    for (;;) {
+      int e = 0;
+      if (lane == 0) e = atomicAdd(&s_mednext, 1);
+      e = __shfl_sync(0xffffffffu, e, 0);
+      if (e >= nmed) break;
+      const int t = medq[e];
+      const float4* src = reinterpret_cast<const float4*>(rec_b + t);
+      const float4 q0 = src[0], q1 = src[1], q2 = src[2], q3 = src[3];
+      const float inv[9] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x};
+      const float zc[3] = {q2.y, q2.z, q2.w};
+      const unsigned bx = __float_as_uint(q3.x), by = __float_as_uint(q3.y);
+      warp_raster(inv, zc, (unsigned)t, max((int)(bx & 0xffff) - tx0, 0), max((int)(by & 0xffff) - ty0, 0),
+                  min((int)(bx >> 16) - tx0, tw - 1), min((int)(by >> 16) - ty0, th - 1));
+    }
+    __syncthreads();
+  }
   // ---- large triangles: whole CTA, one at a time, single writer per pixel
   {
     const int nbig = min(bigq_n, TL_BIGCAP);

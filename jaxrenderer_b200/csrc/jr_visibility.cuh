@@ -151,6 +151,63 @@ __device__ __forceinline__ void raster_hier_warp(const float* inv, const float* 
   }
 }
 
+// Warp-cooperative, EXACT span rasterisation of one triangle's bbox (tile-local, inclusive): for boxes that are
+// mostly empty -- the long thin triangles of a capsule's cylinder on a large canvas fill ~7 % of their box, and
+// there are a thousand of them per 960x540 humanoid frame.  A lane takes one LINE of the box along its longer side
+// (a column when the box is wider than tall, else a row) and finds the interval of the line that is inside: for a
+// fixed line every edge function  fl(fl(p + fl(v * i)) + c)  is monotone in the walked coordinate (each rounded op
+// is, and the pixel -> NDC table is), so "edge k >= 0" holds on a prefix or a suffix of the line.  The switch point
+// is located from the analytic root (approximate arithmetic) and walked to the exact place with the rasterisers' own
+// expression; the pixels of the interval are then evaluated -- and TESTED -- exactly like everywhere else, so the
+// interval only has to contain the inside set for the result to be bit-identical (it is exact, the test is a guard).
+// fp32 addition and multiplication commute, so one expression serves both orientations.
+template <bool K32>
+__device__ __forceinline__ void raster_span_warp(const float* inv, const float* zc, unsigned tri, int x0, int y0,
+                                                 int x1, int y1, int lane, const float* xs, const float* ys,
+                                                 uint32_t keys_saddr, int key_stride, float vp22, float vp23) {
+  const bool cols = (x1 - x0) >= (y1 - y0);          // lanes = columns, walk along y
+  const int u0 = cols ? x0 : y0, u1 = cols ? x1 : y1, v0 = cols ? y0 : x0, v1 = cols ? y1 : x1;
+  const float* __restrict__ us = cols ? xs : ys;
+  const float* __restrict__ vs = cols ? ys : xs;
+  float iu[3], iv[3];                                // rows of inv multiplying the lane's / the walked coordinate
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { iu[k] = cols ? inv[k] : inv[3 + k]; iv[k] = cols ? inv[3 + k] : inv[k]; }
+  const float vs0 = vs[v0];
+  const float idx_per_v = (v1 > v0) ? (float)(v1 - v0) * __fdividef(1.f, vs[v1] - vs0) : 0.f;  // table index per NDC unit
+  for (int u = u0 + lane; u <= u1; u += 32) {
+    const float un = us[u];
+    int lo = v0, hi = v1;
+    bool empty = false;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      if (empty) continue;
+      const float pk = un * iu[k], ik = iv[k], ck = inv[6 + k];
+      const bool in_lo = ((pk + vs[lo] * ik) + ck) >= 0.f;
+      const bool in_hi = ((pk + vs[hi] * ik) + ck) >= 0.f;
+      if (in_lo && in_hi) continue;
+      if (!in_lo && !in_hi) { empty = true; continue; }
+      const float root = (float)v0 + (-(pk + ck) * __fdividef(1.f, ik) - vs0) * idx_per_v;
+      int l = min(max((int)floorf(fminf(fmaxf(root, (float)lo), (float)hi)), lo), hi - 1);
+      while (l > lo && (((pk + vs[l] * ik) + ck) >= 0.f) != in_lo) --l;
+      while (l + 1 < hi && (((pk + vs[l + 1] * ik) + ck) >= 0.f) == in_lo) ++l;
+      if (in_lo) hi = l; else lo = l + 1;
+    }
+    if (empty) continue;
+    for (int v = lo; v <= hi; ++v) {
+      const int x = cols ? u : v, y = cols ? v : u;
+      const float xn = xs[x], yn = ys[y];
+      const float c0 = (xn * inv[0] + yn * inv[3]) + inv[6];
+      const float c1 = (xn * inv[1] + yn * inv[4]) + inv[7];
+      const float c2 = (xn * inv[2] + yn * inv[5]) + inv[8];
+      if (c0 >= 0.f && c1 >= 0.f && c2 >= 0.f) {
+        const float z = (c0 * zc[0] + c1 * zc[1]) + c2 * zc[2];
+        const float zw = z * vp22 + vp23;
+        put_key<K32>(keys_saddr, x * key_stride + y, zw, tri);
+      }
+    }
+  }
+}
+
 struct V2Big {  // 64 bytes
   float inv[9];
   float zc[3];
