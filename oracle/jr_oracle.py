@@ -403,6 +403,12 @@ class RenderOut(NamedTuple):
     chosen: torch.Tensor      # (W,H) int64: argmin index (0 when no candidate)
     has: torch.Tensor         # (W,H) bool: a front-facing candidate exists
     gap: torch.Tensor         # (W,H) second-best minus best depth
+    # (W,H) distance of the sampled atlas coordinate to the nearest texel boundary, in units of the fp32 spacing of
+    # the interpolated uv it came from (ulp(|uv|) x texture size; atlas shaders, else None).  Like `gap` it is a
+    # diagnostic for the tests: where it is a few units, the `floor` of the lookup is decided by the last bits of the
+    # perspective-correct interpolation, which differ between evaluation orders of the same formula (the ground of a
+    # Brax scene carries uv ~ 10^3-10^4: one ulp there is 10^-3 of a texel of its checker).
+    texel_gap: Any = None
 
 
 def _light(extra: Any) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -440,6 +446,7 @@ def render(camera: Any, shader: Any, zbuffer: Any, targets: Sequence[Any], face_
 
     keep = kc.clone()
     colour: Optional[torch.Tensor] = None
+    texel_gap = None
 
     if name == "depth":
         pass                                             # depth.py: default fragment, keeps only
@@ -510,7 +517,11 @@ def render(camera: Any, shader: Any, zbuffer: Any, targets: Sequence[Any], face_
         ti = _t(extra.texture_index, torch.int64)[f_idx[..., 0]]      # first vertex (:149)
         tshape = _t(extra.texture_shape, torch.int64)[ti]
         offset = int(_t(extra.texture_offset, torch.int64))
-        uvr = torch.floor(uv_repeat(uv, tshape, ti, offset)).to(torch.int64)   # :175-184
+        uvc = uv_repeat(uv, tshape, ti, offset)
+        ulp_uv = torch.clamp_min(uv.abs(), 1.0) * 2.0 ** -23 * tshape.to(F32)
+        texel_gap = (uvc - torch.round(uvc)).abs() / ulp_uv
+        texel_gap = torch.where(tshape > 1, texel_gap, torch.full_like(texel_gap, INF)).amin(-1).detach()  # 1 texel: no choice
+        uvr = torch.floor(uvc).to(torch.int64)                        # :175-184
         tcol = _gather_clamped(tex, uvr[..., 0], uvr[..., 1])
         nn = normalise(normal)
         ld = normalise(_t(extra.light_dir_eye))
@@ -547,7 +558,7 @@ def render(camera: Any, shader: Any, zbuffer: Any, targets: Sequence[Any], face_
         assert len(targets) == 1
         outs.append(torch.where(keep[..., None], colour, targets[0]))
     tri = torch.where(keep, idx, torch.full_like(idx, -1))
-    return RenderOut(zbuffer=z_out, targets=tuple(outs), tri_id=tri, chosen=idx, has=has, gap=gap)
+    return RenderOut(zbuffer=z_out, targets=tuple(outs), tri_id=tri, chosen=idx, has=has, gap=gap, texel_gap=texel_gap)
 
 
 # --------------------------------------------------------------------------
