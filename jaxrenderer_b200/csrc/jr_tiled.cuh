@@ -34,7 +34,8 @@ constexpr int TL_BIG_AREA = JR_TL_BIG_AREA;  // bbox (clipped to the tile) above
 #define JR_TL_MASKCAP 1024
 #endif
 #ifndef JR_TL_SPAN
-#define JR_TL_SPAN 1      // warp-cooperative boxes of >= V2_HIER_AREA pixels: span raster (0: hierarchical block raster)
+#define JR_TL_SPAN 2      // warp-cooperative boxes of >= V2_HIER_AREA pixels: span raster from the analytic roots (1: exact
+                          // interval search, 0: hierarchical block raster)
 #endif
 #ifndef JR_TL_BIG_FILL
 #define JR_TL_BIG_FILL 6  // of 16 samples: boxes above TL_BIG_AREA go to the CTA-wide sweep only when this full
@@ -261,7 +262,9 @@ k_raster_tile(const __grid_constant__ JrRenderArgs a, const TriRecord* __restric
     const int sbh = sy1 - sy0 + 1;
     const int n = (sx1 - sx0 + 1) * sbh;
     if (n >= V2_HIER_AREA) {
-      if (JR_TL_SPAN)
+      if (JR_TL_SPAN == 2)
+        raster_span2_warp<K32>(binv, bzc, btri, sx0, sy0, sx1, sy1, lane, xs, ys, keys_saddr, TL_TILE, vp22, vp23);
+      else if (JR_TL_SPAN == 1)
         raster_span_warp<K32>(binv, bzc, btri, sx0, sy0, sx1, sy1, lane, xs, ys, keys_saddr, TL_TILE, vp22, vp23);
       else
         raster_hier_warp<K32>(binv, bzc, btri, sx0, sy0, sx1, sy1, lane, xs, ys, keys_saddr, TL_TILE, vp22, vp23);

@@ -208,6 +208,66 @@ __device__ __forceinline__ void raster_span_warp(const float* inv, const float* 
   }
 }
 
+// The same, with the interval of a line taken from the ANALYTIC roots of the three edge functions, widened by a bound
+// on everything that separates them from the rounded evaluation, instead of an exact search (which costs ~50
+// instructions per edge and line).  The per-pixel test below is the rasterisers' own, so the result is bit-identical
+// as long as the interval CONTAINS every accepted pixel.  Bound, in table-index units, for edge k on the line
+// (p = fl(u * i_u), i = i_v, c):  the rounded value  fl(fl(p + fl(v i)) + c)  differs from the real  p + v i + c  by at
+// most E = 3 * 2^-24 (|p| + |i| max|v| + |c|), so an accepted pixel satisfies  v i >= -(p + c) - E, i.e. lies within
+// E / |i| (x index-per-NDC) of the real root on its inner side; the root itself is evaluated in fp32 with a relative
+// error below 2^-20 (reciprocal approximation, three roundings) and the index <-> NDC table is linear to 10^-3 pixel.
+// Margin used: E-term + |root| 2^-18 + 0.05.  A vanishing i gives a NaN / infinite root, which fmaxf / fminf ignore
+// (no constraint from that edge: every pixel of the line is tested).
+template <bool K32>
+__device__ __forceinline__ void raster_span2_warp(const float* inv, const float* zc, unsigned tri, int x0, int y0,
+                                                  int x1, int y1, int lane, const float* xs, const float* ys,
+                                                  uint32_t keys_saddr, int key_stride, float vp22, float vp23) {
+  const bool cols = (x1 - x0) >= (y1 - y0);          // lanes = columns, walk along y
+  const int u0 = cols ? x0 : y0, u1 = cols ? x1 : y1, v0 = cols ? y0 : x0, v1 = cols ? y1 : x1;
+  const float* __restrict__ us = cols ? xs : ys;
+  const float* __restrict__ vs = cols ? ys : xs;
+  const float vs0 = vs[v0], vs1 = vs[v1];
+  const float idx_per_v = (v1 > v0) ? (float)(v1 - v0) * __fdividef(1.f, vs1 - vs0) : 0.f;  // table index per NDC unit
+  const float vmax = fmaxf(fabsf(vs0), fabsf(vs1));
+  const float v0f = (float)v0;
+  float iu[3], rik[3], ge[3], av[3];
+  bool up[3];                                        // the accepted side of edge k is "index >= root"
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    iu[k] = cols ? inv[k] : inv[3 + k];
+    const float ik = cols ? inv[3 + k] : inv[k];
+    rik[k] = __fdividef(1.f, ik);
+    ge[k] = 1.7881393e-7f * fabsf(rik[k] * idx_per_v);   // 3 * 2^-24 / |i|, in index units
+    av[k] = fabsf(ik) * vmax;
+    up[k] = (ik > 0.f) == (idx_per_v >= 0.f);
+  }
+  for (int u = u0 + lane; u <= u1; u += 32) {
+    const float un = us[u];
+    float lo_f = v0f, hi_f = (float)v1;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float pk = un * iu[k], ck = inv[6 + k];
+      const float root = fmaf(-(pk + ck) * rik[k] - vs0, idx_per_v, v0f);
+      const float m = fmaf(fabsf(root), 3.8146973e-6f, fmaf((fabsf(pk) + fabsf(ck)) + av[k], ge[k], 0.05f));
+      if (up[k]) lo_f = fmaxf(lo_f, root - m); else hi_f = fminf(hi_f, root + m);
+    }
+    if (!(lo_f <= hi_f)) continue;
+    const int lo = (int)ceilf(lo_f), hi = (int)floorf(hi_f);
+    for (int v = lo; v <= hi; ++v) {
+      const int x = cols ? u : v, y = cols ? v : u;
+      const float xn = xs[x], yn = ys[y];
+      const float c0 = (xn * inv[0] + yn * inv[3]) + inv[6];
+      const float c1 = (xn * inv[1] + yn * inv[4]) + inv[7];
+      const float c2 = (xn * inv[2] + yn * inv[5]) + inv[8];
+      if (c0 >= 0.f && c1 >= 0.f && c2 >= 0.f) {
+        const float z = (c0 * zc[0] + c1 * zc[1]) + c2 * zc[2];
+        const float zw = z * vp22 + vp23;
+        put_key<K32>(keys_saddr, x * key_stride + y, zw, tri);
+      }
+    }
+  }
+}
+
 struct V2Big {  // 64 bytes
   float inv[9];
   float zc[3];

@@ -409,6 +409,11 @@ class RenderOut(NamedTuple):
     # perspective-correct interpolation, which differ between evaluation orders of the same formula (the ground of a
     # Brax scene carries uv ~ 10^3-10^4: one ulp there is 10^-3 of a texel of its checker).
     texel_gap: Any = None
+    # (W,H) shadow shaders: how far the shadow test of the pixel is from flipping -- min of |fragment depth in light
+    # space - stored depth| (where the lookup is in range) and, in shadow-map pixels, the distance of the looked-up
+    # position from the rounding boundary between two shadow-map pixels (`Shadow.get` rounds to nearest).
+    shadow_z_gap: Any = None
+    shadow_xy_gap: Any = None
 
 
 def _light(extra: Any) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -446,7 +451,7 @@ def render(camera: Any, shader: Any, zbuffer: Any, targets: Sequence[Any], face_
 
     keep = kc.clone()
     colour: Optional[torch.Tensor] = None
-    texel_gap = None
+    texel_gap = shadow_z_gap = shadow_xy_gap = None
 
     if name == "depth":
         pass                                             # depth.py: default fragment, keeps only
@@ -542,7 +547,11 @@ def render(camera: Any, shader: Any, zbuffer: Any, targets: Sequence[Any], face_
             ss = mat4_vec4(s_vp, sc)
             ss = ss / ss[..., 3:4]                                    # :196-199
             smap = _t(sh.shadow_map)
-            lit = ss[..., 2] <= shadow_get(smap, ss[..., :2].detach())
+            stored = shadow_get(smap, ss[..., :2].detach())
+            lit = ss[..., 2] <= stored
+            shadow_z_gap = torch.where(torch.isfinite(stored), (ss[..., 2] - stored).abs(), torch.full_like(stored, INF)).detach()
+            sxy = ss[..., :2].detach()
+            shadow_xy_gap = ((sxy - torch.floor(sxy)) - 0.5).abs().amin(-1)
             strength = _t(sh.strength)
             shadow = torch.where(lit[..., None], torch.ones_like(strength), 1.0 - strength)
             colour = (amb * tcol
@@ -558,7 +567,8 @@ def render(camera: Any, shader: Any, zbuffer: Any, targets: Sequence[Any], face_
         assert len(targets) == 1
         outs.append(torch.where(keep[..., None], colour, targets[0]))
     tri = torch.where(keep, idx, torch.full_like(idx, -1))
-    return RenderOut(zbuffer=z_out, targets=tuple(outs), tri_id=tri, chosen=idx, has=has, gap=gap, texel_gap=texel_gap)
+    return RenderOut(zbuffer=z_out, targets=tuple(outs), tri_id=tri, chosen=idx, has=has, gap=gap, texel_gap=texel_gap,
+                     shadow_z_gap=shadow_z_gap, shadow_xy_gap=shadow_xy_gap)
 
 
 # --------------------------------------------------------------------------
