@@ -16,17 +16,21 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
-def _scene(seed: int, W: int, H: int, n_tri: int, B: int):
+def _scene(seed: int, W: int, H: int, n_tri: int, B: int, len_px=(0.05, 6.0), aligned: float = 0.0,
+           asp_min: float = 1.0):
+    """`len_px`: range of the long edge in pixels (log-uniform); `aligned`: share of the triangles whose long edge is
+    exactly parallel to a screen axis."""
     rng = np.random.default_rng(seed)
     d = 3.0
     fovy = 50.0
     px = 2 * d * math.tan(math.radians(fovy) / 2) / H            # world size of one pixel at z = 0
     cx = rng.uniform(-W / 2 - 2, W / 2 + 2, size=(B, n_tri)) * px
     cy = rng.uniform(-H / 2 - 2, H / 2 + 2, size=(B, n_tri)) * px
-    L = np.exp(rng.uniform(math.log(0.05), math.log(6.0), size=(B, n_tri))) * px
-    asp = np.exp(rng.uniform(0.0, math.log(3000.0), size=(B, n_tri)))
+    L = np.exp(rng.uniform(math.log(len_px[0]), math.log(len_px[1]), size=(B, n_tri))) * px
+    asp = np.exp(rng.uniform(math.log(asp_min), math.log(3000.0), size=(B, n_tri)))
     h = L / asp
     ang = rng.uniform(0, 2 * math.pi, size=(B, n_tri))
+    ang = np.where(rng.uniform(size=(B, n_tri)) < aligned, np.round(ang / (math.pi / 2)) * (math.pi / 2), ang)
     t = rng.uniform(0.05, 0.95, size=(B, n_tri))                    # foot of the height on the long edge
     flip = rng.uniform(size=(B, n_tri)) < 0.3
     ux, uy = np.cos(ang), np.sin(ang)
@@ -69,6 +73,33 @@ def test_fuzz_small_and_needle_triangles(case):
         print("  cull audit:", audit)
         assert audit["filter_lost_triangles"] == 0 and audit["pixels_outside_bbox"] == 0
         assert audit["pixels_of_rejected_triangles"] == 0 and audit["triangles_kept"] > 0
+
+
+@pytest.mark.parametrize("tri_id", [True, False])
+@pytest.mark.parametrize("case", [(320, 200, 2500, 2, 11, 0.0, 1.0), (640, 360, 3000, 1, 12, 0.25, 1.0),
+                                  (200, 150, 1500, 2, 13, 1.0, 1.0), (640, 360, 20000, 1, 14, 0.1, 30.0)])
+def test_fuzz_long_needles_on_tiled_canvases(case, tri_id):
+    """The span raster of the tiled path (`raster_span2_warp`: line intervals from analytic roots + a rounding-error
+    margin, exact per-pixel test inside): thousands of LONG needles -- 16 to 300 pixels, aspect ratios up to 3000, any
+    orientation, a share of them exactly parallel to a screen axis (the edge coefficient along the line vanishes) --
+    crossing several 64x64 tiles, bit-for-bit against the brute-force C oracle, with packed keys (triangle ids) and with
+    the z-only keys of a depth pass.  A pixel missed by a too-narrow interval shows up as a mismatch."""
+    W, H, n_tri, B, seed, aligned, asp_min = case
+    pos, faces, cam = _scene(seed, W, H, n_tri, B, len_px=(16.0, 300.0), aligned=aligned, asp_min=asp_min)
+    camd = type(cam)(*[t.to(DEV) for t in cam])
+    res = jr.render(camd, DepthShader, jr.Buffers(torch.full((B, W, H), 1.0, device=DEV), ()), faces.to(DEV),
+                    DepthExtraInput(position=pos.to(DEV)), return_tri_id=tri_id)
+    out, tri = res if tri_id else (res, None)
+    zo, to = c_oracle.render_depth(cam.world_to_clip.numpy(), cam.viewport.numpy(), pos.numpy(), faces.numpy(),
+                                   np.ones((B, W, H), np.float32))
+    covered = int((to >= 0).sum())
+    zg = out.zbuffer.cpu().numpy()
+    print(f"{W}x{H} T={n_tri} B={B} aligned={aligned} tri_id={tri_id}: covered {covered} px by {len(np.unique(to)) - 1} "
+          f"triangles, z mismatches {int((zg != zo).sum())}")
+    assert covered > 0.05 * B * W * H
+    if tri_id:
+        assert int((tri.cpu().numpy() != to).sum()) == 0
+    assert np.array_equal(zg, zo)
 
 
 def test_cull_audit_reads_zero_on_brax_scenes():
