@@ -552,9 +552,24 @@ int jr_render_forward(const JrRenderArgs* a, jr_stream_t stream_) {
     if (ctas2 > 2147483647LL) return JR_ERR_DIMS;
     const bool k32t = depth && !a->tri_id && !g_key64;
     const size_t sm = tl_smem(k32t ? 4 : 8).total;
-    if (k32t) k_raster_tile<true, true><<<(unsigned)ctas2, TL_THREADS, sm, stream>>>(*a, recs, masks, TLy);
-    else if (depth) k_raster_tile<true, false><<<(unsigned)ctas2, TL_THREADS, sm, stream>>>(*a, recs, masks, TLy);
-    else k_raster_tile<false, false><<<(unsigned)ctas2, TL_THREADS, sm, stream>>>(*a, recs, masks, TLy);
+    // shaders that go through attribute records: the resolve also builds the visible-triangle lists (TLVis)
+    TLVis tvis{nullptr, nullptr, nullptr, nullptr};
+    if (!depth) {
+      const FwdLayout F = fwd_layout(a);
+      if (F.use_attr && !g_no_fused_mark) {
+        unsigned* flag_words = (unsigned*)(ws + F.flags_off);
+        const size_t n_words = ((size_t)a->B * a->T + 31) / 32;
+        cudaMemsetAsync(flag_words, 0, n_words * 4 + (size_t)a->B * 4, stream);
+        tvis.flags = flag_words;
+        tvis.count = (int*)(flag_words + n_words);
+        tvis.list = (int*)(ws + F.list_off);
+        tvis.slot_map = F.compact ? (int*)(ws + F.map_off) : nullptr;
+        fused_mark = true;
+      }
+    }
+    if (k32t) k_raster_tile<true, true><<<(unsigned)ctas2, TL_THREADS, sm, stream>>>(*a, recs, masks, TLy, tvis);
+    else if (depth) k_raster_tile<true, false><<<(unsigned)ctas2, TL_THREADS, sm, stream>>>(*a, recs, masks, TLy, tvis);
+    else k_raster_tile<false, false><<<(unsigned)ctas2, TL_THREADS, sm, stream>>>(*a, recs, masks, TLy, tvis);
   } else if (nx * ny == 1 && !g_vis2) {
     // single-tile canvases: filtered two-phase kernel (jr_vis3.cuh); z-only 32-bit keys for the depth shader
     // without a triangle-id output

@@ -37,6 +37,9 @@ constexpr int TL_BIG_AREA = JR_TL_BIG_AREA;  // bbox (clipped to the tile) above
 #define JR_TL_SPAN 2      // warp-cooperative boxes of >= V2_HIER_AREA pixels: span raster from the analytic roots (1: exact
                           // interval search, 0: hierarchical block raster)
 #endif
+#ifndef JR_TL_SPAN_AREA
+#define JR_TL_SPAN_AREA 256   // queued boxes from this many pixels: span / hierarchical raster; below: lane per pixel
+#endif
 #ifndef JR_TL_BIG_FILL
 #define JR_TL_BIG_FILL 6  // of 16 samples: boxes above TL_BIG_AREA go to the CTA-wide sweep only when this full
 #endif
@@ -195,11 +198,21 @@ __host__ __device__ inline TLSmem tl_smem(int key_bytes) {
   return S;
 }
 
+// Visible-triangle lists of the attribute stage, built by the resolve (non-depth passes; all NULL: not wanted).  The
+// first pixel of a run of equal ids in a column flags its triangle (atomicOr on the image's flag bits, workspace) and
+// the first to flag it appends it to the image's list -- k_mark_visible's logic without its re-read of the G-buffer.
+struct TLVis {
+  unsigned* flags;  // B*T bits, then B counters (zeroed by the caller before the launch)
+  int* list;        // (B, T)
+  int* count;       // (B)
+  int* slot_map;    // (B, T) triangle -> record slot (compact records), or NULL
+};
+
 // K32: depth shader without a triangle-id output (shadow passes) -- z-only 32-bit keys, see k_vis2.
 template <bool DEPTH, bool K32>
 __global__ void __launch_bounds__(TL_THREADS, K32 ? JR_TL_K32_CTAS : JR_TL_CTAS)
 k_raster_tile(const __grid_constant__ JrRenderArgs a, const TriRecord* __restrict__ recs,
-              const unsigned* __restrict__ masks, TiledLayout L) {
+              const unsigned* __restrict__ masks, TiledLayout L, TLVis vis) {
   static_assert(DEPTH || !K32, "z-only keys are for the depth shader");
   extern __shared__ __align__(16) unsigned char smem[];
   const TLSmem S = tl_smem(K32 ? 4 : 8);
@@ -261,7 +274,7 @@ k_raster_tile(const __grid_constant__ JrRenderArgs a, const TriRecord* __restric
   auto warp_raster = [&](const float* binv, const float* bzc, unsigned btri, int sx0, int sy0, int sx1, int sy1) {
     const int sbh = sy1 - sy0 + 1;
     const int n = (sx1 - sx0 + 1) * sbh;
-    if (n >= V2_HIER_AREA) {
+    if (n >= JR_TL_SPAN_AREA) {
       if (JR_TL_SPAN == 2)
         raster_span2_warp<K32>(binv, bzc, btri, sx0, sy0, sx1, sy1, lane, xs, ys, keys_saddr, TL_TILE, vp22, vp23);
       else if (JR_TL_SPAN == 1)
@@ -494,6 +507,17 @@ k_raster_tile(const __grid_constant__ JrRenderArgs a, const TriRecord* __restric
       if (covered) {
         tri = (int)(unsigned)(key & 0xFFFFFFFFull);
         if (DEPTH) { zv = from_orderable((uint32_t)(key >> 32)); wrote = true; }
+        if (!DEPTH && vis.flags && !(ly > 0 && (unsigned)(keys[i - 1] & 0xFFFFFFFFull) == (unsigned)tri)) {
+          // first pixel of a run of this id in the column (an empty predecessor reads 0xFFFFFFFF: never a triangle)
+          const long long bit = (long long)b * a.T + tri;
+          unsigned* w = vis.flags + (bit >> 5);
+          const unsigned m = 1u << (bit & 31);
+          if (!(*w & m) && !(atomicOr(w, m) & m)) {
+            const int slot = atomicAdd(&vis.count[b], 1);
+            vis.list[(long long)b * a.T + slot] = tri;
+            if (vis.slot_map) vis.slot_map[(long long)b * a.T + tri] = slot;
+          }
+        }
       }
     }
     if (covered) {
