@@ -262,3 +262,42 @@ def test_library_kernel_timing_lists_every_launch_of_a_call():
         assert torch.equal(a.zbuffer, b.zbuffer)
     both()
     assert _native.kernel_times() == []              # switched off: nothing recorded
+
+
+@pytest.mark.gpu
+def test_graphed_replays_the_facade_with_new_inputs():
+    """`jr.graphed` (the role `jax.jit` plays in the reference's examples): one capture, then replays with the inputs
+    copied into the graph's buffers -- bit-equal to the eager call for every new set of transforms / eye positions, one
+    graph per signature, rejected argument kinds reported."""
+    from tests.helpers import load_brax_fixture
+
+    dev = torch.device("cuda", 0)
+    objs, cam = load_brax_fixture()
+    objs = [jr.ModelObject(model=type(o.model)(*[t.to(dev) for t in o.model]), local_scaling=o.local_scaling.to(dev),
+                           transform=o.transform.to(dev), double_sided=o.double_sided.to(dev)) for o in objs]
+    cam = type(cam)(*[v.to(dev) if isinstance(v, torch.Tensor) else v for v in cam])._replace(viewWidth=84, viewHeight=84)
+    light, sp = jr.LightParameters(), jr.ShadowParameters(centre=cam.target)
+
+    def frame(transforms, eye, size=84):
+        moved = [o._replace(transform=t) for o, t in zip(objs, transforms)]
+        return jr.Renderer.get_camera_image(moved, light, cam._replace(position=eye, viewWidth=size, viewHeight=size),
+                                            size, size, shadow_param=sp)
+
+    render = jr.graphed(frame)
+    tf = [o.transform.clone() for o in objs]
+    eye = cam.position.clone()
+    for step in range(3):
+        got = render(tf, eye)
+        want = frame(tf, eye)
+        assert torch.equal(got, want), step
+        tf = [t.clone() for t in tf]
+        for t in tf[1:]:
+            t[..., 2, 3] += 0.04                          # the robot rises, the camera drifts
+        eye = eye + torch.tensor((0.05, -0.02, 0.03), device=dev)
+    assert render.cache_size() == 1
+    small = render(tf, eye, 64)                            # a static argument changed: a second graph
+    assert render.cache_size() == 2 and small.shape[1:3] == (64, 64) and torch.equal(small, frame(tf, eye, 64))
+    with pytest.raises(ValueError, match="integer tensors"):
+        render(tf, eye, objs[0].model.faces)
+    with pytest.raises(ValueError, match="CUDA tensors"):
+        render([t.cpu() for t in tf], eye.cpu())
