@@ -180,7 +180,7 @@ k_setup_bin(const __grid_constant__ JrRenderArgs a, TriRecord* __restrict__ recs
 }
 
 #ifndef JR_TL_MEDCAP
-#define JR_TL_MEDCAP 1024
+#define JR_TL_MEDCAP 2048
 #endif
 constexpr int TL_MEDCAP = JR_TL_MEDCAP;  // warp-cooperative triangles queued per tile for phase 2 (overflow: rasterised in place)
 struct TLSmem { size_t keys, xs, ys, ring, bigq, mask, nz, medq, total; };
