@@ -202,3 +202,15 @@ def test_graft_entry_check_matches_header():
     import __graft_entry__ as g
 
     g.check()
+
+
+def test_graphed_rejects_what_it_cannot_capture():
+    """`jr.graphed` (CUDA-graph counterpart of the reference users' `jax.jit`): argument validation needs no GPU."""
+    g = jr.graphed(lambda x: x * 2)
+    with pytest.raises(ValueError, match="CUDA tensors"):
+        g(torch.ones(3))
+    with pytest.raises(ValueError, match="no tensor"):
+        g(3.0)
+    assert g.cache_size() == 0
+    deco = jr.graphed(copy_outputs=True)(lambda x: x)
+    assert deco.copy_outputs and deco.cache_size() == 0
