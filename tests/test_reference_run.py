@@ -4,7 +4,8 @@
 executed on small scenes through a NumPy stand-in for jax (`tools/jax_numpy_shim`, generator
 `tools/gen_reference_fixtures.py`): all seven built-in shaders through `pipeline.render`, the shadow pass,
 `merge_objects`, `create_camera_from_parameters` and `Renderer.get_camera_image`; `reference_run_large.npz` the same
-seven shaders on a 64x48 canvas covered to 86 % (`tools/gen_reference_fixtures_large.py`), `reference_run_brax84.npz`
+seven shaders on a 64x48 canvas covered to 86 % (`tools/gen_reference_fixtures_large.py`), `reference_run_tiled.npz` on a
+128x96 canvas (the binned CUDA path: 2 x 2 tiles), `reference_run_brax84.npz`
 the facade on the real Brax ant frame at 84x84 (BASELINE.json configs[1]'s canvas).  The CPU tests pin the oracle and
 the host-side glue of the package against it; the GPU tests pin the CUDA path.
 
@@ -27,6 +28,8 @@ _GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 D = dict(np.load(os.path.join(_GOLDEN, "reference_run.npz")))
 # soup5: 64x48, 48 triangles 2.6 x larger, 86 % of the canvas covered (tools/gen_reference_fixtures_large.py)
 D.update(np.load(os.path.join(_GOLDEN, "reference_run_large.npz")))
+# soup6: 128x96 -- 2 x 2 tiles of the binned CUDA path (bitmasks, triangle queue, span raster, CTA-wide sweep)
+D.update(np.load(os.path.join(_GOLDEN, "reference_run_tiled.npz")))
 SOUPS = sorted({k.split("/")[0] for k in D if k.startswith("soup")})
 SHADERS = ("depth", "gouraud", "gouraud_texture", "phong", "phong_darboux", "phong_reflection",
            "phong_reflection_shadow")

@@ -8,6 +8,12 @@ larger: ~1800 covered pixels per shader instead of ~100, dozens of overlapping t
 outermost `vmap` is split over forked workers (JAX_SHIM_PROCS), results identical to the plain loop.
 
   JAX_SHIM_PROCS=8 python tools/gen_reference_fixtures_large.py [/root/reference]      # ~3 minutes on 8 cores
+
+`... tiled` renders a second soup at 128x96 -- 2 x 2 of the 64x64 tiles of the binned CUDA path, so that the two-level
+kernels (bitmasks, triangle queue, span raster, CTA-wide sweep) are pinned against the reference's own output as well
+-> `tests/golden/reference_run_tiled.npz` (~6 minutes on 8 cores).
+
+  JAX_SHIM_PROCS=8 python tools/gen_reference_fixtures_large.py /root/reference tiled
 """
 from __future__ import annotations
 
@@ -19,7 +25,8 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import gen_reference_fixtures as G  # noqa: E402
 import numpy as np  # noqa: E402
 
-SEED, N_TRI, W, H, SPREAD = 5, 48, 64, 48, 2.6
+TILED = len(sys.argv) > 2 and sys.argv[2] == "tiled"
+SEED, N_TRI, W, H, SPREAD = (6, 40, 128, 96, 2.6) if TILED else (5, 48, 64, 48, 2.6)
 
 
 def big_soup(seed, n_tri, W, H, tex=8):
@@ -38,7 +45,7 @@ def main():
     G.run_soup(SEED, n_tri=N_TRI, W=W, H=H)
     cov = float((G.OUT[f"soup{SEED}/depth/zbuffer"] != 1.0).mean())
     assert cov > 0.5, cov
-    dst = os.path.join(G.ROOT, "tests", "golden", "reference_run_large.npz")
+    dst = os.path.join(G.ROOT, "tests", "golden", "reference_run_tiled.npz" if TILED else "reference_run_large.npz")
     np.savez_compressed(dst, **G.OUT)
     print(f"wrote {dst}: {len(G.OUT)} arrays, {os.path.getsize(dst) / 1024:.0f} KB, coverage {cov:.2f}, {time.time() - t0:.0f}s")
 
