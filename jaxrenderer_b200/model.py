@@ -162,7 +162,9 @@ def batch_models(models: Sequence[MergedModel]) -> MergedModel:
             assert all(m.offset == models[0].offset for m in models)
             fields.append(models[0].offset)
         else:
-            fields.append(torch.stack([torch.as_tensor(m[i]) for m in models], dim=0))
+            # (a CUDA merge_objects hands out un-materialised verts / norms: torch.as_tensor would walk them as sequences)
+            vals = [m[i].materialise() if isinstance(m[i], InstancedArray) else torch.as_tensor(m[i]) for m in models]
+            fields.append(torch.stack(vals, dim=0))
     return MergedModel._make(fields)
 
 

@@ -347,3 +347,69 @@ def test_oracle_facade_matches_reference_run_brax_frame(fixture):
     objs, cp, light, sp, want, W, H = _brax_case(fixture)
     canvas, gap = _oracle_facade(objs, cp, light, sp, W, H)
     _assert_only_ties("oracle", canvas, want, gap, _oracle_facade.texel_gap, _oracle_facade.shadow_gaps)
+
+
+# ------------------------------------------------------------------ the reference's batching idiom, run by the reference
+def _vmap_case(dev=None):
+    """`tools/gen_reference_fixtures_vmap.py`: three poses of a small scene through
+    `jax.vmap(lambda model, buffer: Renderer.render(...))(batch_models(merged_models), buffers)`
+    (`examples/batch_rendering.py:83-95`), executed by the unmodified reference."""
+    V = np.load(os.path.join(_GOLDEN, "reference_run_vmap.npz"))
+    mv = (lambda a: torch.from_numpy(np.asarray(a)).to(dev)) if dev else (lambda a: torch.from_numpy(np.asarray(a)))
+    W, H, n = int(V["W"]), int(V["H"]), int(V["poses"])
+    merged = []
+    for k in range(n):
+        objs = []
+        for i in range(3):
+            g = lambda f: mv(V[f"pose{k}/obj{i}/{f}"])  # noqa: E731
+            m = jr.Model(verts=g("verts"), norms=g("norms"), uvs=g("uvs"), faces=g("faces"), faces_norm=g("faces_norm"),
+                         faces_uv=g("faces_uv"), diffuse_map=g("diffuse_map"), specular_map=g("specular_map"))
+            objs.append(jr.ModelObject(model=m, local_scaling=g("local_scaling"), transform=g("transform")))
+        merged.append(jr.merge_objects(objs))
+    cp = jr.CameraParameters(viewWidth=W, viewHeight=H, position=mv(V["cam_position"]), target=mv(V["cam_target"]),
+                             up=mv(V["cam_up"]), hfov=float(V["hfov"]), vfov=float(V["vfov"]))
+    camera = jr.Renderer.create_camera_from_parameters(cp)
+    sp = jr.ShadowParameters(centre=mv(V["shadow_centre"]))
+    return jr.batch_models(merged), jr.LightParameters(), camera, sp, V, W, H, n
+
+
+def _check_vmap(tag, z, c, V):
+    zf, cf = torch.from_numpy(V["zbuffer"]), torch.from_numpy(V["canvas"])
+    z, c = z.detach().cpu(), c.detach().cpu()
+    flips = int(((zf != 1.0) != (z != 1.0)).sum())
+    dz, dc = float((z - zf).abs().max()), float((c - cf).abs().max())
+    print(f"[{tag}] vmap idiom, {tuple(cf.shape)}: covered {int((zf != 1.0).sum())}, coverage flips {flips}, "
+          f"max |dz| {dz:.3g}, max |dcolour| {dc:.3g}")
+    assert tuple(z.shape) == tuple(zf.shape) and tuple(c.shape) == tuple(cf.shape)
+    assert flips == 0 and dz <= Z_ATOL and dc <= 2e-5
+
+
+def test_oracle_matches_reference_run_vmap_idiom():
+    batch, light, camera, sp, V, W, H, n = _vmap_case()
+    zs, cs = [], []
+    for k in range(n):
+        model = type(batch)(*[(f[k] if isinstance(f, torch.Tensor) and name != "offset" else f)
+                              for name, f in zip(batch._fields, batch)])
+        res = O.renderer_render(model, light, camera, torch.ones(W, H), torch.ones(W, H, 3), shadow_param=sp)
+        zs.append(res["out"].zbuffer); cs.append(res["out"].targets[0])
+    _check_vmap("oracle", torch.stack(zs), torch.stack(cs), V)
+
+
+@pytest.mark.gpu
+def test_cuda_native_batch_and_torch_vmap_match_reference_run_vmap_idiom():
+    """The package's leading batch axis IS the reference's `vmap`: `Renderer.render` on `batch_models(...)` with batched
+    buffers, and `torch.func.vmap` of the reference's own lambda, against what the reference's `jax.vmap` produced."""
+    from torch.func import vmap
+
+    dev = torch.device("cuda", 0)
+    batch, light, camera, sp, V, W, H, n = _vmap_case(dev)
+    buffers = jr.Renderer.create_buffers(W, H, batch=n, device=dev)
+    out = jr.Renderer.render(model=batch, light=light, camera=camera, buffers=buffers, shadow_param=sp)
+    _check_vmap("cuda, native batch", out.zbuffer, out.targets[0], V)
+    in_model = type(batch)(*[(None if name == "offset" or not isinstance(f, torch.Tensor) else 0)
+                             for name, f in zip(batch._fields, batch)])
+    zv, cv = vmap(lambda model, z, c: (lambda o: (o.zbuffer, o.targets[0]))(
+        jr.Renderer.render(model=model, light=light, camera=camera, buffers=jr.Buffers(z, (c,)), shadow_param=sp)),
+        in_dims=(in_model, 0, 0))(batch, buffers.zbuffer, buffers.targets[0])
+    _check_vmap("cuda, torch.func.vmap", zv, cv, V)
+    assert torch.equal(zv, out.zbuffer) and torch.equal(cv, out.targets[0])
