@@ -61,3 +61,25 @@ def test_example_plane_as_mesh():
             m = type(m)(*[t.to(dev) for t in m])
         return [jr.ModelObject(model=m).replace_with_orientation((1.0, 0, 0, 0))]
     _compare("plane_as_mesh.py", objs, jr.LightParameters(), cp, jr.ShadowParameters())
+
+
+def test_example_axises_and_plane_growing_object_lists():
+    """`examples/axises_and_plane.py`: a flat cube (texture scaling 16) and capsules along X, Y, Z, rendered four times
+    with a GROWING list of objects -- each list is its own atlas / merged topology (the memoised static half of
+    `merge_objects` must not leak from one list into the next)."""
+    tex = jr.build_texture_from_PyTinyrenderer(RGBW, 2, 2) / 255.0
+    spec = torch.full(tex.shape[:2], 2.0)
+    cp = jr.CameraParameters(viewWidth=W, viewHeight=H, position=(2.0, 4.0, 1.0), target=(0.0, 0.0, 0.0))
+
+    def all_objs(dev):
+        mv = (lambda m: type(m)(*[t.to(dev) for t in m])) if dev is not None else (lambda m: m)
+        cube = mv(jr.create_cube(half_extents=torch.tensor((1.5, 1.5, 0.03)), texture_scaling=torch.tensor((16.0, 16.0)),
+                                 diffuse_map=tex, specular_map=spec))
+        caps = [mv(jr.create_capsule(radius=torch.tensor(0.1), half_height=torch.tensor(0.4), up_axis=ax, diffuse_map=tex,
+                                     specular_map=spec)) for ax in (jr.UpAxis.X, jr.UpAxis.Y, jr.UpAxis.Z)]
+        return [jr.ModelObject(model=cube).replace_with_position((0.0, 0.0, -0.5))] + [jr.ModelObject(model=c) for c in caps]
+
+    cuda_objs, cpu_objs = all_objs(torch.device("cuda", 0)), all_objs(None)
+    for n in (2, 3, 4, 2):                                   # ... and back to the first list
+        _compare(f"axises_and_plane.py, {n} objects", lambda dev, n=n: (cuda_objs if dev is not None else cpu_objs)[:n],
+                 jr.LightParameters(), cp, jr.ShadowParameters())
