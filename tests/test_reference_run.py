@@ -5,7 +5,7 @@ executed on small scenes through a NumPy stand-in for jax (`tools/jax_numpy_shim
 `tools/gen_reference_fixtures.py`): all seven built-in shaders through `pipeline.render`, the shadow pass,
 `merge_objects`, `create_camera_from_parameters` and `Renderer.get_camera_image`; `reference_run_large.npz` the same
 seven shaders on a 64x48 canvas covered to 86 % (`tools/gen_reference_fixtures_large.py`), `reference_run_tiled.npz` on a
-128x96 canvas (the binned CUDA path: 2 x 2 tiles), `reference_run_brax84.npz`
+136x96 canvas (the binned CUDA path: 3 x 2 tiles), `reference_run_brax84.npz`
 the facade on the real Brax ant frame at 84x84 (BASELINE.json configs[1]'s canvas).  The CPU tests pin the oracle and
 the host-side glue of the package against it; the GPU tests pin the CUDA path.
 
@@ -28,7 +28,8 @@ _GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 D = dict(np.load(os.path.join(_GOLDEN, "reference_run.npz")))
 # soup5: 64x48, 48 triangles 2.6 x larger, 86 % of the canvas covered (tools/gen_reference_fixtures_large.py)
 D.update(np.load(os.path.join(_GOLDEN, "reference_run_large.npz")))
-# soup6: 128x96 -- 2 x 2 tiles of the binned CUDA path (bitmasks, triangle queue, span raster, CTA-wide sweep)
+# soup6: 136x96 -- beyond the single-tile kernel's 12 288 pixels: 3 x 2 tiles of the binned CUDA path (bitmasks,
+# triangle queue, span raster, CTA-wide sweep); the GPU test checks that those kernels are the ones that ran
 D.update(np.load(os.path.join(_GOLDEN, "reference_run_tiled.npz")))
 SOUPS = sorted({k.split("/")[0] for k in D if k.startswith("soup")})
 SHADERS = ("depth", "gouraud", "gouraud_texture", "phong", "phong_darboux", "phong_reflection",
@@ -186,11 +187,21 @@ def test_cuda_path_matches_reference_run_all_shaders(p):
     cam, faces, extras, W, H = _scene(p, dev)
     camera = jr.Camera(*[getattr(cam, k, None) if hasattr(cam, k) else None for k in jr.Camera._fields])
     camera = camera._replace(view=T(p + "/view", dev))
+    from jaxrenderer_b200 import _native
+    kernels = set()
     for name in SHADERS:
         shader, extra = extras[name]
         z0, c0 = torch.ones(W, H, device=dev), torch.full((W, H, 3), 0.25, device=dev)
-        out = jr.render(camera, shader, jr.Buffers(z0, () if name == "depth" else (c0,)), faces, extra)
+        _native.kernel_timing(True)
+        try:
+            out = jr.render(camera, shader, jr.Buffers(z0, () if name == "depth" else (c0,)), faces, extra)
+            kernels |= {k for k, _, _ in _native.kernel_times()}
+        finally:
+            _native.kernel_timing(False)
         _check("cuda", out.zbuffer, None if name == "depth" else out.targets[0], p, name)
+    # which visibility path served the scene: the single-tile kernel up to 12 288 pixels, the two-level kernels beyond
+    want = {"k_raster_tile", "memset+k_setup_bin"} if W * H * 8 > 96 * 1024 else {"k_vis3"}
+    assert want <= kernels and not ({"k_raster_tile", "k_vis3"} - want) & kernels, (p, sorted(kernels))
 
 
 @pytest.mark.gpu

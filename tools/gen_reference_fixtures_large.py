@@ -9,7 +9,7 @@ outermost `vmap` is split over forked workers (JAX_SHIM_PROCS), results identica
 
   JAX_SHIM_PROCS=8 python tools/gen_reference_fixtures_large.py [/root/reference]      # ~3 minutes on 8 cores
 
-`... tiled` renders a second soup at 128x96 -- 2 x 2 of the 64x64 tiles of the binned CUDA path, so that the two-level
+`... tiled` renders a second soup at 136x96 -- more pixels than the single-tile kernel takes (12 288), hence 3 x 2 of the 64x64 tiles of the binned CUDA path, the last column 8 pixels wide, so that the two-level
 kernels (bitmasks, triangle queue, span raster, CTA-wide sweep) are pinned against the reference's own output as well
 -> `tests/golden/reference_run_tiled.npz` (~6 minutes on 8 cores).
 
@@ -26,7 +26,7 @@ import gen_reference_fixtures as G  # noqa: E402
 import numpy as np  # noqa: E402
 
 TILED = len(sys.argv) > 2 and sys.argv[2] == "tiled"
-SEED, N_TRI, W, H, SPREAD = (6, 40, 128, 96, 2.6) if TILED else (5, 48, 64, 48, 2.6)
+SEED, N_TRI, W, H, SPREAD = (6, 40, 136, 96, 2.6) if TILED else (5, 48, 64, 48, 2.6)
 
 
 def big_soup(seed, n_tri, W, H, tex=8):
